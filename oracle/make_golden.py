@@ -1,0 +1,195 @@
+"""Freeze reference outputs into ``tests/golden/*.npz`` (run in the build container).
+
+The reference (otmanon/simkit @ 4e19c36) is imported read-only from
+``/root/reference``; inputs are seeded and stored next to the outputs so the
+fixtures replay without the reference (it does not exist on the GPU box).
+
+    python oracle/make_golden.py
+"""
+
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sps
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+
+import simkit  # noqa: E402
+import simkit.energies as ske  # noqa: E402
+from simkit.integrators import backward_euler as ref_be  # noqa: E402
+from simkit.solvers import newton_solver as ref_newton  # noqa: E402
+from simkit.fast_sandwich_transform_clustered import fast_sandwich_transform_clustered as ref_fst  # noqa: E402
+from simkit.rotation_gradient import rotation_gradient_F as ref_rotgrad  # noqa: E402
+
+from simkit_b200 import synthetic as syn  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+MATS = {
+    "stable_neo_hookean": True,
+    "neo_hookean": True,
+    "arap": False,
+    "stvk": True,
+    "linear_elasticity": True,
+}
+
+
+def canon(Q):
+    Q = sps.csr_matrix(Q)
+    Q.sum_duplicates()
+    Q.sort_indices()
+    return Q
+
+
+def golden_mesh(tag, cells, sigma, seed):
+    dim = len(cells)
+    X, T = syn.make_mesh(cells)
+    ext = tuple(1.0 for _ in cells)
+    t = T.shape[0]
+    rng = np.random.default_rng(seed)
+    # shuffle vertex numbering so the caller's order is not lexicographic
+    perm = rng.permutation(X.shape[0])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.shape[0])
+    X = X[perm]
+    T = inv[T]
+    U = syn.jittered_state(X, cells, ext, sigma=sigma, seed=seed)
+    mu, lam = syn.heterogeneous_lame(t, seed=seed + 1)
+    J = simkit.deformation_jacobian(X, T)
+    vol = simkit.volume(X, T)
+    F = np.asarray(J @ U.reshape(-1, 1)).reshape(-1, dim, dim)
+    out = dict(X=X, T=T, U=U, mu=mu, lam=lam, vol=vol, F=F, dim=dim, sigma=sigma,
+               J_data=canon(J).data, J_indices=canon(J).indices, J_indptr=canon(J).indptr)
+    R, S = simkit.polar_svd(F)
+    out["polar_R"], out["polar_S"] = R, S
+    out["rotgrad"] = ref_rotgrad(F)
+    xb = X + 0.02 * rng.standard_normal(X.shape)
+    out["x_bar"] = xb
+    Jxb = J @ xb.reshape(-1, 1)
+    inverted = bool((np.linalg.det(F) <= 0).any())
+    out["inverted"] = inverted
+    for m, has_lam in MATS.items():
+        if m == "neo_hookean" and inverted:
+            continue
+        a = (mu, lam) if has_lam else (mu,)
+        g = lambda kind, tier: getattr(ske, f"{m}_{kind}_{tier}")  # noqa: E731
+        out[f"{m}_psi"] = g("energy", "element_F")(F, *a)
+        out[f"{m}_P"] = g("gradient", "element_F")(F, *a)
+        out[f"{m}_He"] = g("hessian", "element_F")(F, *a)
+        out[f"{m}_E"] = g("energy", "x")(U, J, *a, vol)
+        out[f"{m}_g"] = g("gradient", "x")(U, J, *a, vol)
+        for psd in (True, False):
+            Q = canon(g("hessian", "x")(U, J, *a, vol, psd=psd))
+            k = f"{m}_Q_psd{int(psd)}"
+            out[k + "_data"], out[k + "_indices"], out[k + "_indptr"] = Q.data, Q.indices, Q.indptr
+        out[f"{m}_E_u"] = g("energy", "u")(U - xb, J, Jxb, *a, vol)
+        out[f"{m}_g_u"] = g("gradient", "u")(U - xb, J, Jxb, *a, vol)
+    # elastic dispatcher (psd floor *before* vol): arap + linear-elasticity routes
+    for m, name in (("arap", "arap"), ("linear_elasticity", "linear-elasticity")):
+        Q = canon(ske.elastic_hessian_x(U, J, mu, lam, vol, name, psd=True))
+        k = f"{m}_Qdisp"
+        out[k + "_data"], out[k + "_indices"], out[k + "_indptr"] = Q.data, Q.indices, Q.indptr
+    # psd_project on arbitrary symmetric blocks
+    A = rng.standard_normal((40, dim * dim, dim * dim))
+    A = A + np.swapaxes(A, 1, 2)
+    out["psd_in"] = A
+    out["psd_proj"] = simkit.psd_project(A)
+    out["psd_abs"] = simkit.psd_project(A, "abs")
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print("wrote", tag, "t =", t, "inverted:", inverted)
+
+
+def golden_step(tag, cells, seed):
+    """One backward-Euler step (3 Newton iterations, line search) and plain Newton."""
+    dim = len(cells)
+    X, T = syn.make_mesh(cells)
+    ext = tuple(1.0 for _ in cells)
+    mu, lam = syn.lame()
+    rho, h = 1e3, 1e-2
+    J = simkit.deformation_jacobian(X, T)
+    vol = simkit.volume(X, T)
+    Mv = sps.kron(simkit.massmatrix(X, T, rho), sps.identity(dim)).tocsc()
+    fg = simkit.gravity_force(X, T, -9.8, rho).reshape(-1, 1)
+    out = dict(X=X, T=T, mu=mu, lam=lam, rho=rho, h=h, dim=dim, mass_diag=Mv.diagonal(), fg=fg)
+    for m, has_lam in MATS.items():
+        a = (mu, lam) if has_lam else (mu,)
+        e_x = getattr(ske, f"{m}_energy_x")
+        g_x = getattr(ske, f"{m}_gradient_x")
+        h_x = getattr(ske, f"{m}_hessian_x")
+
+        def E(x):
+            return e_x(x.reshape(-1, dim), J, *a, vol) - float((fg.T @ x).item())
+
+        def G(x):
+            return g_x(x.reshape(-1, dim), J, *a, vol) - fg
+
+        def H(x):
+            return h_x(x.reshape(-1, dim), J, *a, vol)
+
+        x_curr = syn.jittered_state(X, cells, ext, sigma=0.05, seed=seed).reshape(-1, 1)
+        x_prev = X.reshape(-1, 1)
+        x, info = ref_be(x_curr, x_prev, E, G, H, Mv, h, max_iter=3, return_info=True)
+        out[f"{m}_be_x_curr"], out[f"{m}_be_x_prev"] = x_curr, x_prev
+        out[f"{m}_be_x"] = x
+        out[f"{m}_be_alphas"] = np.array(info["alphas"])
+        out[f"{m}_be_iters"] = info["iters"]
+        out[f"{m}_be_dx0"] = info["dx"][0]
+        out[f"{m}_be_g0"] = info["g"][0]
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print("wrote", tag)
+
+
+def golden_reduced(tag, cells, r, seed):
+    """Reduced Hessian through the `_u` tier with a dense operator and FST."""
+    dim = len(cells)
+    X, T = syn.make_mesh(cells)
+    ext = tuple(1.0 for _ in cells)
+    t = T.shape[0]
+    mu, lam = syn.lame()
+    J = simkit.deformation_jacobian(X, T)
+    vol = simkit.volume(X, T)
+    B = syn.smooth_modes(X, r, seed=seed)
+    rng = np.random.default_rng(seed)
+    z = 0.02 * rng.standard_normal((r, 1))
+    JB = np.asarray(J @ B)
+    Jx0 = np.asarray(J @ X.reshape(-1, 1))
+    out = dict(X=X, T=T, B=B, z=z, mu=mu, lam=lam, vol=vol, dim=dim)
+    zz = z.reshape(-1, 1)
+
+    class _Z:  # the `_u` functions only read ``u.shape[1]`` and ``u.reshape(-1,1)``
+        pass
+
+    for m, has_lam in (("stable_neo_hookean", True), ("arap", False)):
+        a = (mu, lam) if has_lam else (mu,)
+        u = np.zeros((r // dim if r % dim == 0 else r, dim)) if False else None
+        # call with u of shape (r/dim, dim) as example 011 does (z.reshape(-1, dim))
+        assert r % dim == 0
+        u = zz.reshape(-1, dim)
+        out[f"{m}_Hr"] = getattr(ske, f"{m}_hessian_u")(u, JB, Jx0, *a, vol)
+        out[f"{m}_gr"] = getattr(ske, f"{m}_gradient_u")(u, JB, Jx0, *a, vol)
+        out[f"{m}_Er"] = getattr(ske, f"{m}_energy_u")(u, JB, Jx0, *a, vol)
+    # FST
+    m1, m2, nc = 6, 5, 4
+    A = rng.standard_normal((m1, dim * dim * t))
+    Bs = sps.random(dim * dim * t, m2, density=0.2, random_state=seed, format="csr")
+    l = rng.integers(0, nc, size=t)
+    l[:nc] = np.arange(nc)
+    f = ref_fst(A, Bs, l, dim=dim)
+    rr = rng.standard_normal((nc, dim, dim))
+    out.update(fst_A=A, fst_B=Bs.toarray(), fst_l=l, fst_ARBs=f.ARBs, fst_r=rr, fst_out=f(rr))
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print("wrote", tag)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    golden_mesh("tet_s01", (3, 2, 2), 0.1, 10)
+    golden_mesh("tet_s04", (3, 2, 2), 0.4, 11)
+    golden_mesh("tri_s01", (5, 4), 0.1, 12)
+    golden_mesh("tri_s04", (5, 4), 0.4, 13)
+    golden_step("step_tet", (3, 3, 2), 20)
+    golden_step("step_tri", (6, 5), 21)
+    golden_reduced("reduced_tet", (3, 2, 2), 12, 30)
+    golden_reduced("reduced_tri", (5, 4), 8, 31)

@@ -1,0 +1,219 @@
+"""Pin the oracle to the reference itself (run in the build container only).
+
+Imports otmanon/simkit read-only from ``/root/reference`` and compares every
+oracle function with the reference function it restates, on seeded inputs that
+include inverted elements, heterogeneous materials, 2D and 3D.  Prints one line
+per check and exits non-zero on any mismatch.  ``/root/reference`` does not
+exist on the GPU box; nothing in tests/bench imports this module.
+"""
+
+import sys
+
+import numpy as np
+import scipy.sparse as sps
+
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, __file__.rsplit("/", 2)[0])
+
+import simkit  # noqa: E402
+import simkit.energies as ske  # noqa: E402
+from simkit.solvers import newton_solver as ref_newton  # noqa: E402
+from simkit.integrators import backward_euler as ref_be, bdf2 as ref_bdf2  # noqa: E402
+from simkit.fast_sandwich_transform_clustered import fast_sandwich_transform_clustered as ref_fst  # noqa: E402
+from simkit.rotation_gradient import rotation_gradient_F as ref_rotgrad  # noqa: E402
+from simkit.svd_rv import svd_rv as ref_svd_rv  # noqa: E402
+
+from oracle import elasticity as oe  # noqa: E402
+from simkit_b200 import synthetic as syn  # noqa: E402
+
+FAIL = []
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / den
+
+
+def check(name, a, b, tol=1e-12):
+    r = rel(a, b)
+    ok = r <= tol
+    print(f"{'ok ' if ok else 'BAD'} {name:60s} rel={r:.3e}")
+    if not ok:
+        FAIL.append(name)
+
+
+REF = {
+    "stable_neo_hookean": ("stable_neo_hookean", True),
+    "neo_hookean": ("neo_hookean", True),
+    "arap": ("arap", False),
+    "stvk": ("stvk", True),
+    "linear_elasticity": ("linear_elasticity", True),
+}
+
+
+def ref_call(material, kind, tier, *args, **kw):
+    stem, _ = REF[material]
+    fn = getattr(ske, f"{stem}_{kind}_{tier}" if tier else f"{stem}_{kind}")
+    return fn(*args, **kw)
+
+
+def main():
+    rng = np.random.default_rng(0)
+    for dim, cells in ((3, (4, 3, 5)), (2, (7, 6))):
+        X, T = syn.make_mesh(cells)
+        n, t = X.shape[0], T.shape[0]
+        ext = tuple(1.0 for _ in cells)
+        J_ref = simkit.deformation_jacobian(X, T)
+        J = oe.deformation_jacobian(X, T)
+        check(f"[{dim}D] deformation_jacobian", J.toarray(), J_ref.toarray(), 1e-13)
+        print("    nnz ours/ref", J.nnz, J_ref.nnz)
+        vol_ref = simkit.volume(X, T)
+        vol = oe.volume(X, T)
+        check(f"[{dim}D] volume", vol, vol_ref, 1e-14)
+        M_ref = simkit.massmatrix(X, T, 1e3)
+        check(f"[{dim}D] massmatrix", oe.massmatrix(X, T, 1e3).diagonal(), M_ref.diagonal(), 1e-14)
+        check(f"[{dim}D] gravity", oe.gravity_force(X, T, -9.8, 1e3), simkit.gravity_force(X, T, -9.8, 1e3), 1e-14)
+        mu_h, lam_h = syn.heterogeneous_lame(t)
+        for sigma in (0.1, 0.4):
+            U = syn.jittered_state(X, cells, ext, sigma=sigma)
+            F = np.asarray(J_ref @ U.reshape(-1, 1)).reshape(-1, dim, dim)
+            ninv = int((np.linalg.det(F) <= 0).sum())
+            print(f"  sigma={sigma}: inverted elements {ninv}/{t}")
+            Ur, Sr, Vr = ref_svd_rv(F)
+            Uo, So, Vo = oe.svd_rv(F)
+            check(f"[{dim}D s={sigma}] svd_rv U", Uo, Ur, 1e-13)
+            check(f"[{dim}D s={sigma}] svd_rv S", So, Sr, 1e-13)
+            check(f"[{dim}D s={sigma}] svd_rv V", Vo, Vr, 1e-13)
+            Rr, SSr = simkit.polar_svd(F)
+            Ro, SSo = oe.polar_svd(F)
+            check(f"[{dim}D s={sigma}] polar R", Ro, Rr, 1e-13)
+            check(f"[{dim}D s={sigma}] polar S", SSo, SSr, 1e-13)
+            check(f"[{dim}D s={sigma}] rotation_gradient_F", oe.rotation_gradient_F(F), ref_rotgrad(F), 1e-12)
+            for material in oe.MATERIALS:
+                if material == "neo_hookean" and ninv > 0:
+                    continue  # NaNs by construction (neo_hookean.py:21-25)
+                has_lam = REF[material][1]
+                margs = (mu_h, lam_h) if has_lam else (mu_h,)
+                tag = f"[{dim}D s={sigma}] {material}"
+                check(tag + " energy_element_F", oe.energy_element_F(material, F, mu_h, lam_h),
+                      ref_call(material, "energy", "element_F", F, *margs))
+                check(tag + " gradient_element_F", oe.gradient_element_F(material, F, mu_h, lam_h),
+                      ref_call(material, "gradient", "element_F", F, *margs))
+                check(tag + " hessian_element_F", oe.hessian_element_F(material, F, mu_h, lam_h),
+                      ref_call(material, "hessian", "element_F", F, *margs), 1e-11)
+                E_ref = ref_call(material, "energy", "x", U, J_ref, *margs, vol_ref)
+                check(tag + " energy_x", oe.energy_x(material, U, J, mu_h, lam_h, vol), E_ref, 1e-13)
+                g_ref = ref_call(material, "gradient", "x", U, J_ref, *margs, vol_ref)
+                check(tag + " gradient_x", oe.gradient_x(material, U, J, mu_h, lam_h, vol), g_ref)
+                for psd in (True, False):
+                    Q_ref = ref_call(material, "hessian", "x", U, J_ref, *margs, vol_ref, psd=psd)
+                    Q = oe.hessian_x(material, U, J, mu_h, lam_h, vol, psd=psd)
+                    check(tag + f" hessian_x psd={psd}", Q.toarray(), Q_ref.toarray(), 1e-11)
+                # _u tier
+                xb = X + 0.01 * rng.standard_normal(X.shape)
+                u = U - xb
+                Jxb = J_ref @ xb.reshape(-1, 1)
+                Q_ref = ref_call(material, "hessian", "u", u, J_ref, Jxb, *margs, vol_ref)
+                Q = oe.hessian_x(material, u, J, mu_h, lam_h, vol, Jx_bar=Jxb)
+                check(tag + " hessian_u", Q.toarray(), Q_ref.toarray(), 1e-11)
+        # psd_project on arbitrary symmetric input
+        A = rng.standard_normal((50, dim * dim, dim * dim))
+        A = A + np.swapaxes(A, 1, 2)
+        check(f"[{dim}D] psd_project proj", oe.psd_project(A), simkit.psd_project(A), 1e-12)
+        check(f"[{dim}D] psd_project abs", oe.psd_project(A, "abs"), simkit.psd_project(A, "abs"), 1e-12)
+
+        # elastic dispatcher: psd before vol (arap, linear-elasticity routed)
+        U = syn.jittered_state(X, cells, ext, sigma=0.4)
+        for material, name in (("arap", "arap"), ("linear_elasticity", "linear-elasticity")):
+            Q_ref = ske.elastic_hessian_x(U, J_ref, mu_h, lam_h, vol_ref, name, psd=True)
+            Q = oe.hessian_x(material, U, J, mu_h, lam_h, vol, psd=True, psd_before_vol=True)
+            check(f"[{dim}D] elastic_hessian_x {name}", Q.toarray(), Q_ref.toarray(), 1e-11)
+
+        # structural pattern is a superset of the canonicalised reference pattern
+        mu0, lam0 = syn.lame()
+        Q_ref = oe.canonical_csr(ske.stable_neo_hookean_hessian_x(U, J_ref, mu0, lam0, vol_ref))
+        indptr, indices, bptr, bcol = oe.structural_pattern(T, n, dim)
+        same = Q_ref.nnz == indices.shape[0] and np.array_equal(Q_ref.indptr, indptr) and np.array_equal(Q_ref.indices, indices)
+        print(f"{'ok ' if same else 'BAD'} [{dim}D] structural pattern == canonical reference pattern (sNH)")
+        if not same:
+            FAIL.append("pattern")
+
+        # Newton / integrators on the small mesh
+        rho, h = 1e3, 1e-2
+        Mv = sps.kron(simkit.massmatrix(X, T, rho), sps.identity(dim)).tocsc()
+        fg = simkit.gravity_force(X, T, -9.8, rho).reshape(-1, 1)
+
+        def mk(mod_e, mod_g, mod_h, Jm, volm):
+            def E(x):
+                return mod_e(x.reshape(-1, dim), Jm, mu0, lam0, volm) - float((fg.T @ x).item())
+
+            def G(x):
+                return mod_g(x.reshape(-1, dim), Jm, mu0, lam0, volm) - fg
+
+            def H(x):
+                return mod_h(x.reshape(-1, dim), Jm, mu0, lam0, volm)
+            return E, G, H
+
+        Er, Gr, Hr = mk(ske.stable_neo_hookean_energy_x, ske.stable_neo_hookean_gradient_x,
+                        ske.stable_neo_hookean_hessian_x, J_ref, vol_ref)
+
+        def oe_e(x, Jm, mu, lam, volm):
+            return oe.energy_x("stable_neo_hookean", x, Jm, mu, lam, volm)
+
+        def oe_g(x, Jm, mu, lam, volm):
+            return oe.gradient_x("stable_neo_hookean", x, Jm, mu, lam, volm)
+
+        def oe_h(x, Jm, mu, lam, volm):
+            return oe.hessian_x("stable_neo_hookean", x, Jm, mu, lam, volm)
+
+        Eo, Go, Ho = mk(oe_e, oe_g, oe_h, J, vol)
+        x0 = U.reshape(-1, 1)
+        x1 = X.reshape(-1, 1)
+        xr, info_r = ref_be(x0, x1, Er, Gr, Hr, Mv, h, max_iter=3, return_info=True)
+        xo, info_o = oe.backward_euler(x0, x1, Eo, Go, Ho, Mv, h, max_iter=3, return_info=True)
+        check(f"[{dim}D] backward_euler iterate", xo, xr, 1e-10)
+        assert info_r["alphas"] == info_o["alphas"] and info_r["iters"] == info_o["iters"], (info_r["alphas"], info_o["alphas"])
+        x2 = x1 + 1e-3 * rng.standard_normal(x1.shape)
+        x3 = x1 + 1e-3 * rng.standard_normal(x1.shape)
+        xr = ref_bdf2(x0, x1, x2, x3, Er, Gr, Hr, Mv, h, max_iter=2)
+        xo = oe.bdf2(x0, x1, x2, x3, Eo, Go, Ho, Mv, h, max_iter=2)
+        check(f"[{dim}D] bdf2 iterate", xo, xr, 1e-10)
+        # plain Newton on the (regularised) static problem
+        Kreg = Mv / h ** 2
+        xs = syn.jittered_state(X, cells, ext, sigma=0.1).reshape(-1, 1)
+
+        def reg(E, G, H):
+            return (lambda x: E(x) + 0.5 * float(((x - x1).T @ Kreg @ (x - x1)).item()),
+                    lambda x: G(x) + Kreg @ (x - x1), lambda x: H(x) + Kreg)
+
+        xr, ir = ref_newton(xs, *reg(Er, Gr, Hr), max_iter=4, return_info=True)
+        xo, io = oe.newton_solver(xs, *reg(Eo, Go, Ho), max_iter=4, return_info=True)
+        check(f"[{dim}D] newton iterate (alphas {ir['alphas']})", xo, xr, 1e-10)
+        # block-Jacobi CG substitute agrees with the direct solve
+        Hm = Hr(x0) + Mv / h ** 2
+        rhs = -Gr(x0)
+        import scipy.sparse.linalg as spla
+        d_ref = spla.spsolve(Hm.tocsc(), rhs)
+        d_cg, its = oe.block_jacobi_cg(Hm, rhs, dim)
+        check(f"[{dim}D] block_jacobi_cg vs spsolve ({its} its)", d_cg, d_ref, 1e-9)
+
+        # FST
+        m1, m2, nc = 5, 4, 3
+        A = sps.random(m1, dim * dim * t, density=0.3, random_state=1, format="csr").toarray()
+        B = sps.random(dim * dim * t, m2, density=0.3, random_state=2, format="csr")
+        l = rng.integers(0, nc, size=t)
+        l[:nc] = np.arange(nc)
+        fr = ref_fst(A, B, l, dim=dim)
+        ARBs = oe.fst_precompute(A, B, l, dim=dim)
+        check(f"[{dim}D] fst ARBs", ARBs, fr.ARBs, 1e-12)
+        r = rng.standard_normal((nc, dim, dim))
+        check(f"[{dim}D] fst eval", oe.fst_eval(ARBs, r, dim), fr(r), 1e-12)
+
+    print("FAILED: " + ", ".join(FAIL) if FAIL else "ALL OK")
+    return 1 if FAIL else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

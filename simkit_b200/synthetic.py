@@ -1,0 +1,136 @@
+"""Synthetic meshes, materials and states for the BASELINE configs.
+
+These generators are host-side numpy utilities shared by ``bench.py`` and the
+tests. They have no reference counterpart (the reference's own generators,
+``examples/interactive_demos/utils.py:33-90``, import polyscope and split cells
+into 5 tets); the meshes here are the ones BASELINE.json's configs name:
+
+* 3D: ``mx*my*mz`` cells, vertex id ``(i*(my+1)+j)*(mz+1)+k``, each cell split
+  into 6 tets along the main diagonal (Kuhn / Freudenthal), all with positive
+  signed volume.
+* 2D: ``m*m`` cells, two triangles ``(v00,v10,v11),(v00,v11,v01)`` per cell.
+"""
+
+from itertools import permutations
+
+import numpy as np
+
+# name -> (dim, cells, extent)   
+CONFIGS = {
+    "C1": dict(dim=3, cells=(20, 20, 20), extent=(1.0, 1.0, 1.0)),
+    "C2": dict(dim=2, cells=(316, 316), extent=(1.0, 1.0)),
+    "C3": dict(dim=3, cells=(32, 32, 163), extent=(1.0, 1.0, 163.0 / 32.0)),
+    "C4": dict(dim=3, cells=(88, 88, 88), extent=(1.0, 1.0, 1.0)),
+    "C5": dict(dim=3, cells=(139, 139, 139), extent=(1.0, 1.0, 1.0)),
+}
+
+
+def kuhn_tet_grid(mx, my, mz, extent=(1.0, 1.0, 1.0), dtype_index=np.int64):
+    """Kuhn 6-tet-per-cell grid.  Returns ``X (n,3) f64``, ``T (6*mx*my*mz,4)``."""
+    nx, ny, nz = mx + 1, my + 1, mz + 1
+    gi, gj, gk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    X = np.stack(
+        [gi * (extent[0] / mx), gj * (extent[1] / my), gk * (extent[2] / mz)], axis=-1
+    ).reshape(-1, 3).astype(np.float64)
+
+    ci, cj, ck = np.meshgrid(np.arange(mx), np.arange(my), np.arange(mz), indexing="ij")
+    ci, cj, ck = ci.ravel(), cj.ravel(), ck.ravel()
+
+    def vid(i, j, k):
+        return (i * ny + j) * nz + k
+
+    tets = []
+    for perm in permutations(range(3)):
+        # walk 000 -> 111 adding one unit step per axis in the order `perm`
+        off = np.zeros(3, dtype=np.int64)
+        corners = [vid(ci, cj, ck)]
+        for ax in perm:
+            off = off.copy()
+            off[ax] = 1
+            corners.append(vid(ci + off[0], cj + off[1], ck + off[2]))
+        tet = np.stack(corners, axis=-1)
+        # orientation of this permutation class is constant over the grid
+        sign = np.linalg.det(np.eye(3)[list(perm)])
+        if sign < 0:
+            tet = tet[:, [0, 2, 1, 3]]
+        tets.append(tet)
+    # cell-major ordering: the 6 tets of a cell are contiguous
+    T = np.stack(tets, axis=1).reshape(-1, 4).astype(dtype_index)
+    return X, T
+
+
+def tri_grid(mx, my, extent=(1.0, 1.0), dtype_index=np.int64):
+    """Two-triangle-per-cell grid.  Returns ``X (n,2) f64``, ``T (2*mx*my,3)``."""
+    nx, ny = mx + 1, my + 1
+    gi, gj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    X = np.stack([gi * (extent[0] / mx), gj * (extent[1] / my)], axis=-1).reshape(-1, 2)
+    X = X.astype(np.float64)
+    ci, cj = np.meshgrid(np.arange(mx), np.arange(my), indexing="ij")
+    ci, cj = ci.ravel(), cj.ravel()
+    v00 = ci * ny + cj
+    v10 = (ci + 1) * ny + cj
+    v11 = (ci + 1) * ny + cj + 1
+    v01 = ci * ny + cj + 1
+    T = np.stack(
+        [np.stack([v00, v10, v11], -1), np.stack([v00, v11, v01], -1)], axis=1
+    ).reshape(-1, 3).astype(dtype_index)
+    return X, T
+
+
+def make_mesh(name_or_cells, extent=None):
+    """Mesh for a named config (``"C1"``..``"C5"``) or an explicit cell tuple."""
+    if isinstance(name_or_cells, str):
+        cfg = CONFIGS[name_or_cells]
+        cells, extent = cfg["cells"], cfg["extent"]
+    else:
+        cells = tuple(name_or_cells)
+        if extent is None:
+            extent = tuple(1.0 for _ in cells)
+    if len(cells) == 3:
+        return kuhn_tet_grid(*cells, extent=extent)
+    return tri_grid(*cells, extent=extent)
+
+
+def cell_size(cells, extent):
+    return min(e / c for e, c in zip(extent, cells))
+
+
+def jittered_state(X, cells, extent, sigma=0.1, seed=0):
+    """``U = X + sigma*(cell size)*N(0,1)`` with ``default_rng(seed)``."""
+    rng = np.random.default_rng(seed)
+    return X + sigma * cell_size(cells, extent) * rng.standard_normal(X.shape)
+
+
+def lame(ym=1e5, pr=0.45):
+    """(mu, lam) from Young's modulus / Poisson ratio (reference ``ympr_to_lame.py:32-33``)."""
+    mu = ym / (2 * (1 + pr))
+    lam = ym * pr / ((1 + pr) * (1 - 2 * pr))
+    return mu, lam
+
+
+def heterogeneous_lame(t, ym=1e5, pr=0.45, seed=1):
+    """Per-element ``ym*10**U(-1,1)`` (SURVEY §8d heterogeneous variant)."""
+    rng = np.random.default_rng(seed)
+    yme = ym * 10.0 ** rng.uniform(-1.0, 1.0, size=(t, 1))
+    return lame(yme, pr)
+
+
+def smooth_modes(X, r, seed=2):
+    """Dense random smooth basis ``B (n*dim, r)`` for the reduced config (C4).
+
+    Low-frequency cosine products with random wave vectors applied per
+    coordinate, then orthonormalised (QR).  Stands in for the reference's
+    skinning eigenmodes, whose eigen-solver needs cvxopt (absent).
+    """
+    rng = np.random.default_rng(seed)
+    n, dim = X.shape
+    Xn = (X - X.min(0)) / (X.max(0) - X.min(0))
+    B = np.empty((n * dim, r))
+    for j in range(r):
+        k = rng.integers(0, 4, size=dim)
+        phase = rng.uniform(0, np.pi, size=dim)
+        f = np.prod(np.cos(np.pi * k[None, :] * Xn + phase[None, :]), axis=1)
+        w = rng.standard_normal(dim)
+        B[:, j] = (f[:, None] * w[None, :]).reshape(-1)
+    Q, _ = np.linalg.qr(B)
+    return np.ascontiguousarray(Q)
