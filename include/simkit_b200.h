@@ -1,0 +1,236 @@
+/*
+ * simkit_b200 -- C ABI of the B200-native per-element FEM elasticity hot path.
+ *
+ * This is the drop-in boundary.  The reference (otmanon/simkit,
+ * pure Python) has no FFI; these entry points are what a binding for the path
+ * would call.  Each one cites the reference interface it replaces
+ * (paths relative to /root/reference/simkit).  INTEGRATION.md shows the ctypes
+ * stubs a simkit maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all floating point is IEEE FP64, indices int32
+ *    unless stated; matrices are C-contiguous (row-major).
+ *  - "host" entry points (skb_*) take HOST pointers, stage through the plan's
+ *    device buffers and are synchronous on return.  "_dev" entry points take
+ *    DEVICE pointers plus a cudaStream_t (as void*) and are asynchronous.
+ *  - every function returns 0 on success, a negative SKB_E* code otherwise;
+ *    skb_last_error() gives the message (thread-local).
+ *  - dim = 2 (triangles, 3 corners) or 3 (tets, 4 corners).
+ *  - mu / lam / vol arguments come with a count: 1 = scalar broadcast, t = per element.
+ *    lam is ignored for SKB_MAT_ARAP (the reference's ARAP functions take no lam).
+ */
+#ifndef SIMKIT_B200_H
+#define SIMKIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKB_OK 0
+#define SKB_EINVAL (-1)  /* bad argument (maps to ValueError)            */
+#define SKB_ECUDA (-2)   /* CUDA runtime failure (maps to RuntimeError)  */
+#define SKB_ENOGPU (-3)  /* no usable CUDA device                        */
+#define SKB_ENOMEM (-4)
+
+/* material ids -- energies/{stable_neo_hookean,neo_hookean,arap,stvk,linear_elasticity}.py */
+#define SKB_MAT_STABLE_NEO_HOOKEAN 0
+#define SKB_MAT_NEO_HOOKEAN 1
+#define SKB_MAT_ARAP 2
+#define SKB_MAT_STVK 3
+#define SKB_MAT_LINEAR_ELASTICITY 4
+
+/* psd modes -- where the 1e-6 eigenvalue floor of psd_project.py:37 sits relative to vol */
+#define SKB_PSD_NONE 0
+#define SKB_PSD_AFTER_VOL 1  /* *_hessian_x/_u : psd_project(vol*He), e.g. stable_neo_hookean.py:533-535 */
+#define SKB_PSD_BEFORE_VOL 2 /* elastic dispatcher / _z tier: vol*psd_project(He), energies/elastic.py:663-664 */
+
+typedef struct skb_plan skb_plan;
+
+const char* skb_last_error(void);
+int skb_device_count(void);
+/* library build info: "simkit_b200 <version> sm_100a" */
+const char* skb_version(void);
+
+/* ------------------------------------------------------------------ plan ---
+ * Per-mesh precompute, built once on the device: element gradient operators
+ * D (replaces deformation_jacobian.py:43-70), quadrature weights (volume.py:14-41),
+ * the canonical CSR pattern of J^T H J (vertex adjacency (x) dim x dim, sorted),
+ * the element-to-slot map and the deterministic reduction schedules.
+ * T is int64 (numpy default) or int32, chosen by index_bytes (8 or 4).
+ * tile_elems = elements per assembly tile (0 = default).
+ */
+int skb_plan_create(const double* X, const void* T, int index_bytes, int64_t n, int64_t t,
+                    int dim, int device, int tile_elems, skb_plan** out);
+/* Same plan from the operator's own data when the caller only holds J (the *_x / *_u tiers take
+ * a prebuilt J, e.g. stable_neo_hookean.py:449-474): T recovered from J's sparsity and
+ * D[e][j][a] = J[e*dim*dim + j, T[e][a]*dim] (t*dim*(dim+1) doubles).  No rest weights are known:
+ * vol must be passed to every evaluation. */
+int skb_plan_create_from_operator(const void* T, const double* D, int index_bytes, int64_t n,
+                                  int64_t t, int dim, int device, int tile_elems, skb_plan** out);
+void skb_plan_destroy(skb_plan* plan);
+
+/* sizes: n, t, dim, nnzb (block non-zeros), nnz (= nnzb*dim*dim), n_tiles, n_block_partials, n_vertex_partials */
+int skb_plan_info(const skb_plan* plan, int64_t info[8]);
+
+/* canonical scalar CSR pattern: indptr[n*dim+1], indices[nnz]  (int32, sorted) */
+int skb_plan_csr_pattern(const skb_plan* plan, int32_t* indptr, int32_t* indices);
+/* block view: bptr[n+1], bcol[nnzb] */
+int skb_plan_block_pattern(const skb_plan* plan, int32_t* bptr, int32_t* bcol);
+/* scalar element-to-slot map slot[e][a][i][b][k] (int32, t*(dim+1)*dim*(dim+1)*dim), SURVEY §7 */
+int skb_plan_slot_map(const skb_plan* plan, int32_t* slot);
+/* D[e][j][a] (t*dim*(dim+1)) with F_ij = sum_a D[e][j][a] x[T[e][a]][i]  (deformation_jacobian.py:58-61) */
+int skb_plan_element_D(const skb_plan* plan, double* D);
+/* vol[e]: signed tet volume / unsigned triangle area  (tetrahedron_volumes.py:26-27, triangle_areas.py:60-79) */
+int skb_plan_volume(const skb_plan* plan, double* vol);
+/* lumped vertex masses m[v] = sum_e rho_e vol_e / (dim+1)   (massmatrix.py:41-49) */
+int skb_plan_vertex_masses(const skb_plan* plan, const double* rho, int64_t rho_n, double* m);
+
+/* ------------------------------------------------------- global tiers ------
+ * x: (n*dim) positions or displacements; Fbar: optional (t*dim*dim) per-element
+ * offset J@x_bar of the _u tier (NULL for the _x tier).
+ *   energy   -> *_energy_x/_u    e.g. stable_neo_hookean.py:449-474, 544-576
+ *   gradient -> *_gradient_x/_u  e.g. stable_neo_hookean.py:477-503, 579-611   g: (n*dim)
+ *   hessian  -> *_hessian_x/_u   e.g. stable_neo_hookean.py:506-538, 614-648   vals: (nnz) in
+ *               the canonical CSR order of skb_plan_csr_pattern
+ */
+int skb_energy(skb_plan* plan, int material, const double* x, const double* Fbar,
+               const double* mu, int64_t mu_n, const double* lam, int64_t lam_n,
+               const double* vol, int64_t vol_n, double* energy);
+int skb_gradient(skb_plan* plan, int material, const double* x, const double* Fbar,
+                 const double* mu, int64_t mu_n, const double* lam, int64_t lam_n,
+                 const double* vol, int64_t vol_n, double* g);
+int skb_hessian(skb_plan* plan, int material, int psd_mode, const double* x, const double* Fbar,
+                const double* mu, int64_t mu_n, const double* lam, int64_t lam_n,
+                const double* vol, int64_t vol_n, double* vals);
+/* fused gradient + Hessian (one pass over the elements); g and/or vals may be NULL */
+int skb_gradient_hessian(skb_plan* plan, int material, int psd_mode, const double* x,
+                         const double* Fbar, const double* mu, int64_t mu_n, const double* lam,
+                         int64_t lam_n, const double* vol, int64_t vol_n, double* g, double* vals);
+
+/* device-resident variants: every pointer is a device pointer; mu/lam/vol are
+ * per-element arrays or 1-element arrays (count given); asynchronous on `stream`.
+ * energy_out is a device double. */
+int skb_set_materials_dev(skb_plan* plan, const double* mu, int64_t mu_n, const double* lam,
+                          int64_t lam_n, const double* vol, int64_t vol_n, void* stream);
+int skb_energy_dev(skb_plan* plan, int material, const double* x, const double* Fbar,
+                   double* energy_out, void* stream);
+int skb_gradient_hessian_dev(skb_plan* plan, int material, int psd_mode, const double* x,
+                             const double* Fbar, double* g, double* vals, void* stream);
+/* number of kernels the last *_dev / host call launched (for bench accounting) */
+int skb_last_launch_count(const skb_plan* plan);
+
+/* ------------------------------------------------------- element tiers -----
+ * Batched per-element functions on arbitrary F (host pointers):
+ *   *_energy_element_F / *_gradient_element_F / *_hessian_element_F
+ *   (e.g. stable_neo_hookean.py:65-129, 132-218, 221-443).  Hessian blocks are
+ *   (t, b, b), b = dim*dim, row-major F layout, unweighted and unprojected.
+ */
+int skb_element_energy(int material, int dim, int64_t t, const double* F, const double* mu,
+                       int64_t mu_n, const double* lam, int64_t lam_n, double* psi);
+int skb_element_gradient(int material, int dim, int64_t t, const double* F, const double* mu,
+                         int64_t mu_n, const double* lam, int64_t lam_n, double* P);
+int skb_element_hessian(int material, int dim, int64_t t, const double* F, const double* mu,
+                        int64_t mu_n, const double* lam, int64_t lam_n, double* H);
+/* psd_project.py:12-47 on (t, b, b) symmetric blocks; method 0 = 'proj' (floor 1e-6), 1 = 'abs' */
+int skb_psd_project(int64_t t, int b, const double* H, int method, double* out);
+/* svd_rv.py:8-53 / polar_svd.py:59-89: U, S (diagonal matrices), V and R = U V^T, SS = V S V^T.
+ * Any output pointer may be NULL. */
+int skb_svd_rv(int dim, int64_t t, const double* F, double* U, double* S, double* V);
+int skb_polar(int dim, int64_t t, const double* F, double* R, double* SS);
+/* rotation_gradient.py:12-75: dR/dF (t, b, b) */
+int skb_rotation_gradient(int dim, int64_t t, const double* F, double* K);
+
+/* --------------------------------------------------------- linear solve ----
+ * Block-Jacobi preconditioned CG on a matrix in the plan's canonical pattern
+ * (replaces scipy.sparse.linalg.spsolve at solvers/newton.py:52).
+ *   vals (nnz), diag_add (n*dim, optional: added to the diagonal, e.g. M/h^2), rhs, x (n*dim).
+ * Returns iterations in *iters and the final relative residual in *relres.
+ */
+int skb_pcg(skb_plan* plan, const double* vals, const double* diag_add, const double* rhs,
+            double rtol, int max_iter, double* x, int* iters, double* relres);
+int skb_pcg_dev(skb_plan* plan, const double* vals, const double* diag_add, const double* rhs,
+                double rtol, int max_iter, double* x, int* iters, double* relres, void* stream);
+/* Same solver for ANY sparse SPD matrix in scalar CSR form (what newton_solver receives from user
+ * callables, solvers/newton.py:51-52); block = size of the Jacobi blocks (1, 2 or 3; n % block == 0). */
+int skb_csr_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const double* vals, int block,
+                const double* rhs, double rtol, int max_iter, double* x, int* iters, double* relres);
+/* Dense LU solve with partial pivoting (replaces scipy.linalg.solve at solvers/newton.py:54, the
+ * reduced-space Newton system); A (n, n) row-major.  SKB_EINVAL if singular. */
+int skb_dense_solve(int64_t n, const double* A, const double* b, double* x);
+/* y = (A + diag(diag_add)) x   on device data */
+int skb_spmv_dev(skb_plan* plan, const double* vals, const double* diag_add, const double* x,
+                 double* y, void* stream);
+
+/* ------------------------------------------------------- Newton step -------
+ * Device-resident implicit step for the framework's own energies: replaces
+ * integrators/backward_euler.py:27-91 / bdf2.py:31-101 + solvers/newton.py:7-75 +
+ * backtracking_line_search.py:8-66 when all three callables are this library's.
+ *   total energy  V(x) = elastic(x) - f_ext . x + 1/2 sum_i pin_k[i] (x[i] - pin_target[i])^2
+ *                        + kin_scale/2 (x - x_tilde)^T M (x - x_tilde),   kin_scale = c/h^2
+ *   (the pin term is the diagonal dirichlet_penalty.py:65-142 / quadratic.py:15-70 energy)
+ * Host pointers in, host pointers out; everything in between stays on the device.
+ */
+typedef struct skb_newton_opts {
+  int material;
+  int psd_mode;
+  int max_iter;        /* Newton iterations (newton.py default 1)           */
+  int do_line_search;  /* backtracking_line_search.py defaults when 1       */
+  double tolerance;    /* stop when |alpha*dx| < tolerance (newton.py:69)   */
+  double ls_alpha;     /* 0.01 */
+  double ls_beta;      /* 0.5  */
+  int ls_max_iter;     /* 100  */
+  double ls_threshold; /* 1e-12 */
+  double pcg_rtol;     /* relative residual for the linear solve            */
+  int pcg_max_iter;
+} skb_newton_opts;
+
+typedef struct skb_newton_info {
+  int iters;           /* index of the last Newton iteration (newton.py:67) */
+  int pcg_iters_total;
+  double last_alpha;
+  double last_step_norm;
+  double last_pcg_relres;
+  double alphas[64];
+} skb_newton_info;
+
+/* x0: start (n*dim); x_tilde: inertial target or NULL (then no kinetic term);
+ * mass: lumped per-dof masses (n*dim) or NULL; kin_scale = c/h^2; f_ext: (n*dim) or NULL;
+ * pin_k / pin_target: per-dof penalty stiffness and target (n*dim) or NULL;
+ * x_out: (n*dim). Materials must have been set with skb_set_materials / *_dev. */
+int skb_set_materials(skb_plan* plan, const double* mu, int64_t mu_n, const double* lam,
+                      int64_t lam_n, const double* vol, int64_t vol_n);
+int skb_newton(skb_plan* plan, const skb_newton_opts* opts, const double* x0,
+               const double* x_tilde, const double* mass, double kin_scale, const double* f_ext,
+               const double* pin_k, const double* pin_target, double* x_out, skb_newton_info* info);
+
+/* ------------------------------------------------------- reduced tier ------
+ * Reduced Hessian / gradient with a dense operator:
+ *   F = JB z + Jx0,  Hr = JB^T blockdiag(vol * psd(He)) JB   (energies/elastic.py:749-782,
+ *   or the *_hessian_u tier called with a dense J).  JB: (t*b, r) row-major, z: (r), Jx0: (t*b).
+ * Hr: (r, r), gr: (r).  Either output may be NULL.
+ */
+int skb_reduced_gradient_hessian(int material, int psd_mode, int dim, int64_t t, int64_t r,
+                                 const double* JB, const double* Jx0, const double* z,
+                                 const double* mu, int64_t mu_n, const double* lam, int64_t lam_n,
+                                 const double* vol, int64_t vol_n, double* energy, double* gr,
+                                 double* Hr);
+/* Same, forming JB rows on the fly from the mesh plan and a dense basis B (n*dim, r):
+ * Hr = B^T J^T H J B without materialising JB.  x0: (n*dim) offset. */
+int skb_reduced_hessian_from_basis(skb_plan* plan, int material, int psd_mode, int64_t r,
+                                   const double* B, const double* x0, const double* z,
+                                   double* energy, double* gr, double* Hr);
+
+/* fast_sandwich_transform_clustered.py:15-158.
+ * A: (m1, b*t) dense row-major, B: (b*t, m2) dense row-major, l: (t) cluster labels,
+ * ARBs: (m1, m2, c, dim, dim).  eval: out (m1, m2) = sum ARBs * r, r: (c, dim, dim). */
+int skb_fst_precompute(int dim, int64_t t, int64_t m1, int64_t m2, int64_t n_clusters,
+                       const double* A, const double* B, const int32_t* l, double* ARBs);
+int skb_fst_eval(int dim, int64_t m1, int64_t m2, int64_t n_clusters, const double* ARBs,
+                 const double* r, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMKIT_B200_H */

@@ -1,0 +1,423 @@
+// C ABI, part 1: plan lifetime, pattern export and the global energy / gradient /
+// Hessian entry points (include/simkit_b200.h).
+#include "capi_common.cuh"
+
+#include <memory>
+
+namespace skb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+int make_args(skb_plan* pl, int material, int psd_mode, const double* x, const double* fbar, double* g,
+              double* vals, EvalArgs& a) {
+  if (material < 0 || material >= MAT_COUNT) return fail(SKB_EINVAL, "unknown material id");
+  if (psd_mode < 0 || psd_mode > PSD_ABS_AFTER_VOL) return fail(SKB_EINVAL, "unknown psd mode");
+  if (!pl->have_materials) return fail(SKB_EINVAL, "materials not set (skb_set_materials)");
+  a.material = material;
+  a.psd_mode = psd_mode;
+  a.x = x;
+  a.Fbar = fbar;
+  a.mu = raw(pl->mu);
+  a.lam = raw(pl->lam);
+  a.vol = raw(pl->vol);
+  a.mu_stride = pl->mu_n > 1 ? 1 : 0;
+  a.lam_stride = pl->lam_n > 1 ? 1 : 0;
+  a.vol_stride = pl->vol_n > 1 ? 1 : 0;
+  a.want_grad = g != nullptr;
+  a.want_hess = vals != nullptr;
+  a.g = g;
+  a.vals = vals;
+  if (a.want_hess && pl->pblocks.size() < (size_t)pl->d.blocks.n_ts * pl->d.dim * pl->d.dim)
+    pl->pblocks.resize((size_t)pl->d.blocks.n_ts * pl->d.dim * pl->d.dim);
+  if (a.want_grad && pl->pverts.size() < (size_t)pl->d.verts.n_ts * pl->d.dim)
+    pl->pverts.resize((size_t)pl->d.verts.n_ts * pl->d.dim);
+  a.pblocks = raw(pl->pblocks);
+  a.pverts = raw(pl->pverts);
+  return SKB_OK;
+}
+
+int upload_materials(skb_plan* pl, const double* mu, int64_t mu_n, const double* lam, int64_t lam_n,
+                     const double* vol, int64_t vol_n, bool from_device, cudaStream_t st) {
+  const int64_t t = pl->d.t;
+  if (!mu || (mu_n != 1 && mu_n != t)) return fail(SKB_EINVAL, "mu must have 1 or t entries");
+  if (lam && lam_n != 1 && lam_n != t) return fail(SKB_EINVAL, "lam must have 1 or t entries");
+  if (vol && vol_n != 1 && vol_n != t) return fail(SKB_EINVAL, "vol must have 1 or t entries");
+  const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  pl->mu.resize(mu_n);
+  SKB_CUDA(cudaMemcpyAsync(raw(pl->mu), mu, mu_n * sizeof(double), kind, st));
+  pl->mu_n = mu_n;
+  if (lam) {
+    pl->lam.resize(lam_n);
+    SKB_CUDA(cudaMemcpyAsync(raw(pl->lam), lam, lam_n * sizeof(double), kind, st));
+    pl->lam_n = lam_n;
+  } else {
+    pl->lam.assign(1, 0.0);
+    pl->lam_n = 1;
+  }
+  if (vol) {
+    pl->vol.resize(vol_n);
+    SKB_CUDA(cudaMemcpyAsync(raw(pl->vol), vol, vol_n * sizeof(double), kind, st));
+    pl->vol_n = vol_n;
+  } else {
+    if (!pl->d.has_vol0) return fail(SKB_EINVAL, "vol is required for a plan built from an operator");
+    pl->vol = pl->d.vol0;
+    pl->vol_n = t;
+  }
+  pl->have_materials = true;
+  return SKB_OK;
+}
+
+template <int D>
+static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
+  const PlanView p = pl->view();
+  const int E = p.tile_elems;
+  const size_t smem = (size_t)E * Sizes<D>::SMEM_DOUBLES * sizeof(double);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[D - 2]) {
+    SKB_CUDA(cudaFuncSetAttribute(assemble_tile_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[D - 2] = true;
+  }
+  assemble_tile_kernel<D><<<p.n_tiles, E, smem, st>>>(p, a);
+  pl->launches++;
+  if (a.want_hess) {
+    const int items = p.nnzb * D;
+    finalize_blocks_kernel<D><<<(items + 255) / 256, 256, 0, st>>>(p, a.pblocks, a.vals);
+    pl->launches++;
+  }
+  if (a.want_grad) {
+    finalize_verts_kernel<D><<<(p.n + 255) / 256, 256, 0, st>>>(p, a.pverts, a.g);
+    pl->launches++;
+  }
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+}
+
+int launch_assemble(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
+  return pl->d.dim == 3 ? launch_assemble_t<3>(pl, a, st) : launch_assemble_t<2>(pl, a, st);
+}
+
+int launch_energy(skb_plan* pl, const EvalArgs& a, double* out_dev, cudaStream_t st) {
+  const PlanView p = pl->view();
+  const int nb = (p.t + 255) / 256;
+  if (pl->esums.size() < (size_t)nb) pl->esums.resize(nb);
+  if (p.dim == 3)
+    energy_kernel<3><<<nb, 256, 0, st>>>(p, a, raw(pl->esums));
+  else
+    energy_kernel<2><<<nb, 256, 0, st>>>(p, a, raw(pl->esums));
+  reduce_final_kernel<<<1, 1024, 0, st>>>(raw(pl->esums), nb, out_dev);
+  pl->launches += 2;
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+}
+
+}  // namespace skb
+
+using namespace skb;
+
+extern "C" {
+
+const char* skb_last_error(void) { return g_err.c_str(); }
+
+const char* skb_version(void) { return "simkit_b200 0.1.0 sm_100a"; }
+
+int skb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static int plan_create_common(const double* X, const double* Dop, const void* T, int index_bytes, int64_t n,
+                              int64_t t, int dim, int device, int tile_elems, skb_plan** out) {
+  if ((!X && !Dop) || !T || !out) return fail(SKB_EINVAL, "null argument");
+  if (dim != 2 && dim != 3) return fail(SKB_EINVAL, "Only dim == 2 or 3 are supported");
+  if (index_bytes != 4 && index_bytes != 8) return fail(SKB_EINVAL, "index_bytes must be 4 or 8");
+  if (n <= 0 || t <= 0) return fail(SKB_EINVAL, "empty mesh");
+  const int K = dim + 1;
+  if (t * K * K >= (int64_t)1 << 31 || n * dim >= (int64_t)1 << 31) return fail(SKB_EINVAL, "mesh too large for int32 indexing");
+  if (tile_elems == 0) tile_elems = 128;
+  if (tile_elems < 32 || tile_elems > 1024 || tile_elems % 32) return fail(SKB_EINVAL, "tile_elems must be a multiple of 32 in [32, 1024]");
+  if (skb_device_count() <= device) return fail(SKB_ENOGPU, "no CUDA device " + std::to_string(device));
+  SKB_CUDA(cudaSetDevice(device));
+  SKB_TRY
+  // validate + narrow indices on the host (one pass; the plan build itself runs on the device)
+  thrust::host_vector<int> Th((size_t)t * K);
+  for (int64_t i = 0; i < t * K; ++i) {
+    int64_t v = index_bytes == 8 ? ((const int64_t*)T)[i] : (int64_t)((const int32_t*)T)[i];
+    if (v < 0 || v >= n) return fail(SKB_EINVAL, "element index out of range");
+    Th[i] = (int)v;
+  }
+  std::unique_ptr<skb_plan> pl(new skb_plan());
+  pl->device = device;
+  SKB_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+  dvec<int> Td = Th;
+  build_plan<DeviceBackend>(pl->d, Td, (int)n, (int)t, dim, tile_elems);
+  if (X) {
+    dvec<double> Xd(X, X + n * dim);
+    set_geometry_from_X<DeviceBackend>(pl->d, Xd);
+  } else {
+    dvec<double> Dd(Dop, Dop + t * dim * K);
+    set_geometry_from_D<DeviceBackend>(pl->d, Dd);
+  }
+  SKB_CUDA(cudaDeviceSynchronize());
+  pl->scalar.resize(8);
+  *out = pl.release();
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_plan_create(const double* X, const void* T, int index_bytes, int64_t n, int64_t t, int dim,
+                    int device, int tile_elems, skb_plan** out) {
+  if (!X) return fail(SKB_EINVAL, "null X");
+  return plan_create_common(X, nullptr, T, index_bytes, n, t, dim, device, tile_elems, out);
+}
+
+int skb_plan_create_from_operator(const void* T, const double* D, int index_bytes, int64_t n, int64_t t,
+                                  int dim, int device, int tile_elems, skb_plan** out) {
+  if (!D) return fail(SKB_EINVAL, "null D");
+  return plan_create_common(nullptr, D, T, index_bytes, n, t, dim, device, tile_elems, out);
+}
+
+void skb_plan_destroy(skb_plan* plan) {
+  if (!plan) return;
+  cudaSetDevice(plan->device);
+  if (plan->stream) cudaStreamDestroy(plan->stream);
+  delete plan;
+}
+
+int skb_plan_info(const skb_plan* pl, int64_t info[8]) {
+  if (!pl || !info) return fail(SKB_EINVAL, "null argument");
+  info[0] = pl->d.n;
+  info[1] = pl->d.t;
+  info[2] = pl->d.dim;
+  info[3] = pl->d.nnzb;
+  info[4] = pl->nnz();
+  info[5] = pl->d.n_tiles;
+  info[6] = pl->d.blocks.n_ts;
+  info[7] = pl->d.verts.n_ts;
+  return SKB_OK;
+}
+
+int skb_plan_block_pattern(const skb_plan* pl, int32_t* bptr, int32_t* bcol) {
+  if (!pl || !bptr || !bcol) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_CUDA(cudaMemcpy(bptr, raw(pl->d.bptr), (pl->d.n + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  SKB_CUDA(cudaMemcpy(bcol, raw(pl->d.bcol), (size_t)pl->d.nnzb * sizeof(int), cudaMemcpyDeviceToHost));
+  return SKB_OK;
+}
+
+int skb_plan_csr_pattern(const skb_plan* pl, int32_t* indptr, int32_t* indices) {
+  if (!pl || !indptr || !indices) return fail(SKB_EINVAL, "null argument");
+  SKB_TRY
+  const int n = pl->d.n, D = pl->d.dim;
+  thrust::host_vector<int> bptr = pl->d.bptr, bcol = pl->d.bcol;
+  int64_t pos = 0;
+  for (int v = 0; v < n; ++v) {
+    const int b0 = bptr[v], nb = bptr[v + 1] - b0;
+    for (int i = 0; i < D; ++i) {
+      indptr[(int64_t)v * D + i] = (int32_t)pos;
+      for (int j = 0; j < nb; ++j)
+        for (int k = 0; k < D; ++k) indices[pos++] = bcol[b0 + j] * D + k;
+    }
+  }
+  indptr[(int64_t)n * D] = (int32_t)pos;
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_plan_slot_map(const skb_plan* pl, int32_t* slot) {
+  if (!pl || !slot) return fail(SKB_EINVAL, "null argument");
+  SKB_TRY
+  const int D = pl->d.dim, K = pl->d.K, t = pl->d.t;
+  thrust::host_vector<int> bptr = pl->d.bptr, bslot = pl->d.bslot, T = pl->d.T32;
+  for (int e = 0; e < t; ++e)
+    for (int a = 0; a < K; ++a) {
+      const int v = T[e * K + a];
+      const int b0 = bptr[v], nb = bptr[v + 1] - b0;
+      for (int i = 0; i < D; ++i)
+        for (int b = 0; b < K; ++b) {
+          const int s = bslot[(e * K + a) * K + b];
+          for (int k = 0; k < D; ++k)
+            slot[((((int64_t)e * K + a) * D + i) * K + b) * D + k] =
+                (int32_t)((int64_t)b0 * D * D + (int64_t)i * nb * D + (int64_t)(s - b0) * D + k);
+        }
+    }
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_plan_element_D(const skb_plan* pl, double* Dout) {
+  if (!pl || !Dout) return fail(SKB_EINVAL, "null argument");
+  SKB_TRY
+  const int D = pl->d.dim, K = pl->d.K, t = pl->d.t;
+  thrust::host_vector<double> Dm = pl->d.Dm;
+  for (int e = 0; e < t; ++e)
+    for (int j = 0; j < D; ++j) {
+      double s0 = 0.0;
+      for (int a = 0; a < D; ++a) {
+        double v = Dm[(size_t)(j * D + a) * t + e];
+        Dout[((size_t)e * D + j) * K + a + 1] = v;
+        s0 -= v;
+      }
+      Dout[((size_t)e * D + j) * K] = s0;
+    }
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_plan_volume(const skb_plan* pl, double* vol) {
+  if (!pl || !vol) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_CUDA(cudaMemcpy(vol, raw(pl->d.vol0), (size_t)pl->d.t * sizeof(double), cudaMemcpyDeviceToHost));
+  return SKB_OK;
+}
+
+int skb_plan_vertex_masses(const skb_plan* pl, const double* rho, int64_t rho_n, double* m) {
+  if (!pl || !rho || !m) return fail(SKB_EINVAL, "null argument");
+  if (rho_n != 1 && rho_n != pl->d.t) return fail(SKB_EINVAL, "rho must have 1 or t entries");
+  SKB_TRY
+  // one-off setup quantity (massmatrix.py:41-49); summed in element order on the host
+  const int K = pl->d.K, t = pl->d.t, n = pl->d.n;
+  thrust::host_vector<double> vol = pl->d.vol0;
+  thrust::host_vector<int> T = pl->d.T32;
+  for (int v = 0; v < n; ++v) m[v] = 0.0;
+  for (int e = 0; e < t; ++e) {
+    const double me = vol[e] * rho[rho_n > 1 ? e : 0];
+    for (int a = 0; a < K; ++a) m[T[e * K + a]] += me;
+  }
+  for (int v = 0; v < n; ++v) m[v] /= K;
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_set_materials(skb_plan* pl, const double* mu, int64_t mu_n, const double* lam, int64_t lam_n,
+                      const double* vol, int64_t vol_n) {
+  if (!pl) return fail(SKB_EINVAL, "null plan");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  int rc = upload_materials(pl, mu, mu_n, lam, lam_n, vol, vol_n, false, pl->stream);
+  if (rc) return rc;
+  SKB_CUDA(cudaStreamSynchronize(pl->stream));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_set_materials_dev(skb_plan* pl, const double* mu, int64_t mu_n, const double* lam, int64_t lam_n,
+                          const double* vol, int64_t vol_n, void* stream) {
+  if (!pl) return fail(SKB_EINVAL, "null plan");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  return upload_materials(pl, mu, mu_n, lam, lam_n, vol, vol_n, true, (cudaStream_t)stream);
+  SKB_CATCH
+}
+
+int skb_last_launch_count(const skb_plan* pl) { return pl ? pl->launches : 0; }
+
+// ---- host-pointer global tiers -------------------------------------------
+static int stage_inputs(skb_plan* pl, const double* x, const double* Fbar, const double* mu, int64_t mu_n,
+                        const double* lam, int64_t lam_n, const double* vol, int64_t vol_n) {
+  if (!x) return fail(SKB_EINVAL, "null x");
+  int rc = upload_materials(pl, mu, mu_n, lam, lam_n, vol, vol_n, false, pl->stream);
+  if (rc) return rc;
+  pl->x.resize(pl->ndof());
+  SKB_CUDA(cudaMemcpyAsync(raw(pl->x), x, pl->ndof() * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+  if (Fbar) {
+    const size_t nf = (size_t)pl->d.t * pl->d.dim * pl->d.dim;
+    pl->fbar.resize(nf);
+    SKB_CUDA(cudaMemcpyAsync(raw(pl->fbar), Fbar, nf * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+  }
+  return SKB_OK;
+}
+
+int skb_energy(skb_plan* pl, int material, const double* x, const double* Fbar, const double* mu,
+               int64_t mu_n, const double* lam, int64_t lam_n, const double* vol, int64_t vol_n,
+               double* energy) {
+  if (!pl || !energy) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  pl->launches = 0;
+  int rc = stage_inputs(pl, x, Fbar, mu, mu_n, lam, lam_n, vol, vol_n);
+  if (rc) return rc;
+  EvalArgs a;
+  rc = make_args(pl, material, PSD_NONE, raw(pl->x), Fbar ? raw(pl->fbar) : nullptr, nullptr, nullptr, a);
+  if (rc) return rc;
+  rc = launch_energy(pl, a, raw(pl->scalar), pl->stream);
+  if (rc) return rc;
+  SKB_CUDA(cudaMemcpyAsync(energy, raw(pl->scalar), sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+  SKB_CUDA(cudaStreamSynchronize(pl->stream));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_gradient_hessian(skb_plan* pl, int material, int psd_mode, const double* x, const double* Fbar,
+                         const double* mu, int64_t mu_n, const double* lam, int64_t lam_n,
+                         const double* vol, int64_t vol_n, double* g, double* vals) {
+  if (!pl) return fail(SKB_EINVAL, "null plan");
+  if (!g && !vals) return fail(SKB_EINVAL, "nothing to compute");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  pl->launches = 0;
+  int rc = stage_inputs(pl, x, Fbar, mu, mu_n, lam, lam_n, vol, vol_n);
+  if (rc) return rc;
+  if (g) pl->g.resize(pl->ndof());
+  if (vals) pl->vals.resize(pl->nnz());
+  EvalArgs a;
+  rc = make_args(pl, material, psd_mode, raw(pl->x), Fbar ? raw(pl->fbar) : nullptr, g ? raw(pl->g) : nullptr,
+                 vals ? raw(pl->vals) : nullptr, a);
+  if (rc) return rc;
+  rc = launch_assemble(pl, a, pl->stream);
+  if (rc) return rc;
+  if (g) SKB_CUDA(cudaMemcpyAsync(g, raw(pl->g), pl->ndof() * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+  if (vals) SKB_CUDA(cudaMemcpyAsync(vals, raw(pl->vals), pl->nnz() * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+  SKB_CUDA(cudaStreamSynchronize(pl->stream));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_gradient(skb_plan* pl, int material, const double* x, const double* Fbar, const double* mu,
+                 int64_t mu_n, const double* lam, int64_t lam_n, const double* vol, int64_t vol_n, double* g) {
+  if (!g) return fail(SKB_EINVAL, "null g");
+  return skb_gradient_hessian(pl, material, SKB_PSD_NONE, x, Fbar, mu, mu_n, lam, lam_n, vol, vol_n, g, nullptr);
+}
+
+int skb_hessian(skb_plan* pl, int material, int psd_mode, const double* x, const double* Fbar,
+                const double* mu, int64_t mu_n, const double* lam, int64_t lam_n, const double* vol,
+                int64_t vol_n, double* vals) {
+  if (!vals) return fail(SKB_EINVAL, "null vals");
+  return skb_gradient_hessian(pl, material, psd_mode, x, Fbar, mu, mu_n, lam, lam_n, vol, vol_n, nullptr, vals);
+}
+
+// ---- device-pointer variants ---------------------------------------------
+int skb_energy_dev(skb_plan* pl, int material, const double* x, const double* Fbar, double* energy_out,
+                   void* stream) {
+  if (!pl || !x || !energy_out) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  EvalArgs a;
+  int rc = make_args(pl, material, PSD_NONE, x, Fbar, nullptr, nullptr, a);
+  if (rc) return rc;
+  return launch_energy(pl, a, energy_out, (cudaStream_t)stream);
+  SKB_CATCH
+}
+
+int skb_gradient_hessian_dev(skb_plan* pl, int material, int psd_mode, const double* x, const double* Fbar,
+                             double* g, double* vals, void* stream) {
+  if (!pl || !x) return fail(SKB_EINVAL, "null argument");
+  if (!g && !vals) return fail(SKB_EINVAL, "nothing to compute");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  EvalArgs a;
+  int rc = make_args(pl, material, psd_mode, x, Fbar, g, vals, a);
+  if (rc) return rc;
+  return launch_assemble(pl, a, (cudaStream_t)stream);
+  SKB_CATCH
+}
+
+}  // extern "C"

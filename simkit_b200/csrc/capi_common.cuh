@@ -1,0 +1,77 @@
+// Shared pieces of the C-ABI translation units: error plumbing and the plan object.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <exception>
+#include <string>
+
+#include "../../include/simkit_b200.h"
+#include "kernels.cuh"
+
+namespace skb {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define SKB_CUDA(call)                                                                    \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return skb::fail(SKB_ECUDA, std::string(#call) + ": " + cudaGetErrorString(_e));    \
+  } while (0)
+
+#define SKB_TRY try {
+#define SKB_CATCH                                                      \
+  }                                                                    \
+  catch (const std::bad_alloc& ex) {                                   \
+    return skb::fail(SKB_ENOMEM, std::string("out of memory: ") + ex.what()); \
+  }                                                                    \
+  catch (const std::exception& ex) {                                   \
+    return skb::fail(SKB_ECUDA, ex.what());                            \
+  }
+
+template <class T>
+using dvec = thrust::device_vector<T>;
+
+template <class T>
+inline T* raw(dvec<T>& v) {
+  return thrust::raw_pointer_cast(v.data());
+}
+template <class T>
+inline const T* raw(const dvec<T>& v) {
+  return thrust::raw_pointer_cast(v.data());
+}
+
+}  // namespace skb
+
+// The opaque plan handle of the C ABI.
+struct skb_plan {
+  int device = 0;
+  skb::PlanData<skb::DeviceBackend> d;
+  cudaStream_t stream = nullptr;  // stream of the host-pointer entry points
+  // device staging of the host-pointer entry points / resident materials
+  skb::dvec<double> x, fbar, mu, lam, vol, g, vals;
+  int64_t mu_n = 0, lam_n = 0, vol_n = 0;
+  bool have_materials = false;
+  // scratch of the reductions
+  skb::dvec<double> pblocks, pverts, esums, scalar;
+  // PCG / Newton work vectors (allocated on first use)
+  skb::dvec<double> w_r, w_z, w_p, w_q, w_dx, w_xt, w_x, w_xtrial, w_dinv, w_diag, w_mass, w_fext, w_xtilde, w_red;
+  int launches = 0;
+
+  skb::PlanView view() const { return d.view(); }
+  int64_t ndof() const { return (int64_t)d.n * d.dim; }
+  int64_t nnz() const { return (int64_t)d.nnzb * d.dim * d.dim; }
+};
+
+namespace skb {
+// launches shared between translation units
+int launch_assemble(skb_plan* pl, const EvalArgs& a, cudaStream_t st);
+int launch_energy(skb_plan* pl, const EvalArgs& a, double* out_dev, cudaStream_t st);
+int make_args(skb_plan* pl, int material, int psd_mode, const double* x, const double* fbar, double* g,
+              double* vals, EvalArgs& a);
+int upload_materials(skb_plan* pl, const double* mu, int64_t mu_n, const double* lam, int64_t lam_n,
+                     const double* vol, int64_t vol_n, bool from_device, cudaStream_t st);
+}  // namespace skb

@@ -1,0 +1,244 @@
+// C ABI, part 2: element-tier batched functions on arbitrary F, psd_project,
+// svd_rv / polar_svd and rotation_gradient_F (host pointers in and out).
+#include "capi_common.cuh"
+
+namespace skb {
+
+enum ElemOp { OP_ENERGY = 0, OP_GRADIENT = 1, OP_HESSIAN = 2, OP_SVD = 3, OP_POLAR = 4, OP_ROTGRAD = 5 };
+
+template <int D>
+__device__ __forceinline__ Mat<D> load_F(const double* F, int64_t e) {
+  Mat<D> f;
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) f.m[i][j] = F[e * D * D + i * D + j];
+  return f;
+}
+
+template <int D>
+__device__ __forceinline__ void store_M(double* out, int64_t e, const Mat<D>& m) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) out[e * D * D + i * D + j] = m.m[i][j];
+}
+
+template <int D>
+__global__ void element_kernel(int op, int material, int64_t t, const double* F, const double* mu, int mu_s,
+                               const double* lam, int lam_s, double* o0, double* o1, double* o2) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= t) return;
+  constexpr int B = D * D;
+  Mat<D> f = load_F<D>(F, e);
+  const double m = mu ? mu[e * mu_s] : 0.0;
+  const double l = lam ? lam[e * lam_s] : 0.0;
+  if (op == OP_ENERGY) {
+    o0[e] = energy_density<D>(material, f, m, l);
+  } else if (op == OP_GRADIENT) {
+    store_M<D>(o0, e, pk1<D>(material, f, m, l));
+  } else if (op == OP_HESSIAN) {
+    double H[B * B];
+    if (material == MAT_LINEAR_ELASTICITY) {
+      linear_elasticity_hessian<D>(m, l, H);
+    } else {
+      Mat<D> U, V;
+      Vec<D> s;
+      svd_rv(f, U, s, V);
+      Principal<D> h = principal_hessian<D>(material, s, m, l);
+      expand_hessian<D>(h, U, V, H);
+    }
+    for (int i = 0; i < B * B; ++i) o0[e * B * B + i] = H[i];
+  } else {
+    Mat<D> U, V;
+    Vec<D> s;
+    svd_rv(f, U, s, V);
+    if (op == OP_SVD) {
+      if (o0) store_M<D>(o0, e, U);
+      if (o1) {
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) o1[e * B + i * D + j] = (i == j) ? s[i] : 0.0;
+      }
+      if (o2) store_M<D>(o2, e, V);
+    } else if (op == OP_POLAR) {
+      if (o0) store_M<D>(o0, e, matmul_nt(U, V));
+      if (o1) {
+        Mat<D> VS;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) VS.m[i][j] = V.m[i][j] * s[j];
+        store_M<D>(o1, e, matmul_nt(VS, V));
+      }
+    } else {  // OP_ROTGRAD: dR/dF = sum_pairs 2/max(s_p+s_q, clamp) t t^T  (rotation_gradient.py:42-72)
+      Principal<D> h;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) h.S.m[i][j] = 0.0;
+      const double clampv = (D == 2) ? 1e-12 : 1e-8;
+#pragma unroll
+      for (int k = 0; k < Principal<D>::NP; ++k) {
+        int p, q, r;
+        pair_index<D>(k, p, q, r);
+        const double tw = 2.0 / fmax(s[p] + s[q], clampv);  // twist eigenvalue, flip = 0
+        h.a[k] = 0.5 * tw;
+        h.b[k] = -0.5 * tw;
+      }
+      double H[B * B];
+      expand_hessian<D>(h, U, V, H);
+      for (int i = 0; i < B * B; ++i) o0[e * B * B + i] = H[i];
+    }
+  }
+}
+
+// psd_project.py:12-47 on arbitrary symmetric blocks: register-resident cyclic Jacobi
+template <int N>
+__global__ void psd_project_kernel(int64_t t, const double* H, int method, double* out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= t) return;
+  Mat<N> a;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j)  // numpy eigh reads the lower triangle (UPLO='L')
+      a.m[i][j] = (i >= j) ? H[e * N * N + i * N + j] : H[e * N * N + j * N + i];
+  Vec<N> w;
+  Mat<N> V;
+  jacobi_eig<N>(a, w, V, 30);
+#pragma unroll
+  for (int i = 0; i < N; ++i) w[i] = (method == 1) ? fabs(w[i]) : (w[i] < SKB_PSD_FLOOR ? SKB_PSD_FLOOR : w[i]);
+  Mat<N> r = rebuild_sym(V, w);
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) out[e * N * N + i * N + j] = r.m[i][j];
+}
+
+// generic block size: Jacobi on per-thread scratch in global memory
+__global__ void psd_project_dyn_kernel(int64_t t, int n, const double* H, int method, double* out, double* work) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= t) return;
+  double* a = work + e * (2 * n * n + n);
+  double* V = a + n * n;
+  double* w = V + n * n;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) a[i * n + j] = (i >= j) ? H[e * n * n + i * n + j] : H[e * n * n + j * n + i];
+  jacobi_eig_dyn(a, w, V, n, 40);
+  for (int i = 0; i < n; ++i) w[i] = (method == 1) ? fabs(w[i]) : (w[i] < SKB_PSD_FLOOR ? SKB_PSD_FLOOR : w[i]);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s += V[i * n + k] * w[k] * V[j * n + k];
+      out[e * n * n + i * n + j] = s;
+    }
+}
+
+static int run_element(int op, int material, int dim, int64_t t, const double* F, const double* mu, int64_t mu_n,
+                       const double* lam, int64_t lam_n, double* h0, size_t n0, double* h1, size_t n1, double* h2,
+                       size_t n2) {
+  if (dim != 2 && dim != 3) return fail(SKB_EINVAL, "Only dim == 2 or 3 are supported");
+  if (t < 0 || !F) return fail(SKB_EINVAL, "bad arguments");
+  if (material < 0 || material >= MAT_COUNT) return fail(SKB_EINVAL, "unknown material id");
+  if (mu && mu_n != 1 && mu_n != t) return fail(SKB_EINVAL, "mu must have 1 or t entries");
+  if (lam && lam_n != 1 && lam_n != t) return fail(SKB_EINVAL, "lam must have 1 or t entries");
+  if (skb_device_count() <= 0) return fail(SKB_ENOGPU, "no CUDA device");
+  if (t == 0) return SKB_OK;
+  SKB_TRY
+  const int b = dim * dim;
+  dvec<double> Fd(F, F + t * b), mud, lamd, d0(h0 ? n0 : 0), d1(h1 ? n1 : 0), d2(h2 ? n2 : 0);
+  if (mu) mud.assign(mu, mu + mu_n);
+  if (lam) lamd.assign(lam, lam + lam_n);
+  const int threads = 128;
+  const int blocks = (int)((t + threads - 1) / threads);
+  if (dim == 3)
+    element_kernel<3><<<blocks, threads>>>(op, material, t, raw(Fd), mu ? raw(mud) : nullptr, mu_n > 1,
+                                            lam ? raw(lamd) : nullptr, lam_n > 1, h0 ? raw(d0) : nullptr,
+                                            h1 ? raw(d1) : nullptr, h2 ? raw(d2) : nullptr);
+  else
+    element_kernel<2><<<blocks, threads>>>(op, material, t, raw(Fd), mu ? raw(mud) : nullptr, mu_n > 1,
+                                            lam ? raw(lamd) : nullptr, lam_n > 1, h0 ? raw(d0) : nullptr,
+                                            h1 ? raw(d1) : nullptr, h2 ? raw(d2) : nullptr);
+  SKB_CUDA(cudaGetLastError());
+  SKB_CUDA(cudaDeviceSynchronize());
+  if (h0) SKB_CUDA(cudaMemcpy(h0, raw(d0), n0 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (h1) SKB_CUDA(cudaMemcpy(h1, raw(d1), n1 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (h2) SKB_CUDA(cudaMemcpy(h2, raw(d2), n2 * sizeof(double), cudaMemcpyDeviceToHost));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+}  // namespace skb
+
+using namespace skb;
+
+extern "C" {
+
+int skb_element_energy(int material, int dim, int64_t t, const double* F, const double* mu, int64_t mu_n,
+                       const double* lam, int64_t lam_n, double* psi) {
+  if (!psi || !mu) return fail(SKB_EINVAL, "null argument");
+  return run_element(OP_ENERGY, material, dim, t, F, mu, mu_n, lam, lam_n, psi, t, nullptr, 0, nullptr, 0);
+}
+
+int skb_element_gradient(int material, int dim, int64_t t, const double* F, const double* mu, int64_t mu_n,
+                         const double* lam, int64_t lam_n, double* P) {
+  if (!P || !mu) return fail(SKB_EINVAL, "null argument");
+  return run_element(OP_GRADIENT, material, dim, t, F, mu, mu_n, lam, lam_n, P, t * dim * dim, nullptr, 0, nullptr, 0);
+}
+
+int skb_element_hessian(int material, int dim, int64_t t, const double* F, const double* mu, int64_t mu_n,
+                        const double* lam, int64_t lam_n, double* H) {
+  if (!H || !mu) return fail(SKB_EINVAL, "null argument");
+  const int64_t b = dim * dim;
+  return run_element(OP_HESSIAN, material, dim, t, F, mu, mu_n, lam, lam_n, H, t * b * b, nullptr, 0, nullptr, 0);
+}
+
+int skb_svd_rv(int dim, int64_t t, const double* F, double* U, double* S, double* V) {
+  const size_t nb = (size_t)t * dim * dim;
+  return run_element(OP_SVD, 0, dim, t, F, nullptr, 0, nullptr, 0, U, nb, S, nb, V, nb);
+}
+
+int skb_polar(int dim, int64_t t, const double* F, double* R, double* SS) {
+  const size_t nb = (size_t)t * dim * dim;
+  return run_element(OP_POLAR, 0, dim, t, F, nullptr, 0, nullptr, 0, R, nb, SS, nb, nullptr, 0);
+}
+
+int skb_rotation_gradient(int dim, int64_t t, const double* F, double* K) {
+  if (!K) return fail(SKB_EINVAL, "null argument");
+  const size_t b = (size_t)dim * dim;
+  return run_element(OP_ROTGRAD, 0, dim, t, F, nullptr, 0, nullptr, 0, K, (size_t)t * b * b, nullptr, 0, nullptr, 0);
+}
+
+int skb_psd_project(int64_t t, int b, const double* H, int method, double* out) {
+  if (!H || !out) return fail(SKB_EINVAL, "null argument");
+  if (b <= 0 || t < 0) return fail(SKB_EINVAL, "bad block size");
+  if (method != 0 && method != 1) return fail(SKB_EINVAL, "method must be 0 ('proj') or 1 ('abs')");
+  if (skb_device_count() <= 0) return fail(SKB_ENOGPU, "no CUDA device");
+  if (t == 0) return SKB_OK;
+  SKB_TRY
+  const size_t nn = (size_t)t * b * b;
+  dvec<double> Hd(H, H + nn), od(nn);
+  const int threads = 64;
+  const int blocks = (int)((t + threads - 1) / threads);
+  switch (b) {
+    case 1: psd_project_kernel<1><<<blocks, threads>>>(t, raw(Hd), method, raw(od)); break;
+    case 2: psd_project_kernel<2><<<blocks, threads>>>(t, raw(Hd), method, raw(od)); break;
+    case 3: psd_project_kernel<3><<<blocks, threads>>>(t, raw(Hd), method, raw(od)); break;
+    case 4: psd_project_kernel<4><<<blocks, threads>>>(t, raw(Hd), method, raw(od)); break;
+    case 6: psd_project_kernel<6><<<blocks, threads>>>(t, raw(Hd), method, raw(od)); break;
+    case 9: psd_project_kernel<9><<<blocks, threads>>>(t, raw(Hd), method, raw(od)); break;
+    default: {
+      dvec<double> work((size_t)t * (2 * b * b + b));
+      psd_project_dyn_kernel<<<blocks, threads>>>(t, b, raw(Hd), method, raw(od), raw(work));
+    }
+  }
+  SKB_CUDA(cudaGetLastError());
+  SKB_CUDA(cudaDeviceSynchronize());
+  SKB_CUDA(cudaMemcpy(out, raw(od), nn * sizeof(double), cudaMemcpyDeviceToHost));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,472 @@
+// C ABI, part 4: reduced (subspace) operators.
+//
+//   Hr = JB^T blockdiag(vol * psd(He)) JB      energies/elastic.py:749-782 and the *_hessian_u
+//                                              tier called with a dense operator
+//   fast_sandwich_transform_clustered          fast_sandwich_transform_clustered.py:15-158
+//
+// Structure of the reduced Hessian: per element chunk the CTA stages the rows
+// JB_e (b x r) and Y_e = He JB_e in shared memory and accumulates JB_e^T Y_e on
+// FP64 tensor-core tiles (mma.sync m8n8k4 -> SASS DMMA.8x8x4, the only FP64 MMA
+// sm_100a has: tcgen05 has no .kind::f64).  CTAs own disjoint element ranges and
+// write per-CTA partial matrices that a second kernel sums in CTA order, so the
+// result is deterministic.
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "capi_common.cuh"
+
+namespace skb {
+
+constexpr int RH_THREADS = 256;  // 8 warps
+constexpr int RH_ELEMS = 4;      // elements per k-chunk (rows = RH_ELEMS * b, multiple of 4 for b in {4, 9})
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// F = rows . z + Jx0 for one element, He and P; writes Y_e rows and P-weighted vector.
+template <int D>
+__device__ __forceinline__ void reduced_element(int material, int psd_mode, const Mat<D>& F, double mu, double lam,
+                                                double vol, double* H /* b*b */, Mat<D>& P, double& psi) {
+  constexpr int B = D * D;
+  psi = vol * energy_density<D>(material, F, mu, lam);
+  P = pk1<D>(material, F, mu, lam);
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) P.m[i][j] *= vol;
+  if (material == MAT_LINEAR_ELASTICITY) {
+    // dispatcher semantics: floor lifts the zero (skew) modes; own-module callers pass PSD_NONE
+    double w_sym = 2.0 * mu, w_tr = 2.0 * mu + D * lam, w_skew = 0.0;
+    const double pre = (psd_mode == PSD_BEFORE_VOL) ? 1.0 : vol;
+    const double post = (psd_mode == PSD_BEFORE_VOL) ? vol : 1.0;
+    w_sym *= pre; w_tr *= pre; w_skew *= pre;
+    if (psd_mode != PSD_NONE) {
+      w_sym = psd_clamp(w_sym, psd_mode);
+      w_tr = psd_clamp(w_tr, psd_mode);
+      w_skew = psd_clamp(w_skew, psd_mode);
+    }
+    w_sym *= post; w_tr *= post; w_skew *= post;
+    const double cI = 0.5 * (w_sym + w_skew), cT = 0.5 * (w_sym - w_skew), cR = (w_tr - w_sym) / D;
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j)
+        for (int k = 0; k < D; ++k)
+          for (int l = 0; l < D; ++l) {
+            double v = 0.0;
+            if (i == k && j == l) v += cI;
+            if (i == l && j == k) v += cT;
+            if (i == j && k == l) v += cR;
+            H[(i * D + j) * B + k * D + l] = v;
+          }
+    return;
+  }
+  Mat<D> U, V;
+  Vec<D> s;
+  svd_rv(F, U, s, V);
+  Principal<D> h = principal_hessian<D>(material, s, mu, lam);
+  weight_and_project<D>(h, vol, psd_mode);
+  expand_hessian<D>(h, U, V, H);
+}
+
+// Pass 1: per element F, He (to global scratch, b*b per element), vol*P, vol*psi.
+// rows(e) come either from a dense JB (t*b, r) or, when JB == nullptr, from the mesh:
+// F = J (B z + x0) was formed by the caller into Fin.
+template <int D>
+__global__ void reduced_pass1_kernel(int material, int psd_mode, int64_t t, const double* Fin, const double* mu,
+                                     int mu_s, const double* lam, int lam_s, const double* vol, int vol_s,
+                                     double* Hout, double* Pout, double* psiout) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= t) return;
+  constexpr int B = D * D;
+  Mat<D> F;
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) F.m[i][j] = Fin[e * B + i * D + j];
+  double H[B * B];
+  Mat<D> P;
+  double psi;
+  reduced_element<D>(material, psd_mode, F, mu[e * mu_s], lam ? lam[e * lam_s] : 0.0, vol[e * vol_s], H, P, psi);
+  for (int i = 0; i < B * B; ++i) Hout[e * B * B + i] = H[i];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) Pout[e * B + i * D + j] = P.m[i][j];
+  psiout[e] = psi;
+}
+
+// y[row] = sum_c M[row][c] z[c] + add[row]   (one warp per row, coalesced)
+__global__ void gemv_rows_kernel(int64_t rows, int cols, const double* M, const double* z, const double* add,
+                                 double* y) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  double s = 0.0;
+  for (int c = lane; c < cols; c += 32) s = fma(M[row * cols + c], z[c], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) y[row] = s + (add ? add[row] : 0.0);
+}
+
+// Rows of the reduced operator for element e, written to shared memory [row][r]:
+//   dense:      JB[(e*b + i*D + j), :]
+//   from basis: sum_a D[j][a] * Bm[T[e][a]*D + i, :]
+template <int D>
+__device__ __forceinline__ void stage_rows(const double* JB, const PlanView* p, const double* Bm, int64_t e, int r,
+                                           int rpad, double* srow /* b x rpad */) {
+  constexpr int B = D * D;
+  constexpr int K = D + 1;
+  if (JB) {
+    for (int idx = threadIdx.x; idx < B * r; idx += blockDim.x) {
+      const int row = idx / r, c = idx - row * r;
+      srow[row * rpad + c] = JB[(e * B + row) * (int64_t)r + c];
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < B * r; idx += blockDim.x) {
+      const int row = idx / r, c = idx - row * r;
+      const int i = row / D, j = row - i * D;
+      double s = 0.0, d0 = 0.0;
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        const double d = p->Dm[(size_t)(j * D + a) * p->t + e];
+        d0 -= d;
+        s = fma(d, Bm[((size_t)p->T32[e * K + a + 1] * D + i) * r + c], s);
+      }
+      s = fma(d0, Bm[((size_t)p->T32[e * K] * D + i) * r + c], s);
+      srow[row * rpad + c] = s;
+    }
+  }
+}
+
+// Pass 2: partial Hr and gr per CTA over its element range.  blockIdx.x = element range,
+// blockIdx.y = output column panel (tile columns [y*tcp, (y+1)*tcp)).  Output tiles are 8x8
+// DMMA tiles; warp w owns panel tiles w, w+nw, ... (fully unrolled so accumulators stay in registers).
+constexpr int RH_MAXT = 44;
+template <int D>
+__global__ void __launch_bounds__(RH_THREADS, 1)
+reduced_pass2_kernel(int64_t t, int r, int tcp, const double* JB, PlanView pv, int use_plan, const double* Bm,
+                     const double* He, const double* Pw, double* Hpart, double* gpart) {
+  constexpr int B = D * D;
+  constexpr int ROWS = RH_ELEMS * B;  // 36 or 16: multiple of 4
+  extern __shared__ double sm[];
+  const int rt = (r + 7) / 8;          // tiles per side
+  const int rpad = rt * 8 + 1;         // +1: de-conflict column reads
+  double* sJ = sm;                     // ROWS x rpad
+  double* sY = sm + (size_t)ROWS * rpad;
+  const PlanView* p = use_plan ? &pv : nullptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int tc0 = blockIdx.y * tcp;
+  const int tc1 = (tc0 + tcp < rt) ? tc0 + tcp : rt;
+  const int ntiles = rt * (tc1 - tc0);
+  double acc[RH_MAXT][2];
+#pragma unroll
+  for (int i = 0; i < RH_MAXT; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double gacc = 0.0;  // thread c (< r) accumulates gr[c]  (panel 0 only)
+
+  const int64_t per = (t + gridDim.x - 1) / gridDim.x;
+  const int64_t e0 = (int64_t)blockIdx.x * per;
+  const int64_t e1 = (e0 + per < t) ? e0 + per : t;
+  for (int64_t eb = e0; eb < e1; eb += RH_ELEMS) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ROWS * rpad; idx += blockDim.x) {
+      sJ[idx] = 0.0;
+      sY[idx] = 0.0;
+    }
+    __syncthreads();
+    for (int le = 0; le < RH_ELEMS; ++le) {
+      const int64_t e = eb + le;
+      if (e < e1) stage_rows<D>(use_plan ? nullptr : JB, p, Bm, e, r, rpad, sJ + (size_t)le * B * rpad);
+    }
+    __syncthreads();
+    // Y_e = He_e * JB_e (panel columns only) and gradient accumulation
+    const int c_lo = tc0 * 8, c_hi = (tc1 * 8 < r) ? tc1 * 8 : r;
+    const int pc = c_hi - c_lo;
+    for (int idx = threadIdx.x; idx < ROWS * pc; idx += blockDim.x) {
+      const int row = idx / pc, c = c_lo + (idx - row * pc);
+      const int le = row / B, rb = row - le * B;
+      const int64_t e = eb + le;
+      if (e < e1) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < B; ++k) s = fma(He[(e * B + rb) * B + k], sJ[(le * B + k) * rpad + c], s);
+        sY[row * rpad + c] = s;
+      }
+    }
+    if (blockIdx.y == 0 && threadIdx.x < r) {
+      const int c = threadIdx.x;
+      for (int row = 0; row < ROWS; ++row) {
+        const int64_t e = eb + row / B;
+        if (e < e1) gacc = fma(sJ[row * rpad + c], Pw[e * B + (row % B)], gacc);
+      }
+    }
+    __syncthreads();
+    // Hr += sJ^T sY on 8x8 tiles: A[m][k] = sJ[k][m], B[k][n] = sY[k][n]
+#pragma unroll
+    for (int slot = 0; slot < RH_MAXT; ++slot) {
+      const int tile = warp + slot * nw;
+      if (tile < ntiles) {
+        const int tm = tile / (tc1 - tc0), tn = tc0 + (tile - tm * (tc1 - tc0));
+        double c0 = acc[slot][0], c1 = acc[slot][1];
+#pragma unroll
+        for (int k0 = 0; k0 < ROWS; k0 += 4) {
+          const double a = sJ[(k0 + (lane & 3)) * rpad + tm * 8 + (lane >> 2)];
+          const double b = sY[(k0 + (lane & 3)) * rpad + tn * 8 + (lane >> 2)];
+          dmma_m8n8k4(c0, c1, a, b);
+        }
+        acc[slot][0] = c0;
+        acc[slot][1] = c1;
+      }
+    }
+  }
+#pragma unroll
+  for (int slot = 0; slot < RH_MAXT; ++slot) {
+    const int tile = warp + slot * nw;
+    if (tile < ntiles) {
+      const int tm = tile / (tc1 - tc0), tn = tc0 + (tile - tm * (tc1 - tc0));
+      const int row = tm * 8 + (lane >> 2), col = tn * 8 + 2 * (lane & 3);
+      if (row < r && col < r) Hpart[((size_t)blockIdx.x * r + row) * r + col] = acc[slot][0];
+      if (row < r && col + 1 < r) Hpart[((size_t)blockIdx.x * r + row) * r + col + 1] = acc[slot][1];
+    }
+  }
+  if (blockIdx.y == 0 && threadIdx.x < r) gpart[(size_t)blockIdx.x * r + threadIdx.x] = gacc;
+}
+
+// out[i] = sum_{c} part[c][i]   in CTA order
+__global__ void sum_partials_kernel(int nparts, int64_t len, const double* part, double* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  double s = 0.0;
+  for (int c = 0; c < nparts; ++c) s += part[(size_t)c * len + i];
+  out[i] = s;
+}
+
+// ---- FST -------------------------------------------------------------------
+// grid (m1, n_clusters); threads over q.  Elements of a cluster are visited in
+// ascending element order, so each ARBs entry has a fixed summation order.
+template <int D>
+__global__ void fst_precompute_kernel(int64_t t, int m1, int m2, int ncl, const double* A, const double* Bm,
+                                      const int* order, const int* cptr, double* ARBs) {
+  constexpr int B = D * D;
+  const int p = blockIdx.x, c = blockIdx.y;
+  for (int q = threadIdx.x; q < m2; q += blockDim.x) {
+    double acc[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) acc[i][j] = 0.0;
+    for (int s = cptr[c]; s < cptr[c + 1]; ++s) {
+      const int64_t e = order[s];
+      double a[B], b[B];
+#pragma unroll
+      for (int k = 0; k < B; ++k) {
+        a[k] = A[(int64_t)p * B * t + e * B + k];
+        b[k] = Bm[(e * B + k) * m2 + q];
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+          for (int k = 0; k < D; ++k) acc[i][j] = fma(a[D * i + k], b[D * j + k], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) ARBs[((((int64_t)p * m2 + q) * ncl + c) * D + i) * D + j] = acc[i][j];
+  }
+}
+
+template <int D>
+static int reduced_run(skb_plan* pl, int material, int psd_mode, int64_t t, int64_t r, const double* JB_h,
+                       const double* Jx0_h, const double* B_h, const double* x0_h, const double* z_h,
+                       const double* mu_h, int64_t mu_n, const double* lam_h, int64_t lam_n, const double* vol_h,
+                       int64_t vol_n, double* energy, double* gr, double* Hr) {
+  constexpr int Bk = D * D;
+  if (r <= 0 || r > RH_THREADS) return fail(SKB_EINVAL, "reduced dimension r must be in [1, 256]");
+  if (material < 0 || material >= MAT_COUNT) return fail(SKB_EINVAL, "unknown material id");
+  SKB_TRY
+  cudaStream_t st = 0;
+  dvec<double> z(z_h, z_h + r), F((size_t)t * Bk), He((size_t)t * Bk * Bk), Pw((size_t)t * Bk), psi(t);
+  dvec<double> JB, Bm, mu, lam, vol;
+  const double *mu_p, *lam_p = nullptr, *vol_p;
+  int mu_s, lam_s = 0, vol_s;
+  if (pl) {
+    // F = J (B z + x0) through the mesh plan
+    const int64_t nd = pl->ndof();
+    Bm.assign(B_h, B_h + nd * r);
+    dvec<double> x(nd), x0;
+    if (x0_h) x0.assign(x0_h, x0_h + nd);
+    gemv_rows_kernel<<<(unsigned)((nd * 32 + 255) / 256), 256, 0, st>>>(nd, (int)r, raw(Bm), raw(z), x0_h ? raw(x0) : nullptr, raw(x));
+    // F_e from x: same gather as load_element in kernels.cuh
+    const PlanView p = pl->view();
+    thrust::counting_iterator<int> it0(0);
+    const double* xp = raw(x);
+    double* Fp = raw(F);
+    thrust::for_each(thrust::cuda::par.on(st), it0, it0 + (int)t, [=] __device__(int e) {
+      Mat<D> Fm;
+      double Dm[D][D];
+      constexpr int K = D + 1;
+      const int* Te = p.T32 + (size_t)e * K;
+      for (int j = 0; j < D; ++j)
+        for (int c = 0; c < D; ++c) Dm[j][c] = p.Dm[(size_t)(j * D + c) * p.t + e];
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) Fm.m[i][j] = 0.0;
+      for (int c = 0; c < D; ++c)
+        for (int i = 0; i < D; ++i) {
+          double d = xp[(size_t)Te[c + 1] * D + i] - xp[(size_t)Te[0] * D + i];
+          for (int j = 0; j < D; ++j) Fm.m[i][j] = fma(Dm[j][c], d, Fm.m[i][j]);
+        }
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) Fp[(size_t)e * D * D + i * D + j] = Fm.m[i][j];
+    });
+    if (!pl->have_materials) return fail(SKB_EINVAL, "materials not set (skb_set_materials)");
+    mu_p = raw(pl->mu); mu_s = pl->mu_n > 1;
+    lam_p = raw(pl->lam); lam_s = pl->lam_n > 1;
+    vol_p = raw(pl->vol); vol_s = pl->vol_n > 1;
+  } else {
+    if (!mu_h || (mu_n != 1 && mu_n != t)) return fail(SKB_EINVAL, "mu must have 1 or t entries");
+    if (lam_h && lam_n != 1 && lam_n != t) return fail(SKB_EINVAL, "lam must have 1 or t entries");
+    if (!vol_h || (vol_n != 1 && vol_n != t)) return fail(SKB_EINVAL, "vol must have 1 or t entries");
+    JB.assign(JB_h, JB_h + t * Bk * r);
+    dvec<double> Jx0;
+    if (Jx0_h) Jx0.assign(Jx0_h, Jx0_h + t * Bk);
+    gemv_rows_kernel<<<(unsigned)((t * Bk * 32 + 255) / 256), 256, 0, st>>>(t * Bk, (int)r, raw(JB), raw(z), Jx0_h ? raw(Jx0) : nullptr, raw(F));
+    mu.assign(mu_h, mu_h + mu_n);
+    if (lam_h) lam.assign(lam_h, lam_h + lam_n);
+    vol.assign(vol_h, vol_h + vol_n);
+    mu_p = raw(mu); mu_s = mu_n > 1;
+    if (lam_h) { lam_p = raw(lam); lam_s = lam_n > 1; }
+    vol_p = raw(vol); vol_s = vol_n > 1;
+  }
+  reduced_pass1_kernel<D><<<(unsigned)((t + 127) / 128), 128, 0, st>>>(material, psd_mode, t, raw(F), mu_p, mu_s, lam_p, lam_s,
+                                                                       vol_p, vol_s, raw(He), raw(Pw), raw(psi));
+  SKB_CUDA(cudaGetLastError());
+  if (energy) {
+    // fixed-order two-stage sum
+    const int nb = 1024;
+    dvec<double> part(nb), out(1);
+    const double* ps = raw(psi);
+    double* pp = raw(part);
+    const int64_t per = (t + nb - 1) / nb;
+    thrust::counting_iterator<int> it0(0);
+    thrust::for_each(thrust::cuda::par.on(st), it0, it0 + nb, [=] __device__(int b) {
+      double s = 0.0;
+      for (int64_t e = b * per; e < (b + 1) * per && e < t; ++e) s += ps[e];
+      pp[b] = s;
+    });
+    reduce_final_kernel<<<1, 1024, 0, st>>>(raw(part), nb, raw(out));
+    SKB_CUDA(cudaMemcpy(energy, raw(out), sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (gr || Hr) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int grid = sms;
+    const int64_t chunks = (t + RH_ELEMS - 1) / RH_ELEMS;
+    if (grid > chunks) grid = (int)chunks;
+    const int rt = (int)(r + 7) / 8;
+    const int nwarps = RH_THREADS / 32;
+    int npanels = 1, tcp = rt;
+    while ((rt * tcp + nwarps - 1) / nwarps > RH_MAXT) {
+      ++npanels;
+      tcp = (rt + npanels - 1) / npanels;
+    }
+    npanels = (rt + tcp - 1) / tcp;
+    const int rpad = rt * 8 + 1;
+    const size_t smem = (size_t)2 * RH_ELEMS * Bk * rpad * sizeof(double);
+    SKB_CUDA(cudaFuncSetAttribute(reduced_pass2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    dvec<double> Hpart((size_t)grid * r * r), gpart((size_t)grid * r), Hd(r * r), gd(r);
+    PlanView pv;
+    memset(&pv, 0, sizeof(pv));
+    if (pl) pv = pl->view();
+    reduced_pass2_kernel<D><<<dim3(grid, npanels), RH_THREADS, smem, st>>>(t, (int)r, tcp, pl ? nullptr : raw(JB), pv, pl ? 1 : 0,
+                                                           pl ? raw(Bm) : nullptr, raw(He), raw(Pw), raw(Hpart), raw(gpart));
+    SKB_CUDA(cudaGetLastError());
+    sum_partials_kernel<<<(unsigned)((r * r + 255) / 256), 256, 0, st>>>(grid, r * r, raw(Hpart), raw(Hd));
+    sum_partials_kernel<<<(unsigned)((r + 255) / 256), 256, 0, st>>>(grid, r, raw(gpart), raw(gd));
+    SKB_CUDA(cudaDeviceSynchronize());
+    if (Hr) SKB_CUDA(cudaMemcpy(Hr, raw(Hd), r * r * sizeof(double), cudaMemcpyDeviceToHost));
+    if (gr) SKB_CUDA(cudaMemcpy(gr, raw(gd), r * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  SKB_CUDA(cudaDeviceSynchronize());
+  return SKB_OK;
+  SKB_CATCH
+}
+
+}  // namespace skb
+
+using namespace skb;
+
+extern "C" {
+
+int skb_reduced_gradient_hessian(int material, int psd_mode, int dim, int64_t t, int64_t r, const double* JB,
+                                 const double* Jx0, const double* z, const double* mu, int64_t mu_n,
+                                 const double* lam, int64_t lam_n, const double* vol, int64_t vol_n,
+                                 double* energy, double* gr, double* Hr) {
+  if (!JB || !z) return fail(SKB_EINVAL, "null argument");
+  if (dim != 2 && dim != 3) return fail(SKB_EINVAL, "Only dim == 2 or 3 are supported");
+  if (skb_device_count() <= 0) return fail(SKB_ENOGPU, "no CUDA device");
+  return dim == 3 ? reduced_run<3>(nullptr, material, psd_mode, t, r, JB, Jx0, nullptr, nullptr, z, mu, mu_n, lam, lam_n, vol, vol_n, energy, gr, Hr)
+                  : reduced_run<2>(nullptr, material, psd_mode, t, r, JB, Jx0, nullptr, nullptr, z, mu, mu_n, lam, lam_n, vol, vol_n, energy, gr, Hr);
+}
+
+int skb_reduced_hessian_from_basis(skb_plan* pl, int material, int psd_mode, int64_t r, const double* B,
+                                   const double* x0, const double* z, double* energy, double* gr, double* Hr) {
+  if (!pl || !B || !z) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  return pl->d.dim == 3 ? reduced_run<3>(pl, material, psd_mode, pl->d.t, r, nullptr, nullptr, B, x0, z, nullptr, 0, nullptr, 0, nullptr, 0, energy, gr, Hr)
+                        : reduced_run<2>(pl, material, psd_mode, pl->d.t, r, nullptr, nullptr, B, x0, z, nullptr, 0, nullptr, 0, nullptr, 0, energy, gr, Hr);
+}
+
+int skb_fst_precompute(int dim, int64_t t, int64_t m1, int64_t m2, int64_t ncl, const double* A, const double* B,
+                       const int32_t* l, double* ARBs) {
+  if (!A || !B || !l || !ARBs) return fail(SKB_EINVAL, "null argument");
+  if (dim != 2 && dim != 3) return fail(SKB_EINVAL, "Only dim == 2 or 3 are supported");
+  if (skb_device_count() <= 0) return fail(SKB_ENOGPU, "no CUDA device");
+  if (m1 <= 0 || m2 <= 0 || ncl <= 0 || t <= 0 || ncl > 65535) return fail(SKB_EINVAL, "bad sizes");
+  SKB_TRY
+  const int b = dim * dim;
+  // cluster -> ascending element list (stable counting sort on the host: one-off setup)
+  std::vector<int> cptr(ncl + 1, 0), order(t);
+  for (int64_t e = 0; e < t; ++e) {
+    if (l[e] < 0 || l[e] >= ncl) return fail(SKB_EINVAL, "cluster label out of range");
+    cptr[l[e] + 1]++;
+  }
+  for (int64_t c = 0; c < ncl; ++c) cptr[c + 1] += cptr[c];
+  {
+    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+    for (int64_t e = 0; e < t; ++e) order[fill[l[e]]++] = (int)e;
+  }
+  dvec<double> Ad(A, A + m1 * b * t), Bd(B, B + b * t * m2), out((size_t)m1 * m2 * ncl * b);
+  dvec<int> od(order.begin(), order.end()), cd(cptr.begin(), cptr.end());
+  dim3 grid((unsigned)m1, (unsigned)ncl);
+  const int threads = m2 >= 128 ? 128 : (int)((m2 + 31) / 32 * 32);
+  if (dim == 3)
+    fst_precompute_kernel<3><<<grid, threads>>>(t, (int)m1, (int)m2, (int)ncl, raw(Ad), raw(Bd), raw(od), raw(cd), raw(out));
+  else
+    fst_precompute_kernel<2><<<grid, threads>>>(t, (int)m1, (int)m2, (int)ncl, raw(Ad), raw(Bd), raw(od), raw(cd), raw(out));
+  SKB_CUDA(cudaGetLastError());
+  SKB_CUDA(cudaDeviceSynchronize());
+  SKB_CUDA(cudaMemcpy(ARBs, raw(out), out.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_fst_eval(int dim, int64_t m1, int64_t m2, int64_t ncl, const double* ARBs, const double* r, double* out) {
+  if (!ARBs || !r || !out) return fail(SKB_EINVAL, "null argument");
+  if (dim != 2 && dim != 3) return fail(SKB_EINVAL, "Only dim == 2 or 3 are supported");
+  if (skb_device_count() <= 0) return fail(SKB_ENOGPU, "no CUDA device");
+  SKB_TRY
+  const int64_t rows = m1 * m2, cols = ncl * dim * dim;
+  dvec<double> Ad(ARBs, ARBs + rows * cols), rd(r, r + cols), od(rows);
+  gemv_rows_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256>>>(rows, (int)cols, raw(Ad), raw(rd), nullptr, raw(od));
+  SKB_CUDA(cudaGetLastError());
+  SKB_CUDA(cudaDeviceSynchronize());
+  SKB_CUDA(cudaMemcpy(out, raw(od), rows * sizeof(double), cudaMemcpyDeviceToHost));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,363 @@
+// C ABI, part 3: SpMV, block-Jacobi PCG and the device-resident Newton step.
+#include <vector>
+
+#include "capi_common.cuh"
+#include "solver.cuh"
+
+namespace skb {
+
+static int pcg_grid(const skb_plan* pl) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+  // fixed grid: a multiple of the SM count, no more CTAs than there is work
+  const int per_cta_rows = PCG_THREADS / SPMV_GROUP;
+  int want = (pl->d.n + per_cta_rows - 1) / per_cta_rows;
+  int grid = sms * 4;
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  if (grid > 1024) grid = 1024;
+  return grid;
+}
+
+struct PcgWork {
+  double *r, *z, *p, *q, *dinv, *part;  // part: 3 * grid doubles
+  PcgScalars* sc;                        // 2 ping-pong slots
+};
+
+static void ensure(dvec<double>& v, size_t n) {
+  if (v.size() < n) v.resize(n);
+}
+
+// PCG driver shared by the plan (block) path and the generic CSR path.
+//   spmv_dot(pvec, q, part_pq, sc) launches  q = A pvec  + partial sums of pvec.q
+//   nb = number of D x D diagonal blocks, dinv already filled
+template <int D, class SpmvDot>
+static int pcg_loop(skb_plan* pl, int nb, int grid, SpmvDot spmv_dot, const double* dinv, const double* rhs,
+                    double rtol, int max_iter, double* x, double* r, double* z, double* pv, double* q,
+                    double* red, int* iters, double* relres, cudaStream_t st, int* launches) {
+  double* part_pq = red;
+  double* part_rz = part_pq + 1024;
+  double* part_rr = part_rz + 1024;
+  PcgScalars* sc = reinterpret_cast<PcgScalars*>(part_rr + 1024);  // two ping-pong slots
+  pcg_init_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, rhs, dinv, x, r, z, pv, part_rz, part_rr);
+  pcg_init_scalars_kernel<<<1, PCG_THREADS, 0, st>>>(part_rz, part_rr, grid, rtol, sc);
+  *launches += 2;
+  int cur = 0;
+  PcgScalars h;
+  const int check_every = 25;
+  int it = 0;
+  bool done = false;
+  while (it < max_iter && !done) {
+    const int batch = (max_iter - it < check_every) ? (max_iter - it) : check_every;
+    for (int b = 0; b < batch; ++b) {
+      spmv_dot(pv, q, part_pq, sc + cur);
+      pcg_update_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, dinv, pv, q, x, r, z, part_pq, grid, part_rz, part_rr, sc + cur);
+      pcg_direction_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, z, pv, part_rz, part_rr, grid, rtol, sc + cur, sc + (cur ^ 1));
+      cur ^= 1;
+      *launches += 3;
+    }
+    it += batch;
+    SKB_CUDA(cudaMemcpyAsync(&h, sc + cur, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+    SKB_CUDA(cudaStreamSynchronize(st));
+    done = h.done != 0;
+  }
+  if (it == 0) {
+    SKB_CUDA(cudaMemcpyAsync(&h, sc + cur, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
+    SKB_CUDA(cudaStreamSynchronize(st));
+  }
+  SKB_CUDA(cudaGetLastError());
+  if (iters) *iters = h.iters;
+  if (relres) *relres = (h.bb > 0.0) ? sqrt(h.rr / h.bb) : 0.0;
+  return SKB_OK;
+}
+
+template <int D>
+static int pcg_run(skb_plan* pl, const double* vals, const double* dadd, const double* rhs, double rtol,
+                   int max_iter, double* x, int* iters, double* relres, cudaStream_t st) {
+  const PlanView p = pl->view();
+  const size_t nd = (size_t)p.n * D;
+  const int grid = pcg_grid(pl);
+  ensure(pl->w_r, nd);
+  ensure(pl->w_z, nd);
+  ensure(pl->w_p, nd);
+  ensure(pl->w_q, nd);
+  ensure(pl->w_dinv, (size_t)p.n * D * D);
+  ensure(pl->w_red, 3 * 1024 + 64);
+  double* dinv = raw(pl->w_dinv);
+  block_jacobi_kernel<D><<<(p.n + 127) / 128, 128, 0, st>>>(p, vals, dadd, dinv);
+  pl->launches++;
+  auto spmv_dot = [&](const double* pvec, double* q, double* part_pq, const PcgScalars* sc) {
+    pcg_spmv_dot_kernel<D><<<grid, PCG_THREADS, 0, st>>>(p, vals, dadd, pvec, q, part_pq, sc);
+  };
+  return pcg_loop<D>(pl, p.n, grid, spmv_dot, dinv, rhs, rtol, max_iter, x, raw(pl->w_r), raw(pl->w_z),
+                     raw(pl->w_p), raw(pl->w_q), raw(pl->w_red), iters, relres, st, &pl->launches);
+}
+
+int pcg_solve(skb_plan* pl, const double* vals, const double* dadd, const double* rhs, double rtol, int max_iter,
+              double* x, int* iters, double* relres, cudaStream_t st) {
+  return pl->d.dim == 3 ? pcg_run<3>(pl, vals, dadd, rhs, rtol, max_iter, x, iters, relres, st)
+                        : pcg_run<2>(pl, vals, dadd, rhs, rtol, max_iter, x, iters, relres, st);
+}
+
+template <int D>
+static int csr_pcg_run(int64_t n, const int32_t* indptr_h, const int32_t* indices_h, const double* vals_h,
+                       const double* rhs_h, double rtol, int max_iter, double* x_h, int* iters, double* relres) {
+  const int nb = (int)(n / D);
+  const int64_t nnz = indptr_h[n];
+  dvec<int> indptr(indptr_h, indptr_h + n + 1), indices(indices_h, indices_h + nnz);
+  dvec<double> vals(vals_h, vals_h + nnz), rhs(rhs_h, rhs_h + n), x(n), r(n), z(n), pv(n), q(n),
+      dinv((size_t)nb * D * D), red(3 * 1024 + 64);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  int grid = sms * 4;
+  const int want = (int)((n + (PCG_THREADS / SPMV_GROUP) - 1) / (PCG_THREADS / SPMV_GROUP));
+  if (grid > want) grid = want;
+  if (grid < 1) grid = 1;
+  if (grid > 1024) grid = 1024;
+  cudaStream_t st = 0;
+  csr_block_jacobi_kernel<D><<<(nb + 127) / 128, 128, 0, st>>>(nb, raw(indptr), raw(indices), raw(vals), raw(dinv));
+  const int* ip = raw(indptr);
+  const int* ix = raw(indices);
+  const double* vp = raw(vals);
+  const int nn = (int)n;
+  auto spmv_dot = [&](const double* pvec, double* qq, double* part_pq, const PcgScalars* sc) {
+    csr_pcg_spmv_dot_kernel<<<grid, PCG_THREADS, 0, st>>>(nn, ip, ix, vp, pvec, qq, part_pq, sc);
+  };
+  int launches = 0;
+  int rc = pcg_loop<D>(nullptr, nb, grid, spmv_dot, raw(dinv), raw(rhs), rtol, max_iter, raw(x), raw(r), raw(z),
+                       raw(pv), raw(q), raw(red), iters, relres, st, &launches);
+  if (rc) return rc;
+  SKB_CUDA(cudaMemcpy(x_h, raw(x), n * sizeof(double), cudaMemcpyDeviceToHost));
+  return SKB_OK;
+}
+
+}  // namespace skb
+
+using namespace skb;
+
+extern "C" {
+
+int skb_spmv_dev(skb_plan* pl, const double* vals, const double* diag_add, const double* x, double* y,
+                 void* stream) {
+  if (!pl || !vals || !x || !y) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  const PlanView p = pl->view();
+  const int grid = pcg_grid(pl);
+  if (p.dim == 3)
+    spmv_kernel<3><<<grid, PCG_THREADS, 0, (cudaStream_t)stream>>>(p, vals, diag_add, x, y);
+  else
+    spmv_kernel<2><<<grid, PCG_THREADS, 0, (cudaStream_t)stream>>>(p, vals, diag_add, x, y);
+  pl->launches++;
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+}
+
+int skb_pcg_dev(skb_plan* pl, const double* vals, const double* diag_add, const double* rhs, double rtol,
+                int max_iter, double* x, int* iters, double* relres, void* stream) {
+  if (!pl || !vals || !rhs || !x) return fail(SKB_EINVAL, "null argument");
+  if (!(rtol >= 0.0) || max_iter < 0) return fail(SKB_EINVAL, "bad tolerance / max_iter");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  return pcg_solve(pl, vals, diag_add, rhs, rtol, max_iter, x, iters, relres, (cudaStream_t)stream);
+  SKB_CATCH
+}
+
+int skb_pcg(skb_plan* pl, const double* vals, const double* diag_add, const double* rhs, double rtol,
+            int max_iter, double* x, int* iters, double* relres) {
+  if (!pl || !vals || !rhs || !x) return fail(SKB_EINVAL, "null argument");
+  if (!(rtol >= 0.0) || max_iter < 0) return fail(SKB_EINVAL, "bad tolerance / max_iter");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  pl->launches = 0;
+  const size_t nd = pl->ndof();
+  pl->vals.resize(pl->nnz());
+  ensure(pl->w_dx, nd);
+  ensure(pl->g, nd);
+  SKB_CUDA(cudaMemcpyAsync(raw(pl->vals), vals, pl->nnz() * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+  SKB_CUDA(cudaMemcpyAsync(raw(pl->g), rhs, nd * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+  const double* dadd = nullptr;
+  if (diag_add) {
+    ensure(pl->w_diag, nd);
+    SKB_CUDA(cudaMemcpyAsync(raw(pl->w_diag), diag_add, nd * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+    dadd = raw(pl->w_diag);
+  }
+  int rc = pcg_solve(pl, raw(pl->vals), dadd, raw(pl->g), rtol, max_iter, raw(pl->w_dx), iters, relres, pl->stream);
+  if (rc) return rc;
+  SKB_CUDA(cudaMemcpyAsync(x, raw(pl->w_dx), nd * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+  SKB_CUDA(cudaStreamSynchronize(pl->stream));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_csr_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const double* vals, int block,
+                const double* rhs, double rtol, int max_iter, double* x, int* iters, double* relres) {
+  if (!indptr || !indices || !vals || !rhs || !x) return fail(SKB_EINVAL, "null argument");
+  if (n <= 0 || n >= ((int64_t)1 << 31)) return fail(SKB_EINVAL, "bad matrix size");
+  if (block < 1 || block > 3 || n % block) return fail(SKB_EINVAL, "block must be 1, 2 or 3 and divide n");
+  if (!(rtol >= 0.0) || max_iter < 0) return fail(SKB_EINVAL, "bad tolerance / max_iter");
+  if (skb_device_count() <= 0) return fail(SKB_ENOGPU, "no CUDA device");
+  SKB_TRY
+  switch (block) {
+    case 1: return csr_pcg_run<1>(n, indptr, indices, vals, rhs, rtol, max_iter, x, iters, relres);
+    case 2: return csr_pcg_run<2>(n, indptr, indices, vals, rhs, rtol, max_iter, x, iters, relres);
+    default: return csr_pcg_run<3>(n, indptr, indices, vals, rhs, rtol, max_iter, x, iters, relres);
+  }
+  SKB_CATCH
+}
+
+int skb_dense_solve(int64_t n, const double* A, const double* b, double* x) {
+  if (!A || !b || !x) return fail(SKB_EINVAL, "null argument");
+  if (n <= 0 || n > 8192) return fail(SKB_EINVAL, "dense solve supports 1 <= n <= 8192");
+  if (skb_device_count() <= 0) return fail(SKB_ENOGPU, "no CUDA device");
+  SKB_TRY
+  dvec<double> Ad(A, A + n * n), bd(b, b + n), xd(n);
+  dvec<int> status(1, 0);
+  dense_solve_kernel<<<1, 1024>>>((int)n, raw(Ad), raw(bd), raw(xd), raw(status));
+  SKB_CUDA(cudaGetLastError());
+  SKB_CUDA(cudaDeviceSynchronize());
+  int st = status[0];
+  if (st) return fail(SKB_EINVAL, "Matrix is singular.");
+  SKB_CUDA(cudaMemcpy(x, raw(xd), n * sizeof(double), cudaMemcpyDeviceToHost));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+// One implicit step: Newton iterations with PCG and Armijo backtracking, all vectors resident.
+// Mirrors solvers/newton.py:42-70 and backtracking_line_search.py:56-66.
+int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const double* x_tilde,
+               const double* mass, double kin_scale, const double* f_ext, const double* pin_k,
+               const double* pin_target, double* x_out, skb_newton_info* info) {
+  if (!pl || !o || !x0 || !x_out) return fail(SKB_EINVAL, "null argument");
+  if (!pl->have_materials) return fail(SKB_EINVAL, "materials not set (skb_set_materials)");
+  if (o->do_line_search) {
+    // backtracking_line_search.py:52-53 (AssertionError in the reference)
+    if (!(o->ls_alpha > 0 && o->ls_alpha <= 0.5) || !(o->ls_beta > 0 && o->ls_beta < 1))
+      return fail(SKB_EINVAL, "line search needs 0 < alpha <= 0.5 and 0 < beta < 1");
+  }
+  if ((pin_k == nullptr) != (pin_target == nullptr)) return fail(SKB_EINVAL, "pin_k and pin_target go together");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  pl->launches = 0;
+  cudaStream_t st = pl->stream;
+  const int nd = (int)pl->ndof();
+  const size_t bytes = (size_t)nd * sizeof(double);
+  ensure(pl->w_x, nd);
+  ensure(pl->w_xtrial, nd);
+  ensure(pl->w_dx, nd);
+  ensure(pl->g, nd);
+  ensure(pl->x, nd);  // rhs
+  ensure(pl->w_diag, nd);
+  pl->vals.resize(pl->nnz());
+  ensure(pl->esums, 3 * 1024 + 8);
+  double* x = raw(pl->w_x);
+  double* xtrial = raw(pl->w_xtrial);
+  double* dx = raw(pl->w_dx);
+  double* g = raw(pl->g);
+  double* rhs = raw(pl->x);
+  double* dadd = raw(pl->w_diag);
+  SKB_CUDA(cudaMemcpyAsync(x, x0, bytes, cudaMemcpyHostToDevice, st));
+  const double *d_xt = nullptr, *d_mass = nullptr, *d_f = nullptr, *d_pk = nullptr, *d_pt = nullptr;
+  auto up = [&](dvec<double>& buf, const double* src) -> const double* {
+    if (!src) return nullptr;
+    ensure(buf, nd);
+    cudaMemcpyAsync(raw(buf), src, bytes, cudaMemcpyHostToDevice, st);
+    return raw(buf);
+  };
+  d_xt = up(pl->w_xtilde, x_tilde);
+  d_mass = up(pl->w_mass, mass);
+  d_f = up(pl->w_fext, f_ext);
+  dvec<double> pinbuf;
+  if (pin_k) {
+    pinbuf.resize(2 * (size_t)nd);
+    SKB_CUDA(cudaMemcpyAsync(raw(pinbuf), pin_k, bytes, cudaMemcpyHostToDevice, st));
+    SKB_CUDA(cudaMemcpyAsync(raw(pinbuf) + nd, pin_target, bytes, cudaMemcpyHostToDevice, st));
+    d_pk = raw(pinbuf);
+    d_pt = raw(pinbuf) + nd;
+  }
+  const int vgrid = pcg_grid(pl);
+  dvec<double> parts(3 * 1024 + 8);
+  double* part_e = raw(parts);
+  double* part_g = part_e + 1024;
+  double* part_d = part_g + 1024;
+  double* red = part_d + 1024;  // 3 sums + elastic energy
+  double hred[4];
+
+  // total energy at x + s*dx (also leaves the trial point in xtrial)
+  auto total_energy = [&](double s, const double* dxp, bool with_gdx, double& e_tot, double& gdx, double& dx2) -> int {
+    newton_energy_terms_kernel<<<vgrid, PCG_THREADS, 0, st>>>(nd, x, dxp, s, d_f, d_mass, d_xt, kin_scale, d_pk, d_pt,
+                                                              with_gdx ? g : nullptr, xtrial, part_e, part_g, part_d);
+    reduce3_kernel<<<1, PCG_THREADS, 0, st>>>(part_e, part_g, part_d, vgrid, red);
+    pl->launches += 2;
+    EvalArgs a;
+    int rc = make_args(pl, o->material, PSD_NONE, xtrial, nullptr, nullptr, nullptr, a);
+    if (rc) return rc;
+    rc = launch_energy(pl, a, red + 3, st);
+    if (rc) return rc;
+    SKB_CUDA(cudaMemcpyAsync(hred, red, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SKB_CUDA(cudaStreamSynchronize(st));
+    e_tot = hred[0] + hred[3];
+    gdx = hred[1];
+    dx2 = hred[2];
+    return SKB_OK;
+  };
+
+  if (info) {
+    memset(info, 0, sizeof(*info));
+    info->iters = -1;
+  }
+  for (int it = 0; it < o->max_iter; ++it) {
+    EvalArgs a;
+    int rc = make_args(pl, o->material, o->psd_mode, x, nullptr, g, raw(pl->vals), a);
+    if (rc) return rc;
+    rc = launch_assemble(pl, a, st);
+    if (rc) return rc;
+    newton_gradient_kernel<<<vgrid, PCG_THREADS, 0, st>>>(nd, x, d_f, d_mass, d_xt, kin_scale, d_pk, d_pt, g, rhs, dadd);
+    pl->launches++;
+    int pit = 0;
+    double relres = 0.0;
+    rc = pcg_solve(pl, raw(pl->vals), dadd, rhs, o->pcg_rtol, o->pcg_max_iter, dx, &pit, &relres, st);
+    if (rc) return rc;
+    double alpha = 1.0, e0 = 0, gdx = 0, dx2 = 0, e1 = 0, t1, t2;
+    if (o->do_line_search) {
+      rc = total_energy(0.0, dx, true, e0, gdx, dx2);
+      if (rc) return rc;
+      double tstep = 1.0;
+      bool ok = false;
+      for (int ls = 0; ls < o->ls_max_iter; ++ls) {
+        rc = total_energy(tstep, dx, false, e1, t1, t2);
+        if (rc) return rc;
+        if (e1 <= e0 + o->ls_alpha * tstep * gdx + o->ls_threshold) {
+          ok = true;
+          break;
+        }
+        tstep *= o->ls_beta;
+      }
+      alpha = ok ? tstep : 0.0;
+    } else {
+      rc = total_energy(1.0, dx, false, e1, t1, dx2);  // leaves x + dx in xtrial, |dx|^2 in dx2
+      if (rc) return rc;
+    }
+    if (alpha == 1.0 || !o->do_line_search) {
+      SKB_CUDA(cudaMemcpyAsync(x, xtrial, bytes, cudaMemcpyDeviceToDevice, st));
+    } else if (alpha > 0.0) {
+      // xtrial currently holds x + alpha*dx (the last accepted trial)
+      SKB_CUDA(cudaMemcpyAsync(x, xtrial, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    const double step_norm = alpha * sqrt(dx2);
+    if (info) {
+      info->iters = it;
+      info->pcg_iters_total += pit;
+      info->last_alpha = alpha;
+      info->last_step_norm = step_norm;
+      info->last_pcg_relres = relres;
+      if (it < 64) info->alphas[it] = alpha;
+    }
+    if (step_norm < o->tolerance) break;
+  }
+  SKB_CUDA(cudaMemcpyAsync(x_out, x, bytes, cudaMemcpyDeviceToHost, st));
+  SKB_CUDA(cudaStreamSynchronize(st));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+}  // extern "C"

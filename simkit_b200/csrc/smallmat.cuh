@@ -1,0 +1,399 @@
+// Small dense FP64 linear algebra kept entirely in registers: Jacobi symmetric
+// eigensolves, the rotation-variant SVD used by the analytic eigensystems, and a
+// generic cyclic Jacobi for standalone psd_project.
+//
+// Everything is SKB_HD (host + device) so tests/host_harness.cu can run the exact
+// same code on the CPU of the build container (test infrastructure only; the
+// product never executes these on the host).
+#pragma once
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define SKB_HD __host__ __device__ __forceinline__
+#else
+#define SKB_HD inline
+#endif
+
+namespace skb {
+
+template <int N>
+struct Vec {
+  double v[N];
+  SKB_HD double& operator[](int i) { return v[i]; }
+  SKB_HD const double& operator[](int i) const { return v[i]; }
+};
+
+// Row-major N x N matrix in registers (all loops are fully unrolled).
+template <int N>
+struct Mat {
+  double m[N][N];
+  SKB_HD double& operator()(int i, int j) { return m[i][j]; }
+  SKB_HD const double& operator()(int i, int j) const { return m[i][j]; }
+};
+
+template <int N>
+SKB_HD Mat<N> identity() {
+  Mat<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) r.m[i][j] = (i == j) ? 1.0 : 0.0;
+  return r;
+}
+
+template <int N>
+SKB_HD Mat<N> matmul(const Mat<N>& a, const Mat<N>& b) {
+  Mat<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) s = fma(a.m[i][k], b.m[k][j], s);
+      r.m[i][j] = s;
+    }
+  return r;
+}
+
+// a * b^T
+template <int N>
+SKB_HD Mat<N> matmul_nt(const Mat<N>& a, const Mat<N>& b) {
+  Mat<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) s = fma(a.m[i][k], b.m[j][k], s);
+      r.m[i][j] = s;
+    }
+  return r;
+}
+
+// a^T * b
+template <int N>
+SKB_HD Mat<N> matmul_tn(const Mat<N>& a, const Mat<N>& b) {
+  Mat<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) s = fma(a.m[k][i], b.m[k][j], s);
+      r.m[i][j] = s;
+    }
+  return r;
+}
+
+SKB_HD double det(const Mat<1>& a) { return a.m[0][0]; }
+SKB_HD Mat<1> cofactor(const Mat<1>&) {
+  Mat<1> c;
+  c.m[0][0] = 1.0;
+  return c;
+}
+SKB_HD double det(const Mat<2>& a) { return a.m[0][0] * a.m[1][1] - a.m[0][1] * a.m[1][0]; }
+SKB_HD double det(const Mat<3>& a) {
+  return a.m[0][0] * (a.m[1][1] * a.m[2][2] - a.m[1][2] * a.m[2][1]) -
+         a.m[0][1] * (a.m[1][0] * a.m[2][2] - a.m[1][2] * a.m[2][0]) +
+         a.m[0][2] * (a.m[1][0] * a.m[2][1] - a.m[1][1] * a.m[2][0]);
+}
+
+// cofactor matrix c = d det / dF
+SKB_HD Mat<2> cofactor(const Mat<2>& f) {
+  Mat<2> c;
+  c.m[0][0] = f.m[1][1];
+  c.m[0][1] = -f.m[1][0];
+  c.m[1][0] = -f.m[0][1];
+  c.m[1][1] = f.m[0][0];
+  return c;
+}
+SKB_HD Mat<3> cofactor(const Mat<3>& f) {
+  Mat<3> c;
+  c.m[0][0] = f.m[1][1] * f.m[2][2] - f.m[1][2] * f.m[2][1];
+  c.m[0][1] = f.m[1][2] * f.m[2][0] - f.m[1][0] * f.m[2][2];
+  c.m[0][2] = f.m[1][0] * f.m[2][1] - f.m[1][1] * f.m[2][0];
+  c.m[1][0] = f.m[0][2] * f.m[2][1] - f.m[0][1] * f.m[2][2];
+  c.m[1][1] = f.m[0][0] * f.m[2][2] - f.m[0][2] * f.m[2][0];
+  c.m[1][2] = f.m[0][1] * f.m[2][0] - f.m[0][0] * f.m[2][1];
+  c.m[2][0] = f.m[0][1] * f.m[1][2] - f.m[0][2] * f.m[1][1];
+  c.m[2][1] = f.m[0][2] * f.m[1][0] - f.m[0][0] * f.m[1][2];
+  c.m[2][2] = f.m[0][0] * f.m[1][1] - f.m[0][1] * f.m[1][0];
+  return c;
+}
+
+// --------------------------------------------------------------------------
+// Jacobi rotation (c, s) that zeroes the (p,q) entry of a symmetric matrix
+// with diagonal entries app, aqq and off-diagonal apq.  Standard stable form
+// (Golub & Van Loan 8.5): t is the smaller root so |theta| <= pi/4.
+// --------------------------------------------------------------------------
+SKB_HD void sym_schur2(double app, double aqq, double apq, double& c, double& s, double& t) {
+  if (apq == 0.0) {
+    c = 1.0;
+    s = 0.0;
+    t = 0.0;
+    return;
+  }
+  double tau = (aqq - app) / (2.0 * apq);
+  t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
+  c = 1.0 / sqrt(fma(t, t, 1.0));
+  s = t * c;
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric N x N matrix held in
+// registers.  On exit  a = V diag(w) V^T,  V orthogonal with det +1.
+// All index arithmetic is compile-time (loops unrolled), so nothing spills to
+// local memory because of dynamic indexing.
+template <int N>
+SKB_HD void jacobi_eig(Mat<N> a, Vec<N>& w, Mat<N>& V, int max_sweeps = 12) {
+  V = identity<N>();
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    double off = 0.0, diag = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      diag = fma(a.m[i][i], a.m[i][i], diag);
+#pragma unroll
+      for (int j = i + 1; j < N; ++j) off = fma(a.m[i][j], a.m[i][j], off);
+    }
+    // converged when the off-diagonal mass is below double rounding of the diagonal;
+    // `!(off > ...)` also stops on NaN input
+    if (!(off > 1e-32 * diag) ) break;
+#pragma unroll
+    for (int p = 0; p < N - 1; ++p)
+#pragma unroll
+      for (int q = p + 1; q < N; ++q) {
+        double c, s, t;
+        sym_schur2(a.m[p][p], a.m[q][q], a.m[p][q], c, s, t);
+        // A <- J^T A J with J = [[c, s], [-s, c]] on (p,q)
+        double apq = a.m[p][q];
+        a.m[p][p] = fma(-t, apq, a.m[p][p]);
+        a.m[q][q] = fma(t, apq, a.m[q][q]);
+        a.m[p][q] = 0.0;
+        a.m[q][p] = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          if (k != p && k != q) {
+            double akp = a.m[k][p], akq = a.m[k][q];
+            double np_ = fma(c, akp, -s * akq);
+            double nq_ = fma(s, akp, c * akq);
+            a.m[k][p] = np_;
+            a.m[p][k] = np_;
+            a.m[k][q] = nq_;
+            a.m[q][k] = nq_;
+          }
+          double vkp = V.m[k][p], vkq = V.m[k][q];
+          V.m[k][p] = fma(c, vkp, -s * vkq);
+          V.m[k][q] = fma(s, vkp, c * vkq);
+        }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) w[i] = a.m[i][i];
+}
+
+// Runtime-sized variant operating on memory (standalone psd_project for block
+// sizes that are not 4 or 9).  a is n x n row-major, overwritten; V n x n.
+SKB_HD void jacobi_eig_dyn(double* a, double* w, double* V, int n, int max_sweeps = 30) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) V[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; ++i) {
+      diag += a[i * n + i] * a[i * n + i];
+      for (int j = i + 1; j < n; ++j) off += a[i * n + j] * a[i * n + j];
+    }
+    if (!(off > 1e-32 * diag)) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        double c, s, t;
+        sym_schur2(a[p * n + p], a[q * n + q], a[p * n + q], c, s, t);
+        double apq = a[p * n + q];
+        a[p * n + p] -= t * apq;
+        a[q * n + q] += t * apq;
+        a[p * n + q] = 0.0;
+        a[q * n + p] = 0.0;
+        for (int k = 0; k < n; ++k) {
+          if (k != p && k != q) {
+            double akp = a[k * n + p], akq = a[k * n + q];
+            double np_ = c * akp - s * akq;
+            double nq_ = s * akp + c * akq;
+            a[k * n + p] = np_;
+            a[p * n + k] = np_;
+            a[k * n + q] = nq_;
+            a[q * n + k] = nq_;
+          }
+          double vkp = V[k * n + p], vkq = V[k * n + q];
+          V[k * n + p] = c * vkp - s * vkq;
+          V[k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < n; ++i) w[i] = a[i * n + i];
+}
+
+// swap columns p,q of A and V, negating the new column q of both (keeps
+// A V^T and det V unchanged)
+template <int N>
+SKB_HD void swap_cols_signed(Mat<N>& A, Mat<N>& V, Vec<N>& nrm, int p, int q, bool doit) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double ap = A.m[k][p], aq = A.m[k][q];
+    A.m[k][p] = doit ? aq : ap;
+    A.m[k][q] = doit ? -ap : aq;
+    double vp = V.m[k][p], vq = V.m[k][q];
+    V.m[k][p] = doit ? vq : vp;
+    V.m[k][q] = doit ? -vp : vq;
+  }
+  double np_ = nrm[p], nq_ = nrm[q];
+  nrm[p] = doit ? nq_ : np_;
+  nrm[q] = doit ? np_ : nq_;
+}
+
+// --------------------------------------------------------------------------
+// Rotation-variant SVD  F = U diag(sig) V^T  with U, V proper rotations, the
+// singular values ordered by decreasing magnitude and the sign of det F carried
+// by the LAST one -- the convention of the reference's svd_rv
+// (/root/reference/simkit/svd_rv.py:33-53, polar_svd.py:34-56).
+//
+// Method: Jacobi eigensolve of C = F^T F for V, then A = F V and ONE one-sided
+// (Hestenes) clean-up sweep on the columns of A, which restores high relative
+// accuracy of the small singular triplets.  U's last column is the cross product
+// of the others, so the result is well defined for rank-deficient and inverted F.
+// --------------------------------------------------------------------------
+template <int N>
+SKB_HD void hestenes_sweep(Mat<N>& A, Mat<N>& V) {
+#pragma unroll
+  for (int p = 0; p < N - 1; ++p)
+#pragma unroll
+    for (int q = p + 1; q < N; ++q) {
+      double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        al = fma(A.m[k][p], A.m[k][p], al);
+        be = fma(A.m[k][q], A.m[k][q], be);
+        ga = fma(A.m[k][p], A.m[k][q], ga);
+      }
+      if (ga * ga > 1e-34 * al * be) {
+        double c, s, t;
+        sym_schur2(al, be, ga, c, s, t);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          double ap = A.m[k][p], aq = A.m[k][q];
+          A.m[k][p] = fma(c, ap, -s * aq);
+          A.m[k][q] = fma(s, ap, c * aq);
+          double vp = V.m[k][p], vq = V.m[k][q];
+          V.m[k][p] = fma(c, vp, -s * vq);
+          V.m[k][q] = fma(s, vp, c * vq);
+        }
+      }
+    }
+}
+
+SKB_HD void svd_rv(const Mat<3>& F, Mat<3>& U, Vec<3>& sig, Mat<3>& V) {
+  Mat<3> C = matmul_tn(F, F);
+  Vec<3> w;
+  jacobi_eig<3>(C, w, V);
+  Mat<3> A = matmul(F, V);
+  hestenes_sweep<3>(A, V);
+  Vec<3> nrm;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    nrm[j] = sqrt(A.m[0][j] * A.m[0][j] + A.m[1][j] * A.m[1][j] + A.m[2][j] * A.m[2][j]);
+  // sort columns by decreasing norm (3-element network)
+  swap_cols_signed<3>(A, V, nrm, 0, 1, nrm[0] < nrm[1]);
+  swap_cols_signed<3>(A, V, nrm, 1, 2, nrm[1] < nrm[2]);
+  swap_cols_signed<3>(A, V, nrm, 0, 1, nrm[0] < nrm[1]);
+  // leading two columns of U by normalisation (Gram-Schmidt guards rank <= 1)
+  double u0[3], u1[3], u2[3];
+  if (nrm[0] > 0.0) {
+    double inv = 1.0 / nrm[0];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u0[k] = A.m[k][0] * inv;
+  } else {
+    u0[0] = 1.0; u0[1] = 0.0; u0[2] = 0.0;
+  }
+  if (nrm[1] > 1e-150 * nrm[0] && nrm[1] > 0.0) {
+    double inv = 1.0 / nrm[1];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u1[k] = A.m[k][1] * inv;
+    // re-orthogonalise against u0 (no-op to rounding when converged)
+    double d = u0[0] * u1[0] + u0[1] * u1[1] + u0[2] * u1[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u1[k] = fma(-d, u0[k], u1[k]);
+    double n1 = 1.0 / sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u1[k] *= n1;
+  } else {
+    // any unit vector orthogonal to u0
+    int kmin = (fabs(u0[0]) <= fabs(u0[1]) && fabs(u0[0]) <= fabs(u0[2])) ? 0 : (fabs(u0[1]) <= fabs(u0[2]) ? 1 : 2);
+    double e[3] = {kmin == 0 ? 1.0 : 0.0, kmin == 1 ? 1.0 : 0.0, kmin == 2 ? 1.0 : 0.0};
+    double d = u0[kmin];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u1[k] = e[k] - d * u0[k];
+    double n1 = 1.0 / sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u1[k] *= n1;
+  }
+  u2[0] = u0[1] * u1[2] - u0[2] * u1[1];
+  u2[1] = u0[2] * u1[0] - u0[0] * u1[2];
+  u2[2] = u0[0] * u1[1] - u0[1] * u1[0];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    U.m[k][0] = u0[k];
+    U.m[k][1] = u1[k];
+    U.m[k][2] = u2[k];
+  }
+  sig[0] = nrm[0];
+  sig[1] = nrm[1];
+  sig[2] = u2[0] * A.m[0][2] + u2[1] * A.m[1][2] + u2[2] * A.m[2][2];  // signed
+}
+
+SKB_HD void svd_rv(const Mat<2>& F, Mat<2>& U, Vec<2>& sig, Mat<2>& V) {
+  Mat<2> C = matmul_tn(F, F);
+  Vec<2> w;
+  jacobi_eig<2>(C, w, V, 2);
+  Mat<2> A = matmul(F, V);
+  hestenes_sweep<2>(A, V);
+  Vec<2> nrm;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) nrm[j] = sqrt(A.m[0][j] * A.m[0][j] + A.m[1][j] * A.m[1][j]);
+  swap_cols_signed<2>(A, V, nrm, 0, 1, nrm[0] < nrm[1]);
+  double u0[2];
+  if (nrm[0] > 0.0) {
+    double inv = 1.0 / nrm[0];
+    u0[0] = A.m[0][0] * inv;
+    u0[1] = A.m[1][0] * inv;
+  } else {
+    u0[0] = 1.0;
+    u0[1] = 0.0;
+  }
+  double u1[2] = {-u0[1], u0[0]};  // +90 degrees: det U = +1
+  U.m[0][0] = u0[0];
+  U.m[1][0] = u0[1];
+  U.m[0][1] = u1[0];
+  U.m[1][1] = u1[1];
+  sig[0] = nrm[0];
+  sig[1] = u1[0] * A.m[0][1] + u1[1] * A.m[1][1];
+}
+
+// symmetric rebuild  V diag(w) V^T
+template <int N>
+SKB_HD Mat<N> rebuild_sym(const Mat<N>& V, const Vec<N>& w) {
+  Mat<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = i; j < N; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) s = fma(V.m[i][k] * w[k], V.m[j][k], s);
+      r.m[i][j] = s;
+      r.m[j][i] = s;
+    }
+  return r;
+}
+
+}  // namespace skb

@@ -1,0 +1,65 @@
+"""Kinetic (inertial) terms of the implicit integrators (reference: energies/kinetic.py:87-119,
+125-194 backward Euler, 200-279 BDF2).  Small host-side vector algebra on the caller's arrays, as in
+the reference; the device-resident Newton step (MeshPlan.newton) fuses these terms on the GPU."""
+
+import numpy as np
+import scipy as sp
+
+_BE_COEFF = 1.0
+_BDF2_COEFF = 9.0 / 4.0
+
+
+def velocity_be(x_curr, x_prev, h):
+    return (x_curr - x_prev) / h
+
+
+def velocity_bdf2(x_curr, x_prev, x_prev2, h):
+    return (3.0 * x_curr - 4.0 * x_prev + x_prev2) / (2.0 * h)
+
+
+def be_target(x_curr, x_prev, h):
+    """Backward-Euler inertial target ``x_curr + h v_curr`` (kinetic.py:87-90)."""
+    return x_curr + h * velocity_be(x_curr, x_prev, h)
+
+
+def bdf2_target(x_curr, x_prev, x_prev2, x_prev3, h):
+    """Constant-step BDF2 inertial target (kinetic.py:92-101)."""
+    v_curr = velocity_bdf2(x_curr, x_prev, x_prev2, h)
+    v_prev = velocity_bdf2(x_prev, x_prev2, x_prev3, h)
+    return (4.0 / 3.0) * x_curr - (1.0 / 3.0) * x_prev + (8.0 * h / 9.0) * v_curr - (2.0 * h / 9.0) * v_prev
+
+
+def kinetic_energy(d, M, h, c):
+    return float((0.5 * c * (d.T @ M @ d) * (1 / (h ** 2))).item())
+
+
+def kinetic_gradient(d, M, h, c):
+    return c * (M @ d) * (1 / (h ** 2))
+
+
+def kinetic_hessian(M, h, c):
+    return M * (c / (h ** 2))
+
+
+def kinetic_energy_be(x, x_curr, x_prev, M, h):
+    return kinetic_energy(x - be_target(x_curr, x_prev, h), M, h, _BE_COEFF)
+
+
+def kinetic_gradient_be(x, x_curr, x_prev, M, h):
+    return kinetic_gradient(x - be_target(x_curr, x_prev, h), M, h, _BE_COEFF)
+
+
+def kinetic_hessian_be(M, h):
+    return kinetic_hessian(M, h, _BE_COEFF)
+
+
+def kinetic_energy_bdf2(x, x_curr, x_prev, x_prev2, x_prev3, M, h):
+    return kinetic_energy(x - bdf2_target(x_curr, x_prev, x_prev2, x_prev3, h), M, h, _BDF2_COEFF)
+
+
+def kinetic_gradient_bdf2(x, x_curr, x_prev, x_prev2, x_prev3, M, h):
+    return kinetic_gradient(x - bdf2_target(x_curr, x_prev, x_prev2, x_prev3, h), M, h, _BDF2_COEFF)
+
+
+def kinetic_hessian_bdf2(M, h):
+    return kinetic_hessian(M, h, _BDF2_COEFF)

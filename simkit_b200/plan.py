@@ -1,0 +1,238 @@
+"""MeshPlan: Python handle on the per-mesh device plan (``skb_plan`` in include/simkit_b200.h).
+
+A plan is what the reference rebuilds implicitly on every call: the operator
+``J`` (deformation_jacobian.py:9-87), the sparsity of ``J^T H J`` and the scatter
+order.  Here it is built once on the device and cached on the ``J`` object the
+drop-in ``deformation_jacobian`` returns (or recovered from a plain scipy ``J``).
+"""
+
+import ctypes
+import weakref
+
+import numpy as np
+import scipy.sparse as sps
+
+from . import _lib
+from ._lib import MATERIAL_IDS, check, f64, material_arg, ptr
+
+
+class MeshPlan:
+    def __init__(self, X=None, T=None, dim=None, n=None, D=None, device=0, tile_elems=0):
+        lib = _lib.load()
+        T = np.ascontiguousarray(T)
+        if T.dtype not in (np.int64, np.int32):
+            T = T.astype(np.int64)
+        self.t = int(T.shape[0])
+        handle = ctypes.c_void_p()
+        if X is not None:
+            X = f64(X)
+            self.n, self.dim = int(X.shape[0]), int(X.shape[1])
+            if T.shape[1] != self.dim + 1:
+                raise ValueError("Only dim == 2 or 3 simplices (dim+1 corners) are supported")
+            check(lib.skb_plan_create(ptr(X), ptr(T), T.dtype.itemsize, self.n, self.t, self.dim, device,
+                                      tile_elems, ctypes.byref(handle)))
+        else:
+            D = f64(D)
+            self.n, self.dim = int(n), int(dim)
+            check(lib.skb_plan_create_from_operator(ptr(T), ptr(D), T.dtype.itemsize, self.n, self.t, self.dim,
+                                                    device, tile_elems, ctypes.byref(handle)))
+        self._lib = lib
+        self._h = handle
+        self.T = T
+        info = np.zeros(8, dtype=np.int64)
+        check(lib.skb_plan_info(self._h, ptr(info)))
+        self.nnzb, self.nnz, self.n_tiles = int(info[3]), int(info[4]), int(info[5])
+        self.n_block_partials, self.n_vertex_partials = int(info[6]), int(info[7])
+        self.ndof = self.n * self.dim
+        self._pattern = None
+        self._finalizer = weakref.finalize(self, lib.skb_plan_destroy, handle)
+
+    # ---------------------------------------------------------------- pattern
+    def csr_pattern(self):
+        """Canonical ``(indptr, indices)`` int32, sorted."""
+        if self._pattern is None:
+            indptr = np.empty(self.ndof + 1, dtype=np.int32)
+            indices = np.empty(self.nnz, dtype=np.int32)
+            check(self._lib.skb_plan_csr_pattern(self._h, ptr(indptr), ptr(indices)))
+            self._pattern = (indptr, indices)
+        return self._pattern
+
+    def block_pattern(self):
+        bptr = np.empty(self.n + 1, dtype=np.int32)
+        bcol = np.empty(self.nnzb, dtype=np.int32)
+        check(self._lib.skb_plan_block_pattern(self._h, ptr(bptr), ptr(bcol)))
+        return bptr, bcol
+
+    def slot_map(self):
+        K = self.dim + 1
+        slot = np.empty((self.t, K, self.dim, K, self.dim), dtype=np.int32)
+        check(self._lib.skb_plan_slot_map(self._h, ptr(slot)))
+        return slot
+
+    def element_D(self):
+        D = np.empty((self.t, self.dim, self.dim + 1))
+        check(self._lib.skb_plan_element_D(self._h, ptr(D)))
+        return D
+
+    def volume(self):
+        vol = np.empty((self.t, 1))
+        check(self._lib.skb_plan_volume(self._h, ptr(vol)))
+        return vol
+
+    def vertex_masses(self, rho=1.0):
+        rho_a, rho_n = material_arg(rho, self.t, "rho")
+        m = np.empty(self.n)
+        check(self._lib.skb_plan_vertex_masses(self._h, ptr(rho_a), rho_n, ptr(m)))
+        return m
+
+    def csr_matrix(self, vals):
+        indptr, indices = self.csr_pattern()
+        return sps.csr_matrix((vals, indices, indptr), shape=(self.ndof, self.ndof))
+
+    # ------------------------------------------------------------- evaluation
+    def _mats(self, mu, lam, vol):
+        mu_a, mu_n = material_arg(mu, self.t, "mu")
+        lam_a, lam_n = material_arg(lam, self.t, "lam")
+        vol_a, vol_n = material_arg(vol, self.t, "vol")
+        return (mu_a, lam_a, vol_a), (ptr(mu_a), mu_n, ptr(lam_a), lam_n, ptr(vol_a), vol_n)
+
+    def _x(self, x):
+        x = f64(x).reshape(-1)
+        if x.size != self.ndof:
+            raise ValueError("x has %d entries, the mesh has %d dofs" % (x.size, self.ndof))
+        return x
+
+    def _fbar(self, Fbar):
+        if Fbar is None:
+            return None
+        Fbar = f64(Fbar).reshape(-1)
+        if Fbar.size != self.t * self.dim * self.dim:
+            raise ValueError("Jx_bar has the wrong size")
+        return Fbar
+
+    def energy(self, material, x, mu, lam, vol, Fbar=None):
+        x = self._x(x)
+        Fbar = self._fbar(Fbar)
+        keep, margs = self._mats(mu, lam, vol)
+        out = ctypes.c_double(0.0)
+        check(self._lib.skb_energy(self._h, MATERIAL_IDS[material], ptr(x), ptr(Fbar), *margs, ctypes.byref(out)))
+        return float(out.value)
+
+    def gradient(self, material, x, mu, lam, vol, Fbar=None):
+        x = self._x(x)
+        Fbar = self._fbar(Fbar)
+        keep, margs = self._mats(mu, lam, vol)
+        g = np.empty((self.ndof, 1))
+        check(self._lib.skb_gradient(self._h, MATERIAL_IDS[material], ptr(x), ptr(Fbar), *margs, ptr(g)))
+        return g
+
+    def hessian_values(self, material, x, mu, lam, vol, psd_mode, Fbar=None, out=None):
+        x = self._x(x)
+        Fbar = self._fbar(Fbar)
+        keep, margs = self._mats(mu, lam, vol)
+        vals = np.empty(self.nnz) if out is None else out
+        check(self._lib.skb_hessian(self._h, MATERIAL_IDS[material], int(psd_mode), ptr(x), ptr(Fbar), *margs, ptr(vals)))
+        return vals
+
+    def hessian(self, material, x, mu, lam, vol, psd_mode, Fbar=None):
+        return self.csr_matrix(self.hessian_values(material, x, mu, lam, vol, psd_mode, Fbar))
+
+    def gradient_hessian(self, material, x, mu, lam, vol, psd_mode, Fbar=None, g_out=None, vals_out=None):
+        x = self._x(x)
+        Fbar = self._fbar(Fbar)
+        keep, margs = self._mats(mu, lam, vol)
+        g = np.empty((self.ndof, 1)) if g_out is None else g_out
+        vals = np.empty(self.nnz) if vals_out is None else vals_out
+        check(self._lib.skb_gradient_hessian(self._h, MATERIAL_IDS[material], int(psd_mode), ptr(x), ptr(Fbar),
+                                             *margs, ptr(g), ptr(vals)))
+        return g, vals
+
+    def set_materials(self, mu, lam, vol):
+        keep, margs = self._mats(mu, lam, vol)
+        check(self._lib.skb_set_materials(self._h, *margs))
+
+    def last_launch_count(self):
+        return int(self._lib.skb_last_launch_count(self._h))
+
+    # ------------------------------------------------------------ linear solve
+    def pcg(self, vals, rhs, diag_add=None, rtol=1e-10, max_iter=10000):
+        vals = f64(vals).reshape(-1)
+        rhs = f64(rhs).reshape(-1)
+        dadd = None if diag_add is None else f64(diag_add).reshape(-1)
+        x = np.empty(self.ndof)
+        iters = ctypes.c_int(0)
+        relres = ctypes.c_double(0.0)
+        check(self._lib.skb_pcg(self._h, ptr(vals), ptr(dadd), ptr(rhs), float(rtol), int(max_iter), ptr(x),
+                                ctypes.byref(iters), ctypes.byref(relres)))
+        return x, int(iters.value), float(relres.value)
+
+    def newton(self, material, x0, psd_mode=1, x_tilde=None, mass=None, kin_scale=0.0, f_ext=None, pin_k=None,
+               pin_target=None, max_iter=1, do_line_search=True, tolerance=1e-6, ls_alpha=0.01, ls_beta=0.5,
+               ls_max_iter=100, ls_threshold=1e-12, pcg_rtol=1e-10, pcg_max_iter=20000):
+        opts = _lib.NewtonOpts(MATERIAL_IDS[material], int(psd_mode), int(max_iter), int(bool(do_line_search)),
+                               float(tolerance), float(ls_alpha), float(ls_beta), int(ls_max_iter),
+                               float(ls_threshold), float(pcg_rtol), int(pcg_max_iter))
+        info = _lib.NewtonInfo()
+        x0 = self._x(x0)
+        opt = [None if a is None else self._x(a) for a in (x_tilde, mass, f_ext, pin_k, pin_target)]
+        out = np.empty((self.ndof, 1))
+        check(self._lib.skb_newton(self._h, ctypes.byref(opts), ptr(x0), ptr(opt[0]), ptr(opt[1]), float(kin_scale),
+                                   ptr(opt[2]), ptr(opt[3]), ptr(opt[4]), ptr(out), ctypes.byref(info)))
+        n_it = info.iters + 1
+        return out, dict(iters=info.iters, alphas=[info.alphas[i] for i in range(min(n_it, 64))],
+                         pcg_iters=info.pcg_iters_total, pcg_relres=info.last_pcg_relres,
+                         step_norm=info.last_step_norm)
+
+    def reduced(self, material, B, z, x0=None, psd_mode=1, want=("E", "g", "H")):
+        B = f64(B)
+        r = B.shape[1]
+        z = f64(z).reshape(-1)
+        x0 = None if x0 is None else self._x(x0)
+        E = ctypes.c_double(0.0)
+        g = np.empty((r, 1)) if "g" in want else None
+        H = np.empty((r, r)) if "H" in want else None
+        check(self._lib.skb_reduced_hessian_from_basis(self._h, MATERIAL_IDS[material], int(psd_mode), r, ptr(B),
+                                                       ptr(x0), ptr(z), ctypes.byref(E), ptr(g), ptr(H)))
+        return float(E.value), g, H
+
+
+# ------------------------------------------------------------------ plan lookup
+_PLAN_CACHE = {}
+
+
+def plan_from_operator(J, dim):
+    """Recover ``(T, D)`` from a scipy ``J`` built by any ``deformation_jacobian`` and
+    build (or fetch) its plan.  SURVEY §7: rows ``e*b + j`` (``i = 0``) hold
+    ``D[j, a]`` in columns ``T[e, a]*dim``; pruned zeros do not hide vertices."""
+    plan = getattr(J, "_skb_plan", None)
+    if plan is not None:
+        return plan
+    key = id(J)
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None and hit[0]() is J:
+        return hit[1]
+    if not sps.issparse(J):
+        raise TypeError("plan_from_operator needs a scipy sparse J")
+    b = dim * dim
+    t = J.shape[0] // b
+    n = J.shape[1] // dim
+    K = dim + 1
+    Jc = J.tocoo()
+    sel = ((Jc.row % b) < dim) & ((Jc.col % dim) == 0)      # rows (i=0, j), columns (v, 0)
+    e = Jc.row[sel] // b
+    j = Jc.row[sel] % b
+    v = Jc.col[sel] // dim
+    val = Jc.data[sel]
+    keys = e.astype(np.int64) * n + v
+    uniq, inv = np.unique(keys, return_inverse=True)
+    if uniq.size != t * K:
+        raise ValueError("could not recover %d corners per element from J" % K)
+    T = (uniq % n).reshape(t, K)
+    D = np.zeros((t, dim, K))
+    np.add.at(D, (e, j, inv % K), val)
+    plan = MeshPlan(T=T, dim=dim, n=n, D=D)
+    try:
+        _PLAN_CACHE[key] = (weakref.ref(J, lambda _r, k=key: _PLAN_CACHE.pop(k, None)), plan)
+    except TypeError:
+        pass
+    return plan

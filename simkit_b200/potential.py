@@ -1,0 +1,95 @@
+"""ElasticPotential: the closures a simkit sim class hands to the solver, as one object.
+
+In the reference a user sim builds ``energy(x) / gradient(x) / hessian(x)`` closures around the
+``*_x`` functions plus external forces and penalty terms and passes them to ``backward_euler`` /
+``newton_solver`` (examples/interactive_demos/010_interactive_contact_plane_3D.py:81-116).  This class
+is that bundle for this library's energies.  Its bound methods work as plain callables with any solver;
+when ``simkit_b200``'s ``newton_solver`` / ``backward_euler`` / ``bdf2`` receive all three methods of
+one instance they run the whole Newton step device-resident (``skb_newton``) instead of crossing the
+host boundary per evaluation.
+"""
+
+import numpy as np
+import scipy.sparse as sps
+
+from ._lib import PSD_AFTER_VOL, PSD_NONE
+from .plan import MeshPlan, plan_from_operator
+
+
+class ElasticPotential:
+    _skb_potential = True
+
+    def __init__(self, material, mu, lam, vol=None, plan=None, J=None, X=None, T=None, dim=None, f_ext=None,
+                 pin_k=None, pin_target=None, psd=True):
+        if plan is None:
+            if J is not None:
+                plan = plan_from_operator(J, dim if dim is not None else (X.shape[1] if X is not None else 3))
+            else:
+                plan = MeshPlan(X=X, T=T)
+        self.plan = plan
+        self.material = material
+        self.mu, self.lam = mu, lam
+        self.vol = plan.volume() if vol is None else vol
+        self.psd_mode = PSD_AFTER_VOL if (psd and material != "linear_elasticity") else PSD_NONE
+        nd = plan.ndof
+        self.f_ext = None if f_ext is None else np.asarray(f_ext, dtype=np.float64).reshape(nd, 1)
+        self.pin_k = None if pin_k is None else np.asarray(pin_k, dtype=np.float64).reshape(nd, 1)
+        self.pin_target = None if pin_target is None else np.asarray(pin_target, dtype=np.float64).reshape(nd, 1)
+        self._materials_set = False
+
+    # -- callables (host boundary per call) -----------------------------------------------------
+    def energy(self, x):
+        xx = np.asarray(x, dtype=np.float64).reshape(-1, 1)
+        e = self.plan.energy(self.material, xx, self.mu, self.lam, self.vol)
+        if self.f_ext is not None:
+            e -= float((self.f_ext.T @ xx).item())
+        if self.pin_k is not None:
+            d = xx - self.pin_target
+            e += 0.5 * float((self.pin_k * d * d).sum())
+        return e
+
+    def gradient(self, x):
+        xx = np.asarray(x, dtype=np.float64).reshape(-1, 1)
+        g = self.plan.gradient(self.material, xx, self.mu, self.lam, self.vol)
+        if self.f_ext is not None:
+            g = g - self.f_ext
+        if self.pin_k is not None:
+            g = g + self.pin_k * (xx - self.pin_target)
+        return g
+
+    def hessian(self, x):
+        H = self.plan.hessian(self.material, x, self.mu, self.lam, self.vol, self.psd_mode)
+        if self.pin_k is not None:
+            H = H + sps.diags(self.pin_k.ravel())
+        return H
+
+    # -- device-resident steps -------------------------------------------------------------------
+    def _ensure_materials(self):
+        if not self._materials_set:
+            self.plan.set_materials(self.mu, self.lam, self.vol)
+            self._materials_set = True
+
+    def _run(self, x0, x_tilde, mass, kin_scale, tolerance, max_iter, do_line_search, return_info, **kw):
+        self.plan.set_materials(self.mu, self.lam, self.vol)
+        x, info = self.plan.newton(self.material, x0, psd_mode=self.psd_mode, x_tilde=x_tilde, mass=mass,
+                                   kin_scale=kin_scale, f_ext=self.f_ext, pin_k=self.pin_k,
+                                   pin_target=self.pin_target, max_iter=max_iter, do_line_search=do_line_search,
+                                   tolerance=tolerance, **kw)
+        return (x, info) if return_info else x
+
+    def newton(self, x0, tolerance=1e-6, max_iter=1, do_line_search=True, return_info=False, **kw):
+        return self._run(x0, None, None, 0.0, tolerance, max_iter, do_line_search, return_info, **kw)
+
+    def implicit_step(self, x_tilde, M, kin_scale, tolerance=1e-6, max_iter=1, do_line_search=True,
+                      return_info=False, **kw):
+        """One implicit step with inertial target ``x_tilde`` and kinetic term ``kin_scale/2 |x - x_tilde|_M^2``."""
+        Md = sps.csr_matrix(M)
+        diag = Md.diagonal()
+        if (Md - sps.diags(diag)).nnz != 0 and abs(Md - sps.diags(diag)).sum() > 0:
+            raise ValueError("the device-resident step needs a lumped (diagonal) mass matrix")
+        nd = self.plan.ndof
+        if diag.size == self.plan.n:            # per-vertex masses: expand to dofs
+            diag = np.repeat(diag, self.plan.dim)
+        if diag.size != nd:
+            raise ValueError("mass matrix size does not match the mesh")
+        return self._run(x_tilde, x_tilde, diag, kin_scale, tolerance, max_iter, do_line_search, return_info, **kw)

@@ -1,0 +1,163 @@
+// TEST INFRASTRUCTURE ONLY -- CPU replay of the kernel phase functions.
+//
+// The build container has no GPU.  The kernel bodies in simkit_b200/csrc are
+// SKB_HD functions and the plan builder is backend-templated, so this harness
+// runs them on the host (thrust::host, plain loops standing in for the thread
+// grid) to debug index logic and element math before spending GPU time.  It is
+// compiled into tests/_build/ by tests/hostsim.py, is never imported by
+// simkit_b200/, and proves nothing about the GPU path: the -m gpu tests do that.
+#include <stdint.h>
+#include <vector>
+
+#include "../simkit_b200/csrc/kernels.cuh"
+
+using namespace skb;
+
+template <int D>
+static void run_assemble(const PlanView& p, const EvalArgs& a, std::vector<double>& esum) {
+  const int E = p.tile_elems;
+  std::vector<double> sK((size_t)Sizes<D>::NK * E), sG((size_t)Sizes<D>::NG * E);
+  for (int tile = 0; tile < p.n_tiles; ++tile) {
+    for (int le = 0; le < E; ++le) {
+      int e = tile * E + le;
+      if (e < p.t) element_phase1<D>(p, a, e, le, E, sK.data(), sG.data());
+    }
+    if (a.want_hess) {
+      int nitems = (p.blocks.tl_ptr[tile + 1] - p.blocks.tl_ptr[tile]) * D;
+      for (int w = 0; w < nitems; ++w) block_phase2<D>(p.blocks, tile, w, E, sK.data(), a.pblocks);
+    }
+    if (a.want_grad) {
+      int nitems = p.verts.tl_ptr[tile + 1] - p.verts.tl_ptr[tile];
+      for (int w = 0; w < nitems; ++w) vert_phase2<D>(p.verts, tile, w, E, sG.data(), a.pverts);
+    }
+  }
+  if (a.want_hess)
+    for (int item = 0; item < p.nnzb * D; ++item) block_finalize<D>(p, item, a.pblocks, a.vals);
+  if (a.want_grad)
+    for (int v = 0; v < p.n; ++v) vert_finalize<D>(p, v, a.pverts, a.g);
+  double s = 0.0;
+  for (int e = 0; e < p.t; ++e) s += energy_element<D>(p, a, e);
+  esum.assign(1, s);
+}
+
+template <int D>
+static void elem_hess(int material, int psd_mode, const double* F, double mu, double lam, double vol, double* H) {
+  Mat<D> f, u, v; Vec<D> s;
+  for (int i = 0; i < D * D; ++i) f.m[i / D][i % D] = F[i];
+  if (material == MAT_LINEAR_ELASTICITY) {
+    linear_elasticity_hessian<D>(mu * vol, lam * vol, H);
+    return;
+  }
+  svd_rv(f, u, s, v);
+  Principal<D> h = principal_hessian<D>(material, s, mu, lam);
+  weight_and_project<D>(h, vol, psd_mode);
+  expand_hessian<D>(h, u, v, H);
+}
+
+extern "C" {
+
+// info: nnzb, n_block_partials, n_vertex_partials.  Outputs may be null (size query).
+int hs_run(const double* X, const int64_t* T, int64_t n, int64_t t, int dim, int tile_elems, int material,
+           int psd_mode, const double* x, const double* Fbar, const double* mu, int64_t mu_n,
+           const double* lam, int64_t lam_n, const double* vol, int64_t vol_n, int64_t* info, int32_t* bptr,
+           int32_t* bcol, int32_t* bslot, double* Dm_out, double* vol_out, double* g, double* vals,
+           double* energy) {
+  const int K = dim + 1;
+  thrust::host_vector<double> Xh(X, X + n * dim);
+  thrust::host_vector<int> Th((size_t)t * K);
+  for (int64_t i = 0; i < t * K; ++i) Th[i] = (int)T[i];
+  PlanData<HostBackend> pd;
+  build_plan<HostBackend>(pd, Th, (int)n, (int)t, dim, tile_elems);
+  set_geometry_from_X<HostBackend>(pd, Xh);
+  info[0] = pd.nnzb;
+  info[1] = pd.blocks.n_ts;
+  info[2] = pd.verts.n_ts;
+  if (!bptr) return 0;
+  for (int i = 0; i <= n; ++i) bptr[i] = pd.bptr[i];
+  for (int i = 0; i < pd.nnzb; ++i) bcol[i] = pd.bcol[i];
+  for (size_t i = 0; i < pd.bslot.size(); ++i) bslot[i] = pd.bslot[i];
+  for (size_t i = 0; i < pd.Dm.size(); ++i) Dm_out[i] = pd.Dm[i];
+  for (int i = 0; i < t; ++i) vol_out[i] = pd.vol0[i];
+  PlanView p = pd.view();
+  std::vector<double> pb((size_t)pd.blocks.n_ts * dim * dim), pv((size_t)pd.verts.n_ts * dim);
+  EvalArgs a;
+  a.material = material;
+  a.psd_mode = psd_mode;
+  a.x = x;
+  a.Fbar = Fbar;
+  a.mu = mu;
+  a.lam = lam;
+  a.vol = vol ? vol : p.vol0;
+  a.mu_stride = mu_n > 1;
+  a.lam_stride = lam_n > 1;
+  a.vol_stride = vol ? (vol_n > 1) : 1;
+  a.want_grad = g != nullptr;
+  a.want_hess = vals != nullptr;
+  a.pblocks = pb.data();
+  a.pverts = pv.data();
+  a.g = g;
+  a.vals = vals;
+  std::vector<double> es;
+  if (dim == 3) run_assemble<3>(p, a, es);
+  else run_assemble<2>(p, a, es);
+  if (energy) *energy = es[0];
+  return 0;
+}
+
+// element-level checks of the principal-stretch machinery
+int hs_svd(int dim, int64_t t, const double* F, double* U, double* S, double* V) {
+  for (int64_t e = 0; e < t; ++e) {
+    if (dim == 3) {
+      Mat<3> f, u, v; Vec<3> s;
+      for (int i = 0; i < 9; ++i) f.m[i / 3][i % 3] = F[e * 9 + i];
+      svd_rv(f, u, s, v);
+      for (int i = 0; i < 9; ++i) { U[e * 9 + i] = u.m[i / 3][i % 3]; V[e * 9 + i] = v.m[i / 3][i % 3]; }
+      for (int i = 0; i < 3; ++i) S[e * 3 + i] = s[i];
+    } else {
+      Mat<2> f, u, v; Vec<2> s;
+      for (int i = 0; i < 4; ++i) f.m[i / 2][i % 2] = F[e * 4 + i];
+      svd_rv(f, u, s, v);
+      for (int i = 0; i < 4; ++i) { U[e * 4 + i] = u.m[i / 2][i % 2]; V[e * 4 + i] = v.m[i / 2][i % 2]; }
+      for (int i = 0; i < 2; ++i) S[e * 2 + i] = s[i];
+    }
+  }
+  return 0;
+}
+
+int hs_element_hessian(int material, int psd_mode, int dim, int64_t t, const double* F, const double* mu,
+                       const double* lam, const double* vol, double* H) {
+  const int b = dim * dim;
+  for (int64_t e = 0; e < t; ++e) {
+    if (dim == 3) elem_hess<3>(material, psd_mode, F + e * b, mu[e], lam[e], vol[e], H + e * b * b);
+    else elem_hess<2>(material, psd_mode, F + e * b, mu[e], lam[e], vol[e], H + e * b * b);
+  }
+  return 0;
+}
+
+int hs_element_energy_gradient(int material, int dim, int64_t t, const double* F, const double* mu,
+                               const double* lam, double* psi, double* P) {
+  const int b = dim * dim;
+  for (int64_t e = 0; e < t; ++e) {
+    if (dim == 3) {
+      Mat<3> f;
+      for (int i = 0; i < 9; ++i) f.m[i / 3][i % 3] = F[e * 9 + i];
+      psi[e] = energy_density<3>(material, f, mu[e], lam[e]);
+      Mat<3> p = pk1<3>(material, f, mu[e], lam[e]);
+      for (int i = 0; i < 9; ++i) P[e * b + i] = p.m[i / 3][i % 3];
+    } else {
+      Mat<2> f;
+      for (int i = 0; i < 4; ++i) f.m[i / 2][i % 2] = F[e * 4 + i];
+      psi[e] = energy_density<2>(material, f, mu[e], lam[e]);
+      Mat<2> p = pk1<2>(material, f, mu[e], lam[e]);
+      for (int i = 0; i < 4; ++i) P[e * b + i] = p.m[i / 2][i % 2];
+    }
+  }
+  return 0;
+}
+
+int hs_jacobi_dyn(int n, const double* A, double* w, double* V) {
+  std::vector<double> a(A, A + n * n);
+  jacobi_eig_dyn(a.data(), w, V, n);
+  return 0;
+}
+}

@@ -1,0 +1,103 @@
+"""CPU replay of the kernel phase functions vs the oracle (debug aid for the GPU-less
+container; the GPU parity tests are in test_gpu_parity.py)."""
+import numpy as np
+import pytest
+
+from oracle import elasticity as oe
+from simkit_b200 import synthetic as syn
+import hostsim
+
+MAT_ID = {m: i for i, m in enumerate(oe.MATERIALS)}
+TOL = 1e-10
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def _mesh(dim, sigma, seed=0):
+    cells = (4, 3, 3) if dim == 3 else (7, 5)
+    X, T = syn.make_mesh(cells)
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(X.shape[0])
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    X, T = X[perm], inv[T]
+    U = syn.jittered_state(X, cells, tuple(1.0 for _ in cells), sigma=sigma, seed=seed)
+    mu, lam = syn.heterogeneous_lame(T.shape[0], seed=seed + 1)
+    return X, T, U, mu, lam
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_svd_matches_convention(dim):
+    rng = np.random.default_rng(3)
+    F = rng.standard_normal((200, dim, dim))
+    F[:20] = np.eye(dim) + 1e-9 * rng.standard_normal((20, dim, dim))   # near-degenerate
+    F[20] = np.eye(dim)
+    F[21] = 0.0
+    F[22, :, -1] = 0.0                                                  # rank deficient
+    U, S, V = hostsim.svd(F)
+    Uo, So, Vo = oe.svd_rv(F)
+    Sd = np.zeros_like(F)
+    Sd[:, np.arange(dim), np.arange(dim)] = S
+    assert rel(U @ Sd @ np.swapaxes(V, 1, 2), F) < 1e-14
+    assert np.allclose(np.linalg.det(U), 1.0, atol=1e-13) and np.allclose(np.linalg.det(V), 1.0, atol=1e-13)
+    assert np.abs(U @ np.swapaxes(U, 1, 2) - np.eye(dim)).max() < 1e-14
+    assert rel(S, So[:, np.arange(dim), np.arange(dim)]) < 1e-13
+    # polar factors are unique where F is well conditioned
+    good = np.abs(So[:, np.arange(dim), np.arange(dim)]).min(axis=1) > 1e-6
+    R = U @ np.swapaxes(V, 1, 2)
+    Ro, _ = oe.polar_svd(F)
+    assert rel(R[good], Ro[good]) < 1e-9
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("material", oe.MATERIALS)
+def test_element_tier(dim, material):
+    X, T, U, mu, lam = _mesh(dim, 0.4 if material != "neo_hookean" else 0.1)
+    J = oe.deformation_jacobian(X, T)
+    vol = oe.volume(X, T)
+    F = np.asarray(J @ U.reshape(-1, 1)).reshape(-1, dim, dim)
+    psi, P = hostsim.element_energy_gradient(MAT_ID[material], F, mu, lam)
+    assert rel(psi, oe.energy_element_F(material, F, mu, lam).ravel()) < 1e-13
+    assert rel(P, oe.gradient_element_F(material, F, mu, lam)) < 1e-12
+    H = hostsim.element_hessian(MAT_ID[material], 0, F, mu, lam, np.ones(F.shape[0]))
+    assert rel(H, oe.hessian_element_F(material, F, mu, lam)) < TOL
+    for mode, before in ((1, False), (2, True)):
+        Hp = hostsim.element_hessian(MAT_ID[material], mode, F, mu, lam, vol)
+        if material == "linear_elasticity" and mode == 1:
+            continue
+        ref = oe.weighted_element_hessians(material, F, mu, lam, vol, psd=True, psd_before_vol=before)
+        assert rel(Hp, ref) < TOL
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("material", oe.MATERIALS)
+@pytest.mark.parametrize("sigma", [0.1, 0.4])
+def test_assembly(dim, material, sigma):
+    if material == "neo_hookean" and sigma > 0.2:
+        pytest.skip("NaN by construction for inverted elements")
+    X, T, U, mu, lam = _mesh(dim, sigma)
+    n = X.shape[0]
+    J = oe.deformation_jacobian(X, T)
+    vol = oe.volume(X, T)
+    psd_mode = 0 if material == "linear_elasticity" else 1
+    out = hostsim.run(X, T, MAT_ID[material], psd_mode, U, mu, lam, vol, tile_elems=32)
+    indptr, indices, bptr, bcol = oe.structural_pattern(T, n, dim)
+    assert np.array_equal(out["bptr"], bptr) and np.array_equal(out["bcol"], bcol)
+    assert rel(out["vol0"], vol.ravel()) < 1e-14
+    E = oe.energy_x(material, U, J, mu, lam, vol)
+    assert abs(out["energy"] - E) <= 1e-12 * abs(E)
+    g = oe.gradient_x(material, U, J, mu, lam, vol)
+    assert rel(out["g"], g.ravel()) < TOL
+    Q = oe.hessian_x(material, U, J, mu, lam, vol, psd=True)
+    Qours = hostsim.csr_from_blocks(out["bptr"], out["bcol"], out["vals"], n, dim)
+    assert rel(Qours.toarray(), Q.toarray()) < TOL
+    # block slot map agrees with its definition
+    for e in range(0, T.shape[0], 7):
+        for a in range(dim + 1):
+            for b in range(dim + 1):
+                s = out["bslot"][e, a, b]
+                assert bptr[T[e, a]] <= s < bptr[T[e, a] + 1] and bcol[s] == T[e, b]
