@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark of simkit_b200 (contract: task brief + SURVEY.md §8d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C5] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input: the fused stable
+neo-Hookean gradient + PSD-projected Hessian + CSR assembly of every element of the workload mesh
+(BASELINE.json `metric`, quoted on the 16M-tet config C5).  One JSON line is printed by rank 0:
+
+  value     tets/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e       same metric through the public host-pointer API (pinned host buffers, H2D of the state and
+            D2H of gradient + CSR values inside the timed region)
+  roofline  dominant kernel (assemble_tile_kernel) against the measured HBM peak; algorithmic bytes per
+            tet from SURVEY.md §8(d); the FP64 fraction is reported beside it
+  cpu_baseline  the numpy/scipy oracle (a port of the reference CPU path) on a bounded sample
+  newton    one backward-Euler Newton step (assembly + block-Jacobi PCG + line search), steps/s
+
+`--impl reference` times the reference algorithm's CPU path (the oracle port: the reference is pure
+Python and cannot travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MATERIAL = "stable_neo_hookean"
+METRIC = "tets/s for stable-NH grad+PSD Hessian+CSR assembly"
+CPU_SAMPLE = "C1"          # 20^3-cell cube, 48,000 tets: the reference's own CPU-runnable case
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def workload_desc(name, t, n, nnz):
+    from simkit_b200 import synthetic as syn
+    cfg = syn.CONFIGS[name]
+    cells = "x".join(str(c) for c in cfg["cells"])
+    kind = "Kuhn 6-tet" if cfg["dim"] == 3 else "2-triangle"
+    return "%s: %s-cell %s grid, %d elements, %d vertices, %d CSR non-zeros; state U = X + 0.1*cell*N(0,1) seed 0; ym=1e5 pr=0.45" % (
+        name, cells, kind, t, n, nnz)
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_pass(sample=CPU_SAMPLE, reps=3):
+    """gradient_x + hessian_x of the reference algorithm (oracle port) on a bounded sample mesh.
+    Returns (tets/s best of reps, seconds per pass, t)."""
+    from oracle import elasticity as oe
+    from simkit_b200 import synthetic as syn
+    cfg = syn.CONFIGS[sample]
+    X, T = syn.make_mesh(sample)
+    U = syn.jittered_state(X, cfg["cells"], cfg["extent"], sigma=0.1)
+    mu, lam = syn.lame()
+    J = oe.deformation_jacobian(X, T)
+    vol = oe.volume(X, T)
+    t = T.shape[0]
+    best = float("inf")
+    for r in range(reps + 1):                      # first pass is the warm-up
+        t0 = time.perf_counter()
+        oe.gradient_x(MATERIAL, U, J, mu, lam, vol)
+        oe.hessian_x(MATERIAL, U, J, mu, lam, vol, psd=True)
+        dt = time.perf_counter() - t0
+        if r > 0:
+            best = min(best, dt)
+    return t / best, best, t
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [p.get("num_threads", 1) for p in threadpool_info()]
+        return max(n) if n else 1
+    except Exception:
+        return 1
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference algorithm's CPU path (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    import warnings
+    warnings.filterwarnings("ignore")
+    from simkit_b200 import synthetic as syn
+    times = []
+    tps, sec, t = None, None, None
+    for s in range(args.warmup + args.steps):
+        tps, sec, t = cpu_reference_pass(CPU_SAMPLE, reps=1)
+        if s >= args.warmup:
+            times.append(sec)
+    sec = float(np.mean(times))
+    value = t / sec
+    cfg = syn.CONFIGS[args.workload]
+    sample = ("each step = gradient_x + hessian_x(psd) of the %s mesh (%d tets) in numpy/scipy: SpMV, batched element "
+              "formulas, LAPACK eigh per 9x9, block_diag, two SpGEMMs -- the reference's algorithm; it is linear in t "
+              "(SURVEY 6), so tets/s carries to %s" % (CPU_SAMPLE, t, args.workload))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "tets/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s (%s cells), timed on a bounded sample" % (args.workload, "x".join(map(str, cfg["cells"]))),
+                   "material": MATERIAL},
+        "cpu_baseline": {"value": value, "unit": "tets/s", "cores": 1, "kind": "port", "sample": sample,
+                         "blas_threads": host_threads(), "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "tets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def load_traffic(kernel_key):
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import simkit_b200 as sk
+    from simkit_b200 import _lib, synthetic as syn
+    from simkit_b200._lib import MATERIAL_IDS, PSD_AFTER_VOL, check, ptr
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; simkit_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    cfg = syn.CONFIGS[args.workload]
+    if world > 1:
+        from simkit_b200 import sharding
+        shard = sharding.make_shard(args.workload, rank, world, device=local_rank)
+        plan, U = shard.plan, shard.U_local
+        t_total, n_total, nnz_total = shard.t_total, shard.n_total, shard.nnz_total
+    else:
+        shard = None
+        X, T = syn.make_mesh(args.workload)
+        plan = sk.MeshPlan(X=X, T=T, device=local_rank)
+        U = syn.jittered_state(X, cfg["cells"], cfg["extent"], sigma=0.1)
+        t_total, n_total, nnz_total = plan.t, plan.n, plan.nnz
+    mu, lam = syn.lame()
+    vol = plan.volume()
+    mat = MATERIAL_IDS[MATERIAL]
+    plan.set_materials(mu, lam, vol)
+
+    f64 = torch.float64
+    x_d = torch.from_numpy(np.ascontiguousarray(U.reshape(-1))).to(dev)
+    g_d = torch.empty(plan.ndof, dtype=f64, device=dev)
+    vals_d = torch.empty(plan.nnz, dtype=f64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_dev():
+        check(lib.skb_gradient_hessian_dev(plan._h, mat, PSD_AFTER_VOL, x_d.data_ptr(), None, g_d.data_ptr(),
+                                           vals_d.data_ptr(), stream.cuda_stream))
+        if shard is not None:
+            shard.exchange(g_d, vals_d)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        tt = torch.tensor([v], dtype=f64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    lib.skb_kernel_timing(plan._h, 1)
+    l0 = plan.last_launch_count()
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_dev()
+        e1.record(stream)
+        barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = plan.last_launch_count() - l0
+    kms = np.zeros(8)
+    kcount = np.zeros(8, dtype=np.int64)
+    check(lib.skb_kernel_times(plan._h, ptr(kms), ptr(kcount)))
+    lib.skb_kernel_timing(plan._h, 0)
+    ms_step = ms_total / args.steps
+    value = t_total / (ms_step * 1e-3)
+    if shard is not None:
+        launches += shard.exchange_launches * args.steps
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    tf = _lib.ctypes.c_double(0.0)
+    check(lib.skb_fp64_peak(local_rank, _lib.ctypes.byref(tf)))
+    fp64_peak = float(tf.value)
+    dim = plan.dim
+    # SURVEY 8(d) algorithmic bytes per element: T (int32 x K) + D (dim*dim f64) + (mu, lam, vol) + block slot map
+    # (K*K int32) + x read and g written once per vertex + CSR values written once
+    K = dim + 1
+    per_elem = 4 * K + 8 * dim * dim + 24 + 4 * K * K
+    alg_bytes = per_elem * plan.t + 2 * 8 * dim * plan.n + 8 * plan.nnz
+    alg_flops = (2600.0 if dim == 3 else 700.0) * plan.t
+    k_ms = kms[0] / max(int(kcount[0]), 1)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    kernel_key = "assemble_tile_kernel<%d>" % dim
+    roofline = {
+        "kernel": kernel_key, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "frac": achieved / hbm_peak, "peak_source": peak_src,
+        "traffic": load_traffic(kernel_key) if (world == 1 and args.workload == "C5") else None,
+        "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_elem": alg_bytes / plan.t,
+        "kernel_ms": k_ms, "kernel_share_of_step": float(kms[0] / max(kms[:3].sum(), 1e-30)),
+        "step_kernels_ms": {"assemble": kms[0] / max(int(kcount[0]), 1), "finalize_blocks": kms[1] / max(int(kcount[1]), 1),
+                            "finalize_verts": kms[2] / max(int(kcount[2]), 1)},
+        "step_frac_hbm": alg_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak if world == 1 else None,
+        "fp64": {"achieved_tflops": alg_flops / (k_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak,
+                 "frac": alg_flops / (k_ms * 1e-3) / 1e12 / max(fp64_peak, 1e-30), "flops_per_elem": alg_flops / plan.t,
+                 "peak_source": "measured here (skb_fp64_peak: 8 DFMA chains/thread, 2048 threads/SM)"},
+    }
+
+    # ---- end to end through the public host API -----------------------------------------------
+    def pinned(n):
+        return torch.empty(n, dtype=f64, pin_memory=True).numpy()
+
+    x_h, g_h, vals_h, vol_h = pinned(plan.ndof), pinned(plan.ndof), pinned(plan.nnz), pinned(plan.t)
+    x_h[:] = U.reshape(-1)
+    vol_h[:] = vol.reshape(-1)
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def step_e2e():
+        plan.gradient_hessian(MATERIAL, x_h, mu, lam, vol_h, PSD_AFTER_VOL, g_out=g_h.reshape(-1, 1), vals_out=vals_h)
+        if shard is not None:
+            raise NotImplementedError
+
+    e2e = None
+    if shard is None:
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        with sampler:
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                step_e2e()
+            barrier()
+            dt = time.perf_counter() - t0
+        dt = max_over_ranks(dt)
+        e2e = {"value": t_total / (dt / e2e_steps), "unit": "tets/s", "ms_per_step": dt / e2e_steps * 1e3,
+               "steps": e2e_steps,
+               "h2d_bytes_per_step": int(8 * (plan.ndof + plan.t + 2)), "d2h_bytes_per_step": int(8 * (plan.ndof + plan.nnz)),
+               "api": "MeshPlan.gradient_hessian -> skb_gradient_hessian (host pointers, pinned buffers)"}
+        # the e2e and device-resident paths must agree bit for bit (same kernels, same reduction order)
+        assert np.array_equal(vals_h, vals_d.cpu().numpy()) and np.array_equal(g_h, g_d.cpu().numpy())
+
+    # ---- Newton step (assembly + PCG + line search), device-resident -------------------------------
+    newton = None
+    if args.newton and shard is None:
+        rho, h = 1e3, 1e-2
+        mass = np.repeat(plan.vertex_masses(rho), dim)
+        fext = np.zeros((plan.n, dim))
+        fext[:, 1] = -9.8
+        fext = fext.reshape(-1) * mass
+        xc = U.reshape(-1)
+        nsteps = max(1, min(args.steps, args.newton_steps))
+        lib.skb_kernel_timing(plan._h, 1)
+        tt, info = [], None
+        for s in range(1 + nsteps):
+            t0 = time.perf_counter()
+            xn, info = plan.newton(MATERIAL, xc, x_tilde=xc, mass=mass, kin_scale=1.0 / h ** 2, f_ext=fext, max_iter=1,
+                                   pcg_rtol=args.pcg_rtol, pcg_max_iter=20000)
+            if s > 0:
+                tt.append(time.perf_counter() - t0)
+            else:
+                check(lib.skb_kernel_times(plan._h, ptr(kms), ptr(kcount)))   # drop the warm-up record
+        nl = plan.last_launch_count()
+        check(lib.skb_kernel_times(plan._h, ptr(kms), ptr(kcount)))
+        lib.skb_kernel_timing(plan._h, 0)
+        sec = float(np.mean(tt))
+        spmv_ms = kms[4] / max(int(kcount[4]), 1)
+        spmv_bytes = (8 * dim * dim + 4) * plan.nnzb + 8 * plan.n + 3 * 8 * plan.ndof
+        newton = {"steps_per_s": 1.0 / sec, "ms_per_step": sec * 1e3, "pcg_iters": info["pcg_iters"],
+                  "pcg_rtol": args.pcg_rtol, "pcg_relres": info["pcg_relres"], "alpha": info["alphas"][:1],
+                  "launches_per_step": nl, "includes": "host->device upload of state and device->host read of x_next",
+                  "spmv": {"ms": spmv_ms, "achieved_gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9,
+                           "frac_hbm": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / hbm_peak, "bytes": spmv_bytes},
+                  "pcg_ms_per_iter": (kms[4] + kms[5]) / max(info["pcg_iters"], 1) / nsteps}
+
+    # ---- CPU baseline (rank 0, N = 1) -----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import warnings
+        warnings.filterwarnings("ignore")
+        tps, sec, tt_ = cpu_reference_pass(CPU_SAMPLE, reps=3)
+        cpu = {"value": tps, "unit": "tets/s", "cores": 1, "kind": "port",
+               "sample": "oracle gradient_x + hessian_x(psd) on the %s mesh (%d tets), best of 3 after a warm-up, %.2f s per pass; "
+                         "numpy/scipy is effectively single-threaded on this path" % (CPU_SAMPLE, tt_, sec),
+               "blas_threads": host_threads(), "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "tets/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_desc(args.workload, t_total, n_total, nnz_total), "material": MATERIAL,
+                       "psd": "analytic eigensystem, floor 1e-6 after vol",
+                       "l2": "no flush needed: per-step inputs+outputs (>= %.1f GB) exceed the 126 MB L2" % (alg_bytes / 1e9),
+                       "sharding": "none" if world == 1 else "contiguous element slabs, NCCL interface exchange"},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "newton": newton,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C5", choices=["C1", "C3", "C4", "C5"])
+    ap.add_argument("--newton", type=int, default=1, help="also time one backward-Euler Newton step (0 = skip)")
+    ap.add_argument("--newton-steps", type=int, default=2)
+    ap.add_argument("--pcg-rtol", type=float, default=1e-10)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run --nproc-per-node %d" % (args.gpus, args.gpus))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,8 +118,23 @@ int skb_energy_dev(skb_plan* plan, int material, const double* x, const double* 
                    double* energy_out, void* stream);
 int skb_gradient_hessian_dev(skb_plan* plan, int material, int psd_mode, const double* x,
                              const double* Fbar, double* g, double* vals, void* stream);
-/* number of kernels the last *_dev / host call launched (for bench accounting) */
+/* number of kernels launched on this plan since the last host-pointer call reset it (bench accounting) */
 int skb_last_launch_count(const skb_plan* plan);
+/* Per-kernel device timing for bench.py's roofline: when enabled every kernel launched on the plan is
+ * bracketed by CUDA events on its own stream.  skb_kernel_times waits for them and returns the summed
+ * milliseconds and launch counts per kernel kind (arrays of SKB_K_COUNT), then clears the record. */
+#define SKB_K_ASSEMBLE 0        /* fused gather -> F -> P, PSD Hessian -> J^T H J -> tile reduction */
+#define SKB_K_FINALIZE_BLOCKS 1 /* level-2 reduction into the CSR values */
+#define SKB_K_FINALIZE_VERTS 2  /* level-2 reduction into the gradient   */
+#define SKB_K_ENERGY 3
+#define SKB_K_SPMV 4            /* PCG: q = (A + diag) p with the p.q partials */
+#define SKB_K_PCG_VECTOR 5      /* PCG: fused vector updates / dots           */
+#define SKB_K_OTHER 6
+#define SKB_K_COUNT 8
+int skb_kernel_timing(skb_plan* plan, int enable);
+int skb_kernel_times(skb_plan* plan, double* ms, int64_t* launches);
+/* measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the compute roofline denominator */
+int skb_fp64_peak(int device, double* tflops);
 
 /* ------------------------------------------------------- element tiers -----
  * Batched per-element functions on arbitrary F (host pointers):

@@ -70,6 +70,9 @@ SIGNATURES = {
     "skb_energy_dev": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "skb_gradient_hessian_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "skb_last_launch_count": (_int, [_vp]),
+    "skb_kernel_timing": (_int, [_vp, _int]),
+    "skb_kernel_times": (_int, [_vp, _vp, _vp]),
+    "skb_fp64_peak": (_int, [_int, ctypes.POINTER(_dbl)]),
     "skb_element_energy": (_int, [_int, _int, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),
     "skb_element_gradient": (_int, [_int, _int, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),
     "skb_element_hessian": (_int, [_int, _int, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),

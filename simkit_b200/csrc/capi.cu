@@ -82,16 +82,15 @@ static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
     SKB_CUDA(cudaFuncSetAttribute(assemble_tile_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[D - 2] = true;
   }
-  assemble_tile_kernel<D><<<p.n_tiles, E, smem, st>>>(p, a);
-  pl->launches++;
+  SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_tile_kernel<D><<<p.n_tiles, E, smem, st>>>(p, a));
   if (a.want_hess) {
     const int items = p.nnzb * D;
-    finalize_blocks_kernel<D><<<(items + 255) / 256, 256, 0, st>>>(p, a.pblocks, a.vals);
-    pl->launches++;
+    SKB_LAUNCH(pl, SKB_K_FINALIZE_BLOCKS, st,
+               finalize_blocks_kernel<D><<<(items + 255) / 256, 256, 0, st>>>(p, a.pblocks, a.vals));
   }
   if (a.want_grad) {
-    finalize_verts_kernel<D><<<(p.n + 255) / 256, 256, 0, st>>>(p, a.pverts, a.g);
-    pl->launches++;
+    SKB_LAUNCH(pl, SKB_K_FINALIZE_VERTS, st,
+               finalize_verts_kernel<D><<<(p.n + 255) / 256, 256, 0, st>>>(p, a.pverts, a.g));
   }
   SKB_CUDA(cudaGetLastError());
   return SKB_OK;
@@ -106,11 +105,10 @@ int launch_energy(skb_plan* pl, const EvalArgs& a, double* out_dev, cudaStream_t
   const int nb = (p.t + 255) / 256;
   if (pl->esums.size() < (size_t)nb) pl->esums.resize(nb);
   if (p.dim == 3)
-    energy_kernel<3><<<nb, 256, 0, st>>>(p, a, raw(pl->esums));
+    SKB_LAUNCH(pl, SKB_K_ENERGY, st, energy_kernel<3><<<nb, 256, 0, st>>>(p, a, raw(pl->esums)));
   else
-    energy_kernel<2><<<nb, 256, 0, st>>>(p, a, raw(pl->esums));
-  reduce_final_kernel<<<1, 1024, 0, st>>>(raw(pl->esums), nb, out_dev);
-  pl->launches += 2;
+    SKB_LAUNCH(pl, SKB_K_ENERGY, st, energy_kernel<2><<<nb, 256, 0, st>>>(p, a, raw(pl->esums)));
+  SKB_LAUNCH(pl, SKB_K_OTHER, st, reduce_final_kernel<<<1, 1024, 0, st>>>(raw(pl->esums), nb, out_dev));
   SKB_CUDA(cudaGetLastError());
   return SKB_OK;
 }
@@ -319,6 +317,33 @@ int skb_set_materials_dev(skb_plan* pl, const double* mu, int64_t mu_n, const do
 }
 
 int skb_last_launch_count(const skb_plan* pl) { return pl ? pl->launches : 0; }
+
+int skb_kernel_timing(skb_plan* pl, int enable) {
+  if (!pl) return fail(SKB_EINVAL, "null plan");
+  pl->timing = enable != 0;
+  return SKB_OK;
+}
+
+int skb_kernel_times(skb_plan* pl, double* ms, int64_t* launches) {
+  if (!pl || !ms || !launches) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  for (int k = 0; k < SKB_K_COUNT; ++k) {
+    ms[k] = 0.0;
+    launches[k] = 0;
+  }
+  for (auto& tl : pl->timed) {
+    SKB_CUDA(cudaEventSynchronize(tl.b));
+    float e = 0.f;
+    SKB_CUDA(cudaEventElapsedTime(&e, tl.a, tl.b));
+    const int k = (tl.kind >= 0 && tl.kind < SKB_K_COUNT) ? tl.kind : SKB_K_OTHER;
+    ms[k] += e;
+    launches[k]++;
+    cudaEventDestroy(tl.a);
+    cudaEventDestroy(tl.b);
+  }
+  pl->timed.clear();
+  return SKB_OK;
+}
 
 // ---- host-pointer global tiers -------------------------------------------
 static int stage_inputs(skb_plan* pl, const double* x, const double* Fbar, const double* mu, int64_t mu_n,

@@ -6,6 +6,7 @@
 
 #include <exception>
 #include <string>
+#include <vector>
 
 #include "../../include/simkit_b200.h"
 #include "kernels.cuh"
@@ -60,11 +61,37 @@ struct skb_plan {
   // PCG / Newton work vectors (allocated on first use)
   skb::dvec<double> w_r, w_z, w_p, w_q, w_dx, w_xt, w_x, w_xtrial, w_dinv, w_diag, w_mass, w_fext, w_xtilde, w_red;
   int launches = 0;
+  // optional per-kernel CUDA-event timing (skb_kernel_timing / skb_kernel_times)
+  bool timing = false;
+  struct TimedLaunch {
+    int kind;
+    cudaEvent_t a, b;
+  };
+  std::vector<TimedLaunch> timed;
 
   skb::PlanView view() const { return d.view(); }
   int64_t ndof() const { return (int64_t)d.n * d.dim; }
   int64_t nnz() const { return (int64_t)d.nnzb * d.dim * d.dim; }
 };
+
+// Wraps one kernel launch: counts it and, when timing is on, brackets it with CUDA events on its stream.
+#define SKB_LAUNCH(pl, kkind, st, ...)                         \
+  do {                                                         \
+    skb_plan::TimedLaunch _tl;                                 \
+    const bool _t = (pl) && (pl)->timing;                      \
+    if (_t) {                                                  \
+      _tl.kind = (kkind);                                      \
+      cudaEventCreate(&_tl.a);                                 \
+      cudaEventCreate(&_tl.b);                                 \
+      cudaEventRecord(_tl.a, (st));                            \
+    }                                                          \
+    __VA_ARGS__;                                               \
+    if (_t) {                                                  \
+      cudaEventRecord(_tl.b, (st));                            \
+      (pl)->timed.push_back(_tl);                              \
+    }                                                          \
+    if (pl) (pl)->launches++;                                  \
+  } while (0)
 
 namespace skb {
 // launches shared between translation units

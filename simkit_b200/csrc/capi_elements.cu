@@ -170,6 +170,17 @@ static int run_element(int op, int material, int dim, int64_t t, const double* F
   SKB_CATCH
 }
 
+
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 }  // namespace skb
 
 using namespace skb;
@@ -237,6 +248,38 @@ int skb_psd_project(int64_t t, int b, const double* H, int method, double* out) 
   SKB_CUDA(cudaGetLastError());
   SKB_CUDA(cudaDeviceSynchronize());
   SKB_CUDA(cudaMemcpy(out, raw(od), nn * sizeof(double), cudaMemcpyDeviceToHost));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+
+// FP64 FMA throughput probe: 8 independent DFMA chains per thread, full occupancy.
+int skb_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(SKB_EINVAL, "null argument");
+  if (skb_device_count() <= device) return fail(SKB_ENOGPU, "no CUDA device");
+  SKB_CUDA(cudaSetDevice(device));
+  SKB_TRY
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int threads = 256, blocks = sms * 8, iters = 8192;
+  dvec<double> out((size_t)threads * blocks);
+  cudaEvent_t a, b;
+  SKB_CUDA(cudaEventCreate(&a));
+  SKB_CUDA(cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    SKB_CUDA(cudaEventRecord(a));
+    fp64_peak_kernel<<<blocks, threads>>>(raw(out), iters, 1.0000001, 1e-9);
+    SKB_CUDA(cudaEventRecord(b));
+    SKB_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    SKB_CUDA(cudaEventElapsedTime(&ms, a, b));
+    const double tf = 2.0 * 8.0 * iters * (double)threads * blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *tflops = best;
   return SKB_OK;
   SKB_CATCH
 }

@@ -34,14 +34,14 @@ static void ensure(dvec<double>& v, size_t n) {
 template <int D, class SpmvDot>
 static int pcg_loop(skb_plan* pl, int nb, int grid, SpmvDot spmv_dot, const double* dinv, const double* rhs,
                     double rtol, int max_iter, double* x, double* r, double* z, double* pv, double* q,
-                    double* red, int* iters, double* relres, cudaStream_t st, int* launches) {
+                    double* red, int* iters, double* relres, cudaStream_t st) {
   double* part_pq = red;
   double* part_rz = part_pq + 1024;
   double* part_rr = part_rz + 1024;
   PcgScalars* sc = reinterpret_cast<PcgScalars*>(part_rr + 1024);  // two ping-pong slots
-  pcg_init_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, rhs, dinv, x, r, z, pv, part_rz, part_rr);
-  pcg_init_scalars_kernel<<<1, PCG_THREADS, 0, st>>>(part_rz, part_rr, grid, rtol, sc);
-  *launches += 2;
+  SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st,
+             pcg_init_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, rhs, dinv, x, r, z, pv, part_rz, part_rr));
+  SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg_init_scalars_kernel<<<1, PCG_THREADS, 0, st>>>(part_rz, part_rr, grid, rtol, sc));
   int cur = 0;
   PcgScalars h;
   const int check_every = 25;
@@ -51,10 +51,13 @@ static int pcg_loop(skb_plan* pl, int nb, int grid, SpmvDot spmv_dot, const doub
     const int batch = (max_iter - it < check_every) ? (max_iter - it) : check_every;
     for (int b = 0; b < batch; ++b) {
       spmv_dot(pv, q, part_pq, sc + cur);
-      pcg_update_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, dinv, pv, q, x, r, z, part_pq, grid, part_rz, part_rr, sc + cur);
-      pcg_direction_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, z, pv, part_rz, part_rr, grid, rtol, sc + cur, sc + (cur ^ 1));
+      SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st,
+                 pcg_update_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, dinv, pv, q, x, r, z, part_pq, grid, part_rz,
+                                                                    part_rr, sc + cur));
+      SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st,
+                 pcg_direction_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, z, pv, part_rz, part_rr, grid, rtol, sc + cur,
+                                                                       sc + (cur ^ 1)));
       cur ^= 1;
-      *launches += 3;
     }
     it += batch;
     SKB_CUDA(cudaMemcpyAsync(&h, sc + cur, sizeof(PcgScalars), cudaMemcpyDeviceToHost, st));
@@ -84,13 +87,12 @@ static int pcg_run(skb_plan* pl, const double* vals, const double* dadd, const d
   ensure(pl->w_dinv, (size_t)p.n * D * D);
   ensure(pl->w_red, 3 * 1024 + 64);
   double* dinv = raw(pl->w_dinv);
-  block_jacobi_kernel<D><<<(p.n + 127) / 128, 128, 0, st>>>(p, vals, dadd, dinv);
-  pl->launches++;
+  SKB_LAUNCH(pl, SKB_K_OTHER, st, block_jacobi_kernel<D><<<(p.n + 127) / 128, 128, 0, st>>>(p, vals, dadd, dinv));
   auto spmv_dot = [&](const double* pvec, double* q, double* part_pq, const PcgScalars* sc) {
-    pcg_spmv_dot_kernel<D><<<grid, PCG_THREADS, 0, st>>>(p, vals, dadd, pvec, q, part_pq, sc);
+    SKB_LAUNCH(pl, SKB_K_SPMV, st, pcg_spmv_dot_kernel<D><<<grid, PCG_THREADS, 0, st>>>(p, vals, dadd, pvec, q, part_pq, sc));
   };
   return pcg_loop<D>(pl, p.n, grid, spmv_dot, dinv, rhs, rtol, max_iter, x, raw(pl->w_r), raw(pl->w_z),
-                     raw(pl->w_p), raw(pl->w_q), raw(pl->w_red), iters, relres, st, &pl->launches);
+                     raw(pl->w_p), raw(pl->w_q), raw(pl->w_red), iters, relres, st);
 }
 
 int pcg_solve(skb_plan* pl, const double* vals, const double* dadd, const double* rhs, double rtol, int max_iter,
@@ -123,9 +125,8 @@ static int csr_pcg_run(int64_t n, const int32_t* indptr_h, const int32_t* indice
   auto spmv_dot = [&](const double* pvec, double* qq, double* part_pq, const PcgScalars* sc) {
     csr_pcg_spmv_dot_kernel<<<grid, PCG_THREADS, 0, st>>>(nn, ip, ix, vp, pvec, qq, part_pq, sc);
   };
-  int launches = 0;
   int rc = pcg_loop<D>(nullptr, nb, grid, spmv_dot, raw(dinv), raw(rhs), rtol, max_iter, raw(x), raw(r), raw(z),
-                       raw(pv), raw(q), raw(red), iters, relres, st, &launches);
+                       raw(pv), raw(q), raw(red), iters, relres, st);
   if (rc) return rc;
   SKB_CUDA(cudaMemcpy(x_h, raw(x), n * sizeof(double), cudaMemcpyDeviceToHost));
   return SKB_OK;
@@ -144,10 +145,11 @@ int skb_spmv_dev(skb_plan* pl, const double* vals, const double* diag_add, const
   const PlanView p = pl->view();
   const int grid = pcg_grid(pl);
   if (p.dim == 3)
-    spmv_kernel<3><<<grid, PCG_THREADS, 0, (cudaStream_t)stream>>>(p, vals, diag_add, x, y);
+    SKB_LAUNCH(pl, SKB_K_SPMV, (cudaStream_t)stream,
+               spmv_kernel<3><<<grid, PCG_THREADS, 0, (cudaStream_t)stream>>>(p, vals, diag_add, x, y));
   else
-    spmv_kernel<2><<<grid, PCG_THREADS, 0, (cudaStream_t)stream>>>(p, vals, diag_add, x, y);
-  pl->launches++;
+    SKB_LAUNCH(pl, SKB_K_SPMV, (cudaStream_t)stream,
+               spmv_kernel<2><<<grid, PCG_THREADS, 0, (cudaStream_t)stream>>>(p, vals, diag_add, x, y));
   SKB_CUDA(cudaGetLastError());
   return SKB_OK;
 }
@@ -284,10 +286,11 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
 
   // total energy at x + s*dx (also leaves the trial point in xtrial)
   auto total_energy = [&](double s, const double* dxp, bool with_gdx, double& e_tot, double& gdx, double& dx2) -> int {
-    newton_energy_terms_kernel<<<vgrid, PCG_THREADS, 0, st>>>(nd, x, dxp, s, d_f, d_mass, d_xt, kin_scale, d_pk, d_pt,
-                                                              with_gdx ? g : nullptr, xtrial, part_e, part_g, part_d);
-    reduce3_kernel<<<1, PCG_THREADS, 0, st>>>(part_e, part_g, part_d, vgrid, red);
-    pl->launches += 2;
+    SKB_LAUNCH(pl, SKB_K_OTHER, st,
+               newton_energy_terms_kernel<<<vgrid, PCG_THREADS, 0, st>>>(nd, x, dxp, s, d_f, d_mass, d_xt, kin_scale, d_pk,
+                                                                         d_pt, with_gdx ? g : nullptr, xtrial, part_e,
+                                                                         part_g, part_d));
+    SKB_LAUNCH(pl, SKB_K_OTHER, st, reduce3_kernel<<<1, PCG_THREADS, 0, st>>>(part_e, part_g, part_d, vgrid, red));
     EvalArgs a;
     int rc = make_args(pl, o->material, PSD_NONE, xtrial, nullptr, nullptr, nullptr, a);
     if (rc) return rc;
@@ -311,8 +314,9 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
     if (rc) return rc;
     rc = launch_assemble(pl, a, st);
     if (rc) return rc;
-    newton_gradient_kernel<<<vgrid, PCG_THREADS, 0, st>>>(nd, x, d_f, d_mass, d_xt, kin_scale, d_pk, d_pt, g, rhs, dadd);
-    pl->launches++;
+    SKB_LAUNCH(pl, SKB_K_OTHER, st,
+               newton_gradient_kernel<<<vgrid, PCG_THREADS, 0, st>>>(nd, x, d_f, d_mass, d_xt, kin_scale, d_pk, d_pt, g, rhs,
+                                                                     dadd));
     int pit = 0;
     double relres = 0.0;
     rc = pcg_solve(pl, raw(pl->vals), dadd, rhs, o->pcg_rtol, o->pcg_max_iter, dx, &pit, &relres, st);
