@@ -2,6 +2,7 @@
 // Hessian entry points (include/simkit_b200.h).
 #include "capi_common.cuh"
 
+#include <algorithm>
 #include <memory>
 
 namespace skb {
@@ -76,7 +77,8 @@ template <int D>
 static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
   const PlanView p = pl->view();
   const int E = p.tile_elems;
-  const size_t smem = (size_t)E * Sizes<D>::SMEM_DOUBLES * sizeof(double);
+  const size_t smem = assemble_smem_bytes<D>(p);
+  if (smem > 227 * 1024) return fail(SKB_EINVAL, "tile_elems too large for the 227 KB of shared memory");
   static bool attr_set[2] = {false, false};
   if (!attr_set[D - 2]) {
     SKB_CUDA(cudaFuncSetAttribute(assemble_tile_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -84,9 +86,8 @@ static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
   }
   SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_tile_kernel<D><<<p.n_tiles, E, smem, st>>>(p, a));
   if (a.want_hess) {
-    const int items = p.nnzb * D;
     SKB_LAUNCH(pl, SKB_K_FINALIZE_BLOCKS, st,
-               finalize_blocks_kernel<D><<<(items + 255) / 256, 256, 0, st>>>(p, a.pblocks, a.vals));
+               finalize_blocks_kernel<D><<<(p.nu + 127) / 128, 128, 0, st>>>(p, a.pblocks, a.vals));
   }
   if (a.want_grad) {
     SKB_LAUNCH(pl, SKB_K_FINALIZE_VERTS, st,
@@ -156,7 +157,8 @@ static int plan_create_common(const double* X, const double* Dop, const void* T,
   pl->device = device;
   SKB_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
   dvec<int> Td = Th;
-  build_plan<DeviceBackend>(pl->d, Td, (int)n, (int)t, dim, tile_elems);
+  if (!build_plan<DeviceBackend>(pl->d, Td, (int)n, (int)t, dim, tile_elems))
+    return fail(SKB_EINVAL, "degenerate element: a vertex is repeated within one element");
   if (X) {
     dvec<double> Xd(X, X + n * dim);
     set_geometry_from_X<DeviceBackend>(pl->d, Xd);
@@ -234,19 +236,24 @@ int skb_plan_slot_map(const skb_plan* pl, int32_t* slot) {
   if (!pl || !slot) return fail(SKB_EINVAL, "null argument");
   SKB_TRY
   const int D = pl->d.dim, K = pl->d.K, t = pl->d.t;
-  thrust::host_vector<int> bptr = pl->d.bptr, bslot = pl->d.bslot, T = pl->d.T32;
-  for (int e = 0; e < t; ++e)
+  thrust::host_vector<int> bptr = pl->d.bptr, bcol = pl->d.bcol, Ts = pl->d.T32;
+  thrust::host_vector<uint8_t> perm = pl->d.perm;
+  for (int e = 0; e < t; ++e) {
+    int To[4];
+    for (int s = 0; s < K; ++s) To[perm[e * K + s]] = Ts[e * K + s];  // caller's corner order
     for (int a = 0; a < K; ++a) {
-      const int v = T[e * K + a];
+      const int v = To[a];
       const int b0 = bptr[v], nb = bptr[v + 1] - b0;
-      for (int i = 0; i < D; ++i)
-        for (int b = 0; b < K; ++b) {
-          const int s = bslot[(e * K + a) * K + b];
+      for (int b = 0; b < K; ++b) {
+        const int* lo = &bcol[b0];
+        const int s = b0 + (int)(std::lower_bound(lo, lo + nb, To[b]) - lo);
+        for (int i = 0; i < D; ++i)
           for (int k = 0; k < D; ++k)
             slot[((((int64_t)e * K + a) * D + i) * K + b) * D + k] =
                 (int32_t)((int64_t)b0 * D * D + (int64_t)i * nb * D + (int64_t)(s - b0) * D + k);
-        }
+      }
     }
+  }
   return SKB_OK;
   SKB_CATCH
 }
@@ -256,15 +263,16 @@ int skb_plan_element_D(const skb_plan* pl, double* Dout) {
   SKB_TRY
   const int D = pl->d.dim, K = pl->d.K, t = pl->d.t;
   thrust::host_vector<double> Dm = pl->d.Dm;
+  thrust::host_vector<uint8_t> perm = pl->d.perm;
   for (int e = 0; e < t; ++e)
     for (int j = 0; j < D; ++j) {
       double s0 = 0.0;
-      for (int a = 0; a < D; ++a) {
-        double v = Dm[(size_t)(j * D + a) * t + e];
-        Dout[((size_t)e * D + j) * K + a + 1] = v;
+      for (int s = 1; s < K; ++s) {
+        double v = Dm[(size_t)(j * D + (s - 1)) * t + e];
+        Dout[((size_t)e * D + j) * K + perm[e * K + s]] = v;
         s0 -= v;
       }
-      Dout[((size_t)e * D + j) * K] = s0;
+      Dout[((size_t)e * D + j) * K + perm[e * K]] = s0;
     }
   return SKB_OK;
   SKB_CATCH

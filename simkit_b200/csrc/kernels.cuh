@@ -240,73 +240,97 @@ SKB_HD void element_phase1(const PlanView& p, const EvalArgs& a, int e, int le, 
   }
 }
 
-// Phase 2 (blocks): work item = (tile-slot entry, block row i).  Sums the
-// entry's contributions in their fixed order and writes one partial-record row.
+// local corners (a <= b) of pair index pp, K corners: row-major over the upper triangle
+template <int K>
+SKB_HD void pair_ab(int pp, int& a, int& b) {
+  a = 0;
+#pragma unroll
+  for (int r = 1; r < K; ++r) a += (pp >= r * K - (r * (r - 1)) / 2) ? 1 : 0;
+  b = a + pp - (a * K - (a * (a - 1)) / 2);
+}
+
+// Phase 2 (blocks): work item = tile-slot entry of an UPPER block (row vertex <= col vertex).
+// Sums the entry's contributions in their fixed order and writes one dim x dim partial record.
+// Corners are sorted per element, so a contribution is always a local pair a <= b and its block
+// K[(a,i),(b,k)] is read straight from the packed upper triangle; diagonal pairs mirror k < i.
 template <int D>
-SKB_HD void block_phase2(const ReduceSchedView& s, int tile, int w, int E, const double* sK, double* pblocks) {
+SKB_HD void block_phase2(const SchedEntry* ent, const uint16_t* src, int w, int E, const double* sK, double* pblocks) {
   constexpr int K = D + 1;
   constexpr int NL = K * D;
-  const int entry = s.tl_ptr[tile] + w / D;
-  const int i = w - (w / D) * D;
-  const int q = s.tl_q[entry];
-  double acc[D];
+  constexpr int NP = K * (K + 1) / 2;
+  const SchedEntry en = ent[w];
+  if (en.q == 0xffffffffu) return;  // alignment padding
+  double acc[D * D];
 #pragma unroll
-  for (int k = 0; k < D; ++k) acc[k] = 0.0;
-  const int c1 = s.tl_cptr[entry + 1];
-  for (int c = s.tl_cptr[entry]; c < c1; ++c) {
-    const int src = s.tc_src[c];
-    const int le = src / (K * K);
-    const int ab = src - le * (K * K);
-    const int ca = ab / K, cb = ab - ca * K;
-    const int r = ca * D + i;
+  for (int k = 0; k < D * D; ++k) acc[k] = 0.0;
+  const int c1 = (int)(en.range >> 16);
+  for (int c = (int)(en.range & 0xffffu); c < c1; ++c) {
+    const int sc = src[c];
+    const int le = sc / NP;
+    int a, b;
+    pair_ab<K>(sc - le * NP, a, b);
+    const bool dg = (a == b);
+    const double* base = sK + le;
 #pragma unroll
-    for (int k = 0; k < D; ++k) acc[k] += sK[sym_idx(NL, r, cb * D + k) * E + le];
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        int r = a * D + i, cc = b * D + k;
+        if (k < i && dg) {
+          r = a * D + k;
+          cc = b * D + i;
+        }
+        acc[i * D + k] += base[((r * (2 * NL - 1 - r)) / 2 + cc) * E];
+      }
   }
 #pragma unroll
-  for (int k = 0; k < D; ++k) pblocks[(size_t)q * (D * D) + i * D + k] = acc[k];
+  for (int k = 0; k < D * D; ++k) pblocks[(size_t)en.q * (D * D) + k] = acc[k];
 }
 
 // Phase 2 (vertices): work item = tile-vertex entry.
 template <int D>
-SKB_HD void vert_phase2(const ReduceSchedView& s, int tile, int w, int E, const double* sG, double* pverts) {
+SKB_HD void vert_phase2(const SchedEntry* ent, const uint16_t* src, int w, int E, const double* sG, double* pverts) {
   constexpr int K = D + 1;
-  const int entry = s.tl_ptr[tile] + w;
-  const int q = s.tl_q[entry];
+  const SchedEntry en = ent[w];
+  if (en.q == 0xffffffffu) return;
   double acc[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) acc[i] = 0.0;
-  const int c1 = s.tl_cptr[entry + 1];
-  for (int c = s.tl_cptr[entry]; c < c1; ++c) {
-    const int src = s.tc_src[c];
-    const int le = src / K;
-    const int ca = src - le * K;
+  const int c1 = (int)(en.range >> 16);
+  for (int c = (int)(en.range & 0xffffu); c < c1; ++c) {
+    const int sc = src[c];
+    const int le = sc / K;
+    const int ca = sc - le * K;
 #pragma unroll
     for (int i = 0; i < D; ++i) acc[i] += sG[(ca * D + i) * E + le];
   }
 #pragma unroll
-  for (int i = 0; i < D; ++i) pverts[(size_t)q * D + i] = acc[i];
+  for (int i = 0; i < D; ++i) pverts[(size_t)en.q * D + i] = acc[i];
 }
 
-// Level 2 (blocks): item = (slot, row i): sum the slot's partial records in
-// tile order, write row i of the block into the canonical scalar-CSR layout.
+// Level 2 (blocks): item = upper slot u: sum its partial records in tile order, write the block
+// into the canonical scalar-CSR layout at (v, w) and its transpose at (w, v).
 template <int D>
-SKB_HD void block_finalize(const PlanView& p, int item, const double* pblocks, double* vals) {
-  const int s = item / D;
-  const int i = item - s * D;
-  double acc[D];
+SKB_HD void block_finalize(const PlanView& p, int u, const double* pblocks, double* vals) {
+  double acc[D * D];
 #pragma unroll
-  for (int k = 0; k < D; ++k) acc[k] = 0.0;
-  const int q1 = p.blocks.sp_ptr[s + 1];
-  for (int q = p.blocks.sp_ptr[s]; q < q1; ++q) {
+  for (int k = 0; k < D * D; ++k) acc[k] = 0.0;
+  const int q1 = p.blocks.sp_ptr[u + 1];
+  for (int q = p.blocks.sp_ptr[u]; q < q1; ++q) {
 #pragma unroll
-    for (int k = 0; k < D; ++k) acc[k] += pblocks[(size_t)q * (D * D) + i * D + k];
+    for (int k = 0; k < D * D; ++k) acc[k] += pblocks[(size_t)q * (D * D) + k];
   }
-  const int v = p.brow[s];
-  const int b0 = p.bptr[v];
-  const int nb = p.bptr[v + 1] - b0;
-  const size_t pos = (size_t)b0 * (D * D) + (size_t)i * nb * D + (size_t)(s - b0) * D;
+  const UpperPos up = p.upos[u];
 #pragma unroll
-  for (int k = 0; k < D; ++k) vals[pos + k] = acc[k];
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int k = 0; k < D; ++k) vals[(size_t)up.base + (size_t)i * up.stride + k] = acc[i * D + k];
+  if (up.tbase != up.base) {
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int k = 0; k < D; ++k) vals[(size_t)up.tbase + (size_t)k * up.tstride + i] = acc[i * D + k];
+  }
 }
 
 template <int D>
@@ -323,33 +347,100 @@ SKB_HD void vert_finalize(const PlanView& p, int v, const double* pverts, double
   for (int i = 0; i < D; ++i) g[(size_t)v * D + i] = acc[i];
 }
 
+// shared-memory footprint of one assembly CTA (bytes); every region starts 16-byte aligned
+template <int D>
+inline size_t assemble_smem_bytes(const PlanView& p) {
+  constexpr int K = D + 1;
+  constexpr int NP = K * (K + 1) / 2;
+  const size_t E = p.tile_elems;
+  size_t b = (size_t)Sizes<D>::SMEM_DOUBLES * E * sizeof(double);
+  b += (size_t)p.blocks.max_entries * sizeof(SchedEntry) + E * NP * sizeof(uint16_t);
+  b += (size_t)p.verts.max_entries * sizeof(SchedEntry) + E * K * sizeof(uint16_t);
+  return b + 16;  // mbarrier
+}
+
 #if defined(__CUDACC__)
+// ------------------------------------------------------------ TMA helpers ---
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit (SASS UBLKCP); 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(mbar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
 // ------------------------------------------------------------ __global__ ---
+// One CTA per tile of E elements, one thread per element in phase 1.  The tile's reduction
+// schedule (entries + packed sources, four contiguous ranges) is fetched by the TMA unit into
+// shared memory while phase 1 computes; phase 2 then never touches global memory for indices.
 template <int D>
 __global__ void assemble_tile_kernel(PlanView p, EvalArgs a) {
-  extern __shared__ double smem[];
+  constexpr int K = D + 1;
+  constexpr int NP = K * (K + 1) / 2;
+  extern __shared__ __align__(16) double smem[];
   const int E = blockDim.x;
   double* sK = smem;
   double* sG = smem + (size_t)Sizes<D>::NK * E;
+  unsigned char* sp = reinterpret_cast<unsigned char*>(smem + (size_t)Sizes<D>::SMEM_DOUBLES * E);
+  SchedEntry* sBE = reinterpret_cast<SchedEntry*>(sp);
+  sp += (size_t)p.blocks.max_entries * sizeof(SchedEntry);
+  uint16_t* sBS = reinterpret_cast<uint16_t*>(sp);
+  sp += (size_t)E * NP * sizeof(uint16_t);
+  SchedEntry* sVE = reinterpret_cast<SchedEntry*>(sp);
+  sp += (size_t)p.verts.max_entries * sizeof(SchedEntry);
+  uint16_t* sVS = reinterpret_cast<uint16_t*>(sp);
+  sp += (size_t)E * K * sizeof(uint16_t);
+  const unsigned mbar = smem_u32(sp);
+
   const int tile = blockIdx.x;
   const int le = threadIdx.x;
   const int e = tile * E + le;
-  if (e < p.t) element_phase1<D>(p, a, e, le, E, sK, sG);
+  const int nbe = a.want_hess ? p.blocks.tl_ptr[tile + 1] - p.blocks.tl_ptr[tile] : 0;
+  const int nve = a.want_grad ? p.verts.tl_ptr[tile + 1] - p.verts.tl_ptr[tile] : 0;
+  if (threadIdx.x == 0) mbar_init(mbar, 1);
   __syncthreads();
-  if (a.want_hess) {
-    const int nitems = (p.blocks.tl_ptr[tile + 1] - p.blocks.tl_ptr[tile]) * D;
-    for (int w = threadIdx.x; w < nitems; w += blockDim.x) block_phase2<D>(p.blocks, tile, w, E, sK, a.pblocks);
+  if (threadIdx.x == 0) {
+    unsigned bytes = 0;
+    if (nbe) bytes += nbe * (unsigned)sizeof(SchedEntry) + E * NP * (unsigned)sizeof(uint16_t);
+    if (nve) bytes += nve * (unsigned)sizeof(SchedEntry) + E * K * (unsigned)sizeof(uint16_t);
+    mbar_expect_tx(mbar, bytes);
+    if (nbe) {
+      tma_bulk_g2s(smem_u32(sBE), p.blocks.tl_ent + p.blocks.tl_ptr[tile], nbe * (unsigned)sizeof(SchedEntry), mbar);
+      tma_bulk_g2s(smem_u32(sBS), p.blocks.tc_src + (size_t)tile * E * NP, E * NP * (unsigned)sizeof(uint16_t), mbar);
+    }
+    if (nve) {
+      tma_bulk_g2s(smem_u32(sVE), p.verts.tl_ent + p.verts.tl_ptr[tile], nve * (unsigned)sizeof(SchedEntry), mbar);
+      tma_bulk_g2s(smem_u32(sVS), p.verts.tc_src + (size_t)tile * E * K, E * K * (unsigned)sizeof(uint16_t), mbar);
+    }
   }
-  if (a.want_grad) {
-    const int nitems = p.verts.tl_ptr[tile + 1] - p.verts.tl_ptr[tile];
-    for (int w = threadIdx.x; w < nitems; w += blockDim.x) vert_phase2<D>(p.verts, tile, w, E, sG, a.pverts);
-  }
+  if (e < p.t) element_phase1<D>(p, a, e, le, E, sK, sG);
+  mbar_wait(mbar, 0);
+  __syncthreads();
+  for (int w = threadIdx.x; w < nbe; w += blockDim.x) block_phase2<D>(sBE, sBS, w, E, sK, a.pblocks);
+  for (int w = threadIdx.x; w < nve; w += blockDim.x) vert_phase2<D>(sVE, sVS, w, E, sG, a.pverts);
 }
 
 template <int D>
 __global__ void finalize_blocks_kernel(PlanView p, const double* pblocks, double* vals) {
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
-  if (item < p.nnzb * D) block_finalize<D>(p, item, pblocks, vals);
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < p.nu) block_finalize<D>(p, u, pblocks, vals);
 }
 
 template <int D>

@@ -1,12 +1,15 @@
 // Per-mesh plan: everything that depends only on (X, T), built once.
 //
 // HBM layout (all arrays live on the device; SoA so that a warp's loads coalesce):
-//   T32   [t][K]        int32   element corners, K = dim+1               (16 B/tet)
+//   T32   [t][K]        int32   element corners, K = dim+1, sorted ascending per element  (16 B/tet)
 //   Dm    [dim*dim][t]  f64     D[j][a], a = 1..dim (corner 0 = -sum)    (72 B/tet)
 //   vol0  [t]           f64     rest quadrature weights
 //   bptr  [n+1], bcol[nnzb], brow[nnzb]  canonical block pattern (vertex adjacency, sorted)
-//   bslot [t][K][K]     int32   element-to-block-slot map
-// plus two deterministic reduction schedules (blocks and vertices), see ReduceSched.
+//   upos  [nu]          4xint32 where upper block (v<=w) and its transpose sit in the CSR values
+// plus two deterministic reduction schedules (upper blocks and vertices), see ReduceSched.
+// The stiffness is symmetric, so only the blocks with row vertex <= column vertex are reduced;
+// the finalize kernel writes each sum to (v,w) and its transpose to (w,v).  Corners are sorted per
+// element so that a local corner pair a <= b is always such an upper block (no runtime transposes).
 //
 // The builder is written against thrust with a backend tag so that the exact
 // same code runs with thrust::device in the product and thrust::host inside the
@@ -16,6 +19,7 @@
 #include <thrust/binary_search.h>
 #include <thrust/copy.h>
 #include <thrust/device_vector.h>
+#include <thrust/extrema.h>
 #include <thrust/execution_policy.h>
 #include <thrust/for_each.h>
 #include <thrust/gather.h>
@@ -45,82 +49,119 @@ struct DeviceBackend {
 
 // Deterministic two-level reduction schedule ("who sums what, in which order").
 //
-// Contributions c (one per (element, corner[, corner]) pair) are grouped by
-// (slot, tile) where tile = element / tile_elems.  Each group is a *tile-slot*;
-// level 1 (inside the assembly kernel, from shared memory) sums a tile-slot's
-// contributions in ascending c and writes ONE partial record; level 2 (the
-// finalize kernel) sums the partial records of a slot in ascending tile order.
-// Partial records are numbered slot-major, so level 2 reads a contiguous run.
-// No atomics anywhere: the result is bitwise reproducible.
+// Contributions c (one per (element, corner) for the gradient, one per (element, corner pair a<=b)
+// for the stiffness) are grouped by (slot, tile) where tile = element / tile_elems.  Each group is
+// a *tile-slot*; level 1 (inside the assembly kernel, from shared memory) sums a tile-slot's
+// contributions in ascending c and writes ONE partial record; level 2 (the finalize kernel) sums
+// the partial records of a slot in ascending tile order.  Partial records are numbered slot-major,
+// so level 2 reads a contiguous run.  No atomics anywhere: the result is bitwise reproducible.
+//
+// Layout, chosen so that a tile's whole schedule is two contiguous, 8/16-byte aligned ranges the
+// kernel prefetches into shared memory with cp.async while phase 1 computes:
+//   tl_ptr  [n_tiles+1]        tile -> its entries
+//   tl_ent  [n_ts] (uint2)     .x = partial record index q, .y = cbeg | cend << 16  (offsets into
+//                              the tile's tc_src range, contributions of the entry are contiguous)
+//   tc_src  [n_tiles * tile_elems * per_elem] (uint16)   packed (local element * per_elem + which),
+//                              tile-major at a FIXED stride per tile
+//   sp_ptr  [n_slots+1]        slot -> contiguous range of partial records
+struct SchedEntry {
+  unsigned q;
+  unsigned range;  // cbeg | cend << 16
+};
+
 struct ReduceSchedView {
   int n_slots;
-  int n_ts;            // number of tile-slots == number of partial records
+  int n_ts;  // number of tile-slots == number of partial records
   int n_contrib;
-  const int* tl_ptr;   // [n_tiles+1]  tile -> its tile-slot entries (tile-major list)
-  const int* tl_q;     // [n_ts]       partial record index of each entry
-  const int* tl_cptr;  // [n_ts+1]     entry -> contribution range in tc_src
-  const uint16_t* tc_src;  // [n_contrib] packed (local element, corner[s])
-  const int* sp_ptr;   // [n_slots+1]  slot -> contiguous range of partial records
+  int per_elem;
+  int max_entries;  // max over tiles of the entry count (shared-memory sizing)
+  const int* tl_ptr;
+  const SchedEntry* tl_ent;
+  const uint16_t* tc_src;
+  const int* sp_ptr;
 };
 
 template <class B>
 struct ReduceSched {
-  int n_slots = 0, n_ts = 0, n_contrib = 0;
-  typename B::template vec<int> tl_ptr, tl_q, tl_cptr, sp_ptr;
+  int n_slots = 0, n_ts = 0, n_contrib = 0, per_elem = 0, max_entries = 0;
+  typename B::template vec<int> tl_ptr, sp_ptr;
+  typename B::template vec<SchedEntry> tl_ent;
   typename B::template vec<uint16_t> tc_src;
   ReduceSchedView view() const {
     ReduceSchedView v;
     v.n_slots = n_slots;
     v.n_ts = n_ts;
     v.n_contrib = n_contrib;
+    v.per_elem = per_elem;
+    v.max_entries = max_entries;
     v.tl_ptr = thrust::raw_pointer_cast(tl_ptr.data());
-    v.tl_q = thrust::raw_pointer_cast(tl_q.data());
-    v.tl_cptr = thrust::raw_pointer_cast(tl_cptr.data());
+    v.tl_ent = thrust::raw_pointer_cast(tl_ent.data());
     v.tc_src = thrust::raw_pointer_cast(tc_src.data());
     v.sp_ptr = thrust::raw_pointer_cast(sp_ptr.data());
     return v;
   }
 };
 
+// where an upper block (v <= w) and its transpose live in the canonical scalar CSR values
+struct UpperPos {
+  int base, stride;    // block (v, w): row i of the block starts at base + i * stride
+  int tbase, tstride;  // block (w, v) (== base/stride when v == w)
+};
+
 struct PlanView {
   int dim, K;
   int n, t;
   int tile_elems, n_tiles;
-  int nnzb;
-  const int* T32;
+  int nnzb;  // block non-zeros of the full (both triangles) pattern
+  int nu;    // upper block slots (v <= w)
+  const int* T32;   // [t][K] corners sorted ascending by vertex id (internal order)
   const double* Dm;
   const double* vol0;
   const int* bptr;
   const int* bcol;
   const int* brow;
-  const int* bslot;
+  const UpperPos* upos;  // [nu]
   ReduceSchedView blocks;
   ReduceSchedView verts;
 };
 
 template <class B>
 struct PlanData {
-  int dim = 0, K = 0, n = 0, t = 0, tile_elems = 0, n_tiles = 0, nnzb = 0;
+  int dim = 0, K = 0, n = 0, t = 0, tile_elems = 0, n_tiles = 0, nnzb = 0, nu = 0;
   bool has_vol0 = false;
-  typename B::template vec<int> T32, bptr, bcol, brow, bslot;
+  typename B::template vec<int> T32, bptr, bcol, brow;
+  typename B::template vec<uint8_t> perm;  // [t][K]: internal corner s is the caller's corner perm[s]
+  typename B::template vec<UpperPos> upos;
   typename B::template vec<double> Dm, vol0;
   ReduceSched<B> blocks, verts;
   PlanView view() const {
     PlanView v;
     v.dim = dim; v.K = K; v.n = n; v.t = t;
-    v.tile_elems = tile_elems; v.n_tiles = n_tiles; v.nnzb = nnzb;
+    v.tile_elems = tile_elems; v.n_tiles = n_tiles; v.nnzb = nnzb; v.nu = nu;
     v.T32 = thrust::raw_pointer_cast(T32.data());
     v.Dm = thrust::raw_pointer_cast(Dm.data());
     v.vol0 = thrust::raw_pointer_cast(vol0.data());
     v.bptr = thrust::raw_pointer_cast(bptr.data());
     v.bcol = thrust::raw_pointer_cast(bcol.data());
     v.brow = thrust::raw_pointer_cast(brow.data());
-    v.bslot = thrust::raw_pointer_cast(bslot.data());
+    v.upos = thrust::raw_pointer_cast(upos.data());
     v.blocks = blocks.view();
     v.verts = verts.view();
     return v;
   }
 };
+
+// pair index p in [0, K(K+1)/2) -> local corners (a <= b), row-major over the upper triangle
+SKB_HD void pair_corners(int K, int p, int& a, int& b) {
+  a = 0;
+  int rowlen = K;
+  while (p >= rowlen) {
+    p -= rowlen;
+    ++a;
+    --rowlen;
+  }
+  b = a + p;
+}
 
 // ------------------------------------------------------------------ functors
 struct HeadFlag64 {
@@ -128,14 +169,50 @@ struct HeadFlag64 {
   SKB_HD int operator()(int i) const { return (i == 0 || k[i] != k[i - 1]) ? 1 : 0; }
 };
 
-// key of a block contribution c = e*K*K + a*K + b : (row vertex, col vertex)
-struct BlockKey {
-  const int* T;
+// sorts the corners of element e ascending by vertex id (insertion sort, K <= 4); flags repeats
+struct SortCorners {
+  const int* Tin;
+  int* Tout;
+  uint8_t* perm;
+  int* bad;
   int K;
+  SKB_HD void operator()(int e) const {
+    int v[4];
+    uint8_t pm[4];
+    for (int a = 0; a < K; ++a) {
+      v[a] = Tin[e * K + a];
+      pm[a] = (uint8_t)a;
+    }
+    for (int a = 1; a < K; ++a) {
+      int x = v[a];
+      uint8_t px = pm[a];
+      int b = a - 1;
+      while (b >= 0 && v[b] > x) {
+        v[b + 1] = v[b];
+        pm[b + 1] = pm[b];
+        --b;
+      }
+      v[b + 1] = x;
+      pm[b + 1] = px;
+    }
+    bool rep = false;
+    for (int a = 0; a < K; ++a) {
+      Tout[e * K + a] = v[a];
+      perm[e * K + a] = pm[a];
+      if (a > 0 && v[a] == v[a - 1]) rep = true;
+    }
+    if (rep) bad[0] = 1;  // benign race: every writer stores the same value
+  }
+};
+
+// key of an upper block contribution c = e*NP + p : (row vertex, col vertex), row <= col
+struct UpperKey {
+  const int* T;  // sorted corners
+  int K, NP;
   SKB_HD uint64_t operator()(int c) const {
-    int e = c / (K * K);
-    int ab = c - e * K * K;
-    int a = ab / K, b = ab - a * K;
+    int e = c / NP;
+    int a, b;
+    pair_corners(K, c - e * NP, a, b);
     return ((uint64_t)(uint32_t)T[e * K + a] << 32) | (uint32_t)T[e * K + b];
   }
 };
@@ -143,6 +220,12 @@ struct BlockKey {
 struct VertKey {
   const int* T;
   SKB_HD uint64_t operator()(int c) const { return (uint64_t)(uint32_t)T[c]; }
+};
+struct SwapKey {
+  SKB_HD uint64_t operator()(uint64_t k) const { return (k << 32) | (k >> 32); }
+};
+struct IsOffDiag {
+  SKB_HD bool operator()(uint64_t k) const { return (uint32_t)(k >> 32) != (uint32_t)(k & 0xffffffffu); }
 };
 
 // (slot, tile) key of the i-th contribution in slot-sorted order
@@ -166,14 +249,38 @@ struct TileQKey {
     return ((uint64_t)(uint32_t)(e / tile_elems) << 32) | (uint32_t)q_sorted[i];
   }
 };
-struct PackSrc {
-  const int* c;
+// writes the packed source of the i-th contribution (tile-major order) at its fixed-stride position
+struct ScatterSrc {
+  const int* c;  // contribution ids, tile-major
+  uint16_t* tc_src;
   int per_elem;
   int tile_elems;
-  SKB_HD uint16_t operator()(int i) const {
-    int e = c[i] / per_elem;
-    int rem = c[i] - e * per_elem;
-    return (uint16_t)((e % tile_elems) * per_elem + rem);
+  int tile_stride;  // tile_elems * per_elem
+  SKB_HD void operator()(int i) const {
+    const int e = c[i] / per_elem;
+    const int rem = c[i] - e * per_elem;
+    const int tile = e / tile_elems;
+    // every tile before `tile` is full, so position i is tile * tile_stride + local offset
+    tc_src[i] = (uint16_t)((e - tile * tile_elems) * per_elem + rem);
+    (void)tile_stride;
+  }
+};
+struct MakeEntry {
+  const uint64_t* head_key;  // (tile, q)
+  const int* head_pos;       // position of the entry's first contribution (tile-major order)
+  const int* dense_ptr;      // tile -> first entry (dense numbering)
+  const int* pad_ptr;        // tile -> first entry (padded numbering)
+  int n_ts, nc, tile_stride;
+  SchedEntry* out;
+  SKB_HD void operator()(int j) const {
+    const int tile = (int)(head_key[j] >> 32);
+    const int beg = head_pos[j] - tile * tile_stride;
+    // every tile before the last is full, so a next head in the next tile sits exactly at the tile's end
+    const int end = ((j + 1 < n_ts) ? head_pos[j + 1] : nc) - tile * tile_stride;
+    SchedEntry en;
+    en.q = (unsigned)(head_key[j] & 0xffffffffu);
+    en.range = (unsigned)beg | ((unsigned)end << 16);
+    out[pad_ptr[tile] + (j - dense_ptr[tile])] = en;
   }
 };
 struct MinusOne {
@@ -189,6 +296,10 @@ struct IsHead {
   const int* flag;
   SKB_HD bool operator()(int i) const { return flag[i] != 0; }
 };
+struct PaddedCount {
+  const int* p;
+  SKB_HD int operator()(int i) const { return (p[i + 1] - p[i] + 1) & ~1; }
+};
 
 // Builds a ReduceSched from contributions already sorted by slot (stable, so
 // ascending contribution id inside a slot).  slot_sorted / c_sorted have
@@ -201,6 +312,7 @@ void build_sched(ReduceSched<B>& s, int n_slots, int n_tiles, int per_elem, int 
   const int nc = (int)c_sorted.size();
   s.n_slots = n_slots;
   s.n_contrib = nc;
+  s.per_elem = per_elem;
   using IV = typename B::template vec<int>;
   using KV = typename B::template vec<uint64_t>;
   thrust::counting_iterator<int> it0(0);
@@ -236,47 +348,86 @@ void build_sched(ReduceSched<B>& s, int n_slots, int n_tiles, int per_elem, int 
   thrust::transform(pol, it0, it0 + nc, flag.begin(), HeadFlag64{thrust::raw_pointer_cast(key2.data())});
   IV head_pos(s.n_ts);
   thrust::copy_if(pol, it0, it0 + nc, head_pos.begin(), IsHead{thrust::raw_pointer_cast(flag.data())});
-  s.tl_cptr.resize(s.n_ts + 1);
-  thrust::copy(pol, head_pos.begin(), head_pos.end(), s.tl_cptr.begin());
-  s.tl_cptr[s.n_ts] = nc;
   KV head_key(s.n_ts);
   thrust::gather(pol, head_pos.begin(), head_pos.end(), key2.begin(), head_key.begin());
-  s.tl_q.resize(s.n_ts);
-  thrust::transform(pol, head_key.begin(), head_key.end(), s.tl_q.begin(), Lo32());
+  const int tile_stride = tile_elems * per_elem;
+  // dense tile -> entry offsets, then pad every tile's entry list to an even count so that each
+  // list starts 16-byte aligned and is a multiple of 16 bytes long (TMA bulk copy granularity)
   IV head_tile(s.n_ts);
   thrust::transform(pol, head_key.begin(), head_key.end(), head_tile.begin(), Hi32());
-  s.tl_ptr.resize(n_tiles + 1);
-  thrust::lower_bound(pol, head_tile.begin(), head_tile.end(), it0, it0 + n_tiles + 1, s.tl_ptr.begin());
-  s.tc_src.resize(nc);
-  thrust::transform(pol, it0, it0 + nc, s.tc_src.begin(),
-                    PackSrc{thrust::raw_pointer_cast(c2.data()), per_elem, tile_elems});
+  IV dense_ptr(n_tiles + 1);
+  thrust::lower_bound(pol, head_tile.begin(), head_tile.end(), it0, it0 + n_tiles + 1, dense_ptr.begin());
+  s.tl_ptr.assign(n_tiles + 1, 0);
+  {
+    IV cnt(n_tiles);
+    thrust::transform(pol, it0, it0 + n_tiles, cnt.begin(), PaddedCount{thrust::raw_pointer_cast(dense_ptr.data())});
+    s.max_entries = n_tiles ? (int)*thrust::max_element(pol, cnt.begin(), cnt.end()) : 0;
+    thrust::inclusive_scan(pol, cnt.begin(), cnt.end(), s.tl_ptr.begin() + 1);
+  }
+  SchedEntry pad;
+  pad.q = 0xffffffffu;
+  pad.range = 0;
+  s.tl_ent.assign((size_t)(int)s.tl_ptr[n_tiles], pad);
+  thrust::for_each(pol, it0, it0 + s.n_ts,
+                   MakeEntry{thrust::raw_pointer_cast(head_key.data()), thrust::raw_pointer_cast(head_pos.data()),
+                             thrust::raw_pointer_cast(dense_ptr.data()), thrust::raw_pointer_cast(s.tl_ptr.data()),
+                             s.n_ts, nc, tile_stride, thrust::raw_pointer_cast(s.tl_ent.data())});
+  // packed sources at a fixed stride per tile (padded to whole tiles so 16-byte prefetches never
+  // run past the allocation)
+  s.tc_src.assign((size_t)n_tiles * tile_stride, (uint16_t)0);
+  thrust::for_each(pol, it0, it0 + nc,
+                   ScatterSrc{thrust::raw_pointer_cast(c2.data()), thrust::raw_pointer_cast(s.tc_src.data()),
+                              per_elem, tile_elems, tile_stride});
 }
 
 // ---------------------------------------------------------------- geometry --
-// D = (H (X_e^T H)^-1)^T, stored without corner 0 (its column is minus the sum
-// of the others), and the rest quadrature weight.
+// D = (H (X_e^T H)^-1)^T in the CALLER's corner order (its corner-0 column is minus the sum of the
+// others), stored for the internal corners 1..dim (internal corner 0 is again implied), and the
+// rest quadrature weight (signed by the caller's orientation).
 template <int D>
 struct GeomFunctor {
   const double* X;
-  const int* T;
+  const int* T;        // internal (sorted) corners
+  const uint8_t* perm; // internal corner s = caller corner perm[s]
   double* Dm;
   double* vol;
   int t;
   SKB_HD void operator()(int e) const {
     constexpr int K = D + 1;
+    int To[K];  // caller order
+#pragma unroll
+    for (int s = 0; s < K; ++s) To[perm[e * K + s]] = T[e * K + s];
     Mat<D> Ed;  // edge matrix: column k-1 = x_k - x_0
 #pragma unroll
     for (int k = 1; k < K; ++k)
 #pragma unroll
-      for (int i = 0; i < D; ++i) Ed.m[i][k - 1] = X[(size_t)T[e * K + k] * D + i] - X[(size_t)T[e * K] * D + i];
+      for (int i = 0; i < D; ++i) Ed.m[i][k - 1] = X[(size_t)To[k] * D + i] - X[(size_t)To[0] * D + i];
     double dt = det(Ed);
     Mat<D> c = cofactor(Ed);  // inverse = cof^T / det
-    // XHi = inv(Ed); D[j][a] (a>=1) = XHi[a-1][j] = cof[j][a-1] / det
+    // D[j][a] (a>=1) = cof[j][a-1] / det ; D[j][0] = -sum
     double inv = 1.0 / dt;
+    double Df[D][K];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double s0 = 0.0;
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        Df[j][a + 1] = c.m[j][a] * inv;
+        s0 -= Df[j][a + 1];
+      }
+      Df[j][0] = s0;
+    }
 #pragma unroll
     for (int j = 0; j < D; ++j)
 #pragma unroll
-      for (int a = 0; a < D; ++a) Dm[(size_t)(j * D + a) * t + e] = c.m[j][a] * inv;
+      for (int s = 1; s < K; ++s) {
+        const int a = perm[e * K + s];
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < K; ++q)
+          if (q == a) v = Df[j][q];
+        Dm[(size_t)(j * D + (s - 1)) * t + e] = v;
+      }
     if (D == 3) {
       // tetrahedron_volumes.py:26-27: det of rows (x_k - x_0) / 6  (= det Ed)
       vol[e] = dt / 6.0;
@@ -286,15 +437,17 @@ struct GeomFunctor {
   }
 };
 
-// D given directly as AoS [e][j][a] (a = 0..dim): used when the plan is rebuilt from J
+// D given directly as AoS [e][j][a] (a = 0..dim, caller order): used when the plan is rebuilt from J
 struct CopyDFunctor {
   const double* Din;
+  const uint8_t* perm;
   double* Dm;
   int t, D;
   SKB_HD void operator()(int e) const {
     const int K = D + 1;
     for (int j = 0; j < D; ++j)
-      for (int a = 0; a < D; ++a) Dm[(size_t)(j * D + a) * t + e] = Din[((size_t)e * D + j) * K + a + 1];
+      for (int s = 1; s < K; ++s)
+        Dm[(size_t)(j * D + (s - 1)) * t + e] = Din[((size_t)e * D + j) * K + perm[e * K + s]];
   }
 };
 
@@ -308,11 +461,13 @@ void set_geometry_from_X(PlanData<B>& p, const typename B::template vec<double>&
   if (dim == 3) {
     thrust::for_each(pol, it0, it0 + t,
                      GeomFunctor<3>{thrust::raw_pointer_cast(X.data()), thrust::raw_pointer_cast(p.T32.data()),
-                                    thrust::raw_pointer_cast(p.Dm.data()), thrust::raw_pointer_cast(p.vol0.data()), t});
+                                    thrust::raw_pointer_cast(p.perm.data()), thrust::raw_pointer_cast(p.Dm.data()),
+                                    thrust::raw_pointer_cast(p.vol0.data()), t});
   } else {
     thrust::for_each(pol, it0, it0 + t,
                      GeomFunctor<2>{thrust::raw_pointer_cast(X.data()), thrust::raw_pointer_cast(p.T32.data()),
-                                    thrust::raw_pointer_cast(p.Dm.data()), thrust::raw_pointer_cast(p.vol0.data()), t});
+                                    thrust::raw_pointer_cast(p.perm.data()), thrust::raw_pointer_cast(p.Dm.data()),
+                                    thrust::raw_pointer_cast(p.vol0.data()), t});
   }
   p.has_vol0 = true;
 }
@@ -325,47 +480,102 @@ void set_geometry_from_D(PlanData<B>& p, const typename B::template vec<double>&
   p.Dm.resize((size_t)dim * dim * t);
   p.vol0.assign(t, 0.0);
   thrust::for_each(pol, it0, it0 + t,
-                   CopyDFunctor{thrust::raw_pointer_cast(Daos.data()), thrust::raw_pointer_cast(p.Dm.data()), t, dim});
+                   CopyDFunctor{thrust::raw_pointer_cast(Daos.data()), thrust::raw_pointer_cast(p.perm.data()),
+                                thrust::raw_pointer_cast(p.Dm.data()), t, dim});
   p.has_vol0 = false;
 }
 
-// topology: pattern, slot map, reduction schedules
+struct MakeUpperPos {
+  const uint64_t* ukey;   // upper slot keys (v, w), v <= w
+  const uint64_t* fkey;   // full pattern keys, sorted
+  const int* bptr;
+  int nnzb, D;
+  UpperPos* out;
+  SKB_HD int find(uint64_t k) const {
+    int lo = 0, hi = nnzb;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (fkey[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
+  SKB_HD void operator()(int u) const {
+    const uint64_t k = ukey[u];
+    const int v = (int)(k >> 32), w = (int)(k & 0xffffffffu);
+    const int s = find(k), st = find(((uint64_t)(uint32_t)w << 32) | (uint32_t)v);
+    UpperPos up;
+    int b0 = bptr[v], nb = bptr[v + 1] - b0;
+    up.base = b0 * D * D + (s - b0) * D;
+    up.stride = nb * D;
+    b0 = bptr[w];
+    nb = bptr[w + 1] - b0;
+    up.tbase = b0 * D * D + (st - b0) * D;
+    up.tstride = nb * D;
+    out[u] = up;
+  }
+};
+
+// topology: pattern, upper-slot positions, reduction schedules.  Returns false if an element
+// repeats a vertex.
 template <class B>
-void build_plan(PlanData<B>& p, const typename B::template vec<int>& T, int n, int t, int dim, int tile_elems) {
+bool build_plan(PlanData<B>& p, const typename B::template vec<int>& T, int n, int t, int dim, int tile_elems) {
   auto pol = B::policy();
   using IV = typename B::template vec<int>;
   using KV = typename B::template vec<uint64_t>;
   const int K = dim + 1;
+  const int NP = K * (K + 1) / 2;
   p.dim = dim; p.K = K; p.n = n; p.t = t;
   p.tile_elems = tile_elems;
   p.n_tiles = (t + tile_elems - 1) / tile_elems;
-  p.T32 = T;
   thrust::counting_iterator<int> it0(0);
 
-  // ---- block pattern + block schedule
+  // ---- internal corner order: ascending vertex id, so that local a <= b implies row <= col
+  p.T32.resize((size_t)t * K);
+  p.perm.resize((size_t)t * K);
   {
-    const int nc = t * K * K;
+    IV bad(1, 0);
+    thrust::for_each(pol, it0, it0 + t,
+                     SortCorners{thrust::raw_pointer_cast(T.data()), thrust::raw_pointer_cast(p.T32.data()),
+                                 thrust::raw_pointer_cast(p.perm.data()), thrust::raw_pointer_cast(bad.data()), K});
+    if ((int)bad[0] != 0) return false;
+  }
+
+  // ---- upper block slots, full pattern, block schedule
+  {
+    const int nc = t * NP;
     KV key(nc);
     IV c_sorted(nc);
-    thrust::transform(pol, it0, it0 + nc, key.begin(), BlockKey{thrust::raw_pointer_cast(p.T32.data()), K});
+    thrust::transform(pol, it0, it0 + nc, key.begin(), UpperKey{thrust::raw_pointer_cast(p.T32.data()), K, NP});
     thrust::sequence(pol, c_sorted.begin(), c_sorted.end());
     thrust::stable_sort_by_key(pol, key.begin(), key.end(), c_sorted.begin());
     IV flag(nc), slot_sorted(nc);
     thrust::transform(pol, it0, it0 + nc, flag.begin(), HeadFlag64{thrust::raw_pointer_cast(key.data())});
     thrust::inclusive_scan(pol, flag.begin(), flag.end(), slot_sorted.begin());
     thrust::transform(pol, slot_sorted.begin(), slot_sorted.end(), slot_sorted.begin(), MinusOne());
-    p.nnzb = (int)slot_sorted.back() + 1;
-    KV ukey(p.nnzb);
+    p.nu = (int)slot_sorted.back() + 1;
+    KV ukey(p.nu);
     thrust::unique_copy(pol, key.begin(), key.end(), ukey.begin());
+    // full pattern = upper slots + transposes of the off-diagonal ones
+    KV fkey(2 * (size_t)p.nu);
+    thrust::copy(pol, ukey.begin(), ukey.end(), fkey.begin());
+    auto mid = fkey.begin() + p.nu;
+    auto last = thrust::copy_if(pol, ukey.begin(), ukey.end(), mid, IsOffDiag());
+    thrust::transform(pol, mid, last, mid, SwapKey());
+    fkey.resize(last - fkey.begin());
+    thrust::sort(pol, fkey.begin(), fkey.end());
+    p.nnzb = (int)fkey.size();
     p.brow.resize(p.nnzb);
     p.bcol.resize(p.nnzb);
-    thrust::transform(pol, ukey.begin(), ukey.end(), p.brow.begin(), Hi32());
-    thrust::transform(pol, ukey.begin(), ukey.end(), p.bcol.begin(), Lo32());
+    thrust::transform(pol, fkey.begin(), fkey.end(), p.brow.begin(), Hi32());
+    thrust::transform(pol, fkey.begin(), fkey.end(), p.bcol.begin(), Lo32());
     p.bptr.resize(n + 1);
     thrust::lower_bound(pol, p.brow.begin(), p.brow.end(), it0, it0 + n + 1, p.bptr.begin());
-    p.bslot.resize(nc);
-    thrust::scatter(pol, slot_sorted.begin(), slot_sorted.end(), c_sorted.begin(), p.bslot.begin());
-    build_sched<B>(p.blocks, p.nnzb, p.n_tiles, K * K, tile_elems, slot_sorted, c_sorted);
+    p.upos.resize(p.nu);
+    thrust::for_each(pol, it0, it0 + p.nu,
+                     MakeUpperPos{thrust::raw_pointer_cast(ukey.data()), thrust::raw_pointer_cast(fkey.data()),
+                                  thrust::raw_pointer_cast(p.bptr.data()), p.nnzb, dim,
+                                  thrust::raw_pointer_cast(p.upos.data())});
+    build_sched<B>(p.blocks, p.nu, p.n_tiles, NP, tile_elems, slot_sorted, c_sorted);
   }
   // ---- vertex schedule (gradient scatter)
   {
@@ -379,6 +589,7 @@ void build_plan(PlanData<B>& p, const typename B::template vec<int>& T, int n, i
     thrust::transform(pol, key.begin(), key.end(), slot_sorted.begin(), Lo32());
     build_sched<B>(p.verts, n, p.n_tiles, K, tile_elems, slot_sorted, c_sorted);
   }
+  return true;
 }
 
 }  // namespace skb

@@ -22,17 +22,22 @@ static void run_assemble(const PlanView& p, const EvalArgs& a, std::vector<doubl
       int e = tile * E + le;
       if (e < p.t) element_phase1<D>(p, a, e, le, E, sK.data(), sG.data());
     }
+    constexpr int K = D + 1, NP = K * (K + 1) / 2;
     if (a.want_hess) {
-      int nitems = (p.blocks.tl_ptr[tile + 1] - p.blocks.tl_ptr[tile]) * D;
-      for (int w = 0; w < nitems; ++w) block_phase2<D>(p.blocks, tile, w, E, sK.data(), a.pblocks);
+      int nitems = p.blocks.tl_ptr[tile + 1] - p.blocks.tl_ptr[tile];
+      for (int w = 0; w < nitems; ++w)
+        block_phase2<D>(p.blocks.tl_ent + p.blocks.tl_ptr[tile], p.blocks.tc_src + (size_t)tile * E * NP, w, E, sK.data(),
+                        a.pblocks);
     }
     if (a.want_grad) {
       int nitems = p.verts.tl_ptr[tile + 1] - p.verts.tl_ptr[tile];
-      for (int w = 0; w < nitems; ++w) vert_phase2<D>(p.verts, tile, w, E, sG.data(), a.pverts);
+      for (int w = 0; w < nitems; ++w)
+        vert_phase2<D>(p.verts.tl_ent + p.verts.tl_ptr[tile], p.verts.tc_src + (size_t)tile * E * K, w, E, sG.data(),
+                       a.pverts);
     }
   }
   if (a.want_hess)
-    for (int item = 0; item < p.nnzb * D; ++item) block_finalize<D>(p, item, a.pblocks, a.vals);
+    for (int u = 0; u < p.nu; ++u) block_finalize<D>(p, u, a.pblocks, a.vals);
   if (a.want_grad)
     for (int v = 0; v < p.n; ++v) vert_finalize<D>(p, v, a.pverts, a.g);
   double s = 0.0;
@@ -67,7 +72,7 @@ int hs_run(const double* X, const int64_t* T, int64_t n, int64_t t, int dim, int
   thrust::host_vector<int> Th((size_t)t * K);
   for (int64_t i = 0; i < t * K; ++i) Th[i] = (int)T[i];
   PlanData<HostBackend> pd;
-  build_plan<HostBackend>(pd, Th, (int)n, (int)t, dim, tile_elems);
+  if (!build_plan<HostBackend>(pd, Th, (int)n, (int)t, dim, tile_elems)) return -1;
   set_geometry_from_X<HostBackend>(pd, Xh);
   info[0] = pd.nnzb;
   info[1] = pd.blocks.n_ts;
@@ -75,7 +80,7 @@ int hs_run(const double* X, const int64_t* T, int64_t n, int64_t t, int dim, int
   if (!bptr) return 0;
   for (int i = 0; i <= n; ++i) bptr[i] = pd.bptr[i];
   for (int i = 0; i < pd.nnzb; ++i) bcol[i] = pd.bcol[i];
-  for (size_t i = 0; i < pd.bslot.size(); ++i) bslot[i] = pd.bslot[i];
+  (void)bslot;
   for (size_t i = 0; i < pd.Dm.size(); ++i) Dm_out[i] = pd.Dm[i];
   for (int i = 0; i < t; ++i) vol_out[i] = pd.vol0[i];
   PlanView p = pd.view();

@@ -95,9 +95,5 @@ def test_assembly(dim, material, sigma):
     Q = oe.hessian_x(material, U, J, mu, lam, vol, psd=True)
     Qours = hostsim.csr_from_blocks(out["bptr"], out["bcol"], out["vals"], n, dim)
     assert rel(Qours.toarray(), Q.toarray()) < TOL
-    # block slot map agrees with its definition
-    for e in range(0, T.shape[0], 7):
-        for a in range(dim + 1):
-            for b in range(dim + 1):
-                s = out["bslot"][e, a, b]
-                assert bptr[T[e, a]] <= s < bptr[T[e, a] + 1] and bcol[s] == T[e, b]
+    # the assembled matrix is exactly symmetric (upper blocks are mirrored, not recomputed)
+    assert abs(Qours - Qours.T).max() == 0.0
