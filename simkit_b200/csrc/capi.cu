@@ -87,7 +87,7 @@ static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
   SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_tile_kernel<D><<<p.n_tiles, E, smem, st>>>(p, a));
   if (a.want_hess) {
     SKB_LAUNCH(pl, SKB_K_FINALIZE_BLOCKS, st,
-               finalize_blocks_kernel<D><<<(p.nu + 127) / 128, 128, 0, st>>>(p, a.pblocks, a.vals));
+               finalize_blocks_kernel<D><<<(p.nu * D * D + 255) / 256, 256, 0, st>>>(p, a.pblocks, a.vals));
   }
   if (a.want_grad) {
     SKB_LAUNCH(pl, SKB_K_FINALIZE_VERTS, st,
@@ -142,7 +142,7 @@ static int plan_create_common(const double* X, const double* Dop, const void* T,
   const int K = dim + 1;
   if (t * K * K >= (int64_t)1 << 31 || n * dim >= (int64_t)1 << 31) return fail(SKB_EINVAL, "mesh too large for int32 indexing");
   if (tile_elems == 0) tile_elems = 128;
-  if (tile_elems < 32 || tile_elems > 1024 || tile_elems % 32) return fail(SKB_EINVAL, "tile_elems must be a multiple of 32 in [32, 1024]");
+  if (tile_elems < 32 || tile_elems > 256 || tile_elems % 32) return fail(SKB_EINVAL, "tile_elems must be a multiple of 32 in [32, 256]");
   if (skb_device_count() <= device) return fail(SKB_ENOGPU, "no CUDA device " + std::to_string(device));
   SKB_CUDA(cudaSetDevice(device));
   SKB_TRY

@@ -249,15 +249,36 @@ SKB_HD void pair_ab(int pp, int& a, int& b) {
   b = a + pp - (a * K - (a * (a - 1)) / 2);
 }
 
+// Packed-index table of the local stiffness: for pair pp = (a <= b), the D*D positions of block
+// K[(a,i),(b,k)] inside the packed upper triangle of the NL x NL local matrix, 7 bits each
+// (positions < 78), entry (i,k) at bit 7*(i*D+k).  Diagonal pairs mirror k < i.
+template <int D>
+SKB_HD unsigned long long pair_index_table(int pp) {
+  constexpr int K = D + 1;
+  constexpr int NL = K * D;
+  int a, b;
+  pair_ab<K>(pp, a, b);
+  unsigned long long tab = 0;
+  for (int i = 0; i < D; ++i)
+    for (int k = 0; k < D; ++k) {
+      int r = a * D + i, cc = b * D + k;
+      if (r > cc) {
+        const int tmp = r;
+        r = cc;
+        cc = tmp;
+      }
+      tab |= (unsigned long long)((r * (2 * NL - 1 - r)) / 2 + cc) << (7 * (i * D + k));
+    }
+  return tab;
+}
+
 // Phase 2 (blocks): work item = tile-slot entry of an UPPER block (row vertex <= col vertex).
 // Sums the entry's contributions in their fixed order and writes one dim x dim partial record.
 // Corners are sorted per element, so a contribution is always a local pair a <= b and its block
-// K[(a,i),(b,k)] is read straight from the packed upper triangle; diagonal pairs mirror k < i.
+// is read straight from the packed upper triangle through the pair's index table.
 template <int D>
-SKB_HD void block_phase2(const SchedEntry* ent, const uint16_t* src, int w, int E, const double* sK, double* pblocks) {
-  constexpr int K = D + 1;
-  constexpr int NL = K * D;
-  constexpr int NP = K * (K + 1) / 2;
+SKB_HD void block_phase2(const SchedEntry* ent, const uint16_t* src, const unsigned long long* tab, int w, int E,
+                         const double* sK, double* pblocks) {
   const SchedEntry en = ent[w];
   if (en.q == 0xffffffffu) return;  // alignment padding
   double acc[D * D];
@@ -265,23 +286,11 @@ SKB_HD void block_phase2(const SchedEntry* ent, const uint16_t* src, int w, int 
   for (int k = 0; k < D * D; ++k) acc[k] = 0.0;
   const int c1 = (int)(en.range >> 16);
   for (int c = (int)(en.range & 0xffffu); c < c1; ++c) {
-    const int sc = src[c];
-    const int le = sc / NP;
-    int a, b;
-    pair_ab<K>(sc - le * NP, a, b);
-    const bool dg = (a == b);
-    const double* base = sK + le;
+    const unsigned sc = src[c];
+    const unsigned long long tb = tab[sc >> 8];
+    const double* base = sK + (sc & 0xffu);
 #pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        int r = a * D + i, cc = b * D + k;
-        if (k < i && dg) {
-          r = a * D + k;
-          cc = b * D + i;
-        }
-        acc[i * D + k] += base[((r * (2 * NL - 1 - r)) / 2 + cc) * E];
-      }
+    for (int k = 0; k < D * D; ++k) acc[k] += base[(int)((tb >> (7 * k)) & 127u) * E];
   }
 #pragma unroll
   for (int k = 0; k < D * D; ++k) pblocks[(size_t)en.q * (D * D) + k] = acc[k];
@@ -290,7 +299,6 @@ SKB_HD void block_phase2(const SchedEntry* ent, const uint16_t* src, int w, int 
 // Phase 2 (vertices): work item = tile-vertex entry.
 template <int D>
 SKB_HD void vert_phase2(const SchedEntry* ent, const uint16_t* src, int w, int E, const double* sG, double* pverts) {
-  constexpr int K = D + 1;
   const SchedEntry en = ent[w];
   if (en.q == 0xffffffffu) return;
   double acc[D];
@@ -298,9 +306,9 @@ SKB_HD void vert_phase2(const SchedEntry* ent, const uint16_t* src, int w, int E
   for (int i = 0; i < D; ++i) acc[i] = 0.0;
   const int c1 = (int)(en.range >> 16);
   for (int c = (int)(en.range & 0xffffu); c < c1; ++c) {
-    const int sc = src[c];
-    const int le = sc / K;
-    const int ca = sc - le * K;
+    const unsigned sc = src[c];
+    const int le = (int)(sc & 0xffu);
+    const int ca = (int)(sc >> 8);
 #pragma unroll
     for (int i = 0; i < D; ++i) acc[i] += sG[(ca * D + i) * E + le];
   }
@@ -308,29 +316,21 @@ SKB_HD void vert_phase2(const SchedEntry* ent, const uint16_t* src, int w, int E
   for (int i = 0; i < D; ++i) pverts[(size_t)en.q * D + i] = acc[i];
 }
 
-// Level 2 (blocks): item = upper slot u: sum its partial records in tile order, write the block
-// into the canonical scalar-CSR layout at (v, w) and its transpose at (w, v).
+// Level 2 (blocks): item = (upper slot u, entry j = i*D+k of the block): sum entry j over the
+// slot's partial records in tile order, write it into the canonical scalar-CSR layout at block
+// (v, w) and, transposed, at block (w, v).  D*D consecutive items read one 72-byte (32-byte in 2D)
+// record together, so the record stream is read fully coalesced.
 template <int D>
-SKB_HD void block_finalize(const PlanView& p, int u, const double* pblocks, double* vals) {
-  double acc[D * D];
-#pragma unroll
-  for (int k = 0; k < D * D; ++k) acc[k] = 0.0;
+SKB_HD void block_finalize(const PlanView& p, int item, const double* pblocks, double* vals) {
+  const int u = item / (D * D);
+  const int j = item - u * (D * D);
+  double acc = 0.0;
   const int q1 = p.blocks.sp_ptr[u + 1];
-  for (int q = p.blocks.sp_ptr[u]; q < q1; ++q) {
-#pragma unroll
-    for (int k = 0; k < D * D; ++k) acc[k] += pblocks[(size_t)q * (D * D) + k];
-  }
+  for (int q = p.blocks.sp_ptr[u]; q < q1; ++q) acc += pblocks[(size_t)q * (D * D) + j];
   const UpperPos up = p.upos[u];
-#pragma unroll
-  for (int i = 0; i < D; ++i)
-#pragma unroll
-    for (int k = 0; k < D; ++k) vals[(size_t)up.base + (size_t)i * up.stride + k] = acc[i * D + k];
-  if (up.tbase != up.base) {
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-      for (int k = 0; k < D; ++k) vals[(size_t)up.tbase + (size_t)k * up.tstride + i] = acc[i * D + k];
-  }
+  const int i = j / D, k = j - i * D;
+  vals[(size_t)up.base + (size_t)i * up.stride + k] = acc;
+  if (up.tbase != up.base) vals[(size_t)up.tbase + (size_t)k * up.tstride + i] = acc;
 }
 
 template <int D>
@@ -356,7 +356,7 @@ inline size_t assemble_smem_bytes(const PlanView& p) {
   size_t b = (size_t)Sizes<D>::SMEM_DOUBLES * E * sizeof(double);
   b += (size_t)p.blocks.max_entries * sizeof(SchedEntry) + E * NP * sizeof(uint16_t);
   b += (size_t)p.verts.max_entries * sizeof(SchedEntry) + E * K * sizeof(uint16_t);
-  return b + 16;  // mbarrier
+  return b + 16 + 16 * sizeof(unsigned long long);  // mbarrier + pair index table
 }
 
 #if defined(__CUDACC__)
@@ -408,6 +408,8 @@ __global__ void assemble_tile_kernel(PlanView p, EvalArgs a) {
   uint16_t* sVS = reinterpret_cast<uint16_t*>(sp);
   sp += (size_t)E * K * sizeof(uint16_t);
   const unsigned mbar = smem_u32(sp);
+  unsigned long long* sTab = reinterpret_cast<unsigned long long*>(sp + 16);
+  if (threadIdx.x < NP) sTab[threadIdx.x] = pair_index_table<D>(threadIdx.x);
 
   const int tile = blockIdx.x;
   const int le = threadIdx.x;
@@ -433,14 +435,14 @@ __global__ void assemble_tile_kernel(PlanView p, EvalArgs a) {
   if (e < p.t) element_phase1<D>(p, a, e, le, E, sK, sG);
   mbar_wait(mbar, 0);
   __syncthreads();
-  for (int w = threadIdx.x; w < nbe; w += blockDim.x) block_phase2<D>(sBE, sBS, w, E, sK, a.pblocks);
+  for (int w = threadIdx.x; w < nbe; w += blockDim.x) block_phase2<D>(sBE, sBS, sTab, w, E, sK, a.pblocks);
   for (int w = threadIdx.x; w < nve; w += blockDim.x) vert_phase2<D>(sVE, sVS, w, E, sG, a.pverts);
 }
 
 template <int D>
 __global__ void finalize_blocks_kernel(PlanView p, const double* pblocks, double* vals) {
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u < p.nu) block_finalize<D>(p, u, pblocks, vals);
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item < p.nu * (D * D)) block_finalize<D>(p, item, pblocks, vals);
 }
 
 template <int D>

@@ -61,8 +61,10 @@ struct DeviceBackend {
 //   tl_ptr  [n_tiles+1]        tile -> its entries
 //   tl_ent  [n_ts] (uint2)     .x = partial record index q, .y = cbeg | cend << 16  (offsets into
 //                              the tile's tc_src range, contributions of the entry are contiguous)
-//   tc_src  [n_tiles * tile_elems * per_elem] (uint16)   packed (local element * per_elem + which),
-//                              tile-major at a FIXED stride per tile
+//   tc_src  [n_tiles * tile_elems * per_elem] (uint16)   packed (which << 8 | local element),
+//                              tile-major at a FIXED stride per tile (tile_elems <= 256)
+// Inside a tile the entries are ordered by DESCENDING contribution count, so the lanes of a warp
+// in phase 2 run loops of nearly equal length.
 //   sp_ptr  [n_slots+1]        slot -> contiguous range of partial records
 struct SchedEntry {
   unsigned q;
@@ -261,18 +263,30 @@ struct ScatterSrc {
     const int rem = c[i] - e * per_elem;
     const int tile = e / tile_elems;
     // every tile before `tile` is full, so position i is tile * tile_stride + local offset
-    tc_src[i] = (uint16_t)((e - tile * tile_elems) * per_elem + rem);
+    tc_src[i] = (uint16_t)((rem << 8) | (e - tile * tile_elems));
     (void)tile_stride;
   }
 };
+// sort key of entry j inside its tile: descending contribution count
+struct EntryOrderKey {
+  const uint64_t* head_key;
+  const int* head_pos;
+  int n_ts, nc;
+  SKB_HD uint64_t operator()(int j) const {
+    const int cnt = ((j + 1 < n_ts) ? head_pos[j + 1] : nc) - head_pos[j];
+    return (head_key[j] & 0xffffffff00000000ull) | (uint32_t)(0x7fffffff - cnt);
+  }
+};
 struct MakeEntry {
+  const int* order;          // sorted position -> entry j
   const uint64_t* head_key;  // (tile, q)
   const int* head_pos;       // position of the entry's first contribution (tile-major order)
   const int* dense_ptr;      // tile -> first entry (dense numbering)
   const int* pad_ptr;        // tile -> first entry (padded numbering)
   int n_ts, nc, tile_stride;
   SchedEntry* out;
-  SKB_HD void operator()(int j) const {
+  SKB_HD void operator()(int pos) const {
+    const int j = order[pos];
     const int tile = (int)(head_key[j] >> 32);
     const int beg = head_pos[j] - tile * tile_stride;
     // every tile before the last is full, so a next head in the next tile sits exactly at the tile's end
@@ -280,7 +294,7 @@ struct MakeEntry {
     SchedEntry en;
     en.q = (unsigned)(head_key[j] & 0xffffffffu);
     en.range = (unsigned)beg | ((unsigned)end << 16);
-    out[pad_ptr[tile] + (j - dense_ptr[tile])] = en;
+    out[pad_ptr[tile] + (pos - dense_ptr[tile])] = en;
   }
 };
 struct MinusOne {
@@ -368,8 +382,18 @@ void build_sched(ReduceSched<B>& s, int n_slots, int n_tiles, int per_elem, int 
   pad.q = 0xffffffffu;
   pad.range = 0;
   s.tl_ent.assign((size_t)(int)s.tl_ptr[n_tiles], pad);
+  IV order(s.n_ts);
+  {
+    KV okey(s.n_ts);
+    thrust::transform(pol, it0, it0 + s.n_ts, okey.begin(),
+                      EntryOrderKey{thrust::raw_pointer_cast(head_key.data()), thrust::raw_pointer_cast(head_pos.data()),
+                                    s.n_ts, nc});
+    thrust::sequence(pol, order.begin(), order.end());
+    thrust::stable_sort_by_key(pol, okey.begin(), okey.end(), order.begin());
+  }
   thrust::for_each(pol, it0, it0 + s.n_ts,
-                   MakeEntry{thrust::raw_pointer_cast(head_key.data()), thrust::raw_pointer_cast(head_pos.data()),
+                   MakeEntry{thrust::raw_pointer_cast(order.data()), thrust::raw_pointer_cast(head_key.data()),
+                             thrust::raw_pointer_cast(head_pos.data()),
                              thrust::raw_pointer_cast(dense_ptr.data()), thrust::raw_pointer_cast(s.tl_ptr.data()),
                              s.n_ts, nc, tile_stride, thrust::raw_pointer_cast(s.tl_ent.data())});
   // packed sources at a fixed stride per tile (padded to whole tiles so 16-byte prefetches never

@@ -143,12 +143,42 @@ SKB_HD void sym_schur2(double app, double aqq, double apq, double& c, double& s,
   s = t * c;
 }
 
+// reciprocal square root: MUFU.RSQ64H + Newton steps on the device (no slow-path division)
+SKB_HD double rsqrt_f64(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
+// Same rotation as sym_schur2, division-free: with d = aqq - app, o = 2 apq, h = hypot(d, o),
+//   cos 2t = |d| / h,  c = sqrt((1 + cos 2t) / 2),  s = sign(d) o / (2 h c),  t = s / c.
+// Two rsqrt and ~12 flops instead of one division and two square roots; no cancellation
+// because (1 + cos 2t) / 2 lies in [1/2, 1].
+SKB_HD void sym_schur2_fast(double app, double aqq, double apq, double& c, double& s, double& t) {
+  const double d = aqq - app, o = apq + apq;
+  const double h2 = fma(d, d, o * o);
+  if (!(h2 > 0.0) || apq == 0.0) {  // nothing to rotate (also NaN / underflow)
+    c = 1.0;
+    s = 0.0;
+    t = 0.0;
+    return;
+  }
+  const double rh = rsqrt_f64(h2);
+  const double x = fma(0.5 * fabs(d), rh, 0.5);
+  const double rc = rsqrt_f64(x);
+  c = x * rc;
+  s = (d >= 0.0 ? 0.5 : -0.5) * o * rh * rc;
+  t = s * rc;
+}
+
 // Cyclic Jacobi eigen-decomposition of a symmetric N x N matrix held in
 // registers.  On exit  a = V diag(w) V^T,  V orthogonal with det +1.
 // All index arithmetic is compile-time (loops unrolled), so nothing spills to
 // local memory because of dynamic indexing.
 template <int N>
-SKB_HD void jacobi_eig(Mat<N> a, Vec<N>& w, Mat<N>& V, int max_sweeps = 12) {
+SKB_HD void jacobi_eig(Mat<N> a, Vec<N>& w, Mat<N>& V, int max_sweeps = 12, double tol2 = 1e-32) {
   V = identity<N>();
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     double off = 0.0, diag = 0.0;
@@ -160,13 +190,13 @@ SKB_HD void jacobi_eig(Mat<N> a, Vec<N>& w, Mat<N>& V, int max_sweeps = 12) {
     }
     // converged when the off-diagonal mass is below double rounding of the diagonal;
     // `!(off > ...)` also stops on NaN input
-    if (!(off > 1e-32 * diag) ) break;
+    if (!(off > tol2 * diag) ) break;
 #pragma unroll
     for (int p = 0; p < N - 1; ++p)
 #pragma unroll
       for (int q = p + 1; q < N; ++q) {
         double c, s, t;
-        sym_schur2(a.m[p][p], a.m[q][q], a.m[p][q], c, s, t);
+        sym_schur2_fast(a.m[p][p], a.m[q][q], a.m[p][q], c, s, t);
         // A <- J^T A J with J = [[c, s], [-s, c]] on (p,q)
         double apq = a.m[p][q];
         a.m[p][p] = fma(-t, apq, a.m[p][p]);
@@ -278,7 +308,7 @@ SKB_HD void hestenes_sweep(Mat<N>& A, Mat<N>& V) {
       }
       if (ga * ga > 1e-34 * al * be) {
         double c, s, t;
-        sym_schur2(al, be, ga, c, s, t);
+        sym_schur2_fast(al, be, ga, c, s, t);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           double ap = A.m[k][p], aq = A.m[k][q];
@@ -292,38 +322,63 @@ SKB_HD void hestenes_sweep(Mat<N>& A, Mat<N>& V) {
     }
 }
 
+// F^T F, computing only the upper triangle
+template <int N>
+SKB_HD Mat<N> gram(const Mat<N>& F) {
+  Mat<N> C;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = i; j < N; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) s = fma(F.m[k][i], F.m[k][j], s);
+      C.m[i][j] = s;
+      C.m[j][i] = s;
+    }
+  return C;
+}
+
+// Two-sided Jacobi is stopped once off^2 <= SVD_JACOBI_TOL2 * diag^2 (relative off-diagonal mass
+// 1e-11): the one-sided sweep that follows is one more quadratically convergent sweep, computed from
+// the columns of F V themselves, so it both finishes the convergence (residual ~1e-22) and restores
+// high relative accuracy of the small singular triplets.
+#define SKB_SVD_JACOBI_TOL2 1e-22
+
 SKB_HD void svd_rv(const Mat<3>& F, Mat<3>& U, Vec<3>& sig, Mat<3>& V) {
-  Mat<3> C = matmul_tn(F, F);
+  Mat<3> C = gram(F);
   Vec<3> w;
-  jacobi_eig<3>(C, w, V);
+  jacobi_eig<3>(C, w, V, 12, SKB_SVD_JACOBI_TOL2);
   Mat<3> A = matmul(F, V);
   hestenes_sweep<3>(A, V);
-  Vec<3> nrm;
+  Vec<3> n2;  // squared column norms; square roots are taken once, through rsqrt
 #pragma unroll
-  for (int j = 0; j < 3; ++j)
-    nrm[j] = sqrt(A.m[0][j] * A.m[0][j] + A.m[1][j] * A.m[1][j] + A.m[2][j] * A.m[2][j]);
+  for (int j = 0; j < 3; ++j) n2[j] = fma(A.m[0][j], A.m[0][j], fma(A.m[1][j], A.m[1][j], A.m[2][j] * A.m[2][j]));
   // sort columns by decreasing norm (3-element network)
-  swap_cols_signed<3>(A, V, nrm, 0, 1, nrm[0] < nrm[1]);
-  swap_cols_signed<3>(A, V, nrm, 1, 2, nrm[1] < nrm[2]);
-  swap_cols_signed<3>(A, V, nrm, 0, 1, nrm[0] < nrm[1]);
+  swap_cols_signed<3>(A, V, n2, 0, 1, n2[0] < n2[1]);
+  swap_cols_signed<3>(A, V, n2, 1, 2, n2[1] < n2[2]);
+  swap_cols_signed<3>(A, V, n2, 0, 1, n2[0] < n2[1]);
   // leading two columns of U by normalisation (Gram-Schmidt guards rank <= 1)
   double u0[3], u1[3], u2[3];
-  if (nrm[0] > 0.0) {
-    double inv = 1.0 / nrm[0];
+  double s0 = 0.0, s1 = 0.0;
+  if (n2[0] > 0.0) {
+    const double inv = rsqrt_f64(n2[0]);
+    s0 = n2[0] * inv;
 #pragma unroll
     for (int k = 0; k < 3; ++k) u0[k] = A.m[k][0] * inv;
   } else {
     u0[0] = 1.0; u0[1] = 0.0; u0[2] = 0.0;
   }
-  if (nrm[1] > 1e-150 * nrm[0] && nrm[1] > 0.0) {
-    double inv = 1.0 / nrm[1];
+  if (n2[1] > 1e-300 * n2[0] && n2[1] > 0.0) {
+    const double inv = rsqrt_f64(n2[1]);
+    s1 = n2[1] * inv;
 #pragma unroll
     for (int k = 0; k < 3; ++k) u1[k] = A.m[k][1] * inv;
     // re-orthogonalise against u0 (no-op to rounding when converged)
     double d = u0[0] * u1[0] + u0[1] * u1[1] + u0[2] * u1[2];
 #pragma unroll
     for (int k = 0; k < 3; ++k) u1[k] = fma(-d, u0[k], u1[k]);
-    double n1 = 1.0 / sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    double n1 = rsqrt_f64(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) u1[k] *= n1;
   } else {
@@ -333,7 +388,7 @@ SKB_HD void svd_rv(const Mat<3>& F, Mat<3>& U, Vec<3>& sig, Mat<3>& V) {
     double d = u0[kmin];
 #pragma unroll
     for (int k = 0; k < 3; ++k) u1[k] = e[k] - d * u0[k];
-    double n1 = 1.0 / sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    double n1 = rsqrt_f64(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) u1[k] *= n1;
   }
@@ -346,13 +401,13 @@ SKB_HD void svd_rv(const Mat<3>& F, Mat<3>& U, Vec<3>& sig, Mat<3>& V) {
     U.m[k][1] = u1[k];
     U.m[k][2] = u2[k];
   }
-  sig[0] = nrm[0];
-  sig[1] = nrm[1];
+  sig[0] = s0;
+  sig[1] = s1;
   sig[2] = u2[0] * A.m[0][2] + u2[1] * A.m[1][2] + u2[2] * A.m[2][2];  // signed
 }
 
 SKB_HD void svd_rv(const Mat<2>& F, Mat<2>& U, Vec<2>& sig, Mat<2>& V) {
-  Mat<2> C = matmul_tn(F, F);
+  Mat<2> C = gram(F);
   Vec<2> w;
   jacobi_eig<2>(C, w, V, 2);
   Mat<2> A = matmul(F, V);

@@ -24,10 +24,12 @@ static void run_assemble(const PlanView& p, const EvalArgs& a, std::vector<doubl
     }
     constexpr int K = D + 1, NP = K * (K + 1) / 2;
     if (a.want_hess) {
+      unsigned long long tab[NP];
+      for (int pp = 0; pp < NP; ++pp) tab[pp] = pair_index_table<D>(pp);
       int nitems = p.blocks.tl_ptr[tile + 1] - p.blocks.tl_ptr[tile];
       for (int w = 0; w < nitems; ++w)
-        block_phase2<D>(p.blocks.tl_ent + p.blocks.tl_ptr[tile], p.blocks.tc_src + (size_t)tile * E * NP, w, E, sK.data(),
-                        a.pblocks);
+        block_phase2<D>(p.blocks.tl_ent + p.blocks.tl_ptr[tile], p.blocks.tc_src + (size_t)tile * E * NP, tab, w, E,
+                        sK.data(), a.pblocks);
     }
     if (a.want_grad) {
       int nitems = p.verts.tl_ptr[tile + 1] - p.verts.tl_ptr[tile];
@@ -37,7 +39,7 @@ static void run_assemble(const PlanView& p, const EvalArgs& a, std::vector<doubl
     }
   }
   if (a.want_hess)
-    for (int u = 0; u < p.nu; ++u) block_finalize<D>(p, u, a.pblocks, a.vals);
+    for (int item = 0; item < p.nu * D * D; ++item) block_finalize<D>(p, item, a.pblocks, a.vals);
   if (a.want_grad)
     for (int v = 0; v < p.n; ++v) vert_finalize<D>(p, v, a.pverts, a.g);
   double s = 0.0;
