@@ -208,7 +208,9 @@ def run_ours(args, rank, world, local_rank):
         from simkit_b200 import sharding
         shard = sharding.make_shard(args.workload, rank, world, device=local_rank)
         plan, U = shard.plan, shard.U_local
-        t_total, n_total, nnz_total = shard.t_total, shard.n_total, shard.nnz_total
+        tt = torch.tensor([shard.nnz_owned], dtype=torch.int64, device=dev)
+        dist.all_reduce(tt)
+        t_total, n_total, nnz_total = shard.t_total, shard.n_total, int(tt.item())
     else:
         shard = None
         X, T = syn.make_mesh(args.workload)
@@ -227,10 +229,11 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
 
     def step_dev():
-        check(lib.skb_gradient_hessian_dev(plan._h, mat, PSD_AFTER_VOL, x_d.data_ptr(), None, g_d.data_ptr(),
-                                           vals_d.data_ptr(), stream.cuda_stream))
         if shard is not None:
-            shard.exchange(g_d, vals_d)
+            shard.gradient_hessian_dev(MATERIAL, PSD_AFTER_VOL, x_d, g_d, vals_d)
+        else:
+            check(lib.skb_gradient_hessian_dev(plan._h, mat, PSD_AFTER_VOL, x_d.data_ptr(), None, g_d.data_ptr(),
+                                               vals_d.data_ptr(), stream.cuda_stream))
 
     def barrier():
         torch.cuda.synchronize()
@@ -310,34 +313,48 @@ def run_ours(args, rank, world, local_rank):
     def pinned(n):
         return torch.empty(n, dtype=f64, pin_memory=True).numpy()
 
-    x_h, g_h, vals_h, vol_h = pinned(plan.ndof), pinned(plan.ndof), pinned(plan.nnz), pinned(plan.t)
+    e2e_steps = max(2, min(args.steps, 5))
+    x_h, vol_h = pinned(plan.ndof), pinned(plan.t)
     x_h[:] = U.reshape(-1)
     vol_h[:] = vol.reshape(-1)
-    e2e_steps = max(2, min(args.steps, 5))
-
-    def step_e2e():
-        plan.gradient_hessian(MATERIAL, x_h, mu, lam, vol_h, PSD_AFTER_VOL, g_out=g_h.reshape(-1, 1), vals_out=vals_h)
-        if shard is not None:
-            raise NotImplementedError
-
-    e2e = None
     if shard is None:
-        for _ in range(2):
+        g_h, vals_h = pinned(plan.ndof), pinned(plan.nnz)
+        api = "MeshPlan.gradient_hessian -> skb_gradient_hessian (host pointers, pinned buffers)"
+
+        def step_e2e():
+            plan.gradient_hessian(MATERIAL, x_h, mu, lam, vol_h, PSD_AFTER_VOL, g_out=g_h.reshape(-1, 1), vals_out=vals_h)
+    else:
+        v0, v1 = shard.owned_value_range()
+        o0, o1 = shard.layout.own_lo * dim, shard.layout.own_hi * dim
+        g_h, vals_h = pinned(o1 - o0), pinned(v1 - v0)
+        api = "Shard.gradient_hessian per rank: H2D state, fused assembly, NCCL interface exchange, D2H owned rows"
+
+        def step_e2e():
+            shard.gradient_hessian(MATERIAL, x_h, mu, lam, vol_h, PSD_AFTER_VOL, g_out=g_h, vals_out=vals_h)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    with sampler:
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
             step_e2e()
         barrier()
-        with sampler:
-            t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                step_e2e()
-            barrier()
-            dt = time.perf_counter() - t0
-        dt = max_over_ranks(dt)
-        e2e = {"value": t_total / (dt / e2e_steps), "unit": "tets/s", "ms_per_step": dt / e2e_steps * 1e3,
-               "steps": e2e_steps,
-               "h2d_bytes_per_step": int(8 * (plan.ndof + plan.t + 2)), "d2h_bytes_per_step": int(8 * (plan.ndof + plan.nnz)),
-               "api": "MeshPlan.gradient_hessian -> skb_gradient_hessian (host pointers, pinned buffers)"}
+        dt = time.perf_counter() - t0
+    dt = max_over_ranks(dt)
+    h2d = 8 * (plan.ndof + plan.t + 2)
+    d2h = 8 * (g_h.size + vals_h.size)
+    if world > 1:
+        tt = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
+        dist.all_reduce(tt)
+        h2d, d2h = int(tt[0].item()), int(tt[1].item())
+    e2e = {"value": t_total / (dt / e2e_steps), "unit": "tets/s", "ms_per_step": dt / e2e_steps * 1e3,
+           "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "api": api}
+    if shard is None:
         # the e2e and device-resident paths must agree bit for bit (same kernels, same reduction order)
         assert np.array_equal(vals_h, vals_d.cpu().numpy()) and np.array_equal(g_h, g_d.cpu().numpy())
+    else:
+        assert np.array_equal(vals_h, vals_d[v0:v1].cpu().numpy()) and np.array_equal(g_h, g_d[o0:o1].cpu().numpy())
 
     # ---- Newton step (assembly + PCG + line search), device-resident -------------------------------
     newton = None

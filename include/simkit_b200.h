@@ -69,6 +69,13 @@ int skb_plan_create(const double* X, const void* T, int index_bytes, int64_t n, 
  * vol must be passed to every evaluation. */
 int skb_plan_create_from_operator(const void* T, const double* D, int index_bytes, int64_t n,
                                   int64_t t, int dim, int device, int tile_elems, skb_plan** out);
+/* Plan of ONE RANK of an element-sharded mesh (DESIGN.md "Multi-GPU"; no reference counterpart -- the
+ * reference is single-process).  X, T use the rank's local vertex numbering.  The first t_active
+ * elements are this rank's own; the remaining t_total - t_active "pattern-only" elements are the
+ * neighbours' elements that touch vertices this rank owns: they are never evaluated, they only reserve
+ * CSR slots so that the neighbours' interface block-rows can be added in place. */
+int skb_plan_create_sharded(const double* X, const void* T, int index_bytes, int64_t n, int64_t t_active,
+                            int64_t t_total, int dim, int device, int tile_elems, skb_plan** out);
 void skb_plan_destroy(skb_plan* plan);
 
 /* sizes: n, t, dim, nnzb (block non-zeros), nnz (= nnzb*dim*dim), n_tiles, n_block_partials, n_vertex_partials */
@@ -133,6 +140,11 @@ int skb_last_launch_count(const skb_plan* plan);
 #define SKB_K_COUNT 8
 int skb_kernel_timing(skb_plan* plan, int enable);
 int skb_kernel_times(skb_plan* plan, double* ms, int64_t* launches);
+/* interface exchange helpers on device data: dst[i] = src[idx[i]] and dst[idx[i]] += src[i]
+ * (idx distinct within a call => race-free, order-independent).  Used to pack / apply the
+ * interface-vertex gradient rows and Hessian block-rows that travel over NCCL. */
+int skb_gather_dev(const double* src, const int32_t* idx, int64_t n, double* dst, void* stream);
+int skb_scatter_add_dev(double* dst, const int32_t* idx, int64_t n, const double* src, void* stream);
 /* measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the compute roofline denominator */
 int skb_fp64_peak(int device, double* tflops);
 

@@ -53,6 +53,7 @@ SIGNATURES = {
     "skb_version": (ctypes.c_char_p, []),
     "skb_plan_create": (_int, [_vp, _vp, _int, _i64, _i64, _int, _int, _int, ctypes.POINTER(_vp)]),
     "skb_plan_create_from_operator": (_int, [_vp, _vp, _int, _i64, _i64, _int, _int, _int, ctypes.POINTER(_vp)]),
+    "skb_plan_create_sharded": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _int, _int, _int, ctypes.POINTER(_vp)]),
     "skb_plan_destroy": (None, [_vp]),
     "skb_plan_info": (_int, [_vp, _vp]),
     "skb_plan_csr_pattern": (_int, [_vp, _vp, _vp]),
@@ -72,6 +73,8 @@ SIGNATURES = {
     "skb_last_launch_count": (_int, [_vp]),
     "skb_kernel_timing": (_int, [_vp, _int]),
     "skb_kernel_times": (_int, [_vp, _vp, _vp]),
+    "skb_gather_dev": (_int, [_vp, _vp, _i64, _vp, _vp]),
+    "skb_scatter_add_dev": (_int, [_vp, _vp, _i64, _vp, _vp]),
     "skb_fp64_peak": (_int, [_int, ctypes.POINTER(_dbl)]),
     "skb_element_energy": (_int, [_int, _int, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),
     "skb_element_gradient": (_int, [_int, _int, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),

@@ -114,6 +114,17 @@ int launch_energy(skb_plan* pl, const EvalArgs& a, double* out_dev, cudaStream_t
   return SKB_OK;
 }
 
+// dst[i] = src[idx[i]]  /  dst[idx[i]] += src[i]  (idx entries are distinct within one call, so the
+// scatter is race-free and the result does not depend on thread order)
+__global__ void gather_kernel(const double* src, const int32_t* idx, int64_t n, double* dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void scatter_add_kernel(double* dst, const int32_t* idx, int64_t n, const double* src) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] += src[i];
+}
+
 }  // namespace skb
 
 using namespace skb;
@@ -134,21 +145,22 @@ int skb_device_count(void) {
 }
 
 static int plan_create_common(const double* X, const double* Dop, const void* T, int index_bytes, int64_t n,
-                              int64_t t, int dim, int device, int tile_elems, skb_plan** out) {
+                              int64_t t, int dim, int device, int tile_elems, skb_plan** out, int64_t t_total = -1) {
+  if (t_total < t) t_total = t;
   if ((!X && !Dop) || !T || !out) return fail(SKB_EINVAL, "null argument");
   if (dim != 2 && dim != 3) return fail(SKB_EINVAL, "Only dim == 2 or 3 are supported");
   if (index_bytes != 4 && index_bytes != 8) return fail(SKB_EINVAL, "index_bytes must be 4 or 8");
   if (n <= 0 || t <= 0) return fail(SKB_EINVAL, "empty mesh");
   const int K = dim + 1;
-  if (t * K * K >= (int64_t)1 << 31 || n * dim >= (int64_t)1 << 31) return fail(SKB_EINVAL, "mesh too large for int32 indexing");
+  if (t_total * K * K >= (int64_t)1 << 31 || n * dim >= (int64_t)1 << 31) return fail(SKB_EINVAL, "mesh too large for int32 indexing");
   if (tile_elems == 0) tile_elems = 128;
   if (tile_elems < 32 || tile_elems > 256 || tile_elems % 32) return fail(SKB_EINVAL, "tile_elems must be a multiple of 32 in [32, 256]");
   if (skb_device_count() <= device) return fail(SKB_ENOGPU, "no CUDA device " + std::to_string(device));
   SKB_CUDA(cudaSetDevice(device));
   SKB_TRY
   // validate + narrow indices on the host (one pass; the plan build itself runs on the device)
-  thrust::host_vector<int> Th((size_t)t * K);
-  for (int64_t i = 0; i < t * K; ++i) {
+  thrust::host_vector<int> Th((size_t)t_total * K);
+  for (int64_t i = 0; i < t_total * K; ++i) {
     int64_t v = index_bytes == 8 ? ((const int64_t*)T)[i] : (int64_t)((const int32_t*)T)[i];
     if (v < 0 || v >= n) return fail(SKB_EINVAL, "element index out of range");
     Th[i] = (int)v;
@@ -157,7 +169,7 @@ static int plan_create_common(const double* X, const double* Dop, const void* T,
   pl->device = device;
   SKB_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
   dvec<int> Td = Th;
-  if (!build_plan<DeviceBackend>(pl->d, Td, (int)n, (int)t, dim, tile_elems))
+  if (!build_plan<DeviceBackend>(pl->d, Td, (int)n, (int)t, dim, tile_elems, (int)t_total))
     return fail(SKB_EINVAL, "degenerate element: a vertex is repeated within one element");
   if (X) {
     dvec<double> Xd(X, X + n * dim);
@@ -177,6 +189,13 @@ int skb_plan_create(const double* X, const void* T, int index_bytes, int64_t n, 
                     int device, int tile_elems, skb_plan** out) {
   if (!X) return fail(SKB_EINVAL, "null X");
   return plan_create_common(X, nullptr, T, index_bytes, n, t, dim, device, tile_elems, out);
+}
+
+int skb_plan_create_sharded(const double* X, const void* T, int index_bytes, int64_t n, int64_t t_active,
+                            int64_t t_total, int dim, int device, int tile_elems, skb_plan** out) {
+  if (!X) return fail(SKB_EINVAL, "null X");
+  if (t_total < t_active) return fail(SKB_EINVAL, "t_total must be >= t_active");
+  return plan_create_common(X, nullptr, T, index_bytes, n, t_active, dim, device, tile_elems, out, t_total);
 }
 
 int skb_plan_create_from_operator(const void* T, const double* D, int index_bytes, int64_t n, int64_t t,
@@ -451,6 +470,24 @@ int skb_gradient_hessian_dev(skb_plan* pl, int material, int psd_mode, const dou
   if (rc) return rc;
   return launch_assemble(pl, a, (cudaStream_t)stream);
   SKB_CATCH
+}
+
+
+// ---- interface exchange helpers (device pointers) --------------------------
+int skb_gather_dev(const double* src, const int32_t* idx, int64_t n, double* dst, void* stream) {
+  if (n == 0) return SKB_OK;
+  if (!src || !idx || !dst || n < 0) return fail(SKB_EINVAL, "bad argument");
+  gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, dst);
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+}
+
+int skb_scatter_add_dev(double* dst, const int32_t* idx, int64_t n, const double* src, void* stream) {
+  if (n == 0) return SKB_OK;
+  if (!src || !idx || !dst || n < 0) return fail(SKB_EINVAL, "bad argument");
+  scatter_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst, idx, n, src);
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
 }
 
 }  // extern "C"

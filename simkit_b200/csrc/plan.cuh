@@ -539,10 +539,21 @@ struct MakeUpperPos {
   }
 };
 
+struct LessThan {
+  int bound;
+  SKB_HD bool operator()(int c) const { return c < bound; }
+};
+
 // topology: pattern, upper-slot positions, reduction schedules.  Returns false if an element
 // repeats a vertex.
+// T holds t_total >= t elements: the first t are ACTIVE (evaluated, reduced); the remaining
+// "pattern-only" elements (another rank's elements that touch vertices this rank owns, see
+// simkit_b200/sharding.py) only reserve their slots in the CSR pattern so that the neighbour's
+// interface contributions have somewhere to land.
 template <class B>
-bool build_plan(PlanData<B>& p, const typename B::template vec<int>& T, int n, int t, int dim, int tile_elems) {
+bool build_plan(PlanData<B>& p, const typename B::template vec<int>& T, int n, int t, int dim, int tile_elems,
+                int t_total = -1) {
+  if (t_total < t) t_total = t;
   auto pol = B::policy();
   using IV = typename B::template vec<int>;
   using KV = typename B::template vec<uint64_t>;
@@ -554,11 +565,11 @@ bool build_plan(PlanData<B>& p, const typename B::template vec<int>& T, int n, i
   thrust::counting_iterator<int> it0(0);
 
   // ---- internal corner order: ascending vertex id, so that local a <= b implies row <= col
-  p.T32.resize((size_t)t * K);
-  p.perm.resize((size_t)t * K);
+  p.T32.resize((size_t)t_total * K);
+  p.perm.resize((size_t)t_total * K);
   {
     IV bad(1, 0);
-    thrust::for_each(pol, it0, it0 + t,
+    thrust::for_each(pol, it0, it0 + t_total,
                      SortCorners{thrust::raw_pointer_cast(T.data()), thrust::raw_pointer_cast(p.T32.data()),
                                  thrust::raw_pointer_cast(p.perm.data()), thrust::raw_pointer_cast(bad.data()), K});
     if ((int)bad[0] != 0) return false;
@@ -566,7 +577,7 @@ bool build_plan(PlanData<B>& p, const typename B::template vec<int>& T, int n, i
 
   // ---- upper block slots, full pattern, block schedule
   {
-    const int nc = t * NP;
+    const int nc = t_total * NP;
     KV key(nc);
     IV c_sorted(nc);
     thrust::transform(pol, it0, it0 + nc, key.begin(), UpperKey{thrust::raw_pointer_cast(p.T32.data()), K, NP});
@@ -599,7 +610,16 @@ bool build_plan(PlanData<B>& p, const typename B::template vec<int>& T, int n, i
                      MakeUpperPos{thrust::raw_pointer_cast(ukey.data()), thrust::raw_pointer_cast(fkey.data()),
                                   thrust::raw_pointer_cast(p.bptr.data()), p.nnzb, dim,
                                   thrust::raw_pointer_cast(p.upos.data())});
-    build_sched<B>(p.blocks, p.nu, p.n_tiles, NP, tile_elems, slot_sorted, c_sorted);
+    if (t_total > t) {
+      // the schedule covers active elements only (stable filter keeps ascending c inside a slot)
+      const int nact = t * NP;
+      IV s2(nact), c2(nact);
+      thrust::copy_if(pol, slot_sorted.begin(), slot_sorted.end(), c_sorted.begin(), s2.begin(), LessThan{nact});
+      thrust::copy_if(pol, c_sorted.begin(), c_sorted.end(), c2.begin(), LessThan{nact});
+      build_sched<B>(p.blocks, p.nu, p.n_tiles, NP, tile_elems, s2, c2);
+    } else {
+      build_sched<B>(p.blocks, p.nu, p.n_tiles, NP, tile_elems, slot_sorted, c_sorted);
+    }
   }
   // ---- vertex schedule (gradient scatter)
   {

@@ -17,7 +17,7 @@ from ._lib import MATERIAL_IDS, check, f64, material_arg, ptr
 
 
 class MeshPlan:
-    def __init__(self, X=None, T=None, dim=None, n=None, D=None, device=0, tile_elems=0):
+    def __init__(self, X=None, T=None, dim=None, n=None, D=None, device=0, tile_elems=0, t_active=None):
         lib = _lib.load()
         T = np.ascontiguousarray(T)
         if T.dtype not in (np.int64, np.int32):
@@ -29,8 +29,14 @@ class MeshPlan:
             self.n, self.dim = int(X.shape[0]), int(X.shape[1])
             if T.shape[1] != self.dim + 1:
                 raise ValueError("Only dim == 2 or 3 simplices (dim+1 corners) are supported")
-            check(lib.skb_plan_create(ptr(X), ptr(T), T.dtype.itemsize, self.n, self.t, self.dim, device,
-                                      tile_elems, ctypes.byref(handle)))
+            if t_active is not None and t_active != self.t:
+                # one rank of a sharded mesh: trailing elements only reserve pattern slots
+                t_total, self.t = self.t, int(t_active)
+                check(lib.skb_plan_create_sharded(ptr(X), ptr(T), T.dtype.itemsize, self.n, self.t, t_total, self.dim,
+                                                  device, tile_elems, ctypes.byref(handle)))
+            else:
+                check(lib.skb_plan_create(ptr(X), ptr(T), T.dtype.itemsize, self.n, self.t, self.dim, device,
+                                          tile_elems, ctypes.byref(handle)))
         else:
             D = f64(D)
             self.n, self.dim = int(n), int(dim)

@@ -1,0 +1,306 @@
+"""Element-sharded meshes across the GPUs of one node (no reference counterpart --
+the reference is a single CPU process).
+
+One process per GPU.  Rank ``p`` owns a contiguous block of elements ``[e_p, e_{p+1})`` and a contiguous
+range of vertex rows ``[v_p, v_{p+1})`` with ``v_p`` = smallest vertex id its elements reference, so every
+vertex an element touches is owned by its own rank or a HIGHER one.  For rank ``q``:
+
+* own elements                 evaluated here;
+* ghost vertices               referenced by own elements, owned by a higher rank: the partial gradient rows
+                               and Hessian block-rows computed here travel to the owner (one NCCL send per
+                               neighbour per assembly) and are added there, in rank order -> deterministic;
+* pattern-only elements        lower ranks' elements that touch vertices owned here.  They are never
+                               evaluated: they only reserve CSR slots (``skb_plan_create_sharded``), so the
+                               rows this rank owns have the full global pattern (columns reaching into the
+                               lower neighbour = "halo" vertices);
+* local vertex numbering       sorted global ids of (halo | owned | ghost) -- monotone, so sorted local
+                               patterns are sorted global patterns.
+
+Both sides derive the exchange lists from the same element sets (the sender's own elements touching the
+receiver's vertices ARE the receiver's pattern-only elements), sorted by global id, so no index metadata has
+to be communicated.
+
+Everything in :class:`ShardLayout` is host-side numpy and is unit-tested on CPU (``tests/test_sharding.py``,
+including a world_size-2 gloo run); :class:`Shard` adds the device plan and the NCCL exchange.
+"""
+
+import numpy as np
+
+
+def element_cuts(t, world, align=1):
+    """Contiguous element blocks; cuts rounded to multiples of ``align`` (grid slabs: elements per plane of cells)."""
+    cuts = [int(round(p * (t / align) / world)) * align for p in range(world + 1)]
+    cuts[0], cuts[-1] = 0, t
+    return np.asarray(cuts, dtype=np.int64)
+
+
+def vertex_cuts(T, ecuts, n):
+    """v_p = smallest vertex referenced by block p (v_0 = 0, v_world = n); must be non-decreasing."""
+    world = len(ecuts) - 1
+    v = np.zeros(world + 1, dtype=np.int64)
+    v[world] = n
+    for p in range(1, world):
+        blk = T[ecuts[p]:ecuts[p + 1]]
+        v[p] = blk.min() if blk.size else v[p - 1]
+    for p in range(world - 1, 0, -1):           # empty blocks / non-monotone meshes: keep ranges ordered
+        v[p] = min(v[p], v[p + 1])
+    if np.any(np.diff(v) < 0):
+        raise ValueError("elements are not ordered by vertex id; reorder the mesh before sharding")
+    return v
+
+
+class ShardLayout:
+    """Host-side description of one rank of a sharded mesh (numpy only)."""
+
+    def __init__(self, rank, world, dim, T_own, T_pattern, pattern_rank, vcuts):
+        """``T_own``: (t_own, K) global ids of this rank's elements; ``T_pattern``: (t_pat, K) global ids of
+        lower ranks' elements touching vertices owned here, ``pattern_rank`` their owning ranks; ``vcuts`` the
+        global vertex ownership cuts."""
+        self.rank, self.world, self.dim = rank, world, dim
+        K = dim + 1
+        T_own = np.asarray(T_own, dtype=np.int64).reshape(-1, K)
+        T_pattern = np.asarray(T_pattern, dtype=np.int64).reshape(-1, K)
+        self.vcuts = np.asarray(vcuts, dtype=np.int64)
+        self.v_lo, self.v_hi = int(self.vcuts[rank]), int(self.vcuts[rank + 1])
+        self.t_own, self.t_pattern = T_own.shape[0], T_pattern.shape[0]
+        if T_own.size and T_own.min() < self.v_lo:
+            raise ValueError("an element references a vertex owned by a lower rank")
+        owned = np.arange(self.v_lo, self.v_hi, dtype=np.int64)
+        self.l2g = np.unique(np.concatenate([owned, T_own.ravel(), T_pattern.ravel()]))
+        self.n_local = self.l2g.size
+        self.own_lo = int(np.searchsorted(self.l2g, self.v_lo))      # local ids [own_lo, own_hi) are owned
+        self.own_hi = int(np.searchsorted(self.l2g, self.v_hi))
+        self.T_local = np.searchsorted(self.l2g, np.concatenate([T_own, T_pattern], axis=0)).astype(np.int64)
+        self.T_own_global, self.T_pattern_global = T_own, T_pattern
+        self.pattern_rank = np.asarray(pattern_rank, dtype=np.int64).reshape(-1)
+
+        # ---- sends: ghost rows grouped by owner (higher ranks), derived from own elements
+        self.send = {}
+        ghost = T_own[T_own >= self.v_hi] if T_own.size else np.zeros(0, np.int64)
+        for q in np.unique(np.searchsorted(self.vcuts, ghost, side="right") - 1):
+            q = int(q)
+            mask = np.any((T_own >= self.vcuts[q]) & (T_own < self.vcuts[q + 1]), axis=1)
+            self.send[q] = _interface_rows(T_own[mask], int(self.vcuts[q]), int(self.vcuts[q + 1]))
+        # ---- receives: from each lower rank p, the same lists derived from its pattern-only elements
+        self.recv = {}
+        for p in np.unique(self.pattern_rank):
+            p = int(p)
+            self.recv[p] = _interface_rows(T_pattern[self.pattern_rank == p], self.v_lo, self.v_hi)
+
+    # ------------------------------------------------------------------ index maps
+    def to_local(self, g):
+        loc = np.searchsorted(self.l2g, g)
+        assert np.array_equal(self.l2g[loc], g)
+        return loc
+
+    def exchange_maps(self, bptr, bcol):
+        """Scalar index lists into this rank's gradient (n_local*dim) and CSR values for every neighbour.
+
+        Returns ``(send, recv)``: dicts ``rank -> (g_idx, h_idx)`` int32 arrays.  ``send[q]`` gathers the partial
+        gradient entries / Hessian values of the ghost rows owned by ``q``; ``recv[p]`` are the positions in the
+        OWNED rows where the values arriving from ``p`` are added.  Orders match by construction."""
+        d = self.dim
+        out_s, out_r = {}, {}
+        for table, out in ((self.send, out_s), (self.recv, out_r)):
+            for r, (rows, rptr, cols) in table.items():
+                lr = self.to_local(rows)
+                lc = self.to_local(cols)
+                g_idx = (lr[:, None] * d + np.arange(d)[None, :]).ravel()
+                h_idx = _row_value_positions(lr, rptr, lc, bptr, bcol, d)
+                out[r] = (g_idx.astype(np.int32), h_idx.astype(np.int32))
+        return out_s, out_r
+
+
+def _interface_rows(Tsub, v_lo, v_hi):
+    """For the elements ``Tsub`` (global ids): rows = sorted vertices in [v_lo, v_hi) they touch, and for each
+    row its sorted column vertices (all vertices sharing an element with it).  Returns (rows, rptr, cols)."""
+    K = Tsub.shape[1]
+    a = np.repeat(Tsub, K, axis=1).ravel()                     # row vertex of every (a, b) pair
+    b = np.tile(Tsub, (1, K)).ravel()
+    keep = (a >= v_lo) & (a < v_hi)
+    pairs = np.unique(np.stack([a[keep], b[keep]], axis=1), axis=0)
+    if pairs.size == 0:
+        return np.zeros(0, np.int64), np.zeros(1, np.int64), np.zeros(0, np.int64)
+    rows, first = np.unique(pairs[:, 0], return_index=True)
+    rptr = np.concatenate([first, [pairs.shape[0]]]).astype(np.int64)
+    return rows, rptr, pairs[:, 1].copy()
+
+
+def _row_value_positions(lrows, rptr, lcols, bptr, bcol, d):
+    """Positions, in the canonical scalar-CSR value array, of the blocks (row, col) listed per row, in the order
+    row -> block-row i -> listed column -> k  (the order both sides of an exchange use)."""
+    out = []
+    for j, r in enumerate(lrows):
+        b0, b1 = int(bptr[r]), int(bptr[r + 1])
+        nb = b1 - b0
+        cols = lcols[rptr[j]:rptr[j + 1]]
+        s = np.searchsorted(bcol[b0:b1], cols)
+        if np.any(s >= nb) or not np.array_equal(bcol[b0:b1][s], cols):
+            raise ValueError("interface block missing from the local pattern")
+        base = b0 * d * d + s * d                               # (ncols,)
+        pos = base[None, :, None] + (np.arange(d) * nb * d)[:, None, None] + np.arange(d)[None, None, :]
+        out.append(pos.reshape(-1))
+    return np.concatenate(out) if out else np.zeros(0, np.int64)
+
+
+# ---------------------------------------------------------------------------------- builders
+def layout_from_global(T, n, dim, rank, world, align=1):
+    """Shard layout of ``rank`` from the full element list (tests and small meshes)."""
+    T = np.asarray(T, dtype=np.int64)
+    ecuts = element_cuts(T.shape[0], world, align)
+    vcuts = vertex_cuts(T, ecuts, n)
+    own = T[ecuts[rank]:ecuts[rank + 1]]
+    lower = T[:ecuts[rank]]
+    touch = np.any((lower >= vcuts[rank]) & (lower < vcuts[rank + 1]), axis=1)
+    pat = lower[touch]
+    pat_rank = np.searchsorted(ecuts, np.nonzero(touch)[0], side="right") - 1
+    return ShardLayout(rank, world, dim, own, pat, pat_rank, vcuts), ecuts
+
+
+def layout_grid_slab(cells, rank, world):
+    """Same layout for the synthetic Kuhn / 2-triangle grids WITHOUT materialising the global mesh: rank ``p``
+    gets the cell planes ``[i_p, i_{p+1})`` along the slowest axis (elements are cell-major, so this is a
+    contiguous element block) plus, as pattern-only elements, the lower neighbour's last plane of cells."""
+    from . import synthetic as syn
+    cells = tuple(cells)
+    dim = len(cells)
+    mx = cells[0]
+    per_cell = 6 if dim == 3 else 2
+    plane_cells = int(np.prod(cells[1:]))
+    plane_verts = int(np.prod([c + 1 for c in cells[1:]]))
+    icuts = [int(round(p * mx / world)) for p in range(world + 1)]
+    i0, i1 = icuts[rank], icuts[rank + 1]
+    n = (mx + 1) * plane_verts
+    vcuts = np.asarray([icuts[p] * plane_verts for p in range(world)] + [n], dtype=np.int64)
+    T_own = syn.grid_elements(cells, i0, i1)
+    if rank > 0 and i0 > 0:
+        T_pat = syn.grid_elements(cells, i0 - 1, i0)
+        T_pat = T_pat[np.any(T_pat >= vcuts[rank], axis=1)]
+        pat_rank = np.full(T_pat.shape[0], np.searchsorted(icuts, i0 - 1, side="right") - 1, dtype=np.int64)
+    else:
+        T_pat = np.zeros((0, dim + 1), dtype=np.int64)
+        pat_rank = np.zeros(0, dtype=np.int64)
+    lay = ShardLayout(rank, world, dim, T_own, T_pat, pat_rank, vcuts)
+    lay.t_total = mx * plane_cells * per_cell
+    lay.n_total = n
+    return lay
+
+
+class Shard:
+    """One rank's device plan + NCCL interface exchange (needs a GPU and an initialised process group)."""
+
+    def __init__(self, layout, X_local, device=0, tile_elems=0):
+        import torch
+        from .plan import MeshPlan
+        self.layout = layout
+        self.plan = MeshPlan(X=X_local, T=layout.T_local, device=device, tile_elems=tile_elems,
+                             t_active=layout.t_own)
+        bptr, bcol = self.plan.block_pattern()
+        send, recv = layout.exchange_maps(bptr, bcol)
+        dev = torch.device("cuda", device)
+        self.device = dev
+        mk = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+        self.send = {r: (mk(g), mk(h)) for r, (g, h) in send.items()}
+        self.recv = {r: (mk(g), mk(h)) for r, (g, h) in recv.items()}
+        f64 = torch.float64
+        self.sbuf = {r: torch.empty(g.numel() + h.numel(), dtype=f64, device=dev) for r, (g, h) in self.send.items()}
+        self.rbuf = {r: torch.empty(g.numel() + h.numel(), dtype=f64, device=dev) for r, (g, h) in self.recv.items()}
+        self.exchange_launches = 2 * (len(self.send) + len(self.recv))
+        self.exchange_bytes = 8 * sum(b.numel() for b in self.sbuf.values())
+        d = layout.dim
+        self.nnz_owned = int(bptr[layout.own_hi] - bptr[layout.own_lo]) * d * d
+
+    def exchange(self, g_d, vals_d):
+        """Adds the lower neighbours' interface contributions into the owned rows of ``g_d`` / ``vals_d`` (device
+        tensors in this rank's local numbering).  Pack -> NCCL send/recv -> scatter-add, all on the current stream."""
+        import torch
+        import torch.distributed as dist
+        from ._lib import check, load
+        lib = load()
+        st = torch.cuda.current_stream().cuda_stream
+        ops = []
+        for q, (gi, hi) in sorted(self.send.items()):
+            buf = self.sbuf[q]
+            check(lib.skb_gather_dev(g_d.data_ptr(), gi.data_ptr(), gi.numel(), buf.data_ptr(), st))
+            check(lib.skb_gather_dev(vals_d.data_ptr(), hi.data_ptr(), hi.numel(), buf.data_ptr() + 8 * gi.numel(), st))
+            ops.append(dist.P2POp(dist.isend, buf, q))
+        for p in sorted(self.recv):
+            ops.append(dist.P2POp(dist.irecv, self.rbuf[p], p))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for p, (gi, hi) in sorted(self.recv.items()):          # fixed rank order -> deterministic sums
+            buf = self.rbuf[p]
+            check(lib.skb_scatter_add_dev(g_d.data_ptr(), gi.data_ptr(), gi.numel(), buf.data_ptr(), st))
+            check(lib.skb_scatter_add_dev(vals_d.data_ptr(), hi.data_ptr(), hi.numel(), buf.data_ptr() + 8 * gi.numel(), st))
+
+
+    # ------------------------------------------------------------------ public entry points
+    def set_materials(self, mu, lam, vol=None):
+        self.plan.set_materials(mu, lam, self.plan.volume() if vol is None else vol)
+
+    def gradient_hessian_dev(self, material, psd_mode, x_d, g_d, vals_d):
+        """Device-resident sharded assembly: local fused kernel chain, then the interface exchange.  On return
+        (stream-ordered) the OWNED rows ``[own_lo*dim, own_hi*dim)`` of ``g_d`` / ``vals_d`` are globally complete."""
+        import torch
+        from ._lib import MATERIAL_IDS, check, load
+        st = torch.cuda.current_stream().cuda_stream
+        check(load().skb_gradient_hessian_dev(self.plan._h, MATERIAL_IDS[material], int(psd_mode), x_d.data_ptr(), None,
+                                              g_d.data_ptr(), vals_d.data_ptr(), st))
+        self.exchange(g_d, vals_d)
+
+    def gradient_hessian(self, material, x_host, mu, lam, vol=None, psd_mode=1, g_out=None, vals_out=None):
+        """Host-pointer version (the call a user makes per rank): uploads this rank's state, assembles, exchanges and
+        returns the owned gradient rows and the owned CSR value rows (local numbering, see ``owned_csr``)."""
+        import torch
+        f64 = torch.float64
+        if not hasattr(self, "_x_d"):
+            self._x_d = torch.empty(self.plan.ndof, dtype=f64, device=self.device)
+            self._g_d = torch.empty(self.plan.ndof, dtype=f64, device=self.device)
+            self._vals_d = torch.empty(self.plan.nnz, dtype=f64, device=self.device)
+        self.set_materials(mu, lam, vol)
+        xh = torch.from_numpy(np.ascontiguousarray(np.asarray(x_host, dtype=np.float64).reshape(-1)))
+        self._x_d.copy_(xh, non_blocking=True)
+        self.gradient_hessian_dev(material, psd_mode, self._x_d, self._g_d, self._vals_d)
+        d = self.layout.dim
+        g0, g1 = self.layout.own_lo * d, self.layout.own_hi * d
+        v0, v1 = self.owned_value_range()
+        g_out = np.empty(g1 - g0) if g_out is None else g_out
+        vals_out = np.empty(v1 - v0) if vals_out is None else vals_out
+        torch.from_numpy(g_out).copy_(self._g_d[g0:g1], non_blocking=True)
+        torch.from_numpy(vals_out).copy_(self._vals_d[v0:v1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return g_out, vals_out
+
+    def owned_value_range(self):
+        """[v0, v1): the contiguous slice of the local CSR value array that holds the owned rows."""
+        if not hasattr(self, "_vrange"):
+            bptr, _ = self.plan.block_pattern()
+            d = self.layout.dim
+            self._vrange = (int(bptr[self.layout.own_lo]) * d * d, int(bptr[self.layout.own_hi]) * d * d)
+        return self._vrange
+
+    def owned_csr(self, vals_owned):
+        """scipy CSR of the owned rows in GLOBAL numbering, shape (n_owned*dim, n_total*dim)."""
+        import scipy.sparse as sps
+        d = self.layout.dim
+        indptr, indices = self.plan.csr_pattern()
+        r0, r1 = self.layout.own_lo * d, self.layout.own_hi * d
+        ip = indptr[r0:r1 + 1].astype(np.int64)
+        gdof = (self.layout.l2g[:, None] * d + np.arange(d)[None, :]).ravel()
+        cols = gdof[indices[ip[0]:ip[-1]]]
+        n_total = int(self.layout.vcuts[-1])
+        return sps.csr_matrix((vals_owned, cols, ip - ip[0]), shape=(r1 - r0, n_total * d))
+
+
+def make_shard(workload, rank, world, device=0, tile_elems=0, sigma=0.1):
+    """Shard of a named synthetic config with its jittered state (bench.py, N > 1)."""
+    from . import synthetic as syn
+    cfg = syn.CONFIGS[workload]
+    lay = layout_grid_slab(cfg["cells"], rank, world)
+    X_local = syn.grid_vertices(cfg["cells"], cfg["extent"], lay.l2g)
+    sh = Shard(lay, X_local, device=device, tile_elems=tile_elems)
+    sh.U_local = syn.jittered_state_rows(cfg["cells"], cfg["extent"], lay.l2g, sigma=sigma)
+    sh.t_total, sh.n_total = lay.t_total, lay.n_total
+    sh.nnz_total = None
+    return sh

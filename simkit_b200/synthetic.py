@@ -32,8 +32,13 @@ def kuhn_tet_grid(mx, my, mz, extent=(1.0, 1.0, 1.0), dtype_index=np.int64):
     X = np.stack(
         [gi * (extent[0] / mx), gj * (extent[1] / my), gk * (extent[2] / mz)], axis=-1
     ).reshape(-1, 3).astype(np.float64)
+    return X, kuhn_tets(mx, my, mz, 0, mx, dtype_index)
 
-    ci, cj, ck = np.meshgrid(np.arange(mx), np.arange(my), np.arange(mz), indexing="ij")
+
+def kuhn_tets(mx, my, mz, i0, i1, dtype_index=np.int64):
+    """Elements of the cell planes ``i0 <= i < i1`` of the Kuhn grid (global vertex ids, global element order)."""
+    ny, nz = my + 1, mz + 1
+    ci, cj, ck = np.meshgrid(np.arange(i0, i1), np.arange(my), np.arange(mz), indexing="ij")
     ci, cj, ck = ci.ravel(), cj.ravel(), ck.ravel()
 
     def vid(i, j, k):
@@ -55,8 +60,7 @@ def kuhn_tet_grid(mx, my, mz, extent=(1.0, 1.0, 1.0), dtype_index=np.int64):
             tet = tet[:, [0, 2, 1, 3]]
         tets.append(tet)
     # cell-major ordering: the 6 tets of a cell are contiguous
-    T = np.stack(tets, axis=1).reshape(-1, 4).astype(dtype_index)
-    return X, T
+    return np.stack(tets, axis=1).reshape(-1, 4).astype(dtype_index)
 
 
 def tri_grid(mx, my, extent=(1.0, 1.0), dtype_index=np.int64):
@@ -65,16 +69,45 @@ def tri_grid(mx, my, extent=(1.0, 1.0), dtype_index=np.int64):
     gi, gj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
     X = np.stack([gi * (extent[0] / mx), gj * (extent[1] / my)], axis=-1).reshape(-1, 2)
     X = X.astype(np.float64)
-    ci, cj = np.meshgrid(np.arange(mx), np.arange(my), indexing="ij")
+    return X, grid_tris(mx, my, 0, mx, dtype_index)
+
+
+def grid_tris(mx, my, i0, i1, dtype_index=np.int64):
+    """Triangles of the cell columns ``i0 <= i < i1`` (global vertex ids, global element order)."""
+    ny = my + 1
+    ci, cj = np.meshgrid(np.arange(i0, i1), np.arange(my), indexing="ij")
     ci, cj = ci.ravel(), cj.ravel()
     v00 = ci * ny + cj
     v10 = (ci + 1) * ny + cj
     v11 = (ci + 1) * ny + cj + 1
     v01 = ci * ny + cj + 1
-    T = np.stack(
+    return np.stack(
         [np.stack([v00, v10, v11], -1), np.stack([v00, v11, v01], -1)], axis=1
     ).reshape(-1, 3).astype(dtype_index)
-    return X, T
+
+
+def grid_elements(cells, i0, i1):
+    """Elements of the cell planes ``[i0, i1)`` along the slowest axis of a synthetic grid."""
+    cells = tuple(cells)
+    return kuhn_tets(*cells, i0, i1) if len(cells) == 3 else grid_tris(*cells, i0, i1)
+
+
+def grid_vertices(cells, extent, ids):
+    """Rest positions of the vertices ``ids`` (global ids) of a synthetic grid, without building the whole grid."""
+    cells = tuple(cells)
+    ids = np.asarray(ids, dtype=np.int64)
+    dims = [c + 1 for c in cells]
+    idx = np.unravel_index(ids, dims)
+    return np.stack([idx[a] * (extent[a] / cells[a]) for a in range(len(cells))], axis=-1).astype(np.float64)
+
+
+def jittered_state_rows(cells, extent, ids, sigma=0.1, seed=0):
+    """Rows ``ids`` of ``jittered_state`` of the full grid (same random stream), for one rank of a sharded run."""
+    cells = tuple(cells)
+    n = int(np.prod([c + 1 for c in cells]))
+    rng = np.random.default_rng(seed)
+    noise = rng.standard_normal((n, len(cells)))[np.asarray(ids, dtype=np.int64)]
+    return grid_vertices(cells, extent, ids) + sigma * cell_size(cells, extent) * noise
 
 
 def make_mesh(name_or_cells, extent=None):

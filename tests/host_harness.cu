@@ -64,7 +64,7 @@ static void elem_hess(int material, int psd_mode, const double* F, double mu, do
 extern "C" {
 
 // info: nnzb, n_block_partials, n_vertex_partials.  Outputs may be null (size query).
-int hs_run(const double* X, const int64_t* T, int64_t n, int64_t t, int dim, int tile_elems, int material,
+int hs_run(const double* X, const int64_t* T, int64_t n, int64_t t, int64_t t_active, int dim, int tile_elems, int material,
            int psd_mode, const double* x, const double* Fbar, const double* mu, int64_t mu_n,
            const double* lam, int64_t lam_n, const double* vol, int64_t vol_n, int64_t* info, int32_t* bptr,
            int32_t* bcol, int32_t* bslot, double* Dm_out, double* vol_out, double* g, double* vals,
@@ -74,7 +74,8 @@ int hs_run(const double* X, const int64_t* T, int64_t n, int64_t t, int dim, int
   thrust::host_vector<int> Th((size_t)t * K);
   for (int64_t i = 0; i < t * K; ++i) Th[i] = (int)T[i];
   PlanData<HostBackend> pd;
-  if (!build_plan<HostBackend>(pd, Th, (int)n, (int)t, dim, tile_elems)) return -1;
+  if (!build_plan<HostBackend>(pd, Th, (int)n, (int)t_active, dim, tile_elems, (int)t)) return -1;
+  t = t_active;
   set_geometry_from_X<HostBackend>(pd, Xh);
   info[0] = pd.nnzb;
   info[1] = pd.blocks.n_ts;

@@ -48,12 +48,14 @@ def _c(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
 
-def run(X, T, material, psd_mode, x, mu, lam, vol=None, Fbar=None, tile_elems=32, want_g=True, want_h=True):
+def run(X, T, material, psd_mode, x, mu, lam, vol=None, Fbar=None, tile_elems=32, want_g=True, want_h=True,
+        t_active=None):
     lib = load()
     X = _c(X)
     T = np.ascontiguousarray(T, dtype=np.int64)
     n, dim = X.shape
     t = T.shape[0]
+    t_active = t if t_active is None else int(t_active)
     K = dim + 1
     x = _c(x)
     mu = _c(np.asarray(mu, dtype=np.float64).reshape(-1))
@@ -61,9 +63,9 @@ def run(X, T, material, psd_mode, x, mu, lam, vol=None, Fbar=None, tile_elems=32
     vol = _c(np.asarray(vol, dtype=np.float64).reshape(-1)) if vol is not None else None
     Fbar = _c(Fbar)
     info = np.zeros(3, dtype=np.int64)
-    args = [_p(X), _p(T, _lp), n, t, dim, tile_elems, material, psd_mode, _p(x), _p(Fbar), _p(mu), mu.size,
+    args = [_p(X), _p(T, _lp), n, t, t_active, dim, tile_elems, material, psd_mode, _p(x), _p(Fbar), _p(mu), mu.size,
             _p(lam), lam.size, _p(vol), 0 if vol is None else vol.size, _p(info, _lp)]
-    lib.hs_run.argtypes = [_dp, _lp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+    lib.hs_run.argtypes = [_dp, _lp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                            ctypes.c_int, _dp, _dp, _dp, ctypes.c_int64, _dp, ctypes.c_int64, _dp, ctypes.c_int64,
                            _lp, _ip, _ip, _ip, _dp, _dp, _dp, _dp, _dp]
     lib.hs_run(*args, None, None, None, None, None, None, None, None)
@@ -71,13 +73,13 @@ def run(X, T, material, psd_mode, x, mu, lam, vol=None, Fbar=None, tile_elems=32
     bptr = np.zeros(n + 1, dtype=np.int32)
     bcol = np.zeros(nnzb, dtype=np.int32)
     bslot = np.zeros(t * K * K, dtype=np.int32)
-    Dm = np.zeros(dim * dim * t)
-    vol0 = np.zeros(t)
+    Dm = np.zeros(dim * dim * t_active)
+    vol0 = np.zeros(t_active)
     g = np.zeros(n * dim) if want_g else None
     vals = np.zeros(nnzb * dim * dim) if want_h else None
     energy = np.zeros(1)
     lib.hs_run(*args, _p(bptr, _ip), _p(bcol, _ip), _p(bslot, _ip), _p(Dm), _p(vol0), _p(g), _p(vals), _p(energy))
-    return dict(bptr=bptr, bcol=bcol, bslot=bslot.reshape(t, K, K), Dm=Dm.reshape(dim, dim, t), vol0=vol0,
+    return dict(bptr=bptr, bcol=bcol, bslot=bslot.reshape(t, K, K), Dm=Dm.reshape(dim, dim, t_active), vol0=vol0,
                 g=g, vals=vals, energy=float(energy[0]), info=info)
 
 
