@@ -294,7 +294,7 @@ def run_ours(args, rank, world, local_rank):
     alg_flops = (2600.0 if dim == 3 else 700.0) * plan.t
     k_ms = kms[0] / max(int(kcount[0]), 1)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    kernel_key = "assemble_tile_kernel<%d>" % dim
+    kernel_key = "assemble_pipelined_kernel<%d>" % dim
     roofline = {
         "kernel": kernel_key, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
         "frac": achieved / hbm_peak, "peak_source": peak_src,

@@ -2,6 +2,8 @@
 // Hessian entry points (include/simkit_b200.h).
 #include "capi_common.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <memory>
 
@@ -73,18 +75,60 @@ int upload_materials(skb_plan* pl, const double* mu, int64_t mu_n, const double*
   return SKB_OK;
 }
 
+template <int D, int G, int NBUF, int MAT>
+static int launch_pipelined(skb_plan* pl, const PlanView& p, const EvalArgs& a, size_t psmem, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SKB_CUDA(cudaFuncSetAttribute(assemble_pipelined_kernel<D, G, NBUF, MAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024));
+    attr_set = true;
+  }
+  SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_pipelined_kernel<D, G, NBUF, MAT><<<grid, G * 128, psmem, st>>>(p, a));
+  return SKB_OK;
+}
+
 template <int D>
 static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
   const PlanView p = pl->view();
   const int E = p.tile_elems;
   const size_t smem = assemble_smem_bytes<D>(p);
   if (smem > 227 * 1024) return fail(SKB_EINVAL, "tile_elems too large for the 227 KB of shared memory");
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[D - 2]) {
-    SKB_CUDA(cudaFuncSetAttribute(assemble_tile_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[D - 2] = true;
+  // pipelined persistent kernel (3 groups, 2 staging buffers) when the tile is 128 elements and its schedule fits
+  constexpr int G = 3, NBUF = 2;
+  const size_t psmem = PipeSmem<D>::total(p, G, NBUF);
+  static int use_pipe_env = -1;
+  if (use_pipe_env < 0) {
+    const char* ev = getenv("SKB_ASSEMBLE");
+    use_pipe_env = (ev && strcmp(ev, "tile") == 0) ? 0 : 1;
   }
-  SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_tile_kernel<D><<<p.n_tiles, E, smem, st>>>(p, a));
+  const bool pipe = use_pipe_env && E == 128 && psmem <= 227 * 1024 && p.n_tiles >= 2 * G;
+  if (pipe) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+    int grid = sms;
+    if (grid * G > p.n_tiles) grid = (p.n_tiles + G - 1) / G;
+    int rc = SKB_OK;
+    if (D == 3) {
+      // tets: one kernel per material (compile-time constitutive model)
+      switch (a.material) {
+        case MAT_STABLE_NEO_HOOKEAN: rc = launch_pipelined<3, G, NBUF, MAT_STABLE_NEO_HOOKEAN>(pl, p, a, psmem, grid, st); break;
+        case MAT_NEO_HOOKEAN: rc = launch_pipelined<3, G, NBUF, MAT_NEO_HOOKEAN>(pl, p, a, psmem, grid, st); break;
+        case MAT_ARAP: rc = launch_pipelined<3, G, NBUF, MAT_ARAP>(pl, p, a, psmem, grid, st); break;
+        case MAT_STVK: rc = launch_pipelined<3, G, NBUF, MAT_STVK>(pl, p, a, psmem, grid, st); break;
+        default: rc = launch_pipelined<3, G, NBUF, MAT_LINEAR_ELASTICITY>(pl, p, a, psmem, grid, st); break;
+      }
+    } else {
+      rc = launch_pipelined<2, G, NBUF, -1>(pl, p, a, psmem, grid, st);
+    }
+    if (rc) return rc;
+  } else {
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[D - 2]) {
+      SKB_CUDA(cudaFuncSetAttribute(assemble_tile_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set[D - 2] = true;
+    }
+    SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_tile_kernel<D><<<p.n_tiles, E, smem, st>>>(p, a));
+  }
   if (a.want_hess) {
     SKB_LAUNCH(pl, SKB_K_FINALIZE_BLOCKS, st,
                finalize_blocks_kernel<D><<<(p.nu * D * D + 255) / 256, 256, 0, st>>>(p, a.pblocks, a.vals));

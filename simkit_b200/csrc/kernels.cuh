@@ -50,36 +50,63 @@ struct Sizes {
   static constexpr int SMEM_DOUBLES = NK + NG;    // per element
 };
 
-// F_ij = sum_{a>=1} D[j][a] (x_a[i] - x_0[i])  (+ Fbar)      -- the "J @ x" of the reference
+// Raw inputs of one element, as loaded from HBM: corner positions (gathered through T), the element
+// operator D, material and weight.  Kept separate from the math so that the pipelined kernel can issue
+// these loads for its NEXT tile before the shared-memory phase of the current one.
 template <int D>
-SKB_HD void load_element(const PlanView& p, const EvalArgs& a, int e, Mat<D>& F, double Dm[D][D],
-                         double& mu, double& lam, double& vol) {
+struct ElemRaw {
+  double xs[D + 1][D];
+  double Dm[D][D];
+  double mu, lam, vol;
+};
+
+template <int D>
+SKB_HD void load_raw(const PlanView& p, const EvalArgs& a, int e, const int* Te, ElemRaw<D>& r) {
   constexpr int K = D + 1;
-  const int* Te = p.T32 + (size_t)e * K;
-  double x0[D];
 #pragma unroll
-  for (int i = 0; i < D; ++i) x0[i] = a.x[(size_t)Te[0] * D + i];
+  for (int c = 0; c < K; ++c)
+#pragma unroll
+    for (int i = 0; i < D; ++i) r.xs[c][i] = a.x[(size_t)Te[c] * D + i];
 #pragma unroll
   for (int j = 0; j < D; ++j)
 #pragma unroll
-    for (int c = 0; c < D; ++c) Dm[j][c] = p.Dm[(size_t)(j * D + c) * p.t + e];
+    for (int c = 0; c < D; ++c) r.Dm[j][c] = p.Dm[(size_t)(j * D + c) * p.t + e];
+  r.mu = a.mu[(size_t)e * a.mu_stride];
+  r.lam = a.lam ? a.lam[(size_t)e * a.lam_stride] : 0.0;
+  r.vol = a.vol[(size_t)e * a.vol_stride];
+}
+
+// F_ij = sum_{a>=1} D[j][a] (x_a[i] - x_0[i])  (+ Fbar)      -- the "J @ x" of the reference
+template <int D>
+SKB_HD void build_F(const EvalArgs& a, int e, const ElemRaw<D>& r, Mat<D>& F) {
 #pragma unroll
   for (int i = 0; i < D; ++i)
 #pragma unroll
     for (int j = 0; j < D; ++j) F.m[i][j] = a.Fbar ? a.Fbar[(size_t)e * D * D + i * D + j] : 0.0;
 #pragma unroll
   for (int c = 0; c < D; ++c) {
-    const size_t v = (size_t)Te[c + 1] * D;
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-      double d = a.x[v + i] - x0[i];
+      double d = r.xs[c + 1][i] - r.xs[0][i];
 #pragma unroll
-      for (int j = 0; j < D; ++j) F.m[i][j] = fma(Dm[j][c], d, F.m[i][j]);
+      for (int j = 0; j < D; ++j) F.m[i][j] = fma(r.Dm[j][c], d, F.m[i][j]);
     }
   }
-  mu = a.mu[(size_t)e * a.mu_stride];
-  lam = a.lam ? a.lam[(size_t)e * a.lam_stride] : 0.0;
-  vol = a.vol[(size_t)e * a.vol_stride];
+}
+
+template <int D>
+SKB_HD void load_element(const PlanView& p, const EvalArgs& a, int e, Mat<D>& F, double Dm[D][D],
+                         double& mu, double& lam, double& vol) {
+  ElemRaw<D> r;
+  load_raw<D>(p, a, e, p.T32 + (size_t)e * (D + 1), r);
+  build_F<D>(a, e, r, F);
+#pragma unroll
+  for (int j = 0; j < D; ++j)
+#pragma unroll
+    for (int c = 0; c < D; ++c) Dm[j][c] = r.Dm[j][c];
+  mu = r.mu;
+  lam = r.lam;
+  vol = r.vol;
 }
 
 template <int D>
@@ -90,34 +117,48 @@ SKB_HD double energy_element(const PlanView& p, const EvalArgs& a, int e) {
   return vol * energy_density<D>(a.material, F, mu, lam);
 }
 
-// Phase 1: one thread per element.  Writes the element's packed (K*D)x(K*D)
-// local stiffness and its local gradient to staging memory laid out [value][le]
-// (stride E) so that a warp's stores hit consecutive banks.
+// Per-element state carried from the register-only math (element_math) to the shared-memory
+// staging (element_store).  Isotropic models: SVD frame U, principal-stretch Hessian h (weighted and
+// projected), W[c][q] = sum_j D[j][c] V[j][q].  Linear elasticity: W holds d[c][j] and (cI, cT, cR) the
+// coefficients of the constant block.
 template <int D>
-SKB_HD void element_phase1(const PlanView& p, const EvalArgs& a, int e, int le, int E, double* sK, double* sG) {
-  constexpr int K = D + 1;
-  constexpr int NL = K * D;
-  constexpr int NP = D * (D - 1) / 2;
-  Mat<D> F;
-  double Dm[D][D], mu, lam, vol;
-  load_element<D>(p, a, e, F, Dm, mu, lam, vol);
+struct ElemState {
+  Mat<D> U;
+  Principal<D> h;
+  double W[D + 1][D];
+  double cI, cT, cR;
+};
 
-  Mat<D> U, V;
+// Phase 1a: one thread per element, registers only: gather, F, SVD, stress, principal-stretch
+// Hessian with quadrature weight and eigenvalue floor.  The local gradient (12 values) goes straight
+// to its staging area sG [value][le]; everything the stiffness blocks need stays in `st`.
+// MAT >= 0 fixes the material at compile time (dead constitutive branches vanish, fewer live
+// registers); MAT = -1 reads it from the arguments.
+template <int D, int MAT = -1>
+SKB_HD void element_math(const EvalArgs& a, int e, const ElemRaw<D>& raw, int le, int E, double* sG, ElemState<D>& st) {
+  constexpr int K = D + 1;
+  const int material = (MAT >= 0) ? MAT : a.material;
+  Mat<D> F;
+  build_F<D>(a, e, raw, F);
+  const double mu = raw.mu, lam = raw.lam, vol = raw.vol;
+  const double (&Dm)[D][D] = raw.Dm;
+
+  Mat<D> V;
   Vec<D> sig;
-  const bool iso = (a.material != MAT_LINEAR_ELASTICITY);
-  const bool need_svd = (a.want_hess && iso) || (a.want_grad && a.material == MAT_ARAP);
-  if (need_svd) svd_rv(F, U, sig, V);
+  const bool iso = (material != MAT_LINEAR_ELASTICITY);
+  const bool need_svd = (a.want_hess && iso) || (a.want_grad && material == MAT_ARAP);
+  if (need_svd) svd_rv(F, st.U, sig, V);
 
   if (a.want_grad) {
     Mat<D> P;
-    if (a.material == MAT_ARAP) {
-      Mat<D> R = matmul_nt(U, V);
+    if (material == MAT_ARAP) {
+      Mat<D> R = matmul_nt(st.U, V);
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
         for (int j = 0; j < D; ++j) P.m[i][j] = mu * (F.m[i][j] - R.m[i][j]);
     } else {
-      P = pk1<D>(a.material, F, mu, lam);
+      P = pk1<D>(material, F, mu, lam);
     }
     // g_a[i] = vol * sum_j P[i][j] D[j][a];  corner 0 is minus the sum
 #pragma unroll
@@ -138,10 +179,9 @@ SKB_HD void element_phase1(const PlanView& p, const EvalArgs& a, int e, int le, 
   if (!a.want_hess) return;
 
   if (iso) {
-    Principal<D> h = principal_hessian<D>(a.material, sig, mu, lam);
-    weight_and_project<D>(h, vol, a.psd_mode);
+    st.h = principal_hessian<D>(material, sig, mu, lam);
+    weight_and_project<D>(st.h, vol, a.psd_mode);
     // W[c][q] = sum_j D[j][c] V[j][q]   (c = corner, corner 0 = minus the sum)
-    double W[K][D];
 #pragma unroll
     for (int q = 0; q < D; ++q) {
       double s0 = 0.0;
@@ -150,62 +190,27 @@ SKB_HD void element_phase1(const PlanView& p, const EvalArgs& a, int e, int le, 
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < D; ++j) s = fma(Dm[j][c], V.m[j][q], s);
-        W[c + 1][q] = s;
+        st.W[c + 1][q] = s;
         s0 -= s;
       }
-      W[0][q] = s0;
+      st.W[0][q] = s0;
     }
-    // block (ca, cb), ca <= cb:  K = U M U^T,
-    //   M[p][p] = S_pp Wa_p Wb_p + sum_{q != p} a_pq Wa_q Wb_q
-    //   M[p][r] = S_pr Wa_p Wb_r + b_pr Wa_r Wb_p
-#pragma unroll
-    for (int ca = 0; ca < K; ++ca)
-#pragma unroll
-      for (int cb = ca; cb < K; ++cb) {
-        Mat<D> M;
-#pragma unroll
-        for (int pp = 0; pp < D; ++pp)
-#pragma unroll
-          for (int r = 0; r < D; ++r) M.m[pp][r] = h.S.m[pp][r] * W[ca][pp] * W[cb][r];
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-          int pp, q, r3;
-          pair_index<D>(k, pp, q, r3);
-          M.m[pp][pp] = fma(h.a[k] * W[ca][q], W[cb][q], M.m[pp][pp]);
-          M.m[q][q] = fma(h.a[k] * W[ca][pp], W[cb][pp], M.m[q][q]);
-          M.m[pp][q] = fma(h.b[k] * W[ca][q], W[cb][pp], M.m[pp][q]);
-          M.m[q][pp] = fma(h.b[k] * W[ca][pp], W[cb][q], M.m[q][pp]);
-        }
-        Mat<D> UM = matmul(U, M);
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-          for (int kk = 0; kk < D; ++kk) {
-            if (ca == cb && kk < i) continue;
-            double s = 0.0;
-#pragma unroll
-            for (int r = 0; r < D; ++r) s = fma(UM.m[i][r], U.m[kk][r], s);
-            sK[sym_idx(NL, ca * D + i, cb * D + kk) * E + le] = s;
-          }
-      }
   } else {
     // linear elasticity: constant Hessian mu (I + T) + lam tr^T tr; psd flag ignored in its
     // own module (linear_elasticity.py:199-230) but honoured through the dispatcher, where
     // the floor only lifts the exact zero modes.  K_ab[i][k] = vol (mu (d_ik da.db + da[k] db[i]) + lam da[i] db[k])
-    double d[K][D];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
       double s0 = 0.0;
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        d[c + 1][j] = Dm[j][c];
+        st.W[c + 1][j] = Dm[j][c];
         s0 -= Dm[j][c];
       }
-      d[0][j] = s0;
+      st.W[0][j] = s0;
     }
     // dispatcher PSD on the constant block: eigenvalues of mu(I+T)+lam tr^T tr are
-    // 2mu (sym traceless, and twist -> 0), 2mu + D*lam (trace mode), 0 (skew modes).
-    // Floor / weight handling: skew (zero) modes become `fl0`.
+    // 2mu (sym traceless), 2mu + D*lam (trace mode), 0 (skew modes).
     double w_sym = 2.0 * mu, w_tr = 2.0 * mu + D * lam, w_skew = 0.0;
     const double pre = (a.psd_mode == PSD_BEFORE_VOL) ? 1.0 : vol;
     const double post = (a.psd_mode == PSD_BEFORE_VOL) ? vol : 1.0;
@@ -219,25 +224,84 @@ SKB_HD void element_phase1(const PlanView& p, const EvalArgs& a, int e, int le, 
     // H = w_sym * Psym0 + w_tr * Ptr + w_skew * Pskew, with projectors
     //   Psym = (I+T)/2, Pskew = (I-T)/2, Ptr = tr^T tr / D, Psym0 = Psym - Ptr
     // => H = cI * I + cT * T + cR * tr^T tr
-    const double cI = 0.5 * (w_sym + w_skew), cT = 0.5 * (w_sym - w_skew), cR = (w_tr - w_sym) / D;
+    st.cI = 0.5 * (w_sym + w_skew);
+    st.cT = 0.5 * (w_sym - w_skew);
+    st.cR = (w_tr - w_sym) / D;
+  }
+}
+
+// Phase 1b: writes the element's packed (K*D)x(K*D) local stiffness and its local gradient to
+// staging memory laid out [value][le] (stride E) so that a warp's stores hit consecutive banks.
+template <int D, int MAT = -1>
+SKB_HD void element_store(const EvalArgs& a, const ElemState<D>& st, int le, int E, double* sK) {
+  constexpr int K = D + 1;
+  constexpr int NL = K * D;
+  constexpr int NP = D * (D - 1) / 2;
+  const int material = (MAT >= 0) ? MAT : a.material;
+  if (!a.want_hess) return;
+  if (material != MAT_LINEAR_ELASTICITY) {
+    // block (ca, cb), ca <= cb:  K = U M U^T,
+    //   M[p][p] = S_pp Wa_p Wb_p + sum_{q != p} a_pq Wa_q Wb_q
+    //   M[p][r] = S_pr Wa_p Wb_r + b_pr Wa_r Wb_p
+#pragma unroll
+    for (int ca = 0; ca < K; ++ca)
+#pragma unroll
+      for (int cb = ca; cb < K; ++cb) {
+        Mat<D> M;
+#pragma unroll
+        for (int pp = 0; pp < D; ++pp)
+#pragma unroll
+          for (int r = 0; r < D; ++r) M.m[pp][r] = st.h.S.m[pp][r] * st.W[ca][pp] * st.W[cb][r];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          int pp, q, r3;
+          pair_index<D>(k, pp, q, r3);
+          M.m[pp][pp] = fma(st.h.a[k] * st.W[ca][q], st.W[cb][q], M.m[pp][pp]);
+          M.m[q][q] = fma(st.h.a[k] * st.W[ca][pp], st.W[cb][pp], M.m[q][q]);
+          M.m[pp][q] = fma(st.h.b[k] * st.W[ca][q], st.W[cb][pp], M.m[pp][q]);
+          M.m[q][pp] = fma(st.h.b[k] * st.W[ca][pp], st.W[cb][q], M.m[q][pp]);
+        }
+        Mat<D> UM = matmul(st.U, M);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int kk = 0; kk < D; ++kk) {
+            if (ca == cb && kk < i) continue;
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < D; ++r) s = fma(UM.m[i][r], st.U.m[kk][r], s);
+            sK[sym_idx(NL, ca * D + i, cb * D + kk) * E + le] = s;
+          }
+      }
+  } else {
 #pragma unroll
     for (int ca = 0; ca < K; ++ca)
 #pragma unroll
       for (int cb = ca; cb < K; ++cb) {
         double dot = 0.0;
 #pragma unroll
-        for (int j = 0; j < D; ++j) dot = fma(d[ca][j], d[cb][j], dot);
+        for (int j = 0; j < D; ++j) dot = fma(st.W[ca][j], st.W[cb][j], dot);
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
           for (int kk = 0; kk < D; ++kk) {
             if (ca == cb && kk < i) continue;
-            double v = cT * d[ca][kk] * d[cb][i] + cR * d[ca][i] * d[cb][kk];
-            if (i == kk) v = fma(cI, dot, v);
+            double v = st.cT * st.W[ca][kk] * st.W[cb][i] + st.cR * st.W[ca][i] * st.W[cb][kk];
+            if (i == kk) v = fma(st.cI, dot, v);
             sK[sym_idx(NL, ca * D + i, cb * D + kk) * E + le] = v;
           }
       }
   }
+}
+
+// Phase 1 = 1a + 1b (single-tile kernel and the CPU replay)
+template <int D>
+SKB_HD void element_phase1(const PlanView& p, const EvalArgs& a, int e, int le, int E, double* sK, double* sG) {
+  ElemRaw<D> raw;
+  load_raw<D>(p, a, e, p.T32 + (size_t)e * (D + 1), raw);
+  ElemState<D> st;
+  element_math<D>(a, e, raw, le, E, sG, st);
+  element_store<D>(a, st, le, E, sK);
 }
 
 // local corners (a <= b) of pair index pp, K corners: row-major over the upper triangle
@@ -437,6 +501,138 @@ __global__ void assemble_tile_kernel(PlanView p, EvalArgs a) {
   __syncthreads();
   for (int w = threadIdx.x; w < nbe; w += blockDim.x) block_phase2<D>(sBE, sBS, sTab, w, E, sK, a.pblocks);
   for (int w = threadIdx.x; w < nve; w += blockDim.x) vert_phase2<D>(sVE, sVS, w, E, sG, a.pverts);
+}
+
+// ------------------------------------------------------------ pipelined --
+// Persistent variant: one CTA per SM, G groups of E threads, NBUF < G staging buffers.  The
+// register-only math of phase 1a needs no shared memory, so all G groups (G*E/32 warps) keep the FP64
+// pipe busy while only NBUF tiles' worth of staging exists: a group takes a buffer just for
+// phase 1b + phase 2 and hands it back.  Groups synchronise with named barriers (bar.sync id, E);
+// buffers are handed over through shared-memory flags.  Results are identical to the single-tile
+// kernel (same per-tile schedule, same summation order).
+template <int D>
+struct PipeSmem {
+  SKB_HD static size_t sched_bytes(const PlanView& p) {
+    constexpr int K = D + 1;
+    constexpr int NP = K * (K + 1) / 2;
+    const size_t E = p.tile_elems;
+    size_t b = (size_t)p.blocks.max_entries * sizeof(SchedEntry) + E * NP * sizeof(uint16_t);
+    b += (size_t)p.verts.max_entries * sizeof(SchedEntry) + E * K * sizeof(uint16_t);
+    return (b + 15) & ~(size_t)15;
+  }
+  // a staging buffer holds the packed stiffness only; every group keeps its own gradient staging
+  SKB_HD static size_t buffer_bytes(const PlanView& p) { return (size_t)Sizes<D>::NK * p.tile_elems * sizeof(double); }
+  SKB_HD static size_t grad_bytes(const PlanView& p) { return (size_t)Sizes<D>::NG * p.tile_elems * sizeof(double); }
+  SKB_HD static size_t total(const PlanView& p, int G, int NBUF) {
+    return NBUF * buffer_bytes(p) + G * (grad_bytes(p) + sched_bytes(p)) + 16 * sizeof(unsigned long long) + 8 * (size_t)G + 64;
+  }
+};
+
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int D, int G, int NBUF, int MAT>
+__global__ void __launch_bounds__(G * 128, 1) assemble_pipelined_kernel(PlanView p, EvalArgs a) {
+  constexpr int K = D + 1;
+  constexpr int NP = K * (K + 1) / 2;
+  constexpr int E = 128;
+  extern __shared__ __align__(16) double smem[];
+  const int grp = threadIdx.x / E;
+  const int gt = threadIdx.x - grp * E;
+  unsigned char* base = reinterpret_cast<unsigned char*>(smem);
+  const size_t bufB = PipeSmem<D>::buffer_bytes(p), schB = PipeSmem<D>::sched_bytes(p) + PipeSmem<D>::grad_bytes(p);
+  unsigned char* sp = base + NBUF * bufB + (size_t)grp * schB;
+  double* sG = reinterpret_cast<double*>(sp);
+  sp += PipeSmem<D>::grad_bytes(p);
+  SchedEntry* sBE = reinterpret_cast<SchedEntry*>(sp);
+  sp += (size_t)p.blocks.max_entries * sizeof(SchedEntry);
+  uint16_t* sBS = reinterpret_cast<uint16_t*>(sp);
+  sp += (size_t)E * NP * sizeof(uint16_t);
+  SchedEntry* sVE = reinterpret_cast<SchedEntry*>(sp);
+  sp += (size_t)p.verts.max_entries * sizeof(SchedEntry);
+  uint16_t* sVS = reinterpret_cast<uint16_t*>(sp);
+  unsigned char* tail = base + NBUF * bufB + G * schB;
+  unsigned long long* sTab = reinterpret_cast<unsigned long long*>(tail);
+  unsigned long long* sBar = sTab + 16;              // G mbarriers
+  int* sBusy = reinterpret_cast<int*>(sBar + G);     // NBUF flags, then G buffer indices
+  int* sPick = sBusy + NBUF;
+  const unsigned mbar = smem_u32(sBar + grp);
+
+  if (threadIdx.x < NP) sTab[threadIdx.x] = pair_index_table<D>(threadIdx.x);
+  if (threadIdx.x < NBUF) sBusy[threadIdx.x] = 0;
+  if (gt == 0) mbar_init(mbar, 1);
+  __syncthreads();
+
+  unsigned parity = 0;
+  const int tstep = gridDim.x * G;
+  int tile = blockIdx.x * G + grp;
+  // software pipeline over tiles: the corner indices of the next tile are fetched at the top of an
+  // iteration and its raw inputs are issued before the shared-memory phase of the current tile, so
+  // the gather latency is hidden behind phase 2 instead of stalling all four warps of the group
+  int Tn[K];
+  ElemRaw<D> raw;
+  if (tile < p.n_tiles) {
+    const int e0 = tile * E + gt;
+    if (e0 < p.t) {
+#pragma unroll
+      for (int c = 0; c < K; ++c) Tn[c] = p.T32[(size_t)e0 * K + c];
+      load_raw<D>(p, a, e0, Tn, raw);
+    }
+  }
+  for (; tile < p.n_tiles; tile += tstep) {
+    const int e = tile * E + gt;
+    const int en = e + tstep * E;  // this thread's element in the group's next tile
+    const bool have_next = (tile + tstep < p.n_tiles) && (en < p.t);
+    const int nbe = a.want_hess ? p.blocks.tl_ptr[tile + 1] - p.blocks.tl_ptr[tile] : 0;
+    const int nve = a.want_grad ? p.verts.tl_ptr[tile + 1] - p.verts.tl_ptr[tile] : 0;
+    if (gt == 0) {
+      unsigned bytes = 0;
+      if (nbe) bytes += nbe * (unsigned)sizeof(SchedEntry) + E * NP * (unsigned)sizeof(uint16_t);
+      if (nve) bytes += nve * (unsigned)sizeof(SchedEntry) + E * K * (unsigned)sizeof(uint16_t);
+      mbar_expect_tx(mbar, bytes);
+      if (nbe) {
+        tma_bulk_g2s(smem_u32(sBE), p.blocks.tl_ent + p.blocks.tl_ptr[tile], nbe * (unsigned)sizeof(SchedEntry), mbar);
+        tma_bulk_g2s(smem_u32(sBS), p.blocks.tc_src + (size_t)tile * E * NP, E * NP * (unsigned)sizeof(uint16_t), mbar);
+      }
+      if (nve) {
+        tma_bulk_g2s(smem_u32(sVE), p.verts.tl_ent + p.verts.tl_ptr[tile], nve * (unsigned)sizeof(SchedEntry), mbar);
+        tma_bulk_g2s(smem_u32(sVS), p.verts.tc_src + (size_t)tile * E * K, E * K * (unsigned)sizeof(uint16_t), mbar);
+      }
+    }
+    if (have_next) {
+#pragma unroll
+      for (int c = 0; c < K; ++c) Tn[c] = p.T32[(size_t)en * K + c];
+    }
+    ElemState<D> st;
+    if (e < p.t) element_math<D, MAT>(a, e, raw, gt, E, sG, st);
+    // take a staging buffer
+    if (gt == 0) {
+      int b = -1;
+      while (b < 0) {
+#pragma unroll
+        for (int k = 0; k < NBUF; ++k)
+          if (b < 0 && atomicCAS(&sBusy[k], 0, 1) == 0) b = k;
+        if (b < 0) __nanosleep(64);
+      }
+      sPick[grp] = b;
+    }
+    group_barrier(grp + 1, E);
+    const int b = sPick[grp];
+    double* sK = reinterpret_cast<double*>(base + (size_t)b * bufB);
+    if (e < p.t) element_store<D, MAT>(a, st, gt, E, sK);
+    mbar_wait(mbar, parity);
+    parity ^= 1u;
+    group_barrier(grp + 1, E);
+    if (have_next) load_raw<D>(p, a, en, Tn, raw);  // in flight during phase 2
+    for (int w = gt; w < nbe; w += E) block_phase2<D>(sBE, sBS, sTab, w, E, sK, a.pblocks);
+    for (int w = gt; w < nve; w += E) vert_phase2<D>(sVE, sVS, w, E, sG, a.pverts);
+    group_barrier(grp + 1, E);
+    if (gt == 0) {
+      __threadfence_block();
+      atomicExch(&sBusy[b], 0);
+    }
+  }
 }
 
 template <int D>

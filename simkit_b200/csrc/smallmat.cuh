@@ -146,7 +146,13 @@ SKB_HD void sym_schur2(double app, double aqq, double apq, double& c, double& s,
 // reciprocal square root: MUFU.RSQ64H + Newton steps on the device (no slow-path division)
 SKB_HD double rsqrt_f64(double x) {
 #if defined(__CUDA_ARCH__)
-  return rsqrt(x);
+  // hardware seed (MUFU.RSQ64H, ~22 bits) + one third-order step  y <- y + y e (1/2 + 3/8 e),
+  // e = 1 - x y^2: full double accuracy for normal positive x; no range checks or slow path
+  // (callers guarantee x > 0 and finite)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(x * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
 #else
   return 1.0 / sqrt(x);
 #endif
