@@ -145,6 +145,29 @@ int skb_kernel_times(skb_plan* plan, double* ms, int64_t* launches);
  * interface-vertex gradient rows and Hessian block-rows that travel over NCCL. */
 int skb_gather_dev(const double* src, const int32_t* idx, int64_t n, double* dst, void* stream);
 int skb_scatter_add_dev(double* dst, const int32_t* idx, int64_t n, const double* src, void* stream);
+/* dst[idx[i]] = src[i]: refreshes the non-owned (halo / ghost) copies of a vector after a neighbour exchange */
+int skb_scatter_dev(double* dst, const int32_t* idx, int64_t n, const double* src, void* stream);
+/* ---- distributed PCG / Newton building blocks (one rank of a sharded mesh; DESIGN.md "Multi-GPU").
+ * All pointers are device pointers in the rank's local numbering; [v0, v1) are the vertex rows the rank owns.
+ * scalars: >= 8 doubles on the device: [0] r.z  [1] r.r  [2] p.q  [3] new r.z  [4] new r.r  -- rank-local sums over the
+ * owned dofs that the host all-reduces (NCCL, in place) between the calls; work: >= 3*1024 doubles of scratch.
+ * Replaces, together with the halo exchange of p, spsolve at solvers/newton.py:52 for a mesh spread over GPUs. */
+int skb_dist_pcg_init_dev(skb_plan* plan, const double* vals, const double* diag_add, int v0, int v1, const double* rhs,
+                          double* dinv, double* x, double* r, double* z, double* p, double* scalars, double* work,
+                          void* stream);
+int skb_dist_spmv_dot_dev(skb_plan* plan, const double* vals, const double* diag_add, int v0, int v1, const double* p,
+                          double* q, double* scalars, double* work, void* stream);
+int skb_dist_pcg_update_dev(skb_plan* plan, int v0, int v1, const double* dinv, const double* p, const double* q, double* x,
+                            double* r, double* z, double* scalars, double* work, void* stream);
+int skb_dist_pcg_direction_dev(skb_plan* plan, int v0, int v1, const double* z, double* p, double* scalars, void* stream);
+/* implicit-step vector terms on the owned dofs (same formulas as skb_newton uses on one GPU) */
+int skb_dist_newton_rhs_dev(skb_plan* plan, int v0, int v1, const double* x, const double* f_ext, const double* mass,
+                            const double* x_tilde, double kin_scale, const double* pin_k, const double* pin_t, double* g,
+                            double* rhs, double* diag, void* stream);
+int skb_dist_newton_terms_dev(skb_plan* plan, int v0, int v1, const double* x, const double* dx, double s,
+                              const double* f_ext, const double* mass, const double* x_tilde, double kin_scale,
+                              const double* pin_k, const double* pin_t, const double* g, double* xtrial, double* out,
+                              double* work, void* stream);
 /* measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the compute roofline denominator */
 int skb_fp64_peak(int device, double* tflops);
 

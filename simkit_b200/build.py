@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libsimkit_b200.so")
-SOURCES = ["capi.cu", "capi_elements.cu", "capi_solver.cu", "capi_reduced.cu"]
+SOURCES = ["capi.cu", "capi_elements.cu", "capi_solver.cu", "capi_reduced.cu", "capi_dist.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -64,7 +64,7 @@ def build(force=False, verbose=False, ptxas_info=False):
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
         return obj, r.stderr
 
-    with ThreadPoolExecutor(max_workers=min(4, len(srcs))) as ex:
+    with ThreadPoolExecutor(max_workers=min(5, len(srcs))) as ex:
         results = list(ex.map(compile_one, srcs))
     objs = [o for o, _ in results]
     if verbose or ptxas_info:

@@ -164,6 +164,10 @@ __global__ void gather_kernel(const double* src, const int32_t* idx, int64_t n, 
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[idx[i]];
 }
+__global__ void scatter_kernel(double* dst, const int32_t* idx, int64_t n, const double* src) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = src[i];
+}
 __global__ void scatter_add_kernel(double* dst, const int32_t* idx, int64_t n, const double* src) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[idx[i]] += src[i];
@@ -522,6 +526,14 @@ int skb_gather_dev(const double* src, const int32_t* idx, int64_t n, double* dst
   if (n == 0) return SKB_OK;
   if (!src || !idx || !dst || n < 0) return fail(SKB_EINVAL, "bad argument");
   gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, dst);
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+}
+
+int skb_scatter_dev(double* dst, const int32_t* idx, int64_t n, const double* src, void* stream) {
+  if (n == 0) return SKB_OK;
+  if (!src || !idx || !dst || n < 0) return fail(SKB_EINVAL, "bad argument");
+  scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dst, idx, n, src);
   SKB_CUDA(cudaGetLastError());
   return SKB_OK;
 }

@@ -87,7 +87,29 @@ class ShardLayout:
             p = int(p)
             self.recv[p] = _interface_rows(T_pattern[self.pattern_rank == p], self.v_lo, self.v_hi)
 
+        # ---- vector halo lists: which owned vertices each neighbour needs / which local copies it refreshes
+        #   to a LOWER rank p: its ghost vertices owned here  == rows of recv[p]
+        #   to a HIGHER rank q: the vertices owned here among my elements that touch q's vertices (q's halo)
+        self.vsend, self.vrecv = {}, {}
+        for p, (rows, _, _) in self.recv.items():
+            self.vsend[p] = rows
+        for q in self.send:
+            mask = np.any((T_own >= self.vcuts[q]) & (T_own < self.vcuts[q + 1]), axis=1)
+            vs = np.unique(T_own[mask])
+            self.vsend[q] = vs[(vs >= self.v_lo) & (vs < self.v_hi)]
+        for q, (rows, _, _) in self.send.items():          # my ghosts owned by q
+            self.vrecv[q] = rows
+        for p in self.recv:                                # my halo vertices owned by p
+            vs = np.unique(T_pattern[self.pattern_rank == p])
+            self.vrecv[p] = vs[(vs >= self.vcuts[p]) & (vs < self.vcuts[p + 1])]
+
     # ------------------------------------------------------------------ index maps
+    def vector_maps(self):
+        """``(send, recv)``: rank -> int32 local DOF indices for refreshing the non-owned copies of a vector."""
+        d = self.dim
+        f = lambda vs: (self.to_local(vs)[:, None] * d + np.arange(d)[None, :]).ravel().astype(np.int32)  # noqa: E731
+        return {r: f(v) for r, v in self.vsend.items()}, {r: f(v) for r, v in self.vrecv.items()}
+
     def to_local(self, g):
         loc = np.searchsorted(self.l2g, g)
         assert np.array_equal(self.l2g[loc], g)
@@ -234,6 +256,160 @@ class Shard:
             check(lib.skb_scatter_add_dev(g_d.data_ptr(), gi.data_ptr(), gi.numel(), buf.data_ptr(), st))
             check(lib.skb_scatter_add_dev(vals_d.data_ptr(), hi.data_ptr(), hi.numel(), buf.data_ptr() + 8 * gi.numel(), st))
 
+
+    # ------------------------------------------------------------------ vectors
+    def _vector_lists(self):
+        if not hasattr(self, "_vsend"):
+            import torch
+            vs, vr = self.layout.vector_maps()
+            mk = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)  # noqa: E731
+            self._vsend = {r: mk(i) for r, i in vs.items()}
+            self._vrecv = {r: mk(i) for r, i in vr.items()}
+            f64 = torch.float64
+            self._vsbuf = {r: torch.empty(i.numel(), dtype=f64, device=self.device) for r, i in self._vsend.items()}
+            self._vrbuf = {r: torch.empty(i.numel(), dtype=f64, device=self.device) for r, i in self._vrecv.items()}
+        return self._vsend, self._vrecv
+
+    def halo_exchange(self, v_d):
+        """Refreshes the non-owned (halo / ghost) entries of the local vector ``v_d`` from their owners."""
+        import torch
+        import torch.distributed as dist
+        from ._lib import check, load
+        lib = load()
+        vsend, vrecv = self._vector_lists()
+        st = torch.cuda.current_stream().cuda_stream
+        ops = []
+        for r, idx in sorted(vsend.items()):
+            check(lib.skb_gather_dev(v_d.data_ptr(), idx.data_ptr(), idx.numel(), self._vsbuf[r].data_ptr(), st))
+            ops.append(dist.P2POp(dist.isend, self._vsbuf[r], r))
+        for r in sorted(vrecv):
+            ops.append(dist.P2POp(dist.irecv, self._vrbuf[r], r))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for r, idx in sorted(vrecv.items()):
+            check(lib.skb_scatter_dev(v_d.data_ptr(), idx.data_ptr(), idx.numel(), self._vrbuf[r].data_ptr(), st))
+
+    # ------------------------------------------------------------------ distributed PCG / Newton
+    def _work(self):
+        if not hasattr(self, "_w"):
+            import torch
+            f64 = torch.float64
+            nd = self.plan.ndof
+            z = lambda n: torch.zeros(n, dtype=f64, device=self.device)  # noqa: E731
+            self._w = dict(r=z(nd), z=z(nd), p=z(nd), q=z(nd), dx=z(nd), rhs=z(nd), diag=z(nd), g=z(nd), xtrial=z(nd),
+                           dinv=z(self.plan.n * self.layout.dim ** 2), vals=z(self.plan.nnz), s=z(8), work=z(3 * 1024),
+                           ls=z(4))
+        return self._w
+
+    def pcg(self, vals_d, diag_d, rhs_d, x_d, rtol=1e-10, max_iter=20000, check_every=10):
+        """Block-Jacobi PCG on the distributed matrix (owned rows per rank, complete after the interface exchange).
+        Per iteration: halo exchange of p, SpMV + p.q, all-reduce, fused update, all-reduce, direction."""
+        import torch
+        import torch.distributed as dist
+        from ._lib import check, load
+        lib = load()
+        w = self._work()
+        h = self.plan._h
+        v0, v1 = self.layout.own_lo, self.layout.own_hi
+        st = torch.cuda.current_stream().cuda_stream
+        s = w["s"]
+        P = lambda t: t.data_ptr()  # noqa: E731
+        dp = 0 if diag_d is None else P(diag_d)
+        check(lib.skb_dist_pcg_init_dev(h, P(vals_d), dp, v0, v1, P(rhs_d), P(w["dinv"]), P(x_d), P(w["r"]), P(w["z"]),
+                                        P(w["p"]), P(s), P(w["work"]), st))
+        dist.all_reduce(s[0:2])
+        bb = float(s[1].item())
+        it = 0
+        rr = bb
+        if not bb > 0.0:
+            return 0, 0.0
+        while it < max_iter:
+            for _ in range(min(check_every, max_iter - it)):
+                self.halo_exchange(w["p"])
+                check(lib.skb_dist_spmv_dot_dev(h, P(vals_d), dp, v0, v1, P(w["p"]), P(w["q"]), P(s), P(w["work"]), st))
+                dist.all_reduce(s[2:3])
+                check(lib.skb_dist_pcg_update_dev(h, v0, v1, P(w["dinv"]), P(w["p"]), P(w["q"]), P(x_d), P(w["r"]),
+                                                  P(w["z"]), P(s), P(w["work"]), st))
+                dist.all_reduce(s[3:5])
+                check(lib.skb_dist_pcg_direction_dev(h, v0, v1, P(w["z"]), P(w["p"]), P(s), st))
+                it += 1
+            rr = float(s[1].item())
+            if not rr > rtol * rtol * bb:
+                break
+        return it, float(np.sqrt(rr / bb))
+
+    def newton_step(self, material, x_d, x_tilde_d=None, mass_d=None, kin_scale=0.0, fext_d=None, psd_mode=1,
+                    max_iter=1, do_line_search=True, tolerance=1e-6, ls_alpha=0.01, ls_beta=0.5, ls_max_iter=100,
+                    ls_threshold=1e-12, pcg_rtol=1e-10, pcg_max_iter=20000):
+        """One implicit step on the sharded mesh (same loop as ``skb_newton`` / solvers/newton.py:42-70): assembly +
+        interface exchange, distributed PCG, Armijo backtracking on the all-reduced total energy.  ``x_d`` (local
+        numbering, all local vertices) is updated in place; materials must have been set."""
+        import torch
+        import torch.distributed as dist
+        from ._lib import MATERIAL_IDS, check, load
+        lib = load()
+        w = self._work()
+        h = self.plan._h
+        v0, v1 = self.layout.own_lo, self.layout.own_hi
+        st = torch.cuda.current_stream().cuda_stream
+        P = lambda t: 0 if t is None else t.data_ptr()  # noqa: E731
+        mat = MATERIAL_IDS[material]
+        info = dict(iters=-1, alphas=[], pcg_iters=0, pcg_relres=0.0, step_norm=0.0)
+        ls = w["ls"]
+
+        def total_energy(sstep, with_g):
+            check(lib.skb_dist_newton_terms_dev(h, v0, v1, P(x_d), P(w["dx"]), float(sstep), P(fext_d), P(mass_d),
+                                                P(x_tilde_d), float(kin_scale), 0, 0, P(w["g"]) if with_g else 0,
+                                                P(w["xtrial"]), P(ls), P(w["work"]), st))
+            self.halo_exchange(w["xtrial"])
+            check(lib.skb_energy_dev(h, mat, P(w["xtrial"]), 0, P(ls) + 24, st))
+            dist.all_reduce(ls)
+            e = ls.cpu().numpy()
+            return float(e[0] + e[3]), float(e[1]), float(e[2])
+
+        self.halo_exchange(x_d)
+        for it in range(max_iter):
+            self.gradient_hessian_dev(material, psd_mode, x_d, w["g"], w["vals"])
+            check(lib.skb_dist_newton_rhs_dev(h, v0, v1, P(x_d), P(fext_d), P(mass_d), P(x_tilde_d), float(kin_scale), 0, 0,
+                                              P(w["g"]), P(w["rhs"]), P(w["diag"]), st))
+            pit, relres = self.pcg(w["vals"], w["diag"], w["rhs"], w["dx"], rtol=pcg_rtol, max_iter=pcg_max_iter)
+            alpha = 1.0
+            if do_line_search:
+                e0, gdx, dx2 = total_energy(0.0, True)
+                t, ok = 1.0, False
+                for _ in range(ls_max_iter):
+                    e1, _, _ = total_energy(t, False)
+                    if e1 <= e0 + ls_alpha * t * gdx + ls_threshold:
+                        ok = True
+                        break
+                    t *= ls_beta
+                alpha = t if ok else 0.0
+            else:
+                _, _, dx2 = total_energy(1.0, False)
+            if alpha > 0.0:
+                x_d.copy_(w["xtrial"])          # holds x + alpha*dx with refreshed halo / ghost copies
+            step = alpha * float(np.sqrt(dx2))
+            info["iters"] = it
+            info["alphas"].append(alpha)
+            info["pcg_iters"] += pit
+            info["pcg_relres"] = relres
+            info["step_norm"] = step
+            if step < tolerance:
+                break
+        return info
+
+    def lumped_mass_dofs(self, rho=1.0):
+        """Device vector (local dofs) of the lumped masses ``massmatrix.py:41-49`` of the GLOBAL mesh on this rank's
+        owned dofs: local element sums, then the same interface exchange as the gradient."""
+        import torch
+        w = self._work()
+        d = self.layout.dim
+        m = np.repeat(self.plan.vertex_masses(rho), d)
+        m_d = torch.from_numpy(m).to(self.device)
+        w["vals"].zero_()
+        self.exchange(m_d, w["vals"])
+        return m_d
 
     # ------------------------------------------------------------------ public entry points
     def set_materials(self, mu, lam, vol=None):

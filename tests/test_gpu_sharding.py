@@ -77,3 +77,66 @@ def test_sharded_device_assembly(cells, world):
         ip, ix, _, _ = oe.structural_pattern(T, n, dim)
         ref_nnz = ip[gdof[own] + 1] - ip[gdof[own]]
         assert np.array_equal(np.diff(indptr)[own], ref_nnz)
+
+
+# ------------------------------------------------------------------ 2 GPUs: NCCL exchange + distributed Newton
+def _nccl_worker(rank, world, port, cells, tmp):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dim = len(cells)
+    extent = tuple(1.0 for _ in cells)
+    lay = sh.layout_grid_slab(cells, rank, world)
+    shard = sh.Shard(lay, syn.grid_vertices(cells, extent, lay.l2g), device=rank, tile_elems=32)
+    U = syn.jittered_state_rows(cells, extent, lay.l2g, sigma=0.2)
+    mu, lam = syn.lame()
+    shard.set_materials(mu, lam)
+    rho, h = 1e3, 1e-2
+    x_d = torch.from_numpy(U.reshape(-1).copy()).to(dev)
+    mass_d = shard.lumped_mass_dofs(rho)
+    fext_d = torch.zeros(lay.n_local, dim, dtype=torch.float64, device=dev)
+    fext_d[:, 1] = -9.8
+    fext_d = fext_d.reshape(-1) * mass_d
+    xs = x_d.clone()
+    info = shard.newton_step(MAT, xs, x_tilde_d=x_d, mass_d=mass_d, kin_scale=1.0 / h ** 2, fext_d=fext_d, max_iter=3,
+                             pcg_rtol=1e-12)
+    o0, o1 = lay.own_lo * dim, lay.own_hi * dim
+    np.savez(os.path.join(tmp, "newton%d.npz" % rank), x=xs.cpu().numpy()[o0:o1], lo=lay.v_lo, hi=lay.v_hi,
+             alphas=np.asarray(info["alphas"]), mass=mass_d.cpu().numpy()[o0:o1])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_newton_matches_single_gpu(tmp_path):
+    import os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    import simkit_b200 as sk
+    cells, world = (8, 5, 5), 2
+    port = 29600 + (os.getpid() % 1000)
+    mp.spawn(_nccl_worker, args=(world, port, cells, str(tmp_path)), nprocs=world, join=True)
+    X, T = syn.make_mesh(cells)
+    U = syn.jittered_state(X, cells, (1.0, 1.0, 1.0), sigma=0.2)
+    mu, lam = syn.lame()
+    rho, h = 1e3, 1e-2
+    plan = sk.MeshPlan(X=X, T=T, tile_elems=32)
+    plan.set_materials(mu, lam, plan.volume())
+    mass = np.repeat(plan.vertex_masses(rho), 3)
+    fext = np.zeros_like(X)
+    fext[:, 1] = -9.8
+    fext = fext.reshape(-1) * mass
+    x1, info = plan.newton(MAT, U.reshape(-1), x_tilde=U.reshape(-1), mass=mass, kin_scale=1.0 / h ** 2, f_ext=fext,
+                           max_iter=3, pcg_rtol=1e-12)
+    for r in range(world):
+        d = np.load(os.path.join(str(tmp_path), "newton%d.npz" % r))
+        lo, hi = int(d["lo"]) * 3, int(d["hi"]) * 3
+        assert rel(d["mass"], mass[lo:hi]) < 1e-13
+        assert list(d["alphas"]) == list(info["alphas"])
+        assert rel(d["x"], x1.ravel()[lo:hi]) < 1e-8
