@@ -1,0 +1,14 @@
+#!/bin/bash
+# A/B timing of development builds: scripts/ab.sh tag1 tag2 ...  ("main" = the default library)
+for tag in "$@"; do
+  if [ "$tag" = main ]; then unset SKB_LIB_TAG; else export SKB_LIB_TAG=$tag; fi
+  python bench.py --newton 0 --no-cpu --steps 10 --warmup 3 > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
+  python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/ab_$tag.json")); r=d["roofline"]
+    print("$tag", "step %.3f ms" % d["ms_per_step"], {k: round(v,3) for k,v in r["step_kernels_ms"].items()})
+except Exception as ex:
+    print("$tag", "FAILED", ex)
+PY
+done

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsimkit_b200.so")
+_TAG = os.environ.get("SKB_LIB_TAG", "")  # development: load an A/B build (see build.py)
+LIB_PATH = os.path.join(HERE, "libsimkit_b200" + ("_" + _TAG if _TAG else "") + ".so")
 
 SKB_OK = 0
 SKB_EINVAL = -1

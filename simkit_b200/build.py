@@ -12,8 +12,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "_obj")
-LIB = os.path.join(HERE, "libsimkit_b200.so")
+# development switches: SKB_BUILD_TAG=name builds libsimkit_b200_name.so (objects in _obj_name) with the extra
+# nvcc flags of SKB_BUILD_FLAGS; the loader picks it up through SKB_LIB_TAG (A/B kernel experiments)
+_TAG = os.environ.get("SKB_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "libsimkit_b200" + ("_" + _TAG if _TAG else "") + ".so")
 SOURCES = ["capi.cu", "capi_elements.cu", "capi_solver.cu", "capi_reduced.cu", "capi_dist.cu"]
 
 NVCC_FLAGS = [
@@ -22,7 +25,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr", "--expt-extended-lambda",
     "-Xcompiler", "-fPIC",
     "-Xcudafe", "--diag_suppress=177",
-]
+] + os.environ.get("SKB_BUILD_FLAGS", "").split()
 
 
 def _nvcc():

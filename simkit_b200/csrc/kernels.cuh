@@ -230,6 +230,58 @@ SKB_HD void element_math(const EvalArgs& a, int e, const ElemRaw<D>& raw, int le
   }
 }
 
+// One D x D block K_(ca,cb) of the local stiffness from the element state.  Isotropic models:
+//   K = U M U^T,  M[p][p] = S_pp Wa_p Wb_p + sum_{q != p} a_pq Wa_q Wb_q,  M[p][r] = S_pr Wa_p Wb_r + b_pr Wa_r Wb_p
+// linear elasticity:  K[i][k] = cI d_ik (Wa . Wb) + cT Wa[k] Wb[i] + cR Wa[i] Wb[k].
+template <int D, bool LINEAR>
+SKB_HD Mat<D> local_block(const ElemState<D>& st, int ca, int cb) {
+  constexpr int NP = D * (D - 1) / 2;
+  Mat<D> Kb;
+  if (!LINEAR) {
+    Mat<D> M;
+#pragma unroll
+    for (int pp = 0; pp < D; ++pp)
+#pragma unroll
+      for (int r = 0; r < D; ++r) M.m[pp][r] = st.h.S.m[pp][r] * st.W[ca][pp] * st.W[cb][r];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      int pp, q, r3;
+      pair_index<D>(k, pp, q, r3);
+      M.m[pp][pp] = fma(st.h.a[k] * st.W[ca][q], st.W[cb][q], M.m[pp][pp]);
+      M.m[q][q] = fma(st.h.a[k] * st.W[ca][pp], st.W[cb][pp], M.m[q][q]);
+      M.m[pp][q] = fma(st.h.b[k] * st.W[ca][q], st.W[cb][pp], M.m[pp][q]);
+      M.m[q][pp] = fma(st.h.b[k] * st.W[ca][pp], st.W[cb][q], M.m[q][pp]);
+    }
+    Mat<D> UM = matmul(st.U, M);
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int kk = 0; kk < D; ++kk) {
+        if (ca == cb && kk < i) {
+          Kb.m[i][kk] = Kb.m[kk][i];
+          continue;
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < D; ++r) s = fma(UM.m[i][r], st.U.m[kk][r], s);
+        Kb.m[i][kk] = s;
+      }
+  } else {
+    double dot = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) dot = fma(st.W[ca][j], st.W[cb][j], dot);
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int kk = 0; kk < D; ++kk) {
+        double v = st.cT * st.W[ca][kk] * st.W[cb][i] + st.cR * st.W[ca][i] * st.W[cb][kk];
+        if (i == kk) v = fma(st.cI, dot, v);
+        Kb.m[i][kk] = v;
+      }
+  }
+  return Kb;
+}
+
 // Phase 1b: writes the element's packed (K*D)x(K*D) local stiffness and its local gradient to
 // staging memory laid out [value][le] (stride E) so that a warp's stores hit consecutive banks.
 template <int D, int MAT = -1>
@@ -607,6 +659,9 @@ __global__ void __launch_bounds__(G * 128, 1) assemble_pipelined_kernel(PlanView
     ElemState<D> st;
     if (e < p.t) element_math<D, MAT>(a, e, raw, gt, E, sG, st);
     // take a staging buffer
+#if defined(SKB_EXP_NOSYNC)
+    if (gt == 0) sPick[grp] = grp % NBUF;
+#else
     if (gt == 0) {
       int b = -1;
       while (b < 0) {
@@ -617,6 +672,7 @@ __global__ void __launch_bounds__(G * 128, 1) assemble_pipelined_kernel(PlanView
       }
       sPick[grp] = b;
     }
+#endif
     group_barrier(grp + 1, E);
     const int b = sPick[grp];
     double* sK = reinterpret_cast<double*>(base + (size_t)b * bufB);
@@ -625,8 +681,10 @@ __global__ void __launch_bounds__(G * 128, 1) assemble_pipelined_kernel(PlanView
     parity ^= 1u;
     group_barrier(grp + 1, E);
     if (have_next) load_raw<D>(p, a, en, Tn, raw);  // in flight during phase 2
+#if !defined(SKB_EXP_NOPHASE2)
     for (int w = gt; w < nbe; w += E) block_phase2<D>(sBE, sBS, sTab, w, E, sK, a.pblocks);
     for (int w = gt; w < nve; w += E) vert_phase2<D>(sVE, sVS, w, E, sG, a.pverts);
+#endif
     group_barrier(grp + 1, E);
     if (gt == 0) {
       __threadfence_block();

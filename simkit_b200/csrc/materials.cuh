@@ -67,7 +67,7 @@ SKB_HD double energy_density(int mat, const Mat<D>& F, double mu, double lam) {
     case MAT_STABLE_NEO_HOOKEAN: {
       double IC = frob2(F);
       double J = det(F);
-      double alpha = 1.0 + D * mu / ((D + 1) * lam);
+      double alpha = 1.0 + D * mu * rcp_f64((D + 1) * lam);
       double d = J - alpha;
       return 0.5 * mu * (IC - D) - 0.5 * mu * log(IC + 1.0) + 0.5 * lam * d * d;
     }
@@ -125,8 +125,8 @@ SKB_HD Mat<D> pk1(int mat, const Mat<D>& F, double mu, double lam) {
       double IC = frob2(F);
       double J = det(F);
       Mat<D> c = cofactor(F);
-      double alpha = 1.0 + D * mu / ((D + 1) * lam);
-      double A = mu * (1.0 - 1.0 / (IC + 1.0));
+      double alpha = 1.0 + D * mu * rcp_f64((D + 1) * lam);
+      double A = mu * (1.0 - rcp_f64(IC + 1.0));
       double Dc = lam * (J - alpha);
 #pragma unroll
       for (int i = 0; i < D; ++i)
@@ -137,7 +137,7 @@ SKB_HD Mat<D> pk1(int mat, const Mat<D>& F, double mu, double lam) {
     case MAT_NEO_HOOKEAN: {
       double J = det(F);
       Mat<D> c = cofactor(F);
-      double k = (lam * log(J) - mu) / J;  // F^-T = cof / J
+      double k = (lam * log(J) - mu) * rcp_f64(J);  // F^-T = cof / J
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -215,9 +215,10 @@ SKB_HD Principal<D> principal_hessian(int mat, const Vec<D>& sig, double mu, dou
   }
   switch (mat) {
     case MAT_STABLE_NEO_HOOKEAN: {
-      double alpha = 1.0 + D * mu / ((D + 1) * lam);
-      double A = mu * (1.0 - 1.0 / (IC + 1.0));
-      double B = 2.0 * mu / ((IC + 1.0) * (IC + 1.0));
+      double alpha = 1.0 + D * mu * rcp_f64((D + 1) * lam);
+      double ric = rcp_f64(IC + 1.0);
+      double A = mu * (1.0 - ric);
+      double B = 2.0 * mu * ric * ric;
       double Dc = lam * (J - alpha);
       double ch[D];  // dJ/dsig_p = product of the other stretches
 #pragma unroll
@@ -249,18 +250,21 @@ SKB_HD Principal<D> principal_hessian(int mat, const Vec<D>& sig, double mu, dou
     }
     case MAT_NEO_HOOKEAN: {
       double c1 = lam * log(J) - mu;
+      double rs[D];
+#pragma unroll
+      for (int p = 0; p < D; ++p) rs[p] = rcp_f64(sig[p]);
 #pragma unroll
       for (int p = 0; p < D; ++p)
 #pragma unroll
         for (int q = 0; q < D; ++q) {
-          double inv = 1.0 / (sig[p] * sig[q]);
+          double inv = rs[p] * rs[q];
           h.S.m[p][q] = (p == q) ? (mu + (lam - c1) * inv) : (lam * inv);
         }
 #pragma unroll
       for (int k = 0; k < NP; ++k) {
         int p, q, r;
         pair_index<D>(k, p, q, r);
-        double inv = c1 / (sig[p] * sig[q]);
+        double inv = c1 * rs[p] * rs[q];
         twist[k] = mu + inv;
         flip[k] = mu - inv;
       }
@@ -277,7 +281,7 @@ SKB_HD Principal<D> principal_hessian(int mat, const Vec<D>& sig, double mu, dou
         int p, q, r;
         pair_index<D>(k, p, q, r);
         double den = fmax(sig[p] + sig[q], clampv);
-        twist[k] = mu * (1.0 - 2.0 / den);
+        twist[k] = mu * (1.0 - 2.0 * rcp_f64(den));
         flip[k] = mu;
       }
       break;
@@ -354,7 +358,7 @@ SKB_HD void weight_and_project(Principal<D>& h, double vol, int psd_mode) {
       for (int p = 0; p < D; ++p) {
         double piv = L.m[p][p];
         if (!(piv > 0.0)) need = true;
-        double inv = 1.0 / piv;
+        double inv = rcp_f64(piv);
 #pragma unroll
         for (int q = p + 1; q < D; ++q) {
           double f = L.m[q][p] * inv;

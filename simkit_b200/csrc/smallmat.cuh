@@ -345,18 +345,175 @@ SKB_HD Mat<N> gram(const Mat<N>& F) {
   return C;
 }
 
-// Two-sided Jacobi is stopped once off^2 <= SVD_JACOBI_TOL2 * diag^2 (relative off-diagonal mass
-// 1e-11): the one-sided sweep that follows is one more quadratically convergent sweep, computed from
-// the columns of F V themselves, so it both finishes the convergence (residual ~1e-22) and restores
-// high relative accuracy of the small singular triplets.
-#define SKB_SVD_JACOBI_TOL2 1e-22
+// reciprocal: MUFU.RCP64H seed + one third-order step  y <- y (1 + e + e^2),  e = 1 - x y  (full double
+// accuracy for normal x, 1/0 = inf and 1/inf = 0 kept; no denormal slow path)
+SKB_HD double rcp_f64(double x) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
+  return (e == e) ? fma(y, fma(e, e, e), y) : y;  // x = 0 / inf / NaN: the seed is already the answer
+#else
+  return 1.0 / x;
+#endif
+}
 
+SKB_HD float rsqrt_f32(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+
+// FP32 warm start of the right singular vectors: cyclic Jacobi on the single-precision Gram matrix
+// of F (the FP32 pipe runs beside the FP64 pipe, so these sweeps are nearly free), stopped at a
+// relative off-diagonal mass of ~3e-7.  Returns V as a single-precision matrix that is orthogonal to
+// ~1e-6; the caller re-orthonormalises in double.  NaN / overflow / zero input leaves V = I (the
+// double-precision sweeps that follow then do all the work).
+SKB_HD void jacobi_warm_f32(const Mat<3>& F, float V[3][3]) {
+  float f[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) f[i][j] = (float)F.m[i][j];
+  float a[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j) {
+      float s = f[0][i] * f[0][j];
+      s = fmaf(f[1][i], f[1][j], s);
+      s = fmaf(f[2][i], f[2][j], s);
+      a[i][j] = s;
+      a[j][i] = s;
+    }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0f : 0.0f;
+  for (int sweep = 0; sweep < 6; ++sweep) {
+    const float off = fmaf(a[0][1], a[0][1], fmaf(a[0][2], a[0][2], a[1][2] * a[1][2]));
+    const float dg = fmaf(a[0][0], a[0][0], fmaf(a[1][1], a[1][1], a[2][2] * a[2][2]));
+    if (!(off > 1e-13f * dg) || !(dg < 3e38f)) break;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 3; ++q) {
+        const float apq = a[p][q];
+        const float d = a[q][q] - a[p][p], o = apq + apq;
+        const float h2 = fmaf(d, d, o * o);
+        float c = 1.0f, s = 0.0f, t = 0.0f;
+        if (h2 > 1e-37f && h2 < 3e38f) {
+          const float rh = rsqrt_f32(h2);
+          const float x = fmaf(0.5f * fabsf(d), rh, 0.5f);
+          const float rc = rsqrt_f32(x);
+          c = x * rc;
+          s = (d >= 0.0f ? 0.5f : -0.5f) * o * rh * rc;
+          t = s * rc;
+        }
+        a[p][p] = fmaf(-t, apq, a[p][p]);
+        a[q][q] = fmaf(t, apq, a[q][q]);
+        a[p][q] = 0.0f;
+        a[q][p] = 0.0f;
+        const int k = 3 - p - q;
+        const float akp = a[k][p], akq = a[k][q];
+        const float np_ = fmaf(c, akp, -s * akq), nq_ = fmaf(s, akp, c * akq);
+        a[k][p] = np_;
+        a[p][k] = np_;
+        a[k][q] = nq_;
+        a[q][k] = nq_;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float vp = V[r][p], vq = V[r][q];
+          V[r][p] = fmaf(c, vp, -s * vq);
+          V[r][q] = fmaf(s, vp, c * vq);
+        }
+      }
+  }
+}
+
+// One-sided (Hestenes) sweep over the column pairs of A = F V.  A pair is rotated when its relative
+// inner product exceeds sqrt(thr2); returns whether anything was rotated.
+template <int N>
+SKB_HD bool hestenes_sweep_thr(Mat<N>& A, Mat<N>& V, double thr2) {
+  bool any = false;
+#pragma unroll
+  for (int p = 0; p < N - 1; ++p)
+#pragma unroll
+    for (int q = p + 1; q < N; ++q) {
+      double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        al = fma(A.m[k][p], A.m[k][p], al);
+        be = fma(A.m[k][q], A.m[k][q], be);
+        ga = fma(A.m[k][p], A.m[k][q], ga);
+      }
+      if (ga * ga > thr2 * al * be) {
+        any = true;
+        double c, s, t;
+        sym_schur2_fast(al, be, ga, c, s, t);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          double ap = A.m[k][p], aq = A.m[k][q];
+          A.m[k][p] = fma(c, ap, -s * aq);
+          A.m[k][q] = fma(s, ap, c * aq);
+          double vp = V.m[k][p], vq = V.m[k][q];
+          V.m[k][p] = fma(c, vp, -s * vq);
+          V.m[k][q] = fma(s, vp, c * vq);
+        }
+      }
+    }
+  return any;
+}
+
+// 3x3 rotation-variant SVD.  V starts from the FP32 Jacobi warm start (re-orthonormalised in double by
+// Gram-Schmidt + cross product, so det V = +1 to rounding), then one-sided Hestenes sweeps on the
+// columns of A = F V in double: the first always rotates (quadratic convergence takes the ~1e-6 warm
+// start to ~1e-12), later sweeps only touch pairs whose relative inner product still exceeds 1e-13 and
+// the loop ends when a sweep rotates nothing.  Working on the columns themselves keeps high relative
+// accuracy of the small singular triplets (inverted / flat elements).
 SKB_HD void svd_rv(const Mat<3>& F, Mat<3>& U, Vec<3>& sig, Mat<3>& V) {
+#if defined(SKB_SVD_F64)
+#define SKB_SVD_JACOBI_TOL2 1e-22
   Mat<3> C = gram(F);
   Vec<3> w;
   jacobi_eig<3>(C, w, V, 12, SKB_SVD_JACOBI_TOL2);
   Mat<3> A = matmul(F, V);
   hestenes_sweep<3>(A, V);
+#else
+  {
+    float Vf[3][3];
+    jacobi_warm_f32(F, Vf);
+    double v0[3], v1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      v0[k] = (double)Vf[k][0];
+      v1[k] = (double)Vf[k][1];
+    }
+    const double r0 = rsqrt_f64(fma(v0[0], v0[0], fma(v0[1], v0[1], v0[2] * v0[2])));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v0[k] *= r0;
+    const double d01 = fma(v0[0], v1[0], fma(v0[1], v1[1], v0[2] * v1[2]));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v1[k] = fma(-d01, v0[k], v1[k]);
+    const double r1 = rsqrt_f64(fma(v1[0], v1[0], fma(v1[1], v1[1], v1[2] * v1[2])));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v1[k] *= r1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      V.m[k][0] = v0[k];
+      V.m[k][1] = v1[k];
+    }
+    V.m[0][2] = v0[1] * v1[2] - v0[2] * v1[1];
+    V.m[1][2] = v0[2] * v1[0] - v0[0] * v1[2];
+    V.m[2][2] = v0[0] * v1[1] - v0[1] * v1[0];
+  }
+  Mat<3> A = matmul(F, V);
+  hestenes_sweep_thr<3>(A, V, 1e-34);
+  for (int it = 0; it < 12; ++it)
+    if (!hestenes_sweep_thr<3>(A, V, 1e-26)) break;
+#endif
   Vec<3> n2;  // squared column norms; square roots are taken once, through rsqrt
 #pragma unroll
   for (int j = 0; j < 3; ++j) n2[j] = fma(A.m[0][j], A.m[0][j], fma(A.m[1][j], A.m[1][j], A.m[2][j] * A.m[2][j]));
