@@ -34,12 +34,15 @@ extern "C" {
 #define SKB_ENOGPU (-3)  /* no usable CUDA device                        */
 #define SKB_ENOMEM (-4)
 
-/* material ids -- energies/{stable_neo_hookean,neo_hookean,arap,stvk,linear_elasticity}.py */
+/* material ids -- energies/{stable_neo_hookean,neo_hookean,arap,stvk,linear_elasticity,fcr,
+ * macklin_mueller_neo_hookean}.py */
 #define SKB_MAT_STABLE_NEO_HOOKEAN 0
 #define SKB_MAT_NEO_HOOKEAN 1
 #define SKB_MAT_ARAP 2
 #define SKB_MAT_STVK 3
 #define SKB_MAT_LINEAR_ELASTICITY 4
+#define SKB_MAT_FCR 5                         /* energies/fcr.py:41-302 */
+#define SKB_MAT_MACKLIN_MUELLER_NEO_HOOKEAN 6 /* energies/macklin_mueller_neo_hookean.py:66-370 */
 
 /* psd modes -- where the 1e-6 eigenvalue floor of psd_project.py:37 sits relative to vol */
 #define SKB_PSD_NONE 0

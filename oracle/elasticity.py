@@ -14,7 +14,8 @@ import scipy.sparse as sps
 import scipy.sparse.linalg as spla
 import scipy.linalg
 
-MATERIALS = ("stable_neo_hookean", "neo_hookean", "arap", "stvk", "linear_elasticity")
+MATERIALS = ("stable_neo_hookean", "neo_hookean", "arap", "stvk", "linear_elasticity",
+             "fcr", "macklin_mueller_neo_hookean")
 
 PSD_FLOOR = 1e-6  # psd_project.py:37
 
@@ -214,7 +215,8 @@ def _bc(a, nd):
 
 def energy_element_F(material, F, mu, lam=None):
     """psi (t,1).  sNH stable_neo_hookean.py:65-129; NH neo_hookean.py:64-97;
-    ARAP arap.py:71-91; StVK stvk.py:61-93; LE linear_elasticity.py:43-70."""
+    ARAP arap.py:71-91; StVK stvk.py:61-93; LE linear_elasticity.py:43-70;
+    FCR fcr.py:41-62; Macklin-Mueller NH macklin_mueller_neo_hookean.py:66-122."""
     F = np.asarray(F, dtype=np.float64)
     dim = F.shape[-1]
     F = F.reshape(-1, dim, dim)
@@ -238,6 +240,14 @@ def energy_element_F(material, F, mu, lam=None):
     elif material == "linear_elasticity":
         eps = 0.5 * (F + np.swapaxes(F, 1, 2)) - np.eye(dim)
         psi = mu * np.einsum("tij,tij->t", eps, eps) + 0.5 * lam * np.trace(eps, axis1=1, axis2=2) ** 2
+    elif material == "fcr":
+        # fcr.py:41-62: twice the ARAP shear term plus lam/2 (det F - 1)^2
+        R, _ = polar_svd(F)
+        psi = mu * np.einsum("tij,tij->t", F - R, F - R) + 0.5 * lam * (np.linalg.det(F) - 1.0) ** 2
+    elif material == "macklin_mueller_neo_hookean":
+        # macklin_mueller_neo_hookean.py:66-122: mu (1-J) + lam/2 (1-J)^2 + mu/2 (I_C - d)
+        Jd, _, _ = _det_cof_dcof(F)
+        psi = mu * (1.0 - Jd) + 0.5 * lam * (1.0 - Jd) ** 2 + 0.5 * mu * (I_C - dim)
     else:
         raise ValueError("unknown material " + str(material))
     return psi.reshape(-1, 1)
@@ -270,6 +280,15 @@ def gradient_element_F(material, F, mu, lam=None):
         return F @ S2
     if material == "linear_elasticity":
         return mu * (F + np.swapaxes(F, 1, 2) - 2 * eye) + lam * np.trace(F - eye, axis1=1, axis2=2)[:, None, None] * eye
+    if material == "fcr":
+        # fcr.py:65-125: 2 mu (F - R) + lam (J - 1) cof F
+        Jd, c, _ = _det_cof_dcof(F)
+        R, _ = polar_svd(F)
+        return 2.0 * mu * (F - R) + lam * (Jd[:, None, None] - 1.0) * c
+    if material == "macklin_mueller_neo_hookean":
+        # macklin_mueller_neo_hookean.py:125-185: mu F + (lam (J - 1) - mu) cof F
+        Jd, c, _ = _det_cof_dcof(F)
+        return mu * F + (lam * (Jd[:, None, None] - 1.0) - mu) * c
     raise ValueError("unknown material " + str(material))
 
 
@@ -317,6 +336,20 @@ def hessian_element_F(material, F, mu, lam=None):
             + mu4 * np.einsum("tik,jl->tijkl", FFt, eye)
             + lam4 * np.einsum("tij,tkl->tijkl", F, F)
             + lam4 * trE * II
+        )
+    elif material == "fcr":
+        # fcr.py:128-302: 2 * ARAP Hessian + lam (c c^T + (J - 1) dc/dF)
+        Jd, c, dc = _det_cof_dcof(F)
+        H5 = lam4 * np.einsum("tij,tkl->tijkl", c, c) + lam4 * (Jd.reshape(-1, 1, 1, 1, 1) - 1.0) * dc
+        Hs = 2.0 * mu4.reshape(-1, 1, 1) * (np.eye(b)[None] - rotation_gradient_F(F))
+        return np.ascontiguousarray(H5).reshape(t, b, b) + Hs
+    elif material == "macklin_mueller_neo_hookean":
+        # macklin_mueller_neo_hookean.py:188-370: mu I + lam c c^T + (lam (J - 1) - mu) dc/dF
+        Jd, c, dc = _det_cof_dcof(F)
+        H5 = (
+            mu4 * II
+            + lam4 * np.einsum("tij,tkl->tijkl", c, c)
+            + (lam4 * (Jd.reshape(-1, 1, 1, 1, 1) - 1.0) - mu4) * dc
         )
     elif material == "linear_elasticity":
         TT = np.einsum("il,jk->ijkl", eye, eye)[None]

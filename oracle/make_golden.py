@@ -33,7 +33,11 @@ MATS = {
     "arap": False,
     "stvk": True,
     "linear_elasticity": True,
+    "fcr": True,
+    "macklin_mueller_neo_hookean": True,
 }
+DISPATCH = (("arap", "arap"), ("linear_elasticity", "linear-elasticity"), ("fcr", "fcr"),
+            ("macklin_mueller_neo_hookean", "macklin-mueller-neo-hookean"))
 
 
 def canon(Q):
@@ -86,11 +90,24 @@ def golden_mesh(tag, cells, sigma, seed):
             out[k + "_data"], out[k + "_indices"], out[k + "_indptr"] = Q.data, Q.indices, Q.indptr
         out[f"{m}_E_u"] = g("energy", "u")(U - xb, J, Jxb, *a, vol)
         out[f"{m}_g_u"] = g("gradient", "u")(U - xb, J, Jxb, *a, vol)
-    # elastic dispatcher (psd floor *before* vol): arap + linear-elasticity routes
-    for m, name in (("arap", "arap"), ("linear_elasticity", "linear-elasticity")):
+    # elastic dispatcher (psd floor *before* vol): every routed material
+    for m, name in DISPATCH:
         Q = canon(ske.elastic_hessian_x(U, J, mu, lam, vol, name, psd=True))
         k = f"{m}_Qdisp"
         out[k + "_data"], out[k + "_indices"], out[k + "_indptr"] = Q.data, Q.indices, Q.indptr
+        out[f"{m}_Edisp"] = ske.elastic_energy_x(U, J, mu, lam, vol, name)
+        out[f"{m}_gdisp"] = ske.elastic_gradient_x(U, J, mu, lam, vol, name)
+        out[f"{m}_Hedisp"] = ske.elastic_hessian_element_F(F, mu, lam, name, psd=True)
+    # stretch (S) tier: symmetric stretches of the polar decomposition, full and compact form
+    from simkit.symmetric_stretch_map import symmetric_stretch_map
+    _, Sei = symmetric_stretch_map(1, dim)
+    Sc = S.reshape(t, dim * dim) @ np.asarray(Sei.todense()).T
+    out["S_compact"] = Sc
+    for name, tag_s in (("arap", "arap"), ("macklin-mueller-neo-hookean", "mm")):
+        for form, Sin in (("full", S), ("compact", Sc)):
+            out[f"{tag_s}_S_{form}_E"] = ske.elastic_energy_S(Sin, mu, lam, vol, name)
+            out[f"{tag_s}_S_{form}_g"] = ske.elastic_gradient_S(Sin, mu, lam, vol, name)
+            out[f"{tag_s}_S_{form}_H"] = ske.elastic_hessian_S(Sin, mu, lam, vol, name)
     # psd_project on arbitrary symmetric blocks
     A = rng.standard_normal((40, dim * dim, dim * dim))
     A = A + np.swapaxes(A, 1, 2)

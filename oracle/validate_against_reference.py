@@ -50,6 +50,8 @@ REF = {
     "arap": ("arap", False),
     "stvk": ("stvk", True),
     "linear_elasticity": ("linear_elasticity", True),
+    "fcr": ("fcr", True),
+    "macklin_mueller_neo_hookean": ("macklin_mueller_neo_hookean", True),
 }
 
 
@@ -126,7 +128,8 @@ def main():
 
         # elastic dispatcher: psd before vol (arap, linear-elasticity routed)
         U = syn.jittered_state(X, cells, ext, sigma=0.4)
-        for material, name in (("arap", "arap"), ("linear_elasticity", "linear-elasticity")):
+        for material, name in (("arap", "arap"), ("linear_elasticity", "linear-elasticity"), ("fcr", "fcr"),
+                               ("macklin_mueller_neo_hookean", "macklin-mueller-neo-hookean")):
             Q_ref = ske.elastic_hessian_x(U, J_ref, mu_h, lam_h, vol_ref, name, psd=True)
             Q = oe.hessian_x(material, U, J, mu_h, lam_h, vol, psd=True, psd_before_vol=True)
             check(f"[{dim}D] elastic_hessian_x {name}", Q.toarray(), Q_ref.toarray(), 1e-11)

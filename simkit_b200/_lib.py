@@ -22,6 +22,8 @@ MATERIAL_IDS = {
     "arap": 2,
     "stvk": 3,
     "linear_elasticity": 4,
+    "fcr": 5,
+    "macklin_mueller_neo_hookean": 6,
 }
 PSD_NONE, PSD_AFTER_VOL, PSD_BEFORE_VOL = 0, 1, 2
 

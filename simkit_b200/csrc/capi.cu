@@ -115,6 +115,10 @@ static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
         case MAT_NEO_HOOKEAN: rc = launch_pipelined<3, G, NBUF, MAT_NEO_HOOKEAN>(pl, p, a, psmem, grid, st); break;
         case MAT_ARAP: rc = launch_pipelined<3, G, NBUF, MAT_ARAP>(pl, p, a, psmem, grid, st); break;
         case MAT_STVK: rc = launch_pipelined<3, G, NBUF, MAT_STVK>(pl, p, a, psmem, grid, st); break;
+        case MAT_FCR: rc = launch_pipelined<3, G, NBUF, MAT_FCR>(pl, p, a, psmem, grid, st); break;
+        case MAT_MACKLIN_MUELLER_NEO_HOOKEAN:
+          rc = launch_pipelined<3, G, NBUF, MAT_MACKLIN_MUELLER_NEO_HOOKEAN>(pl, p, a, psmem, grid, st);
+          break;
         default: rc = launch_pipelined<3, G, NBUF, MAT_LINEAR_ELASTICITY>(pl, p, a, psmem, grid, st); break;
       }
     } else {

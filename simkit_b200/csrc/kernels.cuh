@@ -146,7 +146,7 @@ SKB_HD void element_math(const EvalArgs& a, int e, const ElemRaw<D>& raw, int le
   Mat<D> V;
   Vec<D> sig;
   const bool iso = (material != MAT_LINEAR_ELASTICITY);
-  const bool need_svd = (a.want_hess && iso) || (a.want_grad && material == MAT_ARAP);
+  const bool need_svd = (a.want_hess && iso) || (a.want_grad && material_uses_rotation(material));
   if (need_svd) svd_rv(F, st.U, sig, V);
 
   if (a.want_grad) {
@@ -157,6 +157,15 @@ SKB_HD void element_math(const EvalArgs& a, int e, const ElemRaw<D>& raw, int le
       for (int i = 0; i < D; ++i)
 #pragma unroll
         for (int j = 0; j < D; ++j) P.m[i][j] = mu * (F.m[i][j] - R.m[i][j]);
+    } else if (material == MAT_FCR) {
+      // 2 mu (F - R) + lam (J - 1) cof F, with R from the SVD already taken (fcr.py:65-125)
+      Mat<D> R = matmul_nt(st.U, V);
+      Mat<D> c = cofactor(F);
+      const double k = lam * (det(F) - 1.0);
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) P.m[i][j] = fma(2.0 * mu, F.m[i][j] - R.m[i][j], k * c.m[i][j]);
     } else {
       P = pk1<D>(material, F, mu, lam);
     }

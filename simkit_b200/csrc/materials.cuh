@@ -18,6 +18,8 @@
 //   ARAP                energies/arap.py:71-145, rotation_gradient.py:12-75
 //   StVK                energies/stvk.py:61-93,96-127,130-179
 //   linear elasticity   energies/linear_elasticity.py:43-70,73-100,103-136
+//   FCR                 energies/fcr.py:41-62,65-125,128-302 (ARAP shear part x2 + volumetric part)
+//   Macklin-Mueller NH  energies/macklin_mueller_neo_hookean.py:66-122,125-185,188-370
 #pragma once
 #include "smallmat.cuh"
 
@@ -29,8 +31,13 @@ enum Material : int {
   MAT_ARAP = 2,
   MAT_STVK = 3,
   MAT_LINEAR_ELASTICITY = 4,
-  MAT_COUNT = 5
+  MAT_FCR = 5,                          // fixed corotational: 2 psi_arap + lam/2 (J-1)^2
+  MAT_MACKLIN_MUELLER_NEO_HOOKEAN = 6,  // mu (1-J) + lam/2 (1-J)^2 + mu/2 (I_C - d)
+  MAT_COUNT = 7
 };
+
+// models whose stress needs the polar rotation R = U V^T
+SKB_HD bool material_uses_rotation(int mat) { return mat == MAT_ARAP || mat == MAT_FCR; }
 
 // psd_mode: how eigenvalues are floored relative to the quadrature weight
 enum PsdMode : int {
@@ -87,6 +94,24 @@ SKB_HD double energy_density(int mat, const Mat<D>& F, double mu, double lam) {
           s = fma(d, d, s);
         }
       return 0.5 * mu * s;
+    }
+    case MAT_FCR: {
+      Mat<D> R = polar_R(F);
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          double d = F.m[i][j] - R.m[i][j];
+          s = fma(d, d, s);
+        }
+      double dj = det(F) - 1.0;
+      return mu * s + 0.5 * lam * dj * dj;
+    }
+    case MAT_MACKLIN_MUELLER_NEO_HOOKEAN: {
+      double IC = frob2(F);
+      double dj = 1.0 - det(F);
+      return mu * dj + 0.5 * lam * dj * dj + 0.5 * mu * (IC - D);
     }
     case MAT_STVK: {
       Mat<D> C = matmul_tn(F, F);
@@ -150,6 +175,25 @@ SKB_HD Mat<D> pk1(int mat, const Mat<D>& F, double mu, double lam) {
       for (int i = 0; i < D; ++i)
 #pragma unroll
         for (int j = 0; j < D; ++j) P.m[i][j] = mu * (F.m[i][j] - R.m[i][j]);
+      return P;
+    }
+    case MAT_FCR: {
+      Mat<D> R = polar_R(F);
+      Mat<D> c = cofactor(F);
+      double k = lam * (det(F) - 1.0);
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) P.m[i][j] = fma(2.0 * mu, F.m[i][j] - R.m[i][j], k * c.m[i][j]);
+      return P;
+    }
+    case MAT_MACKLIN_MUELLER_NEO_HOOKEAN: {
+      Mat<D> c = cofactor(F);
+      double k = lam * (det(F) - 1.0) - mu;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) P.m[i][j] = fma(mu, F.m[i][j], k * c.m[i][j]);
       return P;
     }
     case MAT_STVK: {
@@ -283,6 +327,46 @@ SKB_HD Principal<D> principal_hessian(int mat, const Vec<D>& sig, double mu, dou
         double den = fmax(sig[p] + sig[q], clampv);
         twist[k] = mu * (1.0 - 2.0 * rcp_f64(den));
         flip[k] = mu;
+      }
+      break;
+    }
+    case MAT_FCR:
+    case MAT_MACKLIN_MUELLER_NEO_HOOKEAN: {
+      // psi = shear(sig) + f(J):  S_pq = shear_pp d_pq + f'' ch_p ch_q + (p != q) f' sig_third,
+      // pair block: twist = tw_shear + f' sig_third, flip = fl_shear - f' sig_third  (d2J/dF2 is the
+      // pure off-diagonal -sig_third on each pair).  FCR: f = lam/2 (J-1)^2, shear = 2 ARAP;
+      // Macklin-Mueller: f = mu (1-J) + lam/2 (1-J)^2, shear = mu/2 I_C.
+      const bool fcr = (mat == MAT_FCR);
+      const double f1 = fcr ? lam * (J - 1.0) : lam * (J - 1.0) - mu;
+      const double sh = fcr ? 2.0 * mu : mu;
+      const double clampv = (D == 2) ? 1e-12 : 1e-8;  // rotation_gradient.py:38,65-67
+      double ch[D];
+#pragma unroll
+      for (int p = 0; p < D; ++p) {
+        double c = 1.0;
+#pragma unroll
+        for (int q = 0; q < D; ++q)
+          if (q != p) c *= sig[q];
+        ch[p] = c;
+      }
+#pragma unroll
+      for (int p = 0; p < D; ++p)
+#pragma unroll
+        for (int q = 0; q < D; ++q) {
+          double v = lam * ch[p] * ch[q];
+          if (p == q) v += sh;
+          else v += f1 * (D == 2 ? 1.0 : sig[3 - p - q]);
+          h.S.m[p][q] = v;
+        }
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        int p, q, r;
+        pair_index<D>(k, p, q, r);
+        const double third = (D == 2) ? 1.0 : sig[r];
+        double tw = sh;
+        if (fcr) tw = sh * (1.0 - 2.0 * rcp_f64(fmax(sig[p] + sig[q], clampv)));
+        twist[k] = tw + f1 * third;
+        flip[k] = sh - f1 * third;
       }
       break;
     }

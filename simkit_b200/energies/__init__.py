@@ -1,8 +1,10 @@
 """Energy modules of the hot path, same star-import surface as simkit/energies/__init__.py:1-16
-restricted to the five materials and the dispatcher this library implements."""
+restricted to the seven materials and the dispatcher this library implements."""
 from .elastic import *  # noqa: F401,F403
 from .arap import *  # noqa: F401,F403
+from .fcr import *  # noqa: F401,F403
 from .linear_elasticity import *  # noqa: F401,F403
+from .macklin_mueller_neo_hookean import *  # noqa: F401,F403
 from .stable_neo_hookean import *  # noqa: F401,F403
 from .stvk import *  # noqa: F401,F403
 from .neo_hookean import *  # noqa: F401,F403

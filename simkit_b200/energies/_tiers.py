@@ -119,6 +119,6 @@ def gradient(material, X, T, mu, lam, U=None):
     return plan.gradient(material, X if U is None else U, mu, lam, None)
 
 
-def hessian(material, X, T, mu, lam, U=None, psd=True):
+def hessian(material, X, T, mu, lam, U=None, psd=True, before_vol=False):
     plan = _self_plan(X, T)
-    return plan.hessian(material, X if U is None else U, mu, lam, None, _psd_mode(material, psd))
+    return plan.hessian(material, X if U is None else U, mu, lam, None, _psd_mode(material, psd, before_vol))

@@ -129,13 +129,54 @@ def test_golden_energies(golden_dir, tag):
         # self-contained tier
         Es = fn(m, "energy", "")(X, T, *a, U)
         assert abs(Es - float(g[f"{m}_E"])) <= ENERGY_TOL * abs(float(g[f"{m}_E"]))
-    for m, name in (("arap", "arap"), ("linear_elasticity", "linear-elasticity")):
+    with pytest.raises(ValueError):
+        sk.elastic_hessian_x(U, J, mu, lam, vol, "no-such-material")
+
+
+DISPATCH = (("arap", "arap"), ("linear_elasticity", "linear-elasticity"), ("fcr", "fcr"),
+            ("macklin_mueller_neo_hookean", "macklin-mueller-neo-hookean"))
+
+
+@pytest.mark.parametrize("tag", MESHES)
+def test_golden_elastic_dispatcher(golden_dir, tag):
+    """energies/elastic.py: every routed material through every tier of the string dispatcher."""
+    g = load(golden_dir, tag)
+    X, T, U, mu, lam, vol, F = (g[k] for k in ("X", "T", "U", "mu", "lam", "vol", "F"))
+    dim = int(g["dim"])
+    n = X.shape[0]
+    J = sk.deformation_jacobian(X, T)
+    xb = g["x_bar"]
+    Jxb = J @ xb.reshape(-1, 1)
+    for m, name in DISPATCH:
         k = f"{m}_Qdisp"
         Qref = sps.csr_matrix((g[k + "_data"], g[k + "_indices"], g[k + "_indptr"]), shape=(n * dim, n * dim))
         Q = sk.elastic_hessian_x(U, J, mu, lam, vol, name, psd=True)
         assert rel(Q.toarray(), Qref.toarray()) < VAL_TOL
+        Qs = sk.elastic_hessian(X, T, mu, lam, name, U=U, psd=True)          # self-contained: same route
+        assert rel(Qs.toarray(), Qref.toarray()) < VAL_TOL
+        Eref = float(g[f"{m}_Edisp"])
+        assert abs(sk.elastic_energy_x(U, J, mu, lam, vol, name) - Eref) <= ENERGY_TOL * abs(Eref)
+        assert abs(sk.elastic_energy(X, T, mu, lam, name, U=U) - Eref) <= ENERGY_TOL * abs(Eref)
+        assert rel(sk.elastic_gradient_x(U, J, mu, lam, vol, name), g[f"{m}_gdisp"]) < VAL_TOL
+        assert rel(sk.elastic_gradient(X, T, mu, lam, name, U=U), g[f"{m}_gdisp"]) < VAL_TOL
+        assert rel(sk.elastic_hessian_element_F(F, mu, lam, name, psd=True), g[f"{m}_Hedisp"]) < VAL_TOL
+        assert rel(sk.elastic_energy_element_F(F, mu, lam, name), g[f"{m}_psi"]) < ENERGY_TOL
+        assert rel(sk.elastic_gradient_element_F(F, mu, lam, name), g[f"{m}_P"]) < VAL_TOL
+        # _u tier dispatches to the per-material modules (floor after vol, LE unprojected)
+        Eu = sk.elastic_energy_u(U - xb, J, Jxb, mu, lam, vol, name)
+        assert abs(Eu - float(g[f"{m}_E_u"])) <= 1e-11 * abs(float(g[f"{m}_E_u"]))
+        assert rel(sk.elastic_gradient_u(U - xb, J, Jxb, mu, lam, vol, name), g[f"{m}_g_u"]) < VAL_TOL
+    # stretch (S) tier: ARAP and Macklin-Mueller, full and compact stretches
+    for name, ts in (("arap", "arap"), ("macklin-mueller-neo-hookean", "mm")):
+        for form, S in (("full", g["polar_S"]), ("compact", g["S_compact"])):
+            Eref = float(g[f"{ts}_S_{form}_E"])
+            assert abs(sk.elastic_energy_S(S, mu, lam, vol, name) - Eref) <= ENERGY_TOL * max(abs(Eref), 1e-300)
+            gs = sk.elastic_gradient_S(S, mu, lam, vol, name)
+            assert gs.shape == g[f"{ts}_S_{form}_g"].shape and rel(gs, g[f"{ts}_S_{form}_g"]) < VAL_TOL
+            Hs = sk.elastic_hessian_S(S, mu, lam, vol, name)
+            assert Hs.shape == g[f"{ts}_S_{form}_H"].shape and rel(Hs, g[f"{ts}_S_{form}_H"]) < VAL_TOL
     with pytest.raises(ValueError):
-        sk.elastic_hessian_x(U, J, mu, lam, vol, "no-such-material")
+        sk.elastic_energy_S(g["polar_S"], mu, lam, vol, "fcr")
 
 
 # --------------------------------------------------------------------------- oracle, config C1 size

@@ -66,11 +66,15 @@ def test_element_and_global_tiers(golden_dir, tag):
             # reference pattern is a subset of the structural pattern
             S = sps.csr_matrix((np.ones(indices.shape[0]), indices, indptr), shape=Qref.shape)
             assert (abs(Qref) > 0).multiply(S).nnz == (abs(Qref) > 0).nnz
-    for m in ("arap", "linear_elasticity"):
+    # elastic dispatcher routes (elastic.py:75): floor before vol, linear elasticity projected too
+    for m in ("arap", "linear_elasticity", "fcr", "macklin_mueller_neo_hookean"):
         k = f"{m}_Qdisp"
         Qref = sps.csr_matrix((g[k + "_data"], g[k + "_indices"], g[k + "_indptr"]), shape=(n * dim, n * dim))
         Q = oe.hessian_x(m, U, J, mu, lam, vol, psd=True, psd_before_vol=True)
         assert rel(Q.toarray(), Qref.toarray()) < 1e-11
+        assert abs(oe.energy_x(m, U, J, mu, lam, vol) - float(g[f"{m}_Edisp"])) <= 1e-13 * abs(float(g[f"{m}_Edisp"]))
+        assert rel(oe.gradient_x(m, U, J, mu, lam, vol), g[f"{m}_gdisp"]) < TOL
+        assert rel(oe.psd_project(oe.hessian_element_F(m, F, mu, lam)), g[f"{m}_Hedisp"]) < 1e-11
 
 
 def test_slot_map_definition(golden_dir):
