@@ -314,6 +314,9 @@ def run_ours(args, rank, world, local_rank):
         return torch.empty(n, dtype=f64, pin_memory=True).numpy()
 
     e2e_steps = max(2, min(args.steps, 5))
+    if args.no_e2e:          # development A/B runs only (scripts/ab.sh): the line then carries no e2e number
+        print(json.dumps({"ms_per_step": ms_step, "roofline": roofline, "dev_only": True}), flush=True)
+        return
     x_h, vol_h = pinned(plan.ndof), pinned(plan.t)
     x_h[:] = U.reshape(-1)
     vol_h[:] = vol.reshape(-1)
@@ -450,6 +453,7 @@ def main():
     ap.add_argument("--newton-steps", type=int, default=2)
     ap.add_argument("--pcg-rtol", type=float, default=1e-10)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="development only: stop after the device-resident timing")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -2,7 +2,8 @@
 # A/B timing of development builds: scripts/ab.sh tag1 tag2 ...  ("main" = the default library)
 for tag in "$@"; do
   if [ "$tag" = main ]; then unset SKB_LIB_TAG; else export SKB_LIB_TAG=$tag; fi
-  python bench.py --newton 0 --no-cpu --steps 10 --warmup 3 > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
+  SKB_VERBOSE=1 python bench.py --newton 0 --no-cpu --no-e2e --steps 10 --warmup 3 > gpurun_out/ab_$tag.json 2> gpurun_out/ab_$tag.err
+  grep simkit_b200: gpurun_out/ab_$tag.err | head -1
   python - <<PY
 import json
 try:

@@ -35,8 +35,9 @@ int make_args(skb_plan* pl, int material, int psd_mode, const double* x, const d
   a.want_hess = vals != nullptr;
   a.g = g;
   a.vals = vals;
-  if (a.want_hess && pl->pblocks.size() < (size_t)pl->d.blocks.n_ts * pl->d.dim * pl->d.dim)
-    pl->pblocks.resize((size_t)pl->d.blocks.n_ts * pl->d.dim * pl->d.dim);
+  const size_t rec_stride = pl->d.dim == 3 ? RecStride<3>::value : RecStride<2>::value;
+  if (a.want_hess && pl->pblocks.size() < (size_t)pl->d.blocks.n_ts * rec_stride)
+    pl->pblocks.resize((size_t)pl->d.blocks.n_ts * rec_stride);
   if (a.want_grad && pl->pverts.size() < (size_t)pl->d.verts.n_ts * pl->d.dim)
     pl->pverts.resize((size_t)pl->d.verts.n_ts * pl->d.dim);
   a.pblocks = raw(pl->pblocks);
@@ -75,15 +76,28 @@ int upload_materials(skb_plan* pl, const double* mu, int64_t mu_n, const double*
   return SKB_OK;
 }
 
+// shape of the pipelined assembly CTA: G groups of E threads (one tile of E elements each) sharing NBUF
+// staging buffers.  Overridable at build time for A/B experiments (scripts/ab.sh).
+#ifndef SKB_PIPE_E
+#define SKB_PIPE_E 128
+#endif
+#ifndef SKB_PIPE_G
+#define SKB_PIPE_G 3
+#endif
+#ifndef SKB_PIPE_NBUF
+#define SKB_PIPE_NBUF 2
+#endif
+
 template <int D, int G, int NBUF, int MAT>
 static int launch_pipelined(skb_plan* pl, const PlanView& p, const EvalArgs& a, size_t psmem, int grid, cudaStream_t st) {
+  constexpr int E = SKB_PIPE_E;
   static bool attr_set = false;
   if (!attr_set) {
-    SKB_CUDA(cudaFuncSetAttribute(assemble_pipelined_kernel<D, G, NBUF, MAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SKB_CUDA(cudaFuncSetAttribute(assemble_pipelined_kernel<D, G, NBUF, MAT, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   227 * 1024));
     attr_set = true;
   }
-  SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_pipelined_kernel<D, G, NBUF, MAT><<<grid, G * 128, psmem, st>>>(p, a));
+  SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_pipelined_kernel<D, G, NBUF, MAT, E><<<grid, G * E, psmem, st>>>(p, a));
   return SKB_OK;
 }
 
@@ -93,15 +107,22 @@ static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
   const int E = p.tile_elems;
   const size_t smem = assemble_smem_bytes<D>(p);
   if (smem > 227 * 1024) return fail(SKB_EINVAL, "tile_elems too large for the 227 KB of shared memory");
-  // pipelined persistent kernel (3 groups, 2 staging buffers) when the tile is 128 elements and its schedule fits
-  constexpr int G = 3, NBUF = 2;
+  // pipelined persistent kernel (default 3 groups, 2 staging buffers) when the tile has SKB_PIPE_E elements and its
+  // schedule fits
+  constexpr int G = SKB_PIPE_G, NBUF = SKB_PIPE_NBUF;
   const size_t psmem = PipeSmem<D>::total(p, G, NBUF);
   static int use_pipe_env = -1;
   if (use_pipe_env < 0) {
     const char* ev = getenv("SKB_ASSEMBLE");
     use_pipe_env = (ev && strcmp(ev, "tile") == 0) ? 0 : 1;
   }
-  const bool pipe = use_pipe_env && E == 128 && psmem <= 227 * 1024 && p.n_tiles >= 2 * G;
+  const bool pipe = use_pipe_env && E == SKB_PIPE_E && psmem <= 227 * 1024 && p.n_tiles >= 2 * G;
+  static bool told = false;
+  if (!told && getenv("SKB_VERBOSE")) {
+    told = true;
+    fprintf(stderr, "simkit_b200: assembly %s, tile %d elements, %d groups, %d buffers, %zu B shared (pipelined) / %zu B (tile)\n",
+            pipe ? "pipelined" : "one CTA per tile", E, G, NBUF, psmem, smem);
+  }
   if (pipe) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
@@ -205,7 +226,7 @@ static int plan_create_common(const double* X, const double* Dop, const void* T,
   if (n <= 0 || t <= 0) return fail(SKB_EINVAL, "empty mesh");
   const int K = dim + 1;
   if (t_total * K * K >= (int64_t)1 << 31 || n * dim >= (int64_t)1 << 31) return fail(SKB_EINVAL, "mesh too large for int32 indexing");
-  if (tile_elems == 0) tile_elems = 128;
+  if (tile_elems == 0) tile_elems = SKB_PIPE_E;
   if (tile_elems < 32 || tile_elems > 256 || tile_elems % 32) return fail(SKB_EINVAL, "tile_elems must be a multiple of 32 in [32, 256]");
   if (skb_device_count() <= device) return fail(SKB_ENOGPU, "no CUDA device " + std::to_string(device));
   SKB_CUDA(cudaSetDevice(device));

@@ -31,6 +31,18 @@ struct EvalArgs {
   double* g;        // (n*dim)
 };
 
+// Doubles per partial block record: the D*D values padded to whole 32-byte sectors (12 for tets, 4 for
+// triangles), so that phase 2 writes every record with 32-byte stores (STG.E.ENL2.256 on sm_100) -- one L2
+// write request per sector and no partially written sector to read-modify-write.
+template <int D>
+struct RecStride {
+  static constexpr int value = ((D * D + 3) / 4) * 4;
+};
+#ifndef SKB_P2_UNROLL
+#define SKB_P2_UNROLL 1
+#endif
+constexpr int kP2Unroll = SKB_P2_UNROLL;  // unroll factor of the phase-2 contribution loops
+
 // packed upper-triangular index of an N x N symmetric matrix
 SKB_HD int sym_idx(int N, int r, int c) {
   if (r > c) {
@@ -39,6 +51,43 @@ SKB_HD int sym_idx(int N, int r, int c) {
     c = tmp;
   }
   return r * N - (r * (r - 1)) / 2 + (c - r);
+}
+
+// Staging layout of one element's local stiffness: the K(K+1)/2 corner pairs (a <= b, row-major over the
+// upper triangle) one after the other; an off-diagonal pair holds its D x D block row-major (D*D values), a
+// diagonal pair the upper triangle of its symmetric block (D(D+1)/2 values).  78 values per tet, 21 per
+// triangle -- the packed upper triangle of the local matrix, regrouped so that phase 2 reads a pair's values
+// at compile-time offsets from one base address.
+template <int K>
+SKB_HD constexpr int diag_pair(int a) { return a * K - (a * (a - 1)) / 2; }  // pair index of (a, a)
+
+template <int K>
+SKB_HD constexpr int pair_of(int a, int b) { return a * K - (a * (a - 1)) / 2 + (b - a); }  // a <= b
+
+template <int D>
+SKB_HD int pair_base(int pp) {
+  constexpr int K = D + 1, DD = D * D, DS = D * (D + 1) / 2;
+  int nd = 0;  // diagonal pairs before pp
+#pragma unroll
+  for (int a = 0; a < K - 1; ++a) nd += (pp > diag_pair<K>(a)) ? 1 : 0;
+  return DD * pp - (DD - DS) * nd;
+}
+
+template <int D>
+SKB_HD bool pair_is_diag(int pp) {
+  constexpr int K = D + 1;
+  bool d = false;
+#pragma unroll
+  for (int a = 0; a < K; ++a) d = d || (pp == diag_pair<K>(a));
+  return d;
+}
+
+// position of entry (i, k) of pair (ca, cb), ca <= cb (i <= k when ca == cb), all compile-time in the callers
+template <int D>
+SKB_HD int stage_idx(int ca, int cb, int i, int k) {
+  constexpr int K = D + 1;
+  const int base = pair_base<D>(pair_of<K>(ca, cb));
+  return base + ((ca == cb) ? (i * D - (i * (i - 1)) / 2 + (k - i)) : (i * D + k));
 }
 
 template <int D>
@@ -300,6 +349,10 @@ SKB_HD void element_store(const EvalArgs& a, const ElemState<D>& st, int le, int
   constexpr int NP = D * (D - 1) / 2;
   const int material = (MAT >= 0) ? MAT : a.material;
   if (!a.want_hess) return;
+#if defined(SKB_EXP_NOSTORE)  // timing experiment only (wrong results): one value instead of the 78
+  sK[le] = st.U.m[0][0] * st.h.S.m[0][0] * st.W[0][0];
+  return;
+#endif
   if (material != MAT_LINEAR_ELASTICITY) {
     // block (ca, cb), ca <= cb:  K = U M U^T,
     //   M[p][p] = S_pp Wa_p Wb_p + sum_{q != p} a_pq Wa_q Wb_q
@@ -331,7 +384,7 @@ SKB_HD void element_store(const EvalArgs& a, const ElemState<D>& st, int le, int
             double s = 0.0;
 #pragma unroll
             for (int r = 0; r < D; ++r) s = fma(UM.m[i][r], st.U.m[kk][r], s);
-            sK[sym_idx(NL, ca * D + i, cb * D + kk) * E + le] = s;
+            sK[stage_idx<D>(ca, cb, i, kk) * E + le] = s;
           }
       }
   } else {
@@ -349,7 +402,7 @@ SKB_HD void element_store(const EvalArgs& a, const ElemState<D>& st, int le, int
             if (ca == cb && kk < i) continue;
             double v = st.cT * st.W[ca][kk] * st.W[cb][i] + st.cR * st.W[ca][i] * st.W[cb][kk];
             if (i == kk) v = fma(st.cI, dot, v);
-            sK[sym_idx(NL, ca * D + i, cb * D + kk) * E + le] = v;
+            sK[stage_idx<D>(ca, cb, i, kk) * E + le] = v;
           }
       }
   }
@@ -399,26 +452,75 @@ SKB_HD unsigned long long pair_index_table(int pp) {
 
 // Phase 2 (blocks): work item = tile-slot entry of an UPPER block (row vertex <= col vertex).
 // Sums the entry's contributions in their fixed order and writes one dim x dim partial record.
-// Corners are sorted per element, so a contribution is always a local pair a <= b and its block
-// is read straight from the packed upper triangle through the pair's index table.
+// Corners are sorted per element, so a contribution is always a local pair a <= b; its values sit at
+// compile-time offsets from (pair base, local element) in the staging buffer, and all of a contribution's
+// loads are issued before the first add.  A slot is either a vertex-vertex block (every contribution a
+// diagonal pair, symmetric, 6 / 3 stored values) or an edge block (every contribution off-diagonal).
 template <int D>
-SKB_HD void block_phase2(const SchedEntry* ent, const uint16_t* src, const unsigned long long* tab, int w, int E,
-                         const double* sK, double* pblocks) {
+SKB_HD void block_phase2(const SchedEntry* ent, const uint16_t* src, int w, int E, const double* sK, double* pblocks) {
   const SchedEntry en = ent[w];
   if (en.q == 0xffffffffu) return;  // alignment padding
-  double acc[D * D];
-#pragma unroll
-  for (int k = 0; k < D * D; ++k) acc[k] = 0.0;
+  constexpr int DD = D * D, DS = D * (D + 1) / 2;
+  double acc[DD];
+  int c = (int)(en.range & 0xffffu);
   const int c1 = (int)(en.range >> 16);
-  for (int c = (int)(en.range & 0xffffu); c < c1; ++c) {
-    const unsigned sc = src[c];
-    const unsigned long long tb = tab[sc >> 8];
-    const double* base = sK + (sc & 0xffu);
+  if (pair_is_diag<D>((int)(src[c] >> 8))) {
+    double sa[DS];
 #pragma unroll
-    for (int k = 0; k < D * D; ++k) acc[k] += base[(int)((tb >> (7 * k)) & 127u) * E];
+    for (int k = 0; k < DS; ++k) sa[k] = 0.0;
+#pragma unroll kP2Unroll
+    for (; c < c1; ++c) {
+      const unsigned sc = src[c];
+      const double* base = sK + pair_base<D>((int)(sc >> 8)) * E + (int)(sc & 0xffu);
+      double v[DS];
+#pragma unroll
+      for (int k = 0; k < DS; ++k) v[k] = base[k * E];
+#pragma unroll
+      for (int k = 0; k < DS; ++k) sa[k] += v[k];
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const int lo = i < k ? i : k, hi = i < k ? k : i;
+        acc[i * D + k] = sa[lo * D - (lo * (lo - 1)) / 2 + (hi - lo)];
+      }
+  } else {
+#pragma unroll
+    for (int k = 0; k < DD; ++k) acc[k] = 0.0;
+#pragma unroll kP2Unroll
+    for (; c < c1; ++c) {
+      const unsigned sc = src[c];
+      const double* base = sK + pair_base<D>((int)(sc >> 8)) * E + (int)(sc & 0xffu);
+      double v[DD];
+#pragma unroll
+      for (int k = 0; k < DD; ++k) v[k] = base[k * E];
+#pragma unroll
+      for (int k = 0; k < DD; ++k) acc[k] += v[k];
+    }
   }
+#if defined(SKB_EXP_NOREC)  // timing experiment only: keep the reduction, drop the record stores
+  {
+    double t = 0.0;
+    for (int k = 0; k < DD; ++k) t += acc[k];
+    if (t != 123.456) return;
+  }
+#endif
+  constexpr int RS = RecStride<D>::value;
+  double* rec = pblocks + (size_t)en.q * RS;
 #pragma unroll
-  for (int k = 0; k < D * D; ++k) pblocks[(size_t)en.q * (D * D) + k] = acc[k];
+  for (int k = 0; k < RS; k += 4) {
+    const double v0 = (k < DD) ? acc[k] : 0.0, v1 = (k + 1 < DD) ? acc[k + 1] : 0.0;
+    const double v2 = (k + 2 < DD) ? acc[k + 2] : 0.0, v3 = (k + 3 < DD) ? acc[k + 3] : 0.0;
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(rec + k), "d"(v0), "d"(v1), "d"(v2), "d"(v3) : "memory");
+#else
+    rec[k] = v0;
+    rec[k + 1] = v1;
+    rec[k + 2] = v2;
+    rec[k + 3] = v3;
+#endif
+  }
 }
 
 // Phase 2 (vertices): work item = tile-vertex entry.
@@ -430,6 +532,7 @@ SKB_HD void vert_phase2(const SchedEntry* ent, const uint16_t* src, int w, int E
 #pragma unroll
   for (int i = 0; i < D; ++i) acc[i] = 0.0;
   const int c1 = (int)(en.range >> 16);
+#pragma unroll kP2Unroll
   for (int c = (int)(en.range & 0xffffu); c < c1; ++c) {
     const unsigned sc = src[c];
     const int le = (int)(sc & 0xffu);
@@ -449,10 +552,24 @@ template <int D>
 SKB_HD void block_finalize(const PlanView& p, int item, const double* pblocks, double* vals) {
   const int u = item / (D * D);
   const int j = item - u * (D * D);
+  constexpr int RS = RecStride<D>::value;
   double acc = 0.0;
+  const int q0 = p.blocks.sp_ptr[u];
   const int q1 = p.blocks.sp_ptr[u + 1];
-  for (int q = p.blocks.sp_ptr[u]; q < q1; ++q) acc += pblocks[(size_t)q * (D * D) + j];
   const UpperPos up = p.upos[u];
+  // memory-level parallelism: the first four records of the slot are requested together (slots have
+  // 2.3 records on average); the summation order stays q0, q0+1, ...
+  const double* r0 = pblocks + (size_t)q0 * RS + j;
+  const int nq = q1 - q0;
+  const double v0 = (nq > 0) ? r0[0] : 0.0;
+  const double v1 = (nq > 1) ? r0[RS] : 0.0;
+  const double v2 = (nq > 2) ? r0[2 * RS] : 0.0;
+  const double v3 = (nq > 3) ? r0[3 * RS] : 0.0;
+  acc = v0;
+  if (nq > 1) acc += v1;
+  if (nq > 2) acc += v2;
+  if (nq > 3) acc += v3;
+  for (int q = q0 + 4; q < q1; ++q) acc += pblocks[(size_t)q * RS + j];
   const int i = j / D, k = j - i * D;
   vals[(size_t)up.base + (size_t)i * up.stride + k] = acc;
   if (up.tbase != up.base) vals[(size_t)up.tbase + (size_t)k * up.tstride + i] = acc;
@@ -534,7 +651,6 @@ __global__ void assemble_tile_kernel(PlanView p, EvalArgs a) {
   sp += (size_t)E * K * sizeof(uint16_t);
   const unsigned mbar = smem_u32(sp);
   unsigned long long* sTab = reinterpret_cast<unsigned long long*>(sp + 16);
-  if (threadIdx.x < NP) sTab[threadIdx.x] = pair_index_table<D>(threadIdx.x);
 
   const int tile = blockIdx.x;
   const int le = threadIdx.x;
@@ -560,7 +676,7 @@ __global__ void assemble_tile_kernel(PlanView p, EvalArgs a) {
   if (e < p.t) element_phase1<D>(p, a, e, le, E, sK, sG);
   mbar_wait(mbar, 0);
   __syncthreads();
-  for (int w = threadIdx.x; w < nbe; w += blockDim.x) block_phase2<D>(sBE, sBS, sTab, w, E, sK, a.pblocks);
+  for (int w = threadIdx.x; w < nbe; w += blockDim.x) block_phase2<D>(sBE, sBS, w, E, sK, a.pblocks);
   for (int w = threadIdx.x; w < nve; w += blockDim.x) vert_phase2<D>(sVE, sVS, w, E, sG, a.pverts);
 }
 
@@ -585,7 +701,7 @@ struct PipeSmem {
   SKB_HD static size_t buffer_bytes(const PlanView& p) { return (size_t)Sizes<D>::NK * p.tile_elems * sizeof(double); }
   SKB_HD static size_t grad_bytes(const PlanView& p) { return (size_t)Sizes<D>::NG * p.tile_elems * sizeof(double); }
   SKB_HD static size_t total(const PlanView& p, int G, int NBUF) {
-    return NBUF * buffer_bytes(p) + G * (grad_bytes(p) + sched_bytes(p)) + 16 * sizeof(unsigned long long) + 8 * (size_t)G + 64;
+    return NBUF * buffer_bytes(p) + G * (grad_bytes(p) + sched_bytes(p)) + 16 * sizeof(unsigned long long) + 8 * (size_t)G + 4 * (size_t)(NBUF + 2 * G) + 32;
   }
 };
 
@@ -593,11 +709,15 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int D, int G, int NBUF, int MAT>
-__global__ void __launch_bounds__(G * 128, 1) assemble_pipelined_kernel(PlanView p, EvalArgs a) {
+#if defined(SKB_PIPE_MAXNREG)  // A/B experiments: explicit register cap instead of the launch-bounds one
+#define SKB_PIPE_BOUNDS(G, E) __maxnreg__(SKB_PIPE_MAXNREG)
+#else
+#define SKB_PIPE_BOUNDS(G, E) __launch_bounds__((G) * (E), 1)
+#endif
+template <int D, int G, int NBUF, int MAT, int E = 128>
+__global__ void SKB_PIPE_BOUNDS(G, E) assemble_pipelined_kernel(PlanView p, EvalArgs a) {
   constexpr int K = D + 1;
   constexpr int NP = K * (K + 1) / 2;
-  constexpr int E = 128;
   extern __shared__ __align__(16) double smem[];
   const int grp = threadIdx.x / E;
   const int gt = threadIdx.x - grp * E;
@@ -618,9 +738,9 @@ __global__ void __launch_bounds__(G * 128, 1) assemble_pipelined_kernel(PlanView
   unsigned long long* sBar = sTab + 16;              // G mbarriers
   int* sBusy = reinterpret_cast<int*>(sBar + G);     // NBUF flags, then G buffer indices
   int* sPick = sBusy + NBUF;
+  int* sNext = sPick + G;                            // per group: next phase-2 chunk
   const unsigned mbar = smem_u32(sBar + grp);
 
-  if (threadIdx.x < NP) sTab[threadIdx.x] = pair_index_table<D>(threadIdx.x);
   if (threadIdx.x < NBUF) sBusy[threadIdx.x] = 0;
   if (gt == 0) mbar_init(mbar, 1);
   __syncthreads();
@@ -682,6 +802,7 @@ __global__ void __launch_bounds__(G * 128, 1) assemble_pipelined_kernel(PlanView
       sPick[grp] = b;
     }
 #endif
+    if (gt == 0) sNext[grp] = 0;
     group_barrier(grp + 1, E);
     const int b = sPick[grp];
     double* sK = reinterpret_cast<double*>(base + (size_t)b * bufB);
@@ -691,8 +812,33 @@ __global__ void __launch_bounds__(G * 128, 1) assemble_pipelined_kernel(PlanView
     group_barrier(grp + 1, E);
     if (have_next) load_raw<D>(p, a, en, Tn, raw);  // in flight during phase 2
 #if !defined(SKB_EXP_NOPHASE2)
-    for (int w = gt; w < nbe; w += E) block_phase2<D>(sBE, sBS, sTab, w, E, sK, a.pblocks);
+#if defined(SKB_P2_STATIC)
+    for (int w = gt; w < nbe; w += E) block_phase2<D>(sBE, sBS, w, E, sK, a.pblocks);
     for (int w = gt; w < nve; w += E) vert_phase2<D>(sVE, sVS, w, E, sG, a.pverts);
+#else
+    // The entries are sorted by descending contribution count, so chunk 0 (32 entries) takes several
+    // times longer than the last one.  The group's warps therefore pull 32-entry chunks from a shared
+    // counter (greedy longest-first scheduling) instead of striding through them; the vertex chunks are
+    // slotted in after the first block chunks.  Which warp sums a slot does not change its value.
+    {
+      const int lane = gt & 31;
+      const int nbc = (nbe + 31) >> 5, nvc = (nve + 31) >> 5;
+      const int nb_first = nbc < 4 ? nbc : 4;
+      for (;;) {
+        int ch = 0;
+        if (lane == 0) ch = atomicAdd(&sNext[grp], 1);
+        ch = __shfl_sync(0xffffffffu, ch, 0);
+        if (ch >= nbc + nvc) break;
+        if (ch >= nb_first && ch < nb_first + nvc) {
+          const int w = ((ch - nb_first) << 5) + lane;
+          if (w < nve) vert_phase2<D>(sVE, sVS, w, E, sG, a.pverts);
+        } else {
+          const int w = ((ch < nb_first ? ch : ch - nvc) << 5) + lane;
+          if (w < nbe) block_phase2<D>(sBE, sBS, w, E, sK, a.pblocks);
+        }
+      }
+    }
+#endif
 #endif
     group_barrier(grp + 1, E);
     if (gt == 0) {

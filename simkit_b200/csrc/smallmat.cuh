@@ -481,6 +481,9 @@ SKB_HD void svd_rv(const Mat<3>& F, Mat<3>& U, Vec<3>& sig, Mat<3>& V) {
   jacobi_eig<3>(C, w, V, 12, SKB_SVD_JACOBI_TOL2);
   Mat<3> A = matmul(F, V);
   hestenes_sweep<3>(A, V);
+#elif defined(SKB_EXP_NOSVD)  // timing experiment only (wrong results): no warm start, no sweeps
+  V = identity<3>();
+  Mat<3> A = F;
 #else
   {
     float Vf[3][3];

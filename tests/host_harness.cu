@@ -24,11 +24,9 @@ static void run_assemble(const PlanView& p, const EvalArgs& a, std::vector<doubl
     }
     constexpr int K = D + 1, NP = K * (K + 1) / 2;
     if (a.want_hess) {
-      unsigned long long tab[NP];
-      for (int pp = 0; pp < NP; ++pp) tab[pp] = pair_index_table<D>(pp);
       int nitems = p.blocks.tl_ptr[tile + 1] - p.blocks.tl_ptr[tile];
       for (int w = 0; w < nitems; ++w)
-        block_phase2<D>(p.blocks.tl_ent + p.blocks.tl_ptr[tile], p.blocks.tc_src + (size_t)tile * E * NP, tab, w, E,
+        block_phase2<D>(p.blocks.tl_ent + p.blocks.tl_ptr[tile], p.blocks.tc_src + (size_t)tile * E * NP, w, E,
                         sK.data(), a.pblocks);
     }
     if (a.want_grad) {
@@ -87,7 +85,7 @@ int hs_run(const double* X, const int64_t* T, int64_t n, int64_t t, int64_t t_ac
   for (size_t i = 0; i < pd.Dm.size(); ++i) Dm_out[i] = pd.Dm[i];
   for (int i = 0; i < t; ++i) vol_out[i] = pd.vol0[i];
   PlanView p = pd.view();
-  std::vector<double> pb((size_t)pd.blocks.n_ts * dim * dim), pv((size_t)pd.verts.n_ts * dim);
+  std::vector<double> pb((size_t)pd.blocks.n_ts * (dim == 3 ? RecStride<3>::value : RecStride<2>::value)), pv((size_t)pd.verts.n_ts * dim);
   EvalArgs a;
   a.material = material;
   a.psd_mode = psd_mode;
