@@ -10,10 +10,10 @@ timeout 900 python bench.py --workload $WL > gpurun_out/${TAG}_bench.json 2> gpu
 tail -c 3000 gpurun_out/${TAG}_bench.json
 tail -5 gpurun_out/${TAG}_bench.err
 # launch list (cold-cache, serialised): shares of the step
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'assemble_tile|finalize_' -c 30 --csv \
-    --log-file gpurun_out/${TAG}_launches.csv python bench.py --workload $WL --steps 3 --warmup 3 --newton 0 --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'assemble_|finalize_' -c 30 --csv \
+    --log-file gpurun_out/${TAG}_launches.csv python bench.py --workload $WL --steps 3 --warmup 3 --newton 0 --no-cpu --no-e2e > gpurun_out/${TAG}_ncu_bench.log 2>&1
 tail -12 gpurun_out/${TAG}_launches.csv
-# full capture of the dominant kernel (after the warm-up launches)
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:assemble_tile -s 3 -c 1 \
-    -o gpurun_out/${TAG}_assemble -f python bench.py --workload $WL --steps 1 --warmup 3 --newton 0 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
+# full capture of the two kernels of the step (after the warm-up launches)
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'assemble_pipelined|finalize_blocks' -s 6 -c 2 \
+    -o gpurun_out/${TAG}_full -f python bench.py --workload $WL --steps 1 --warmup 3 --newton 0 --no-cpu --no-e2e > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out/

@@ -26,7 +26,7 @@ for r in rows[2:]:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]
-data = [r for r in rows[2:] if len(r) == len(h)]
+data = [r for r in rows[2:] if len(r) == len(h) and r != h]
 iS, iI, iSrc = h.index("# Samples"), h.index("Instructions Executed"), h.index("Source")
 cols = {n: i for i, n in enumerate(h)}
 bars = [k for k, r in enumerate(data) if "BAR.SYNC" in r[iSrc]]

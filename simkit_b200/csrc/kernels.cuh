@@ -43,16 +43,6 @@ struct RecStride {
 #endif
 constexpr int kP2Unroll = SKB_P2_UNROLL;  // unroll factor of the phase-2 contribution loops
 
-// packed upper-triangular index of an N x N symmetric matrix
-SKB_HD int sym_idx(int N, int r, int c) {
-  if (r > c) {
-    int tmp = r;
-    r = c;
-    c = tmp;
-  }
-  return r * N - (r * (r - 1)) / 2 + (c - r);
-}
-
 // Staging layout of one element's local stiffness: the K(K+1)/2 corner pairs (a <= b, row-major over the
 // upper triangle) one after the other; an off-diagonal pair holds its D x D block row-major (D*D values), a
 // diagonal pair the upper triangle of its symmetric block (D(D+1)/2 values).  78 values per tet, 21 per
@@ -418,38 +408,6 @@ SKB_HD void element_phase1(const PlanView& p, const EvalArgs& a, int e, int le, 
   element_store<D>(a, st, le, E, sK);
 }
 
-// local corners (a <= b) of pair index pp, K corners: row-major over the upper triangle
-template <int K>
-SKB_HD void pair_ab(int pp, int& a, int& b) {
-  a = 0;
-#pragma unroll
-  for (int r = 1; r < K; ++r) a += (pp >= r * K - (r * (r - 1)) / 2) ? 1 : 0;
-  b = a + pp - (a * K - (a * (a - 1)) / 2);
-}
-
-// Packed-index table of the local stiffness: for pair pp = (a <= b), the D*D positions of block
-// K[(a,i),(b,k)] inside the packed upper triangle of the NL x NL local matrix, 7 bits each
-// (positions < 78), entry (i,k) at bit 7*(i*D+k).  Diagonal pairs mirror k < i.
-template <int D>
-SKB_HD unsigned long long pair_index_table(int pp) {
-  constexpr int K = D + 1;
-  constexpr int NL = K * D;
-  int a, b;
-  pair_ab<K>(pp, a, b);
-  unsigned long long tab = 0;
-  for (int i = 0; i < D; ++i)
-    for (int k = 0; k < D; ++k) {
-      int r = a * D + i, cc = b * D + k;
-      if (r > cc) {
-        const int tmp = r;
-        r = cc;
-        cc = tmp;
-      }
-      tab |= (unsigned long long)((r * (2 * NL - 1 - r)) / 2 + cc) << (7 * (i * D + k));
-    }
-  return tab;
-}
-
 // Phase 2 (blocks): work item = tile-slot entry of an UPPER block (row vertex <= col vertex).
 // Sums the entry's contributions in their fixed order and writes one dim x dim partial record.
 // Corners are sorted per element, so a contribution is always a local pair a <= b; its values sit at
@@ -598,7 +556,7 @@ inline size_t assemble_smem_bytes(const PlanView& p) {
   size_t b = (size_t)Sizes<D>::SMEM_DOUBLES * E * sizeof(double);
   b += (size_t)p.blocks.max_entries * sizeof(SchedEntry) + E * NP * sizeof(uint16_t);
   b += (size_t)p.verts.max_entries * sizeof(SchedEntry) + E * K * sizeof(uint16_t);
-  return b + 16 + 16 * sizeof(unsigned long long);  // mbarrier + pair index table
+  return b + 16;  // + mbarrier
 }
 
 #if defined(__CUDACC__)
@@ -650,7 +608,6 @@ __global__ void assemble_tile_kernel(PlanView p, EvalArgs a) {
   uint16_t* sVS = reinterpret_cast<uint16_t*>(sp);
   sp += (size_t)E * K * sizeof(uint16_t);
   const unsigned mbar = smem_u32(sp);
-  unsigned long long* sTab = reinterpret_cast<unsigned long long*>(sp + 16);
 
   const int tile = blockIdx.x;
   const int le = threadIdx.x;
@@ -701,7 +658,7 @@ struct PipeSmem {
   SKB_HD static size_t buffer_bytes(const PlanView& p) { return (size_t)Sizes<D>::NK * p.tile_elems * sizeof(double); }
   SKB_HD static size_t grad_bytes(const PlanView& p) { return (size_t)Sizes<D>::NG * p.tile_elems * sizeof(double); }
   SKB_HD static size_t total(const PlanView& p, int G, int NBUF) {
-    return NBUF * buffer_bytes(p) + G * (grad_bytes(p) + sched_bytes(p)) + 16 * sizeof(unsigned long long) + 8 * (size_t)G + 4 * (size_t)(NBUF + 2 * G) + 32;
+    return NBUF * buffer_bytes(p) + G * (grad_bytes(p) + sched_bytes(p)) + 8 * (size_t)G + 4 * (size_t)(NBUF + 2 * G) + 32;
   }
 };
 
@@ -734,8 +691,7 @@ __global__ void SKB_PIPE_BOUNDS(G, E) assemble_pipelined_kernel(PlanView p, Eval
   sp += (size_t)p.verts.max_entries * sizeof(SchedEntry);
   uint16_t* sVS = reinterpret_cast<uint16_t*>(sp);
   unsigned char* tail = base + NBUF * bufB + G * schB;
-  unsigned long long* sTab = reinterpret_cast<unsigned long long*>(tail);
-  unsigned long long* sBar = sTab + 16;              // G mbarriers
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(tail);  // G mbarriers
   int* sBusy = reinterpret_cast<int*>(sBar + G);     // NBUF flags, then G buffer indices
   int* sPick = sBusy + NBUF;
   int* sNext = sPick + G;                            // per group: next phase-2 chunk

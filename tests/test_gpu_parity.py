@@ -232,6 +232,35 @@ def test_deterministic_bitwise():
     assert rel(v3, v1) < 1e-13 and rel(g3, g1) < 1e-12
 
 
+def test_pipelined_many_rounds():
+    """A mesh that takes the persistent pipelined kernel several rounds (staging buffers handed between the
+    groups, chunks of phase 2 pulled dynamically): same matrix as the one-CTA-per-tile kernel (other tile
+    size => other summation tree: equal to rounding), bitwise reproducible, and equal to the oracle on a
+    closed sub-mesh."""
+    cells = (36, 36, 36)
+    X, T = syn.make_mesh(cells)
+    U = syn.jittered_state(X, cells, (1.0, 1.0, 1.0), sigma=0.3)
+    mu, lam = syn.heterogeneous_lame(T.shape[0])
+    plan = sk.MeshPlan(X=X, T=T)                       # 2187 tiles of 128: ~5 rounds of 148 x 3 tiles
+    g1, v1 = plan.gradient_hessian("stable_neo_hookean", U, mu, lam, None, 1)
+    g2, v2 = plan.gradient_hessian("stable_neo_hookean", U, mu, lam, None, 1)
+    assert np.array_equal(g1, g2) and np.array_equal(v1, v2)
+    plan64 = sk.MeshPlan(X=X, T=T, tile_elems=64)      # not the pipelined shape: one CTA per tile
+    g3, v3 = plan64.gradient_hessian("stable_neo_hookean", U, mu, lam, None, 1)
+    assert rel(v1, v3) < 1e-13 and rel(g1, g3) < 1e-12
+    Q = plan.csr_matrix(v1)
+    assert abs(Q - Q.T).max() == 0.0
+    nl = 3                                             # first 3 layers of cells: closed sub-mesh
+    tsub = 6 * nl * 36 * 36
+    Ts = T[:tsub]
+    nsub = int(Ts.max()) + 1
+    Jo, volo = oe.deformation_jacobian(X[:nsub], Ts), oe.volume(X[:nsub], Ts)
+    Qo = oe.canonical_csr(oe.hessian_x("stable_neo_hookean", U[:nsub], Jo, mu[:tsub], lam[:tsub], volo))
+    nfull = nl * 37 * 37
+    d = Q[: nfull * 3][:, : nsub * 3] - Qo[: nfull * 3]
+    assert abs(d).max() / abs(Qo).max() < VAL_TOL
+
+
 def test_argument_errors():
     X, T = syn.make_mesh((3, 3, 3))
     plan = sk.MeshPlan(X=X, T=T)
