@@ -10,7 +10,7 @@ neo-Hookean gradient + PSD-projected Hessian + CSR assembly of every element of 
   value     tets/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e       same metric through the public host-pointer API (pinned host buffers, H2D of the state and
             D2H of gradient + CSR values inside the timed region)
-  roofline  dominant kernel (assemble_tile_kernel) against the measured HBM peak; algorithmic bytes per
+  roofline  dominant kernel (assemble_pipelined_kernel) against the measured HBM peak; algorithmic bytes per
             tet from SURVEY.md §8(d); the FP64 fraction is reported beside it
   cpu_baseline  the numpy/scipy oracle (a port of the reference CPU path) on a bounded sample
   newton    one backward-Euler Newton step (assembly + block-Jacobi PCG + line search), steps/s
@@ -30,6 +30,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (printed at NCCL_DEBUG=VERSION) off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 MATERIAL = "stable_neo_hookean"
 METRIC = "tets/s for stable-NH grad+PSD Hessian+CSR assembly"
@@ -414,6 +417,29 @@ def run_ours(args, rank, world, local_rank):
                   "includes": "device-resident state per rank; assembly + interface exchange + distributed PCG + line search",
                   "pcg_ms_per_iter": sec * 1e3 / max(info["pcg_iters"], 1)}
 
+    # ---- reduced (subspace) Hessian B^T H B, BASELINE config 4 (C4 mesh, r = 200) --------------------
+    reduced = None
+    if args.reduced and shard is None:
+        r = args.reduced
+        Bm = syn.smooth_modes(X, r, seed=2)
+        z = 0.02 * np.random.default_rng(3).standard_normal(r)
+        tt = []
+        times = np.zeros(3)
+        for s_ in range(3):
+            t0 = time.perf_counter()
+            Er, gr_, Hr = plan.reduced(MATERIAL, Bm, z, x0=X.reshape(-1), psd_mode=PSD_AFTER_VOL)
+            tt.append(time.perf_counter() - t0)
+            check(lib.skb_reduced_last_times(ptr(times)))
+        b = dim * dim
+        flops = (2.0 * b * b * r + 2.0 * b * r * r) * plan.t        # Y = He JB, Hr += JB^T Y (no symmetry assumed)
+        reduced = {"r": r, "elements": plan.t, "api_ms": min(tt) * 1e3,
+                   "api_includes": "host->device copy of the basis B (%.2f GB) and of z, device->host copy of Hr" % (Bm.nbytes / 1e9),
+                   "element_pass_ms": float(times[0]), "contraction_ms": float(times[1]), "device_ms": float(times[2]),
+                   "contraction_tflops": flops / (times[1] * 1e-3) / 1e12, "algorithmic_flops": flops,
+                   "frac_fp64_peak": flops / (times[1] * 1e-3) / 1e12 / max(fp64_peak, 1e-30),
+                   "peak_source": "FP64 FMA peak measured here (skb_fp64_peak); the contraction runs on DMMA.8x8x4 tiles",
+                   "hr_symmetry_defect": float(np.abs(Hr - Hr.T).max() / np.abs(Hr).max())}
+
     # ---- CPU baseline (rank 0, N = 1) -----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -437,6 +463,8 @@ def run_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "newton": newton,
         }
+        if reduced is not None:
+            line["reduced"] = reduced
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -452,6 +480,7 @@ def main():
     ap.add_argument("--newton", type=int, default=1, help="also time one backward-Euler Newton step (0 = skip)")
     ap.add_argument("--newton-steps", type=int, default=2)
     ap.add_argument("--pcg-rtol", type=float, default=1e-10)
+    ap.add_argument("--reduced", type=int, default=0, help="also time the reduced Hessian B^T H B with this many modes (config 4: --workload C4 --reduced 200)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="development only: stop after the device-resident timing")
     args = ap.parse_args()

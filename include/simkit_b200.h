@@ -274,6 +274,10 @@ int skb_reduced_gradient_hessian(int material, int psd_mode, int dim, int64_t t,
 int skb_reduced_hessian_from_basis(skb_plan* plan, int material, int psd_mode, int64_t r,
                                    const double* B, const double* x0, const double* z,
                                    double* energy, double* gr, double* Hr);
+/* Measurement hook (bench.py, no reference counterpart): CUDA-event times in ms of the last reduced call on
+ * this thread's device: out[0] element pass (F -> He, P, psi), out[1] the B^T H B contraction kernel
+ * (FP64 DMMA tiles), out[2] whole device section including the partial sums. */
+int skb_reduced_last_times(double out[3]);
 
 /* fast_sandwich_transform_clustered.py:15-158.
  * A: (m1, b*t) dense row-major, B: (b*t, m2) dense row-major, l: (t) cluster labels,

@@ -18,6 +18,8 @@
 
 namespace skb {
 
+static double g_reduced_ms[3] = {0.0, 0.0, 0.0};  // skb_reduced_last_times
+
 constexpr int RH_THREADS = 256;  // 8 warps
 constexpr int RH_ELEMS = 4;      // elements per k-chunk (rows = RH_ELEMS * b, multiple of 4 for b in {4, 9})
 
@@ -341,9 +343,15 @@ static int reduced_run(skb_plan* pl, int material, int psd_mode, int64_t t, int6
     if (lam_h) { lam_p = raw(lam); lam_s = lam_n > 1; }
     vol_p = raw(vol); vol_s = vol_n > 1;
   }
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; ++i) SKB_CUDA(cudaEventCreate(&ev[i]));
+  SKB_CUDA(cudaEventRecord(ev[0], st));
   reduced_pass1_kernel<D><<<(unsigned)((t + 127) / 128), 128, 0, st>>>(material, psd_mode, t, raw(F), mu_p, mu_s, lam_p, lam_s,
                                                                        vol_p, vol_s, raw(He), raw(Pw), raw(psi));
   SKB_CUDA(cudaGetLastError());
+  SKB_CUDA(cudaEventRecord(ev[1], st));
+  SKB_CUDA(cudaEventRecord(ev[2], st));
+  SKB_CUDA(cudaEventRecord(ev[3], st));
   if (energy) {
     // fixed-order two-stage sum
     const int nb = 1024;
@@ -381,9 +389,11 @@ static int reduced_run(skb_plan* pl, int material, int psd_mode, int64_t t, int6
     PlanView pv;
     memset(&pv, 0, sizeof(pv));
     if (pl) pv = pl->view();
+    SKB_CUDA(cudaEventRecord(ev[2], st));
     reduced_pass2_kernel<D><<<dim3(grid, npanels), RH_THREADS, smem, st>>>(t, (int)r, tcp, pl ? nullptr : raw(JB), pv, pl ? 1 : 0,
                                                            pl ? raw(Bm) : nullptr, raw(He), raw(Pw), raw(Hpart), raw(gpart));
     SKB_CUDA(cudaGetLastError());
+    SKB_CUDA(cudaEventRecord(ev[3], st));
     sum_partials_kernel<<<(unsigned)((r * r + 255) / 256), 256, 0, st>>>(grid, r * r, raw(Hpart), raw(Hd));
     sum_partials_kernel<<<(unsigned)((r + 255) / 256), 256, 0, st>>>(grid, r, raw(gpart), raw(gd));
     SKB_CUDA(cudaDeviceSynchronize());
@@ -391,6 +401,16 @@ static int reduced_run(skb_plan* pl, int material, int psd_mode, int64_t t, int6
     if (gr) SKB_CUDA(cudaMemcpy(gr, raw(gd), r * sizeof(double), cudaMemcpyDeviceToHost));
   }
   SKB_CUDA(cudaDeviceSynchronize());
+  {
+    float a = 0.f, b = 0.f, c = 0.f;
+    cudaEventElapsedTime(&a, ev[0], ev[1]);
+    cudaEventElapsedTime(&b, ev[2], ev[3]);
+    cudaEventElapsedTime(&c, ev[0], ev[3]);
+    g_reduced_ms[0] = a;
+    g_reduced_ms[1] = b;
+    g_reduced_ms[2] = c;
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+  }
   return SKB_OK;
   SKB_CATCH
 }
@@ -410,6 +430,12 @@ int skb_reduced_gradient_hessian(int material, int psd_mode, int dim, int64_t t,
   if (skb_device_count() <= 0) return fail(SKB_ENOGPU, "no CUDA device");
   return dim == 3 ? reduced_run<3>(nullptr, material, psd_mode, t, r, JB, Jx0, nullptr, nullptr, z, mu, mu_n, lam, lam_n, vol, vol_n, energy, gr, Hr)
                   : reduced_run<2>(nullptr, material, psd_mode, t, r, JB, Jx0, nullptr, nullptr, z, mu, mu_n, lam, lam_n, vol, vol_n, energy, gr, Hr);
+}
+
+int skb_reduced_last_times(double out[3]) {
+  if (!out) return fail(SKB_EINVAL, "null argument");
+  for (int i = 0; i < 3; ++i) out[i] = g_reduced_ms[i];
+  return SKB_OK;
 }
 
 int skb_reduced_hessian_from_basis(skb_plan* pl, int material, int psd_mode, int64_t r, const double* B,
