@@ -15,10 +15,10 @@
 
 namespace skb {
 
-constexpr int DIST_GRID = 592;  // 4 CTAs per SM on a B200; fixed so that the summation tree is fixed
+constexpr int DIST_GRID = 148 * PCG_CTAS_PER_SM;  // full occupancy on a B200; fixed so that the summation tree is fixed
 
 template <int D>
-__global__ void dist_init_kernel(PlanView p, const double* vals, const double* dadd, int v0, int v1, const double* rhs,
+__global__ void __launch_bounds__(PCG_THREADS, PCG_CTAS_PER_SM) dist_init_kernel(PlanView p, const double* vals, const double* dadd, int v0, int v1, const double* rhs,
                                  double* dinv, double* x, double* r, double* z, double* pv, double* part) {
   __shared__ double sh[32];
   double rz = 0.0, rr = 0.0;
@@ -74,7 +74,7 @@ __global__ void dist_init_kernel(PlanView p, const double* vals, const double* d
 
 // y = (A + diag) x for the block rows [v0, v1); per-thread partial of x.y
 template <int D>
-__global__ void dist_spmv_dot_kernel(PlanView p, const double* __restrict__ vals, const double* __restrict__ dadd,
+__global__ void __launch_bounds__(PCG_THREADS, PCG_CTAS_PER_SM) dist_spmv_dot_kernel(PlanView p, const double* __restrict__ vals, const double* __restrict__ dadd,
                                      const double* __restrict__ x, double* __restrict__ y, int v0, int v1, double* part) {
   __shared__ double sh[32];
   constexpr int GW = 32 / SPMV_GROUP;
@@ -121,7 +121,7 @@ __global__ void dist_spmv_dot_kernel(PlanView p, const double* __restrict__ vals
 }
 
 template <int D>
-__global__ void dist_update_kernel(int v0, int v1, const double* dinv, const double* pv, const double* q, double* x,
+__global__ void __launch_bounds__(PCG_THREADS, PCG_CTAS_PER_SM) dist_update_kernel(int v0, int v1, const double* dinv, const double* pv, const double* q, double* x,
                                    double* r, double* z, const double* s, double* part) {
   __shared__ double sh[32];
   const double alpha = (s[2] != 0.0) ? s[0] / s[2] : 0.0;  // p == 0: already converged exactly

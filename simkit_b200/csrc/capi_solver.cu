@@ -12,10 +12,12 @@ static int pcg_grid(const skb_plan* pl) {
   // fixed grid: a multiple of the SM count, no more CTAs than there is work
   const int per_cta_rows = PCG_THREADS / SPMV_GROUP;
   int want = (pl->d.n + per_cta_rows - 1) / per_cta_rows;
-  int grid = sms * 4;
+  // 8 CTAs of 256 threads per SM = full occupancy: the PCG kernels are latency-bound streams (ncu: long-scoreboard
+  // stalls, 4.3 TB/s at 4 CTAs per SM), bytes in flight scale with resident warps
+  int grid = sms * PCG_CTAS_PER_SM;
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  if (grid > 1024) grid = 1024;
+  if (grid > PCG_MAX_GRID) grid = PCG_MAX_GRID;
   return grid;
 }
 
@@ -36,9 +38,9 @@ static int pcg_loop(skb_plan* pl, int nb, int grid, SpmvDot spmv_dot, const doub
                     double rtol, int max_iter, double* x, double* r, double* z, double* pv, double* q,
                     double* red, int* iters, double* relres, cudaStream_t st) {
   double* part_pq = red;
-  double* part_rz = part_pq + 1024;
-  double* part_rr = part_rz + 1024;
-  PcgScalars* sc = reinterpret_cast<PcgScalars*>(part_rr + 1024);  // two ping-pong slots
+  double* part_rz = part_pq + PCG_MAX_GRID;
+  double* part_rr = part_rz + PCG_MAX_GRID;
+  PcgScalars* sc = reinterpret_cast<PcgScalars*>(part_rr + PCG_MAX_GRID);  // two ping-pong slots
   SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st,
              pcg_init_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, rhs, dinv, x, r, z, pv, part_rz, part_rr));
   SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg_init_scalars_kernel<<<1, PCG_THREADS, 0, st>>>(part_rz, part_rr, grid, rtol, sc));
@@ -85,7 +87,7 @@ static int pcg_run(skb_plan* pl, const double* vals, const double* dadd, const d
   ensure(pl->w_p, nd);
   ensure(pl->w_q, nd);
   ensure(pl->w_dinv, (size_t)p.n * D * D);
-  ensure(pl->w_red, 3 * 1024 + 64);
+  ensure(pl->w_red, 3 * PCG_MAX_GRID + 64);
   double* dinv = raw(pl->w_dinv);
   SKB_LAUNCH(pl, SKB_K_OTHER, st, block_jacobi_kernel<D><<<(p.n + 127) / 128, 128, 0, st>>>(p, vals, dadd, dinv));
   auto spmv_dot = [&](const double* pvec, double* q, double* part_pq, const PcgScalars* sc) {
@@ -108,14 +110,14 @@ static int csr_pcg_run(int64_t n, const int32_t* indptr_h, const int32_t* indice
   const int64_t nnz = indptr_h[n];
   dvec<int> indptr(indptr_h, indptr_h + n + 1), indices(indices_h, indices_h + nnz);
   dvec<double> vals(vals_h, vals_h + nnz), rhs(rhs_h, rhs_h + n), x(n), r(n), z(n), pv(n), q(n),
-      dinv((size_t)nb * D * D), red(3 * 1024 + 64);
+      dinv((size_t)nb * D * D), red(3 * PCG_MAX_GRID + 64);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   int grid = sms * 4;
   const int want = (int)((n + (PCG_THREADS / SPMV_GROUP) - 1) / (PCG_THREADS / SPMV_GROUP));
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
-  if (grid > 1024) grid = 1024;
+  if (grid > PCG_MAX_GRID) grid = PCG_MAX_GRID;
   cudaStream_t st = 0;
   csr_block_jacobi_kernel<D><<<(nb + 127) / 128, 128, 0, st>>>(nb, raw(indptr), raw(indices), raw(vals), raw(dinv));
   const int* ip = raw(indptr);
@@ -250,7 +252,7 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
   ensure(pl->x, nd);  // rhs
   ensure(pl->w_diag, nd);
   pl->vals.resize(pl->nnz());
-  ensure(pl->esums, 3 * 1024 + 8);
+  ensure(pl->esums, 3 * PCG_MAX_GRID + 8);
   double* x = raw(pl->w_x);
   double* xtrial = raw(pl->w_xtrial);
   double* dx = raw(pl->w_dx);
@@ -277,11 +279,11 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
     d_pt = raw(pinbuf) + nd;
   }
   const int vgrid = pcg_grid(pl);
-  dvec<double> parts(3 * 1024 + 8);
+  dvec<double> parts(3 * PCG_MAX_GRID + 8);
   double* part_e = raw(parts);
-  double* part_g = part_e + 1024;
-  double* part_d = part_g + 1024;
-  double* red = part_d + 1024;  // 3 sums + elastic energy
+  double* part_g = part_e + PCG_MAX_GRID;
+  double* part_d = part_g + PCG_MAX_GRID;
+  double* red = part_d + PCG_MAX_GRID;  // 3 sums + elastic energy
   double hred[4];
 
   // total energy at x + s*dx (also leaves the trial point in xtrial)

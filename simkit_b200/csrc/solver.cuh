@@ -16,6 +16,11 @@
 namespace skb {
 
 constexpr int PCG_THREADS = 256;
+#ifndef SKB_PCG_CTAS_PER_SM
+#define SKB_PCG_CTAS_PER_SM 8
+#endif
+constexpr int PCG_MAX_GRID = 2048;  // size of each per-CTA partial-sum array
+constexpr int PCG_CTAS_PER_SM = SKB_PCG_CTAS_PER_SM;  // resident CTAs per SM the PCG kernels are compiled and launched for
 constexpr int SPMV_GROUP = 8;  // lanes cooperating on one block row
 
 // scalars kept on the device between the kernels of an iteration
@@ -98,7 +103,7 @@ __global__ void spmv_kernel(PlanView p, const double* vals, const double* dadd, 
 }
 
 template <int D>
-__global__ void pcg_spmv_dot_kernel(PlanView p, const double* vals, const double* dadd, const double* pvec,
+__global__ void __launch_bounds__(PCG_THREADS, PCG_CTAS_PER_SM) pcg_spmv_dot_kernel(PlanView p, const double* vals, const double* dadd, const double* pvec,
                                     double* q, double* part_pq, const PcgScalars* sc) {
   __shared__ double sh[32];
   if (sc->done) return;
@@ -193,7 +198,7 @@ static __global__ void pcg_init_scalars_kernel(const double* part_rz, const doub
 }
 
 template <int D>
-__global__ void pcg_update_kernel(int nb, const double* dinv, const double* pv, const double* q, double* x,
+__global__ void __launch_bounds__(PCG_THREADS, PCG_CTAS_PER_SM) pcg_update_kernel(int nb, const double* dinv, const double* pv, const double* q, double* x,
                                   double* r, double* z, const double* part_pq, int nparts, double* part_rz,
                                   double* part_rr, const PcgScalars* sc) {
   __shared__ double sh[32];
@@ -227,7 +232,7 @@ __global__ void pcg_update_kernel(int nb, const double* dinv, const double* pv, 
 }
 
 template <int D>
-__global__ void pcg_direction_kernel(int nb, const double* z, double* pv, const double* part_rz,
+__global__ void __launch_bounds__(PCG_THREADS, PCG_CTAS_PER_SM) pcg_direction_kernel(int nb, const double* z, double* pv, const double* part_rz,
                                      const double* part_rr, int nparts, double rtol, PcgScalars* sc,
                                      PcgScalars* sc_next) {
   __shared__ double sh[32];

@@ -298,7 +298,7 @@ class Shard:
             nd = self.plan.ndof
             z = lambda n: torch.zeros(n, dtype=f64, device=self.device)  # noqa: E731
             self._w = dict(r=z(nd), z=z(nd), p=z(nd), q=z(nd), dx=z(nd), rhs=z(nd), diag=z(nd), g=z(nd), xtrial=z(nd),
-                           dinv=z(self.plan.n * self.layout.dim ** 2), vals=z(self.plan.nnz), s=z(8), work=z(3 * 1024),
+                           dinv=z(self.plan.n * self.layout.dim ** 2), vals=z(self.plan.nnz), s=z(8), work=z(3 * 2048),
                            ls=z(4))
         return self._w
 
