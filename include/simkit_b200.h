@@ -173,6 +173,9 @@ int skb_dist_newton_terms_dev(skb_plan* plan, int v0, int v1, const double* x, c
                               double* work, void* stream);
 /* measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the compute roofline denominator */
 int skb_fp64_peak(int device, double* tflops);
+/* measured FP64 tensor-core throughput (DMMA.8x8x4 = mma.sync.m8n8k4.f64, 512 flops per warp instruction):
+ * the roofline denominator of the reduced-Hessian contraction */
+int skb_dmma_peak(int device, double* tflops);
 
 /* ------------------------------------------------------- element tiers -----
  * Batched per-element functions on arbitrary F (host pointers):

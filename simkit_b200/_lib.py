@@ -86,6 +86,7 @@ SIGNATURES = {
     "skb_dist_newton_rhs_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
     "skb_dist_newton_terms_dev": (_int, [_vp, _int, _int, _vp, _vp, _dbl, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "skb_fp64_peak": (_int, [_int, ctypes.POINTER(_dbl)]),
+    "skb_dmma_peak": (_int, [_int, ctypes.POINTER(_dbl)]),
     "skb_element_energy": (_int, [_int, _int, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),
     "skb_element_gradient": (_int, [_int, _int, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),
     "skb_element_hessian": (_int, [_int, _int, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),

@@ -171,6 +171,24 @@ static int run_element(int op, int material, int dim, int64_t t, const double* F
 }
 
 
+// 8 independent DMMA.8x8x4 chains per warp (mma.sync.m8n8k4.f64)
+__global__ void dmma_peak_kernel(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = (double)threadIdx.x * 1e-3 + k;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c[k][0]), "+d"(c[k][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void fp64_peak_kernel(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
 #pragma unroll 4
@@ -252,6 +270,38 @@ int skb_psd_project(int64_t t, int b, const double* H, int method, double* out) 
   SKB_CATCH
 }
 
+
+// FP64 tensor-core throughput probe: 8 independent DMMA.8x8x4 accumulator chains per warp, full occupancy.
+int skb_dmma_peak(int device, double* tflops) {
+  if (!tflops) return fail(SKB_EINVAL, "null argument");
+  if (skb_device_count() <= device) return fail(SKB_ENOGPU, "no CUDA device");
+  SKB_CUDA(cudaSetDevice(device));
+  SKB_TRY
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int threads = 256, blocks = sms * 8, iters = 4096;
+  dvec<double> out((size_t)threads * blocks);
+  cudaEvent_t a, b;
+  SKB_CUDA(cudaEventCreate(&a));
+  SKB_CUDA(cudaEventCreate(&b));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    SKB_CUDA(cudaEventRecord(a));
+    dmma_peak_kernel<<<blocks, threads>>>(raw(out), iters, 1.0000001, 1e-9);
+    SKB_CUDA(cudaEventRecord(b));
+    SKB_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    SKB_CUDA(cudaEventElapsedTime(&ms, a, b));
+    // one m8n8k4 = 8*8*4 FMAs = 512 flops per warp instruction
+    const double tf = 512.0 * 8.0 * iters * (double)(threads / 32) * blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *tflops = best;
+  return SKB_OK;
+  SKB_CATCH
+}
 
 // FP64 FMA throughput probe: 8 independent DFMA chains per thread, full occupancy.
 int skb_fp64_peak(int device, double* tflops) {

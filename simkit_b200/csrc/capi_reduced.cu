@@ -236,6 +236,280 @@ reduced_pass2_kernel(int64_t t, int r, int tcp, const double* JB, PlanView pv, i
   if (blockIdx.y == 0 && threadIdx.x < r) gpart[(size_t)blockIdx.x * r + threadIdx.x] = gacc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pass 2, register-blocked and TMA-staged (used when r is even, so that every operator row is a
+// 16-byte multiple).  One persistent CTA of 8 warps per SM walks its element range in chunks of CE
+// elements:
+//   * the raw operator rows of the NEXT chunk -- the 12 (6 in 2D) rows B[(v_a, i), :] of each element's
+//     corner vertices, or its b rows of a dense JB -- are fetched by the TMA unit (1-D bulk copies
+//     completing on an mbarrier) into a double-buffered landing area while the current chunk computes;
+//   * sJ = rows of J B for the chunk (4 FMAs per value from the landing area), sY = He . sJ;
+//   * Hr += sJ^T sY on FP64 tensor-core tiles (DMMA.8x8x4).  The symmetric output is cut into blocks of
+//     RB_T x RB_T tiles; only the block pairs (bi <= bj) are computed (15 of 25 at r = 200) and a warp
+//     owns up to two of them, so one k-step of a pair loads 2 x RB_T operand fragments from shared memory
+//     for RB_T^2 DMMAs (10 loads per 25 instead of 50 per 25).
+// The shared-memory row stride is = 4 (mod 16) doubles, which makes every fragment load conflict-free.
+// Per-CTA partial matrices are summed in CTA order and the lower triangle is mirrored from the upper one
+// (deterministic, exactly symmetric).
+constexpr int RB_T = 5;           // tiles per block side (40 columns)
+constexpr int RB_THREADS = 256;   // 8 warps
+constexpr int RB_PPW = 2;         // block pairs per warp (2 x 50 accumulator doubles in registers)
+constexpr int RB_MAXPAIRS = RB_PPW * RB_THREADS / 32;  // block pairs per pass
+
+template <int D>
+struct RBShape {
+  static constexpr int B = D * D;
+  static constexpr int CE = (D == 3) ? 2 : 4;            // elements per chunk
+  static constexpr int KR = ((CE * B + 3) / 4) * 4;       // rows per chunk, padded to the DMMA k = 4
+  static constexpr int RAWROWS = (D + 1) * D;             // landing rows per element (from a basis)
+};
+
+// Row stride (doubles) of the sJ / sY staging: every tile column a block pair can touch exists (zero beyond r,
+// so the fragment loads need no guards), rounded to 16 and + 4 so that the stride is = 4 (mod 16).
+__host__ __device__ inline int rb_stride(int r) {
+  const int rt = (r + 7) / 8;
+  const int cols = ((rt + RB_T - 1) / RB_T) * RB_T * 8;
+  return ((cols + 15) / 16) * 16 + 4;
+}
+
+template <int D>
+__global__ void __launch_bounds__(RB_THREADS, 1)
+reduced_pass2_blocked_kernel(int64_t t, int r, const double* JB, PlanView pv, int use_plan, const double* Bm,
+                             const double* He, const double* Pw, double* Hpart, double* gpart) {
+  using S = RBShape<D>;
+  constexpr int B = S::B, CE = S::CE, KR = S::KR, K = D + 1;
+  constexpr int NSMALL = CE * (B * B + B + D * D);         // He, vol*P and D of a chunk: one value per thread
+  static_assert(NSMALL <= RB_THREADS, "small operands are prefetched one per thread");
+  extern __shared__ __align__(16) double sm[];
+  const int rt = (r + 7) / 8;
+  const int RP = rb_stride(r);
+  const int nblk = (rt + RB_T - 1) / RB_T;
+  const int npairs_all = nblk * (nblk + 1) / 2;
+  const int pair0 = blockIdx.y * RB_MAXPAIRS;
+  const int rawrows = use_plan ? S::RAWROWS : B;           // landing rows per element
+  double* sJ = sm;                                         // 2 x KR x RP
+  double* sY = sJ + (size_t)2 * KR * RP;                   // 2 x KR x RP
+  double* sRaw = sY + (size_t)2 * KR * RP;                 // 2 x CE x rawrows x r
+  double* sSmall = sRaw + (size_t)2 * CE * rawrows * r;    // 2 x NSMALL: [He | vol*P | D] of the chunk
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sSmall + 2 * NSMALL);  // 2 mbarriers
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // this warp's block pairs (bi <= bj), enumerated row-major over the upper triangle
+  int pbi[RB_PPW], pbj[RB_PPW];
+#pragma unroll
+  for (int s = 0; s < RB_PPW; ++s) {
+    int pi = pair0 + warp + s * (RB_THREADS / 32);
+    pbi[s] = -1;
+    pbj[s] = -1;
+    if (pi < npairs_all && pi < pair0 + RB_MAXPAIRS) {
+      int bi = 0;
+      while (pi >= nblk - bi) {
+        pi -= nblk - bi;
+        ++bi;
+      }
+      pbi[s] = bi;
+      pbj[s] = bi + pi;
+    }
+  }
+  double acc[RB_PPW][RB_T][RB_T][2];
+#pragma unroll
+  for (int s = 0; s < RB_PPW; ++s)
+#pragma unroll
+    for (int a = 0; a < RB_T; ++a)
+#pragma unroll
+      for (int b = 0; b < RB_T; ++b) acc[s][a][b][0] = acc[s][a][b][1] = 0.0;
+  double gacc = 0.0;
+
+  for (int idx = threadIdx.x; idx < 4 * KR * RP; idx += blockDim.x) sm[idx] = 0.0;  // pad rows / columns stay zero
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(sBar), 1);
+    mbar_init(smem_u32(sBar + 1), 1);
+  }
+  __syncthreads();
+
+  const int64_t per = ((t + gridDim.x - 1) / gridDim.x + CE - 1) / CE * CE;
+  const int64_t e0 = (int64_t)blockIdx.x * per;
+  const int64_t e1 = (e0 + per < t) ? e0 + per : t;
+  const unsigned rowbytes = (unsigned)r * 8u;
+
+  auto issue = [&](int64_t eb, int buf) {  // thread 0: fetch the landing rows of chunk eb into buffer buf
+    const unsigned mbar = smem_u32(sBar + buf);
+    int ne = 0;
+    for (int le = 0; le < CE; ++le) ne += (eb + le < e1) ? 1 : 0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(mbar, (unsigned)(ne * rawrows) * rowbytes);
+    for (int le = 0; le < CE; ++le) {
+      const int64_t e = eb + le;
+      if (e >= e1) break;
+      double* dst = sRaw + ((size_t)buf * CE + le) * rawrows * r;
+      if (use_plan) {
+        for (int a = 0; a < K; ++a) {
+          const int v = pv.T32[e * K + a];
+          // the D rows (v, 0..D-1) of B are contiguous
+          tma_bulk_g2s(smem_u32(dst + (size_t)a * D * r), Bm + (size_t)v * D * r, (unsigned)D * rowbytes, mbar);
+        }
+      } else {
+        tma_bulk_g2s(smem_u32(dst), JB + (size_t)e * B * r, (unsigned)B * rowbytes, mbar);
+      }
+    }
+  };
+  // one small operand of chunk eb per thread (registers; stored to shared memory one iteration later)
+  auto fetch_small = [&](int64_t eb) -> double {
+    const int idx = threadIdx.x;
+    if (idx < CE * B * B) {
+      const int64_t e = eb + idx / (B * B);
+      return (e < e1) ? He[e * B * B + (idx % (B * B))] : 0.0;
+    }
+    if (idx < CE * (B * B + B)) {
+      const int k = idx - CE * B * B;
+      const int64_t e = eb + k / B;
+      return (e < e1) ? Pw[e * B + (k % B)] : 0.0;
+    }
+    if (idx < NSMALL && use_plan) {
+      const int k = idx - CE * (B * B + B);
+      const int64_t e = eb + k / (D * D);
+      return (e < e1) ? pv.Dm[(size_t)(k % (D * D)) * pv.t + e] : 0.0;  // [j*D + c] -> D[j][c+1]
+    }
+    return 0.0;
+  };
+  // sJ / sY of chunk eb into buffer b: a thread owns one column (all rows of both), so nothing it reads was
+  // written by another thread of this phase; sY re-reads the thread's own sJ column from shared memory, which
+  // keeps this phase at a handful of live registers next to the 100 accumulator doubles
+  auto form = [&](int64_t eb, int b) {
+    const int c = threadIdx.x;
+    if (c >= r) return;
+    const double* raw = sRaw + (size_t)b * CE * rawrows * r;
+    const double* sH = sSmall + (size_t)b * NSMALL;
+    const double* sP = sH + CE * B * B;
+    const double* sD = sP + CE * B;
+    double* oJ = sJ + (size_t)b * KR * RP + c;
+    double* oY = sY + (size_t)b * KR * RP + c;
+#pragma unroll 1
+    for (int le = 0; le < CE; ++le) {
+      const bool live = eb + le < e1;
+#pragma unroll 1
+      for (int i = 0; i < D; ++i) {
+        if (use_plan) {
+          const double* rr = raw + (size_t)le * rawrows * r + (size_t)i * r + c;  // + a*D*r for corner a
+          double x[K];
+#pragma unroll
+          for (int a = 0; a < K; ++a) x[a] = live ? rr[(size_t)a * D * r] : 0.0;
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            double v = 0.0, d0 = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+              const double d = sD[le * D * D + j * D + a];
+              d0 -= d;
+              v = fma(d, x[a + 1], v);
+            }
+            oJ[(le * B + i * D + j) * RP] = fma(d0, x[0], v);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < D; ++j)
+            oJ[(le * B + i * D + j) * RP] = live ? raw[(size_t)le * rawrows * r + (size_t)(i * D + j) * r + c] : 0.0;
+        }
+      }
+      double jv[B];
+#pragma unroll
+      for (int k = 0; k < B; ++k) jv[k] = oJ[(le * B + k) * RP];
+      if (blockIdx.y == 0) {
+#pragma unroll
+        for (int k = 0; k < B; ++k) gacc = fma(jv[k], sP[le * B + k], gacc);
+      }
+#pragma unroll 1
+      for (int rb = 0; rb < B; ++rb) {
+        const double* hrow = sH + (le * B + rb) * B;
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < B; ++k) v = fma(hrow[k], jv[k], v);
+        oY[(le * B + rb) * RP] = v;
+      }
+    }
+  };
+  // Hr += sJ^T sY on the warp's block pairs.  Fragment addresses: one base per operand and pair, compile-time
+  // offsets per tile, one pointer bump per k-step -- 10 loads + 25 DMMAs + 2 adds per step.
+  auto contract = [&](int b) {
+    const size_t lane_off = (size_t)(lane & 3) * RP + (lane >> 2);
+    const double* bJ = sJ + (size_t)b * KR * RP + lane_off;
+    const double* bY = sY + (size_t)b * KR * RP + lane_off;
+    const int kstep = 4 * RP;
+#pragma unroll
+    for (int s = 0; s < RB_PPW; ++s) {
+      if (pbi[s] < 0) continue;
+      const double* ja = bJ + pbi[s] * (RB_T * 8);
+      const double* yb = bY + pbj[s] * (RB_T * 8);
+#pragma unroll
+      for (int k0 = 0; k0 < KR; k0 += 4, ja += kstep, yb += kstep) {
+        double fa[RB_T], fb[RB_T];
+#pragma unroll
+        for (int x = 0; x < RB_T; ++x) {
+          fa[x] = ja[x * 8];
+          fb[x] = yb[x * 8];
+        }
+#pragma unroll
+        for (int a = 0; a < RB_T; ++a)
+#pragma unroll
+          for (int bb = 0; bb < RB_T; ++bb) dmma_m8n8k4(acc[s][a][bb][0], acc[s][a][bb][1], fa[a], fb[bb]);
+      }
+    }
+  };
+
+  // software pipeline: while chunk c is contracted, chunk c+1 is formed from its landed rows and the rows of
+  // chunk c+2 are in flight; one CTA barrier per chunk
+  unsigned phase[2] = {0u, 0u};
+  if (e0 < e1) {
+    if (threadIdx.x == 0) issue(e0, 0);
+    double small = fetch_small(e0);
+    mbar_wait(smem_u32(sBar), phase[0]);
+    phase[0] ^= 1u;
+    if (threadIdx.x < NSMALL) sSmall[threadIdx.x] = small;
+    __syncthreads();
+    if (threadIdx.x == 0 && e0 + CE < e1) issue(e0 + CE, 1);
+    small = fetch_small(e0 + CE);
+    form(e0, 0);
+    int b = 0;
+    for (int64_t eb = e0; eb < e1; eb += CE, b ^= 1) {
+      const bool have_next = eb + CE < e1;
+      if (have_next) {
+        mbar_wait(smem_u32(sBar + (b ^ 1)), phase[b ^ 1]);
+        phase[b ^ 1] ^= 1u;
+        if (threadIdx.x < NSMALL) sSmall[(size_t)(b ^ 1) * NSMALL + threadIdx.x] = small;
+      }
+      __syncthreads();  // chunk eb is fully formed; everybody is done contracting chunk eb - CE and forming eb
+      if (have_next) {
+        if (threadIdx.x == 0 && eb + 2 * CE < e1) issue(eb + 2 * CE, b);
+        small = fetch_small(eb + 2 * CE);
+        form(eb + CE, b ^ 1);
+      }
+      contract(b);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < RB_PPW; ++s) {
+    if (pbi[s] < 0) continue;
+#pragma unroll
+    for (int a = 0; a < RB_T; ++a)
+#pragma unroll
+      for (int b = 0; b < RB_T; ++b) {
+        const int tm = pbi[s] * RB_T + a, tn = pbj[s] * RB_T + b;
+        const int row = tm * 8 + (lane >> 2), col = tn * 8 + 2 * (lane & 3);
+        if (row < r && col < r) Hpart[((size_t)blockIdx.x * r + row) * r + col] = acc[s][a][b][0];
+        if (row < r && col + 1 < r) Hpart[((size_t)blockIdx.x * r + row) * r + col + 1] = acc[s][a][b][1];
+      }
+  }
+  if (blockIdx.y == 0 && threadIdx.x < r) gpart[(size_t)blockIdx.x * r + threadIdx.x] = gacc;
+}
+
+// lower triangle := transpose of the upper triangle (the blocked kernel computes block pairs bi <= bj only)
+__global__ void mirror_upper_kernel(int r, double* H) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= r * r) return;
+  const int row = idx / r, col = idx - row * r;
+  if (row > col) H[idx] = H[(size_t)col * r + row];
+}
+
 // out[i] = sum_{c} part[c][i]   in CTA order
 __global__ void sum_partials_kernel(int nparts, int64_t len, const double* part, double* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -389,12 +663,33 @@ static int reduced_run(skb_plan* pl, int material, int psd_mode, int64_t t, int6
     PlanView pv;
     memset(&pv, 0, sizeof(pv));
     if (pl) pv = pl->view();
+    // register-blocked, TMA-staged kernel when every operator row is a 16-byte multiple and it fits
+    using RS = RBShape<D>;
+    const int rawrows = pl ? RS::RAWROWS : Bk;
+    const size_t bsmem = ((size_t)4 * RS::KR * rb_stride((int)r) + (size_t)2 * RS::CE * rawrows * r +
+                          2 * RS::CE * (Bk * Bk + Bk + D * D)) * sizeof(double) + 16;
+    static int blocked_env = -1;
+    if (blocked_env < 0) {
+      const char* evv = getenv("SKB_REDUCED");
+      blocked_env = (evv && strcmp(evv, "simple") == 0) ? 0 : 1;
+    }
+    const bool blocked = blocked_env && (r % 2 == 0) && bsmem <= 227 * 1024;
     SKB_CUDA(cudaEventRecord(ev[2], st));
-    reduced_pass2_kernel<D><<<dim3(grid, npanels), RH_THREADS, smem, st>>>(t, (int)r, tcp, pl ? nullptr : raw(JB), pv, pl ? 1 : 0,
-                                                           pl ? raw(Bm) : nullptr, raw(He), raw(Pw), raw(Hpart), raw(gpart));
+    if (blocked) {
+      const int nblk = (rt + RB_T - 1) / RB_T;
+      const int npasses = (nblk * (nblk + 1) / 2 + RB_MAXPAIRS - 1) / RB_MAXPAIRS;
+      SKB_CUDA(cudaFuncSetAttribute(reduced_pass2_blocked_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SKB_CUDA(cudaMemsetAsync(raw(Hpart), 0, Hpart.size() * sizeof(double), st));
+      reduced_pass2_blocked_kernel<D><<<dim3(grid, npasses), RB_THREADS, bsmem, st>>>(
+          t, (int)r, pl ? nullptr : raw(JB), pv, pl ? 1 : 0, pl ? raw(Bm) : nullptr, raw(He), raw(Pw), raw(Hpart), raw(gpart));
+    } else {
+      reduced_pass2_kernel<D><<<dim3(grid, npanels), RH_THREADS, smem, st>>>(t, (int)r, tcp, pl ? nullptr : raw(JB), pv, pl ? 1 : 0,
+                                                             pl ? raw(Bm) : nullptr, raw(He), raw(Pw), raw(Hpart), raw(gpart));
+    }
     SKB_CUDA(cudaGetLastError());
     SKB_CUDA(cudaEventRecord(ev[3], st));
     sum_partials_kernel<<<(unsigned)((r * r + 255) / 256), 256, 0, st>>>(grid, r * r, raw(Hpart), raw(Hd));
+    if (blocked) mirror_upper_kernel<<<(unsigned)((r * r + 255) / 256), 256, 0, st>>>((int)r, raw(Hd));
     sum_partials_kernel<<<(unsigned)((r + 255) / 256), 256, 0, st>>>(grid, r, raw(gpart), raw(gd));
     SKB_CUDA(cudaDeviceSynchronize());
     if (Hr) SKB_CUDA(cudaMemcpy(Hr, raw(Hd), r * r * sizeof(double), cudaMemcpyDeviceToHost));

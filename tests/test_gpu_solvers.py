@@ -229,3 +229,25 @@ def test_reduced_r200_against_oracle():
     assert rel(Hr, B.T @ (Qo @ B)) < VAL_TOL
     assert rel(gr, B.T @ oe.gradient_x("stable_neo_hookean", x, Jo, mu, lam, vol)) < VAL_TOL
     assert np.abs(Hr - Hr.T).max() <= 1e-12 * np.abs(Hr).max()
+
+
+@pytest.mark.parametrize("r", [33, 64, 250])
+def test_reduced_other_dimensions_against_oracle(r):
+    """odd r (rows are not 16-byte multiples: the simple staging kernel), r = 64 (block pairs with unused
+    tiles) and r = 250 (two passes of block pairs) through the basis form."""
+    cells = (6, 5, 7)
+    X, T = syn.make_mesh(cells)
+    mu, lam = syn.heterogeneous_lame(T.shape[0])
+    B = syn.smooth_modes(X, r, seed=5)
+    z = 0.02 * np.random.default_rng(8).standard_normal(r)
+    plan = sk.MeshPlan(X=X, T=T)
+    vol = plan.volume()
+    plan.set_materials(mu, lam, vol)
+    E, gr, Hr = plan.reduced("stable_neo_hookean", B, z, x0=X.reshape(-1))
+    Jo = oe.deformation_jacobian(X, T)
+    x = (B @ z).reshape(-1, 3) + X
+    Qo = oe.hessian_x("stable_neo_hookean", x, Jo, mu, lam, vol)
+    assert rel(Hr, B.T @ (Qo @ B)) < VAL_TOL
+    assert rel(gr, B.T @ oe.gradient_x("stable_neo_hookean", x, Jo, mu, lam, vol)) < VAL_TOL
+    Eo = oe.energy_x("stable_neo_hookean", x, Jo, mu, lam, vol)
+    assert abs(E - Eo) <= 1e-12 * abs(Eo)
