@@ -423,13 +423,20 @@ def run_ours(args, rank, world, local_rank):
         r = args.reduced
         Bm = syn.smooth_modes(X, r, seed=2)
         z = 0.02 * np.random.default_rng(3).standard_normal(r)
-        tt = []
+        tt, tt_res = [], []
         times = np.zeros(3)
+        for s_ in range(2):
+            t0 = time.perf_counter()
+            Er, gr_, Hr0 = plan.reduced(MATERIAL, Bm, z, x0=X.reshape(-1), psd_mode=PSD_AFTER_VOL)
+            tt.append(time.perf_counter() - t0)
+        plan.set_basis(Bm)                      # basis resident on the device, as ElasticEnergyZPrecomp keeps JB
         for s_ in range(3):
             t0 = time.perf_counter()
-            Er, gr_, Hr = plan.reduced(MATERIAL, Bm, z, x0=X.reshape(-1), psd_mode=PSD_AFTER_VOL)
-            tt.append(time.perf_counter() - t0)
+            Er, gr_, Hr = plan.reduced(MATERIAL, None, z, x0=X.reshape(-1), psd_mode=PSD_AFTER_VOL)
+            tt_res.append(time.perf_counter() - t0)
             check(lib.skb_reduced_last_times(ptr(times)))
+        assert np.array_equal(Hr, Hr0)
+        plan.set_basis(None)
         b = dim * dim
         flops = (2.0 * b * b * r + 2.0 * b * r * r) * plan.t        # Y = He JB, Hr += JB^T Y (no symmetry assumed)
         tfd = _lib.ctypes.c_double(0.0)
@@ -441,6 +448,7 @@ def run_ours(args, rank, world, local_rank):
         exec_flops = (2.0 * b * b * r + 2.0 * 4 * ((2 * b + 3) // 4) * (nblk_ * (nblk_ + 1) // 2) * 25 * 64 / 2.0) * plan.t
         reduced = {"r": r, "elements": plan.t, "api_ms": min(tt) * 1e3,
                    "api_includes": "host->device copy of the basis B (%.2f GB) and of z, device->host copy of Hr" % (Bm.nbytes / 1e9),
+                   "api_resident_basis_ms": min(tt_res) * 1e3,
                    "element_pass_ms": float(times[0]), "contraction_ms": float(times[1]), "device_ms": float(times[2]),
                    "contraction_tflops": flops / (times[1] * 1e-3) / 1e12, "algorithmic_flops": flops,
                    "frac_fp64_peak": flops / (times[1] * 1e-3) / 1e12 / max(fp64_peak, 1e-30),

@@ -277,6 +277,10 @@ int skb_reduced_gradient_hessian(int material, int psd_mode, int dim, int64_t t,
 int skb_reduced_hessian_from_basis(skb_plan* plan, int material, int psd_mode, int64_t r,
                                    const double* B, const double* x0, const double* z,
                                    double* energy, double* gr, double* Hr);
+/* Keeps the basis B (n*dim, r), row-major, resident on the plan's device; skb_reduced_hessian_from_basis may then
+ * be called with B = NULL (the reference rebuilds JB = G J B once per simulation in ElasticEnergyZPrecomp,
+ * energies/elastic.py:214-222; this is the device-side counterpart).  B = NULL or r <= 0 releases it. */
+int skb_plan_set_basis(skb_plan* plan, int64_t r, const double* B);
 /* Measurement hook (bench.py, no reference counterpart): CUDA-event times in ms of the last reduced call on
  * this thread's device: out[0] element pass (F -> He, P, psi), out[1] the B^T H B contraction kernel
  * (FP64 DMMA tiles), out[2] whole device section including the partial sums. */

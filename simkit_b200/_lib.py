@@ -103,6 +103,7 @@ SIGNATURES = {
     "skb_reduced_gradient_hessian": (_int, [_int, _int, _int, _i64, _i64, _vp, _vp, _vp] + _MAT + [_vp, _vp, _vp]),
     "skb_reduced_hessian_from_basis": (_int, [_vp, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "skb_reduced_last_times": (_int, [_vp]),
+    "skb_plan_set_basis": (_int, [_vp, _i64, _vp]),
     "skb_fst_precompute": (_int, [_int, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "skb_fst_eval": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp]),
 }

@@ -60,6 +60,9 @@ struct skb_plan {
   skb::dvec<double> pblocks, pverts, esums, scalar;
   // PCG / Newton work vectors (allocated on first use)
   skb::dvec<double> w_r, w_z, w_p, w_q, w_dx, w_xt, w_x, w_xtrial, w_dinv, w_diag, w_mass, w_fext, w_xtilde, w_red;
+  // resident subspace basis of the reduced tier (skb_plan_set_basis)
+  skb::dvec<double> basis;
+  int64_t basis_r = 0;
   int launches = 0;
   // optional per-kernel CUDA-event timing (skb_kernel_timing / skb_kernel_times)
   bool timing = false;

@@ -568,14 +568,16 @@ static int reduced_run(skb_plan* pl, int material, int psd_mode, int64_t t, int6
   dvec<double> z(z_h, z_h + r), F((size_t)t * Bk), He((size_t)t * Bk * Bk), Pw((size_t)t * Bk), psi(t);
   dvec<double> JB, Bm, mu, lam, vol;
   const double *mu_p, *lam_p = nullptr, *vol_p;
+  const double* Bm_p = nullptr;
   int mu_s, lam_s = 0, vol_s;
   if (pl) {
     // F = J (B z + x0) through the mesh plan
     const int64_t nd = pl->ndof();
-    Bm.assign(B_h, B_h + nd * r);
+    if (B_h) Bm.assign(B_h, B_h + nd * r);  // else: the plan's resident basis (skb_plan_set_basis)
     dvec<double> x(nd), x0;
     if (x0_h) x0.assign(x0_h, x0_h + nd);
-    gemv_rows_kernel<<<(unsigned)((nd * 32 + 255) / 256), 256, 0, st>>>(nd, (int)r, raw(Bm), raw(z), x0_h ? raw(x0) : nullptr, raw(x));
+    Bm_p = B_h ? raw(Bm) : raw(pl->basis);
+    gemv_rows_kernel<<<(unsigned)((nd * 32 + 255) / 256), 256, 0, st>>>(nd, (int)r, Bm_p, raw(z), x0_h ? raw(x0) : nullptr, raw(x));
     // F_e from x: same gather as load_element in kernels.cuh
     const PlanView p = pl->view();
     thrust::counting_iterator<int> it0(0);
@@ -681,10 +683,10 @@ static int reduced_run(skb_plan* pl, int material, int psd_mode, int64_t t, int6
       SKB_CUDA(cudaFuncSetAttribute(reduced_pass2_blocked_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       SKB_CUDA(cudaMemsetAsync(raw(Hpart), 0, Hpart.size() * sizeof(double), st));
       reduced_pass2_blocked_kernel<D><<<dim3(grid, npasses), RB_THREADS, bsmem, st>>>(
-          t, (int)r, pl ? nullptr : raw(JB), pv, pl ? 1 : 0, pl ? raw(Bm) : nullptr, raw(He), raw(Pw), raw(Hpart), raw(gpart));
+          t, (int)r, pl ? nullptr : raw(JB), pv, pl ? 1 : 0, Bm_p, raw(He), raw(Pw), raw(Hpart), raw(gpart));
     } else {
       reduced_pass2_kernel<D><<<dim3(grid, npanels), RH_THREADS, smem, st>>>(t, (int)r, tcp, pl ? nullptr : raw(JB), pv, pl ? 1 : 0,
-                                                             pl ? raw(Bm) : nullptr, raw(He), raw(Pw), raw(Hpart), raw(gpart));
+                                                             Bm_p, raw(He), raw(Pw), raw(Hpart), raw(gpart));
     }
     SKB_CUDA(cudaGetLastError());
     SKB_CUDA(cudaEventRecord(ev[3], st));
@@ -733,9 +735,28 @@ int skb_reduced_last_times(double out[3]) {
   return SKB_OK;
 }
 
+int skb_plan_set_basis(skb_plan* pl, int64_t r, const double* B) {
+  if (!pl) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  if (!B || r <= 0) {
+    pl->basis.clear();
+    pl->basis.shrink_to_fit();
+    pl->basis_r = 0;
+    return SKB_OK;
+  }
+  const int64_t nd = pl->ndof();
+  pl->basis.assign(B, B + nd * r);
+  pl->basis_r = r;
+  return SKB_OK;
+  SKB_CATCH
+}
+
 int skb_reduced_hessian_from_basis(skb_plan* pl, int material, int psd_mode, int64_t r, const double* B,
                                    const double* x0, const double* z, double* energy, double* gr, double* Hr) {
-  if (!pl || !B || !z) return fail(SKB_EINVAL, "null argument");
+  if (!pl || !z) return fail(SKB_EINVAL, "null argument");
+  if (!B && (pl->basis_r != r || pl->basis_r == 0))
+    return fail(SKB_EINVAL, "B is NULL and the plan holds no resident basis of this dimension (skb_plan_set_basis)");
   SKB_CUDA(cudaSetDevice(pl->device));
   return pl->d.dim == 3 ? reduced_run<3>(pl, material, psd_mode, pl->d.t, r, nullptr, nullptr, B, x0, z, nullptr, 0, nullptr, 0, nullptr, 0, energy, gr, Hr)
                         : reduced_run<2>(pl, material, psd_mode, pl->d.t, r, nullptr, nullptr, B, x0, z, nullptr, 0, nullptr, 0, nullptr, 0, energy, gr, Hr);

@@ -189,15 +189,36 @@ class MeshPlan:
                          pcg_iters=info.pcg_iters_total, pcg_relres=info.last_pcg_relres,
                          step_norm=info.last_step_norm)
 
-    def reduced(self, material, B, z, x0=None, psd_mode=1, want=("E", "g", "H")):
+    def set_basis(self, B):
+        """Keeps the subspace basis ``B (n*dim, r)`` resident on the device (``None`` releases it);
+        ``reduced(..., B=None)`` then skips the upload (3.4 GB at BASELINE config 4)."""
+        if B is None:
+            check(self._lib.skb_plan_set_basis(self._h, 0, None))
+            self._basis_r = 0
+            return
         B = f64(B)
-        r = B.shape[1]
+        if B.ndim != 2 or B.shape[0] != self.ndof:
+            raise ValueError("B must be (n*dim, r)")
+        check(self._lib.skb_plan_set_basis(self._h, B.shape[1], ptr(B)))
+        self._basis_r = B.shape[1]
+
+    def reduced(self, material, B, z, x0=None, psd_mode=1, want=("E", "g", "H")):
         z = f64(z).reshape(-1)
+        if B is None:
+            r = getattr(self, "_basis_r", 0)
+            if r == 0:
+                raise ValueError("no resident basis: call set_basis(B) first or pass B")
+        else:
+            B = f64(B)
+            r = B.shape[1]
+        if z.size != r:
+            raise ValueError("reduced coordinates do not match the basis")
         x0 = None if x0 is None else self._x(x0)
         E = ctypes.c_double(0.0)
         g = np.empty((r, 1)) if "g" in want else None
         H = np.empty((r, r)) if "H" in want else None
-        check(self._lib.skb_reduced_hessian_from_basis(self._h, MATERIAL_IDS[material], int(psd_mode), r, ptr(B),
+        check(self._lib.skb_reduced_hessian_from_basis(self._h, MATERIAL_IDS[material], int(psd_mode), r,
+                                                       None if B is None else ptr(B),
                                                        ptr(x0), ptr(z), ctypes.byref(E), ptr(g), ptr(H)))
         return float(E.value), g, H
 

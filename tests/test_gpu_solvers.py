@@ -229,6 +229,15 @@ def test_reduced_r200_against_oracle():
     assert rel(Hr, B.T @ (Qo @ B)) < VAL_TOL
     assert rel(gr, B.T @ oe.gradient_x("stable_neo_hookean", x, Jo, mu, lam, vol)) < VAL_TOL
     assert np.abs(Hr - Hr.T).max() <= 1e-12 * np.abs(Hr).max()
+    # basis kept resident on the device: same bits, no upload
+    with pytest.raises(ValueError):
+        plan.reduced("stable_neo_hookean", None, z, x0=X.reshape(-1))
+    plan.set_basis(B)
+    E2, g2, H2 = plan.reduced("stable_neo_hookean", None, z, x0=X.reshape(-1))
+    assert E2 == E and np.array_equal(g2, gr) and np.array_equal(H2, Hr)
+    plan.set_basis(None)
+    with pytest.raises(ValueError):
+        plan.reduced("stable_neo_hookean", None, z, x0=X.reshape(-1))
 
 
 @pytest.mark.parametrize("r", [33, 64, 250])
