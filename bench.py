@@ -30,9 +30,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (printed at NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+
+
+class StdoutToStderr:
+    """rank 0 prints ONE JSON line on stdout.  NCCL writes its version banner ("NCCL version ...") to file
+    descriptor 1 when the first communicator is created, so for N > 1 everything before the final print runs
+    with fd 1 pointed at stderr; restore() puts stdout back for the JSON line."""
+
+    def __init__(self, active):
+        self.saved = None
+        if active:
+            sys.stdout.flush()
+            self.saved = os.dup(1)
+            os.dup2(2, 1)
+
+    def restore(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+            self.saved = None
 
 MATERIAL = "stable_neo_hookean"
 METRIC = "tets/s for stable-NH grad+PSD Hessian+CSR assembly"
@@ -202,6 +219,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device visible; simkit_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    guard = StdoutToStderr(world > 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -486,6 +504,7 @@ def run_ours(args, rank, world, local_rank):
         }
         if reduced is not None:
             line["reduced"] = reduced
+        guard.restore()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
