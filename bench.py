@@ -390,28 +390,38 @@ def run_ours(args, rank, world, local_rank):
         fext = fext.reshape(-1) * mass
         xc = U.reshape(-1)
         nsteps = max(1, min(args.steps, args.newton_steps))
-        lib.skb_kernel_timing(plan._h, 1)
-        tt, info = [], None
-        for s in range(1 + nsteps):
-            t0 = time.perf_counter()
-            xn, info = plan.newton(MATERIAL, xc, x_tilde=xc, mass=mass, kin_scale=1.0 / h ** 2, f_ext=fext, max_iter=1,
-                                   pcg_rtol=args.pcg_rtol, pcg_max_iter=20000)
-            if s > 0:
-                tt.append(time.perf_counter() - t0)
-            else:
-                check(lib.skb_kernel_times(plan._h, ptr(kms), ptr(kcount)))   # drop the warm-up record
-        nl = plan.last_launch_count()
-        check(lib.skb_kernel_times(plan._h, ptr(kms), ptr(kcount)))
-        lib.skb_kernel_timing(plan._h, 0)
-        sec = float(np.mean(tt))
-        spmv_ms = kms[4] / max(int(kcount[4]), 1)
         spmv_bytes = (8 * dim * dim + 4) * plan.nnzb + 8 * plan.n + 3 * 8 * plan.ndof
-        newton = {"steps_per_s": 1.0 / sec, "ms_per_step": sec * 1e3, "pcg_iters": info["pcg_iters"],
-                  "pcg_rtol": args.pcg_rtol, "pcg_relres": info["pcg_relres"], "alpha": info["alphas"][:1],
-                  "launches_per_step": nl, "includes": "host->device upload of state and device->host read of x_next",
-                  "spmv": {"ms": spmv_ms, "achieved_gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9,
-                           "frac_hbm": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / hbm_peak, "bytes": spmv_bytes},
-                  "pcg_ms_per_iter": (kms[4] + kms[5]) / max(info["pcg_iters"], 1) / nsteps}
+
+        def newton_leg(label):
+            lib.skb_kernel_timing(plan._h, 1)
+            tt, info, xn = [], None, None
+            for s in range(1 + nsteps):
+                t0 = time.perf_counter()
+                xn, info = plan.newton(MATERIAL, xc, x_tilde=xc, mass=mass, kin_scale=1.0 / h ** 2, f_ext=fext, max_iter=1,
+                                       pcg_rtol=args.pcg_rtol, pcg_max_iter=20000)
+                if s > 0:
+                    tt.append(time.perf_counter() - t0)
+                else:
+                    check(lib.skb_kernel_times(plan._h, ptr(kms), ptr(kcount)))   # drop the warm-up record
+            nl = plan.last_launch_count()
+            check(lib.skb_kernel_times(plan._h, ptr(kms), ptr(kcount)))
+            lib.skb_kernel_timing(plan._h, 0)
+            sec = float(np.mean(tt))
+            spmv_ms = kms[4] / max(int(kcount[4]), 1)
+            return xn, {"preconditioner": label, "steps_per_s": 1.0 / sec, "ms_per_step": sec * 1e3, "pcg_iters": info["pcg_iters"],
+                        "pcg_rtol": args.pcg_rtol, "pcg_relres": info["pcg_relres"], "alpha": info["alphas"][:1],
+                        "launches_per_step": nl, "includes": "host->device upload of state and device->host read of x_next",
+                        "spmv": {"ms": spmv_ms, "achieved_gbs": spmv_bytes / (spmv_ms * 1e-3) / 1e9,
+                                 "frac_hbm": spmv_bytes / (spmv_ms * 1e-3) / 1e9 / hbm_peak, "bytes": spmv_bytes},
+                        "pcg_ms_per_iter": (kms[4] + kms[5]) / max(info["pcg_iters"], 1) / nsteps}
+
+        # block-Jacobi alone, then block-Jacobi + rigid-mode coarse correction (csrc/coarse.cuh): same Newton iterate
+        x_bj, newton_bj = newton_leg("3x3 block-Jacobi")
+        n_agg = plan.set_coarse_space(X, args.aggregates)
+        x_tl, newton = newton_leg("3x3 block-Jacobi + rigid-body modes of %d vertex aggregates (two-level, additive)" % n_agg)
+        plan.set_coarse_space(None)
+        newton["block_jacobi_only"] = {k: newton_bj[k] for k in ("steps_per_s", "ms_per_step", "pcg_iters", "pcg_ms_per_iter")}
+        newton["iterate_difference_vs_block_jacobi"] = float(np.abs(x_tl - x_bj).max() / np.abs(x_bj).max())
     elif args.newton:
         # sharded implicit step: device-resident state, distributed PCG (halo exchange + 2 all-reduces per iteration)
         mass_d = shard.lumped_mass_dofs(rho)
@@ -520,6 +530,7 @@ def main():
     ap.add_argument("--newton", type=int, default=1, help="also time one backward-Euler Newton step (0 = skip)")
     ap.add_argument("--newton-steps", type=int, default=2)
     ap.add_argument("--pcg-rtol", type=float, default=1e-10)
+    ap.add_argument("--aggregates", type=int, default=729, help="vertex aggregates of the two-level PCG preconditioner")
     ap.add_argument("--reduced", type=int, default=0, help="also time the reduced Hessian B^T H B with this many modes (config 4: --workload C4 --reduced 200)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="development only: stop after the device-resident timing")

@@ -216,6 +216,11 @@ int skb_csr_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const 
  * reduced-space Newton system); A (n, n) row-major.  SKB_EINVAL if singular. */
 int skb_dense_solve(int64_t n, const double* A, const double* b, double* x);
 /* y = (A + diag(diag_add)) x   on device data */
+/* Two-level preconditioner of the plan's PCG (skb_pcg*, skb_newton): block-Jacobi plus a coarse correction on the
+ * rigid-body modes of vertex aggregates.  agg: (n) aggregate id of every vertex in [0, n_agg); xrel: (n*dim) vertex
+ * position minus the centre of its aggregate.  n_agg = 0 removes it.  The reference solves the Newton system
+ * directly (solvers/newton.py:52); the preconditioner only changes the CG iteration count, not the solution. */
+int skb_pcg_set_coarse(skb_plan* plan, int64_t n_agg, const int32_t* agg, const double* xrel);
 int skb_spmv_dev(skb_plan* plan, const double* vals, const double* diag_add, const double* x,
                  double* y, void* stream);
 

@@ -74,7 +74,9 @@ def build(force=False, verbose=False, ptxas_info=False):
         for _, log in results:
             if log:
                 print(log)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    # cuSOLVER: dense Cholesky inverse of the coarse system of the two-level PCG preconditioner (csrc/coarse.cuh)
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcusolver", "-Xlinker", "-rpath=" + cuda_lib]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -281,6 +281,7 @@ void skb_plan_destroy(skb_plan* plan) {
   if (!plan) return;
   cudaSetDevice(plan->device);
   if (plan->stream) cudaStreamDestroy(plan->stream);
+  if (plan->coarse) skb::coarse_destroy(plan->coarse);
   delete plan;
 }
 

@@ -47,6 +47,11 @@ inline const T* raw(const dvec<T>& v) {
 
 }  // namespace skb
 
+namespace skb {
+struct CoarseSpace;                      // coarse.cuh (two-level PCG preconditioner), owned by the plan
+void coarse_destroy(CoarseSpace* c);     // capi_solver.cu
+}  // namespace skb
+
 // The opaque plan handle of the C ABI.
 struct skb_plan {
   int device = 0;
@@ -60,6 +65,7 @@ struct skb_plan {
   skb::dvec<double> pblocks, pverts, esums, scalar;
   // PCG / Newton work vectors (allocated on first use)
   skb::dvec<double> w_r, w_z, w_p, w_q, w_dx, w_xt, w_x, w_xtrial, w_dinv, w_diag, w_mass, w_fext, w_xtilde, w_red;
+  skb::CoarseSpace* coarse = nullptr;  // skb_pcg_set_coarse
   // resident subspace basis of the reduced tier (skb_plan_set_basis)
   skb::dvec<double> basis;
   int64_t basis_r = 0;

@@ -3,8 +3,62 @@
 
 #include "capi_common.cuh"
 #include "solver.cuh"
+#include "coarse.cuh"
 
 namespace skb {
+
+void coarse_destroy(CoarseSpace* c) { delete c; }
+
+#define SKB_CUSOLVER(call)                                                           \
+  do {                                                                               \
+    cusolverStatus_t _s = (call);                                                    \
+    if (_s != CUSOLVER_STATUS_SUCCESS) return fail(SKB_ECUDA, "cuSOLVER call failed: " #call); \
+  } while (0)
+
+// Per solve: coarse matrix of the current Newton system and its dense inverse (Cholesky).
+template <int D>
+static int coarse_setup(skb_plan* pl, const double* vals, const double* dadd, cudaStream_t st) {
+  CoarseSpace& c = *pl->coarse;
+  constexpr int NC = CoarseDim<D>::NC;
+  const int nc = NC * c.n_agg;
+  const PlanView p = pl->view();
+  SKB_CUDA(cudaMemsetAsync(raw(c.Ac), 0, (size_t)nc * nc * sizeof(double), st));
+  SKB_LAUNCH(pl, SKB_K_OTHER, st,
+             coarse_assemble_kernel<D><<<c.n_cb, 256, 0, st>>>(p, vals, dadd, c.n_agg, raw(c.agg), raw(c.xrel), raw(c.cb_ptr),
+                                                              raw(c.cb_I), raw(c.cb_J), raw(c.fb), raw(c.Ac)));
+  SKB_CUDA(cudaGetLastError());
+  if (!c.handle) SKB_CUSOLVER(cusolverDnCreate(&c.handle));
+  SKB_CUSOLVER(cusolverDnSetStream(c.handle, st));
+  int lw1 = 0, lw2 = 0;
+  SKB_CUSOLVER(cusolverDnDpotrf_bufferSize(c.handle, CUBLAS_FILL_MODE_LOWER, nc, raw(c.Ac), nc, &lw1));
+  SKB_CUSOLVER(cusolverDnDpotri_bufferSize(c.handle, CUBLAS_FILL_MODE_LOWER, nc, raw(c.Ac), nc, &lw2));
+  const int lw = lw1 > lw2 ? lw1 : lw2;
+  if ((int)c.work.size() < lw) c.work.resize(lw);
+  if (c.info.size() < 2) c.info.resize(2);
+  SKB_CUSOLVER(cusolverDnDpotrf(c.handle, CUBLAS_FILL_MODE_LOWER, nc, raw(c.Ac), nc, raw(c.work), lw, raw(c.info)));
+  SKB_CUSOLVER(cusolverDnDpotri(c.handle, CUBLAS_FILL_MODE_LOWER, nc, raw(c.Ac), nc, raw(c.work), lw, raw(c.info) + 1));
+  int hinfo[2] = {0, 0};
+  SKB_CUDA(cudaMemcpyAsync(hinfo, raw(c.info), 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SKB_CUDA(cudaStreamSynchronize(st));
+  if (hinfo[0] != 0 || hinfo[1] != 0) return fail(SKB_ECUDA, "coarse matrix of the two-level preconditioner is not positive definite");
+  coarse_symmetrize_kernel<<<(unsigned)(((size_t)nc * nc + 255) / 256), 256, 0, st>>>(nc, raw(c.Ac));
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+}
+
+static CoarseView coarse_view(CoarseSpace& c, int ncper) {
+  CoarseView v;
+  v.n_agg = c.n_agg;
+  v.nc = ncper * c.n_agg;
+  v.agg = raw(c.agg);
+  v.xrel = raw(c.xrel);
+  v.vord = raw(c.vord);
+  v.aptr = raw(c.aptr);
+  v.Ainv = raw(c.Ac);
+  v.rc = raw(c.rc);
+  v.zc = raw(c.zc);
+  return v;
+}
 
 static int pcg_grid(const skb_plan* pl) {
   int sms = 148;
@@ -36,13 +90,21 @@ static void ensure(dvec<double>& v, size_t n) {
 template <int D, class SpmvDot>
 static int pcg_loop(skb_plan* pl, int nb, int grid, SpmvDot spmv_dot, const double* dinv, const double* rhs,
                     double rtol, int max_iter, double* x, double* r, double* z, double* pv, double* q,
-                    double* red, int* iters, double* relres, cudaStream_t st) {
+                    double* red, int* iters, double* relres, cudaStream_t st, const CoarseView* cv = nullptr) {
   double* part_pq = red;
   double* part_rz = part_pq + PCG_MAX_GRID;
   double* part_rr = part_rz + PCG_MAX_GRID;
   PcgScalars* sc = reinterpret_cast<PcgScalars*>(part_rr + PCG_MAX_GRID);  // two ping-pong slots
+  // coarse correction of the two-level preconditioner: z += P Ainv P^T r, r.z partials recomputed
+  auto coarse_apply = [&](double* p_or_null, const PcgScalars* s) {
+    SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, coarse_restrict_kernel<D><<<cv->n_agg, 256, 0, st>>>(*cv, r, s));
+    SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, coarse_gemv_kernel<<<(cv->nc * 32 + 255) / 256, 256, 0, st>>>(*cv, s));
+    SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st,
+               coarse_add_kernel<D><<<grid, PCG_THREADS, 0, st>>>(*cv, nb, r, z, p_or_null, part_rz, s));
+  };
   SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st,
              pcg_init_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, rhs, dinv, x, r, z, pv, part_rz, part_rr));
+  if (cv) coarse_apply(pv, nullptr);
   SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg_init_scalars_kernel<<<1, PCG_THREADS, 0, st>>>(part_rz, part_rr, grid, rtol, sc));
   int cur = 0;
   PcgScalars h;
@@ -56,6 +118,7 @@ static int pcg_loop(skb_plan* pl, int nb, int grid, SpmvDot spmv_dot, const doub
       SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st,
                  pcg_update_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, dinv, pv, q, x, r, z, part_pq, grid, part_rz,
                                                                     part_rr, sc + cur));
+      if (cv) coarse_apply(nullptr, sc + cur);
       SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st,
                  pcg_direction_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, z, pv, part_rz, part_rr, grid, rtol, sc + cur,
                                                                        sc + (cur ^ 1)));
@@ -93,8 +156,70 @@ static int pcg_run(skb_plan* pl, const double* vals, const double* dadd, const d
   auto spmv_dot = [&](const double* pvec, double* q, double* part_pq, const PcgScalars* sc) {
     SKB_LAUNCH(pl, SKB_K_SPMV, st, pcg_spmv_dot_kernel<D><<<grid, PCG_THREADS, 0, st>>>(p, vals, dadd, pvec, q, part_pq, sc));
   };
+  CoarseView cv;
+  const bool two_level = pl->coarse != nullptr && pl->coarse->n_agg > 0;
+  if (two_level) {
+    int rc = coarse_setup<D>(pl, vals, dadd, st);
+    if (rc) return rc;
+    cv = coarse_view(*pl->coarse, CoarseDim<D>::NC);
+  }
   return pcg_loop<D>(pl, p.n, grid, spmv_dot, dinv, rhs, rtol, max_iter, x, raw(pl->w_r), raw(pl->w_z),
-                     raw(pl->w_p), raw(pl->w_q), raw(pl->w_red), iters, relres, st);
+                     raw(pl->w_p), raw(pl->w_q), raw(pl->w_red), iters, relres, st, two_level ? &cv : nullptr);
+}
+
+// Builds the plan-side data of the coarse space from the vertex -> aggregate map.
+static int coarse_build(skb_plan* pl, int n_agg, const int* agg_h, const double* xrel_h) {
+  if (pl->coarse) {
+    coarse_destroy(pl->coarse);
+    pl->coarse = nullptr;
+  }
+  if (n_agg <= 0) return SKB_OK;
+  const PlanView p = pl->view();
+  const int n = p.n, D = p.dim;
+  const int ncper = D == 3 ? 6 : 3;
+  for (int v = 0; v < n; ++v)
+    if (agg_h[v] < 0 || agg_h[v] >= n_agg) return fail(SKB_EINVAL, "aggregate id out of range");
+  CoarseSpace* c = new CoarseSpace();
+  pl->coarse = c;
+  c->n_agg = n_agg;
+  c->agg.assign(agg_h, agg_h + n);
+  c->xrel.assign(xrel_h, xrel_h + (size_t)n * D);
+  // vertices sorted by aggregate
+  {
+    dvec<int> key = c->agg;
+    c->vord.resize(n);
+    thrust::sequence(thrust::device, c->vord.begin(), c->vord.end());
+    thrust::stable_sort_by_key(thrust::device, key.begin(), key.end(), c->vord.begin());
+    c->aptr.resize(n_agg + 1);
+    thrust::counting_iterator<int> it0(0);
+    thrust::lower_bound(thrust::device, key.begin(), key.end(), it0, it0 + n_agg + 1, c->aptr.begin());
+  }
+  // fine blocks sorted by coarse block (I, J)
+  {
+    const int nnzb = p.nnzb;
+    dvec<uint64_t> key(nnzb);
+    c->fb.resize(nnzb);
+    thrust::sequence(thrust::device, c->fb.begin(), c->fb.end());
+    thrust::transform(thrust::device, c->fb.begin(), c->fb.end(), key.begin(),
+                      CoarseKeyOf{p.brow, p.bcol, raw(c->agg), n_agg});
+    thrust::stable_sort_by_key(thrust::device, key.begin(), key.end(), c->fb.begin());
+    dvec<uint64_t> ukey(nnzb);
+    auto uend = thrust::unique_copy(thrust::device, key.begin(), key.end(), ukey.begin());
+    c->n_cb = (int)(uend - ukey.begin());
+    ukey.resize(c->n_cb);
+    c->cb_ptr.resize(c->n_cb + 1);
+    thrust::lower_bound(thrust::device, key.begin(), key.end(), ukey.begin(), ukey.end(), c->cb_ptr.begin());
+    c->cb_ptr[c->n_cb] = nnzb;
+    c->cb_I.resize(c->n_cb);
+    c->cb_J.resize(c->n_cb);
+    thrust::transform(thrust::device, ukey.begin(), ukey.end(), c->cb_I.begin(), CoarseKeyI{n_agg});
+    thrust::transform(thrust::device, ukey.begin(), ukey.end(), c->cb_J.begin(), CoarseKeyJ{n_agg});
+  }
+  const size_t nc = (size_t)ncper * n_agg;
+  c->Ac.resize(nc * nc);
+  c->rc.resize(nc);
+  c->zc.resize(nc);
+  return SKB_OK;
 }
 
 int pcg_solve(skb_plan* pl, const double* vals, const double* dadd, const double* rhs, double rtol, int max_iter,
@@ -139,6 +264,16 @@ static int csr_pcg_run(int64_t n, const int32_t* indptr_h, const int32_t* indice
 using namespace skb;
 
 extern "C" {
+
+int skb_pcg_set_coarse(skb_plan* pl, int64_t n_agg, const int32_t* agg, const double* xrel) {
+  if (!pl) return fail(SKB_EINVAL, "null argument");
+  if (n_agg > 0 && (!agg || !xrel)) return fail(SKB_EINVAL, "null argument");
+  if (n_agg > 2048) return fail(SKB_EINVAL, "at most 2048 aggregates (the coarse system is inverted densely)");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  return coarse_build(pl, (int)n_agg, agg, xrel);
+  SKB_CATCH
+}
 
 int skb_spmv_dev(skb_plan* pl, const double* vals, const double* diag_add, const double* x, double* y,
                  void* stream) {

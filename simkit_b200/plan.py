@@ -189,6 +189,37 @@ class MeshPlan:
                          pcg_iters=info.pcg_iters_total, pcg_relres=info.last_pcg_relres,
                          step_norm=info.last_step_norm)
 
+    def set_coarse_space(self, X, n_agg_target=729):
+        """Two-level PCG preconditioner (``csrc/coarse.cuh``): vertices are binned by position into about
+        ``n_agg_target`` box-shaped aggregates (at most 2048) whose rigid-body modes form the coarse space.
+        ``X`` are the rest positions ``(n, dim)``.  ``n_agg_target = 0`` (or ``X=None``) removes it.  The reference
+        solves the Newton system directly (solvers/newton.py:52); this only changes the CG iteration count."""
+        if X is None or not n_agg_target:
+            check(self._lib.skb_pcg_set_coarse(self._h, 0, None, None))
+            self.n_agg = 0
+            return 0
+        X = f64(X).reshape(self.n, self.dim)
+        lo, hi = X.min(axis=0), X.max(axis=0)
+        ext = np.maximum(hi - lo, 1e-300)
+        # boxes of equal edge length: bins per axis proportional to the extent
+        edge = (np.prod(ext) / float(min(int(n_agg_target), 2048))) ** (1.0 / self.dim)
+        nb = np.maximum(1, np.floor(ext / edge + 0.5).astype(np.int64))
+        while int(np.prod(nb)) > 2048:
+            nb[np.argmax(nb)] -= 1
+        ib = np.minimum((np.floor((X - lo) / ext * nb)).astype(np.int64), nb - 1)
+        flat = ib[:, 0]
+        for a in range(1, self.dim):
+            flat = flat * nb[a] + ib[:, a]
+        used, agg = np.unique(flat, return_inverse=True)          # drop empty boxes
+        n_agg = int(used.size)
+        cnt = np.bincount(agg, minlength=n_agg).astype(np.float64)
+        cen = np.stack([np.bincount(agg, weights=X[:, a], minlength=n_agg) / cnt for a in range(self.dim)], axis=1)
+        xrel = np.ascontiguousarray(X - cen[agg])
+        agg32 = np.ascontiguousarray(agg.astype(np.int32))
+        check(self._lib.skb_pcg_set_coarse(self._h, n_agg, ptr(agg32), ptr(xrel)))
+        self.n_agg = n_agg
+        return n_agg
+
     def set_basis(self, B):
         """Keeps the subspace basis ``B (n*dim, r)`` resident on the device (``None`` releases it);
         ``reduced(..., B=None)`` then skips the upload (3.4 GB at BASELINE config 4)."""

@@ -260,3 +260,40 @@ def test_reduced_other_dimensions_against_oracle(r):
     assert rel(gr, B.T @ oe.gradient_x("stable_neo_hookean", x, Jo, mu, lam, vol)) < VAL_TOL
     Eo = oe.energy_x("stable_neo_hookean", x, Jo, mu, lam, vol)
     assert abs(E - Eo) <= 1e-12 * abs(Eo)
+
+
+@pytest.mark.parametrize("cells", [(14, 12, 10), (40, 30)])
+def test_two_level_preconditioner(cells):
+    """Block-Jacobi + rigid-mode coarse correction: same solution as the direct solve, fewer iterations, and the
+    Newton step it drives equals the block-Jacobi one to the iterate tolerance."""
+    dim = len(cells)
+    X, T = syn.make_mesh(cells)
+    U = syn.jittered_state(X, cells, tuple(1.0 for _ in cells), sigma=0.2)
+    mu, lam = syn.lame()
+    plan = sk.MeshPlan(X=X, T=T)
+    vol = plan.volume()
+    plan.set_materials(mu, lam, vol)
+    g, vals = plan.gradient_hessian("stable_neo_hookean", U, mu, lam, None, 1)
+    Q = plan.csr_matrix(vals)
+    mass = np.repeat(plan.vertex_masses(1e3), dim)
+    dadd = mass / 1e-2 ** 2
+    rhs = -g.reshape(-1)
+    x1, it1, rr1 = plan.pcg(vals, rhs, diag_add=dadd, rtol=1e-12)
+    n_agg = plan.set_coarse_space(X, 27 if dim == 3 else 16)
+    assert 1 < n_agg <= 64
+    x2, it2, rr2 = plan.pcg(vals, rhs, diag_add=dadd, rtol=1e-12)
+    import scipy.sparse.linalg as spla
+    xo = spla.spsolve((Q + sps.diags(dadd)).tocsc(), rhs)
+    assert rel(x1, xo) < 1e-9 and rel(x2, xo) < 1e-9
+    assert it2 < it1
+    x3, it3, _ = plan.pcg(vals, rhs, diag_add=dadd, rtol=1e-12)
+    assert it3 == it2 and np.array_equal(x3, x2)               # deterministic
+    xc = U.reshape(-1)
+    fext = np.zeros((plan.n, dim))
+    fext[:, 1] = -9.8
+    fext = fext.reshape(-1) * mass
+    xa, ia = plan.newton("stable_neo_hookean", xc, x_tilde=xc, mass=mass, kin_scale=1e4, f_ext=fext, max_iter=2, pcg_rtol=1e-12)
+    plan.set_coarse_space(None)
+    xb, ib = plan.newton("stable_neo_hookean", xc, x_tilde=xc, mass=mass, kin_scale=1e4, f_ext=fext, max_iter=2, pcg_rtol=1e-12)
+    assert rel(xa, xb) < ITER_TOL and ia["alphas"] == ib["alphas"]
+    assert ia["pcg_iters"] < ib["pcg_iters"]
