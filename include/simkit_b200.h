@@ -171,6 +171,17 @@ int skb_dist_newton_terms_dev(skb_plan* plan, int v0, int v1, const double* x, c
                               const double* f_ext, const double* mass, const double* x_tilde, double kin_scale,
                               const double* pin_k, const double* pin_t, const double* g, double* xtrial, double* out,
                               double* work, void* stream);
+/* Two-level preconditioner on a sharded mesh (device pointers, stream-ordered; see skb_pcg_set_coarse).  The
+ * aggregates are global; a rank adds the fine blocks of its owned rows [v0, v1) to the coarse matrix Ac
+ * ((6 n_agg)^2, (3 n_agg)^2 in 2D) and its owned vertices to the restricted residual rc; the caller all-reduces
+ * Ac once per solve (then inverts it) and rc once per iteration. */
+int skb_dist_coarse_set(skb_plan* plan, int64_t n_agg, const int32_t* agg, const double* xrel, int v0, int v1);
+int skb_dist_coarse_assemble_dev(skb_plan* plan, const double* vals, const double* diag_add, double* Ac, void* stream);
+int skb_dist_coarse_invert_dev(skb_plan* plan, double* Ac, void* stream);
+int skb_dist_coarse_restrict_dev(skb_plan* plan, const double* r, double* rc, void* stream);
+int skb_dist_coarse_correct_dev(skb_plan* plan, int v0, int v1, const double* Ainv, double* rc, double* zc,
+                                const double* r, double* z, double* p, double* scalars, int slot, double* work,
+                                void* stream);
 /* measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the compute roofline denominator */
 int skb_fp64_peak(int device, double* tflops);
 /* measured FP64 tensor-core throughput (DMMA.8x8x4 = mma.sync.m8n8k4.f64, 512 flops per warp instruction):

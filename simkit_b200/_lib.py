@@ -85,6 +85,11 @@ SIGNATURES = {
     "skb_dist_pcg_direction_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp]),
     "skb_dist_newton_rhs_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
     "skb_dist_newton_terms_dev": (_int, [_vp, _int, _int, _vp, _vp, _dbl, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "skb_dist_coarse_set": (_int, [_vp, _i64, _vp, _vp, _int, _int]),
+    "skb_dist_coarse_assemble_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "skb_dist_coarse_invert_dev": (_int, [_vp, _vp, _vp]),
+    "skb_dist_coarse_restrict_dev": (_int, [_vp, _vp, _vp, _vp]),
+    "skb_dist_coarse_correct_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp]),
     "skb_fp64_peak": (_int, [_int, ctypes.POINTER(_dbl)]),
     "skb_dmma_peak": (_int, [_int, ctypes.POINTER(_dbl)]),
     "skb_element_energy": (_int, [_int, _int, _i64, _vp, _vp, _i64, _vp, _i64, _vp]),

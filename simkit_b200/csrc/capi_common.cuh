@@ -108,6 +108,7 @@ int launch_assemble(skb_plan* pl, const EvalArgs& a, cudaStream_t st);
 int launch_energy(skb_plan* pl, const EvalArgs& a, double* out_dev, cudaStream_t st);
 int make_args(skb_plan* pl, int material, int psd_mode, const double* x, const double* fbar, double* g,
               double* vals, EvalArgs& a);
+int coarse_build(skb_plan* pl, int n_agg, const int* agg_h, const double* xrel_h, int v0, int v1);  // capi_solver.cu
 int upload_materials(skb_plan* pl, const double* mu, int64_t mu_n, const double* lam, int64_t lam_n,
                      const double* vol, int64_t vol_n, bool from_device, cudaStream_t st);
 }  // namespace skb

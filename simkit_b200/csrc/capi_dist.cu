@@ -12,6 +12,7 @@
 // Reductions use a fixed grid and a fixed tree: bitwise reproducible for a fixed rank count.
 #include "capi_common.cuh"
 #include "solver.cuh"
+#include "coarse.cuh"
 
 namespace skb {
 
@@ -241,6 +242,83 @@ int skb_dist_pcg_direction_dev(skb_plan* pl, int v0, int v1, const double* z, do
   const int D = pl->d.dim;
   SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, dist_direction_kernel<<<DIST_GRID, PCG_THREADS, 0, st>>>(v0 * D, v1 * D, z, p, scalars));
   SKB_LAUNCH(pl, SKB_K_OTHER, st, dist_roll_kernel<<<1, 1, 0, st>>>(scalars));
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+}
+
+// ---- two-level preconditioner on a sharded mesh (csrc/coarse.cuh) -------------------------------------------
+// The coarse space is global (same aggregates on every rank); a rank contributes the fine blocks of its OWNED
+// rows to the coarse matrix and its owned vertices to the restriction, the host side all-reduces both (the
+// coarse matrix once per solve, the restricted residual once per iteration) and every rank applies the same
+// dense inverse.  Buffers (Ac, rc, zc) belong to the caller.
+int skb_dist_coarse_set(skb_plan* pl, int64_t n_agg, const int32_t* agg, const double* xrel, int v0, int v1) {
+  DIST_CHECK(pl)
+  if (n_agg > 0 && (!agg || !xrel)) return fail(SKB_EINVAL, "null argument");
+  if (n_agg > 2048) return fail(SKB_EINVAL, "at most 2048 aggregates (the coarse system is inverted densely)");
+  SKB_TRY
+  return coarse_build(pl, (int)n_agg, agg, xrel, v0, v1);
+  SKB_CATCH
+}
+
+int skb_dist_coarse_assemble_dev(skb_plan* pl, const double* vals, const double* diag_add, double* Ac, void* stream) {
+  if (!pl || !pl->coarse || !vals || !Ac) return fail(SKB_EINVAL, "null argument / no coarse space");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  return pl->d.dim == 3 ? coarse_assemble_launch<3>(pl, vals, diag_add, Ac, (cudaStream_t)stream)
+                        : coarse_assemble_launch<2>(pl, vals, diag_add, Ac, (cudaStream_t)stream);
+  SKB_CATCH
+}
+
+int skb_dist_coarse_invert_dev(skb_plan* pl, double* Ac, void* stream) {
+  if (!pl || !pl->coarse || !Ac) return fail(SKB_EINVAL, "null argument / no coarse space");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  return coarse_invert(pl, Ac, (pl->d.dim == 3 ? 6 : 3) * pl->coarse->n_agg, (cudaStream_t)stream);
+  SKB_CATCH
+}
+
+static CoarseView dist_coarse_view(skb_plan* pl, const double* Ainv, double* rc, double* zc) {
+  CoarseSpace& c = *pl->coarse;
+  CoarseView v;
+  v.n_agg = c.n_agg;
+  v.nc = (pl->d.dim == 3 ? 6 : 3) * c.n_agg;
+  v.agg = raw(c.agg);
+  v.xrel = raw(c.xrel);
+  v.vord = raw(c.vord);
+  v.aptr = raw(c.aptr);
+  v.Ainv = Ainv;
+  v.rc = rc;
+  v.zc = zc;
+  return v;
+}
+
+// rc = sum over the owned vertices of P_v^T r_v  (to be all-reduced by the caller)
+int skb_dist_coarse_restrict_dev(skb_plan* pl, const double* r, double* rc, void* stream) {
+  if (!pl || !pl->coarse || !r || !rc) return fail(SKB_EINVAL, "null argument / no coarse space");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const CoarseView cv = dist_coarse_view(pl, nullptr, rc, nullptr);
+  if (pl->d.dim == 3)
+    SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, coarse_restrict_kernel<3><<<cv.n_agg, 256, 0, st>>>(cv, r, nullptr));
+  else
+    SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, coarse_restrict_kernel<2><<<cv.n_agg, 256, 0, st>>>(cv, r, nullptr));
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+}
+
+// zc = Ainv rc;  z += P zc on the owned vertices (p = z too when p != NULL);  scalars[slot] = r.z over them
+int skb_dist_coarse_correct_dev(skb_plan* pl, int v0, int v1, const double* Ainv, double* rc, double* zc, const double* r,
+                                double* z, double* p, double* scalars, int slot, double* work, void* stream) {
+  DIST_CHECK(pl)
+  if (!pl->coarse || !Ainv || !rc || !zc || !r || !z || !scalars || !work) return fail(SKB_EINVAL, "null argument / no coarse space");
+  cudaStream_t st = (cudaStream_t)stream;
+  const CoarseView cv = dist_coarse_view(pl, Ainv, rc, zc);
+  SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, coarse_gemv_kernel<<<(cv.nc * 32 + 255) / 256, 256, 0, st>>>(cv, nullptr));
+  if (pl->d.dim == 3)
+    SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, coarse_add_kernel<3><<<DIST_GRID, PCG_THREADS, 0, st>>>(cv, v0, v1, r, z, p, work, nullptr));
+  else
+    SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, coarse_add_kernel<2><<<DIST_GRID, PCG_THREADS, 0, st>>>(cv, v0, v1, r, z, p, work, nullptr));
+  SKB_LAUNCH(pl, SKB_K_OTHER, st, dist_reduce_kernel<<<1, PCG_THREADS, 0, st>>>(work, DIST_GRID, scalars, slot, -1));
   SKB_CUDA(cudaGetLastError());
   return SKB_OK;
 }

@@ -9,41 +9,13 @@ namespace skb {
 
 void coarse_destroy(CoarseSpace* c) { delete c; }
 
-#define SKB_CUSOLVER(call)                                                           \
-  do {                                                                               \
-    cusolverStatus_t _s = (call);                                                    \
-    if (_s != CUSOLVER_STATUS_SUCCESS) return fail(SKB_ECUDA, "cuSOLVER call failed: " #call); \
-  } while (0)
-
 // Per solve: coarse matrix of the current Newton system and its dense inverse (Cholesky).
 template <int D>
 static int coarse_setup(skb_plan* pl, const double* vals, const double* dadd, cudaStream_t st) {
   CoarseSpace& c = *pl->coarse;
-  constexpr int NC = CoarseDim<D>::NC;
-  const int nc = NC * c.n_agg;
-  const PlanView p = pl->view();
-  SKB_CUDA(cudaMemsetAsync(raw(c.Ac), 0, (size_t)nc * nc * sizeof(double), st));
-  SKB_LAUNCH(pl, SKB_K_OTHER, st,
-             coarse_assemble_kernel<D><<<c.n_cb, 256, 0, st>>>(p, vals, dadd, c.n_agg, raw(c.agg), raw(c.xrel), raw(c.cb_ptr),
-                                                              raw(c.cb_I), raw(c.cb_J), raw(c.fb), raw(c.Ac)));
-  SKB_CUDA(cudaGetLastError());
-  if (!c.handle) SKB_CUSOLVER(cusolverDnCreate(&c.handle));
-  SKB_CUSOLVER(cusolverDnSetStream(c.handle, st));
-  int lw1 = 0, lw2 = 0;
-  SKB_CUSOLVER(cusolverDnDpotrf_bufferSize(c.handle, CUBLAS_FILL_MODE_LOWER, nc, raw(c.Ac), nc, &lw1));
-  SKB_CUSOLVER(cusolverDnDpotri_bufferSize(c.handle, CUBLAS_FILL_MODE_LOWER, nc, raw(c.Ac), nc, &lw2));
-  const int lw = lw1 > lw2 ? lw1 : lw2;
-  if ((int)c.work.size() < lw) c.work.resize(lw);
-  if (c.info.size() < 2) c.info.resize(2);
-  SKB_CUSOLVER(cusolverDnDpotrf(c.handle, CUBLAS_FILL_MODE_LOWER, nc, raw(c.Ac), nc, raw(c.work), lw, raw(c.info)));
-  SKB_CUSOLVER(cusolverDnDpotri(c.handle, CUBLAS_FILL_MODE_LOWER, nc, raw(c.Ac), nc, raw(c.work), lw, raw(c.info) + 1));
-  int hinfo[2] = {0, 0};
-  SKB_CUDA(cudaMemcpyAsync(hinfo, raw(c.info), 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  SKB_CUDA(cudaStreamSynchronize(st));
-  if (hinfo[0] != 0 || hinfo[1] != 0) return fail(SKB_ECUDA, "coarse matrix of the two-level preconditioner is not positive definite");
-  coarse_symmetrize_kernel<<<(unsigned)(((size_t)nc * nc + 255) / 256), 256, 0, st>>>(nc, raw(c.Ac));
-  SKB_CUDA(cudaGetLastError());
-  return SKB_OK;
+  int rc = coarse_assemble_launch<D>(pl, vals, dadd, raw(c.Ac), st);
+  if (rc) return rc;
+  return coarse_invert(pl, raw(c.Ac), CoarseDim<D>::NC * c.n_agg, st);
 }
 
 static CoarseView coarse_view(CoarseSpace& c, int ncper) {
@@ -100,7 +72,7 @@ static int pcg_loop(skb_plan* pl, int nb, int grid, SpmvDot spmv_dot, const doub
     SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, coarse_restrict_kernel<D><<<cv->n_agg, 256, 0, st>>>(*cv, r, s));
     SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, coarse_gemv_kernel<<<(cv->nc * 32 + 255) / 256, 256, 0, st>>>(*cv, s));
     SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st,
-               coarse_add_kernel<D><<<grid, PCG_THREADS, 0, st>>>(*cv, nb, r, z, p_or_null, part_rz, s));
+               coarse_add_kernel<D><<<grid, PCG_THREADS, 0, st>>>(*cv, 0, nb, r, z, p_or_null, part_rz, s));
   };
   SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st,
              pcg_init_kernel<D><<<grid, PCG_THREADS, 0, st>>>(nb, rhs, dinv, x, r, z, pv, part_rz, part_rr));
@@ -168,7 +140,7 @@ static int pcg_run(skb_plan* pl, const double* vals, const double* dadd, const d
 }
 
 // Builds the plan-side data of the coarse space from the vertex -> aggregate map.
-static int coarse_build(skb_plan* pl, int n_agg, const int* agg_h, const double* xrel_h) {
+int coarse_build(skb_plan* pl, int n_agg, const int* agg_h, const double* xrel_h, int v0, int v1) {
   if (pl->coarse) {
     coarse_destroy(pl->coarse);
     pl->coarse = nullptr;
@@ -182,13 +154,16 @@ static int coarse_build(skb_plan* pl, int n_agg, const int* agg_h, const double*
   CoarseSpace* c = new CoarseSpace();
   pl->coarse = c;
   c->n_agg = n_agg;
+  c->v0 = v0;
+  c->v1 = v1;
   c->agg.assign(agg_h, agg_h + n);
   c->xrel.assign(xrel_h, xrel_h + (size_t)n * D);
   // vertices sorted by aggregate
   {
-    dvec<int> key = c->agg;
+    dvec<int> key(n);
     c->vord.resize(n);
     thrust::sequence(thrust::device, c->vord.begin(), c->vord.end());
+    thrust::transform(thrust::device, c->vord.begin(), c->vord.end(), key.begin(), CoarseVertexKey{raw(c->agg), n_agg, v0, v1});
     thrust::stable_sort_by_key(thrust::device, key.begin(), key.end(), c->vord.begin());
     c->aptr.resize(n_agg + 1);
     thrust::counting_iterator<int> it0(0);
@@ -201,15 +176,16 @@ static int coarse_build(skb_plan* pl, int n_agg, const int* agg_h, const double*
     c->fb.resize(nnzb);
     thrust::sequence(thrust::device, c->fb.begin(), c->fb.end());
     thrust::transform(thrust::device, c->fb.begin(), c->fb.end(), key.begin(),
-                      CoarseKeyOf{p.brow, p.bcol, raw(c->agg), n_agg});
+                      CoarseKeyOf{p.brow, p.bcol, raw(c->agg), n_agg, v0, v1});
     thrust::stable_sort_by_key(thrust::device, key.begin(), key.end(), c->fb.begin());
-    dvec<uint64_t> ukey(nnzb);
-    auto uend = thrust::unique_copy(thrust::device, key.begin(), key.end(), ukey.begin());
+    const int nvalid = (int)(thrust::lower_bound(thrust::device, key.begin(), key.end(), ~0ull) - key.begin());
+    dvec<uint64_t> ukey(nvalid);
+    auto uend = thrust::unique_copy(thrust::device, key.begin(), key.begin() + nvalid, ukey.begin());
     c->n_cb = (int)(uend - ukey.begin());
     ukey.resize(c->n_cb);
     c->cb_ptr.resize(c->n_cb + 1);
-    thrust::lower_bound(thrust::device, key.begin(), key.end(), ukey.begin(), ukey.end(), c->cb_ptr.begin());
-    c->cb_ptr[c->n_cb] = nnzb;
+    thrust::lower_bound(thrust::device, key.begin(), key.begin() + nvalid, ukey.begin(), ukey.end(), c->cb_ptr.begin());
+    c->cb_ptr[c->n_cb] = nvalid;
     c->cb_I.resize(c->n_cb);
     c->cb_J.resize(c->n_cb);
     thrust::transform(thrust::device, ukey.begin(), ukey.end(), c->cb_I.begin(), CoarseKeyI{n_agg});
@@ -271,7 +247,7 @@ int skb_pcg_set_coarse(skb_plan* pl, int64_t n_agg, const int32_t* agg, const do
   if (n_agg > 2048) return fail(SKB_EINVAL, "at most 2048 aggregates (the coarse system is inverted densely)");
   SKB_CUDA(cudaSetDevice(pl->device));
   SKB_TRY
-  return coarse_build(pl, (int)n_agg, agg, xrel);
+  return coarse_build(pl, (int)n_agg, agg, xrel, 0, pl->d.n);
   SKB_CATCH
 }
 

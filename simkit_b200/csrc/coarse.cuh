@@ -111,12 +111,13 @@ static __global__ void coarse_gemv_kernel(CoarseView c, const PcgScalars* sc) {
 // z += P z_c ; partial sums of r.z (replace the block-Jacobi ones); optionally p = z (initialisation)
 template <int D>
 __global__ void __launch_bounds__(PCG_THREADS, PCG_CTAS_PER_SM)
-coarse_add_kernel(CoarseView c, int nb, const double* r, double* z, double* pv, double* part_rz, const PcgScalars* sc) {
+coarse_add_kernel(CoarseView c, int v0, int v1, const double* r, double* z, double* pv, double* part_rz,
+                  const PcgScalars* sc) {
   constexpr int NC = CoarseDim<D>::NC;
   __shared__ double sh[32];
   if (sc && sc->done) return;
   double rz = 0.0;
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nb; v += gridDim.x * blockDim.x) {
+  for (int v = v0 + blockIdx.x * blockDim.x + threadIdx.x; v < v1; v += gridDim.x * blockDim.x) {
     const int I = c.agg[v];
     double x[D], cc[NC], o[D];
 #pragma unroll
@@ -214,10 +215,17 @@ struct CoarseKeyOf {
   const int* brow;
   const int* bcol;
   const int* agg;
-  int n_agg;
+  int n_agg, v0, v1;  // only fine blocks of the owned rows [v0, v1) take part (others sort to the end)
   __host__ __device__ uint64_t operator()(int b) const {
-    return (uint64_t)agg[brow[b]] * (uint64_t)n_agg + (uint64_t)agg[bcol[b]];
+    const int v = brow[b];
+    if (v < v0 || v >= v1) return ~0ull;
+    return (uint64_t)agg[v] * (uint64_t)n_agg + (uint64_t)agg[bcol[b]];
   }
+};
+struct CoarseVertexKey {
+  const int* agg;
+  int n_agg, v0, v1;
+  __host__ __device__ int operator()(int v) const { return (v < v0 || v >= v1) ? n_agg : agg[v]; }
 };
 struct CoarseKeyI {
   int n_agg;
@@ -230,7 +238,7 @@ struct CoarseKeyJ {
 
 // plan-side data of the coarse space (built once by skb_pcg_set_coarse)
 struct CoarseSpace {
-  int n_agg = 0, n_cb = 0;
+  int n_agg = 0, n_cb = 0, v0 = 0, v1 = 0;
   dvec<int> agg, vord, aptr, cb_ptr, cb_I, cb_J, fb;
   dvec<double> xrel, Ac, rc, zc, work;
   dvec<int> info;
@@ -240,5 +248,50 @@ struct CoarseSpace {
     if (handle) cusolverDnDestroy(handle);
   }
 };
+
+
+#define SKB_CUSOLVER(call)                                                                       \
+  do {                                                                                           \
+    cusolverStatus_t _s = (call);                                                                \
+    if (_s != CUSOLVER_STATUS_SUCCESS) return fail(SKB_ECUDA, "cuSOLVER call failed: " #call);   \
+  } while (0)
+
+// Ac (nc x nc, zeroed here) += P^T (A + diag) P over the fine blocks of the owned rows
+template <int D>
+inline int coarse_assemble_launch(skb_plan* pl, const double* vals, const double* dadd, double* Ac, cudaStream_t st) {
+  CoarseSpace& c = *pl->coarse;
+  const size_t nc = (size_t)CoarseDim<D>::NC * c.n_agg;
+  const PlanView p = pl->view();
+  SKB_CUDA(cudaMemsetAsync(Ac, 0, nc * nc * sizeof(double), st));
+  if (c.n_cb > 0)
+    SKB_LAUNCH(pl, SKB_K_OTHER, st,
+               coarse_assemble_kernel<D><<<c.n_cb, 256, 0, st>>>(p, vals, dadd, c.n_agg, raw(c.agg), raw(c.xrel), raw(c.cb_ptr),
+                                                                raw(c.cb_I), raw(c.cb_J), raw(c.fb), Ac));
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+}
+
+// Ac := Ac^-1 (dense Cholesky, cuSOLVER potrf + potri, then the full symmetric matrix)
+inline int coarse_invert(skb_plan* pl, double* Ac, int nc, cudaStream_t st) {
+  CoarseSpace& c = *pl->coarse;
+  if (!c.handle) SKB_CUSOLVER(cusolverDnCreate(&c.handle));
+  SKB_CUSOLVER(cusolverDnSetStream(c.handle, st));
+  int lw1 = 0, lw2 = 0;
+  SKB_CUSOLVER(cusolverDnDpotrf_bufferSize(c.handle, CUBLAS_FILL_MODE_LOWER, nc, Ac, nc, &lw1));
+  SKB_CUSOLVER(cusolverDnDpotri_bufferSize(c.handle, CUBLAS_FILL_MODE_LOWER, nc, Ac, nc, &lw2));
+  const int lw = lw1 > lw2 ? lw1 : lw2;
+  if ((int)c.work.size() < lw) c.work.resize(lw);
+  if (c.info.size() < 2) c.info.resize(2);
+  SKB_CUSOLVER(cusolverDnDpotrf(c.handle, CUBLAS_FILL_MODE_LOWER, nc, Ac, nc, raw(c.work), lw, raw(c.info)));
+  SKB_CUSOLVER(cusolverDnDpotri(c.handle, CUBLAS_FILL_MODE_LOWER, nc, Ac, nc, raw(c.work), lw, raw(c.info) + 1));
+  int hinfo[2] = {0, 0};
+  SKB_CUDA(cudaMemcpyAsync(hinfo, raw(c.info), 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SKB_CUDA(cudaStreamSynchronize(st));
+  if (hinfo[0] != 0 || hinfo[1] != 0)
+    return fail(SKB_ECUDA, "coarse matrix of the two-level preconditioner is not positive definite");
+  coarse_symmetrize_kernel<<<(unsigned)(((size_t)nc * nc + 255) / 256), 256, 0, st>>>(nc, Ac);
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+}
 
 }  // namespace skb

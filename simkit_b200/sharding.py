@@ -215,6 +215,8 @@ class Shard:
         import torch
         from .plan import MeshPlan
         self.layout = layout
+        self.X_local = np.ascontiguousarray(X_local, dtype=np.float64)
+        self.coarse = None
         self.plan = MeshPlan(X=X_local, T=layout.T_local, device=device, tile_elems=tile_elems,
                              t_active=layout.t_own)
         bptr, bcol = self.plan.block_pattern()
@@ -302,6 +304,72 @@ class Shard:
                            ls=z(4))
         return self._w
 
+    def set_coarse_space(self, n_agg_target=729):
+        """Two-level PCG preconditioner on the sharded mesh (``csrc/coarse.cuh``): every rank bins ITS local vertices
+        with the global bounding box, so aggregate ids agree across ranks; centres are global centroids of the owned
+        vertices.  ``n_agg_target = 0`` removes it."""
+        import torch
+        import torch.distributed as dist
+        from ._lib import check, load, ptr
+        lib = load()
+        lay, dim = self.layout, self.layout.dim
+        if not n_agg_target:
+            check(lib.skb_dist_coarse_set(self.plan._h, 0, None, None, lay.own_lo, lay.own_hi))
+            self.coarse = None
+            return 0
+        X = self.X_local
+        f64 = torch.float64
+        lo = torch.from_numpy(X.min(axis=0)).to(self.device)
+        hi = torch.from_numpy(X.max(axis=0)).to(self.device)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        lo, hi = lo.cpu().numpy(), hi.cpu().numpy()
+        ext = np.maximum(hi - lo, 1e-300)
+        edge = (np.prod(ext) / float(min(int(n_agg_target), 2048))) ** (1.0 / dim)
+        nb = np.maximum(1, np.floor(ext / edge + 0.5).astype(np.int64))
+        while int(np.prod(nb)) > 2048:
+            nb[np.argmax(nb)] -= 1
+        ib = np.minimum((np.floor((X - lo) / ext * nb)).astype(np.int64), nb - 1)
+        flat = ib[:, 0]
+        for a in range(1, dim):
+            flat = flat * nb[a] + ib[:, a]
+        nbox = int(np.prod(nb))
+        own = slice(lay.own_lo, lay.own_hi)
+        sums = np.zeros((nbox, dim + 1))
+        sums[:, 0] = np.bincount(flat[own], minlength=nbox)
+        for a in range(dim):
+            sums[:, 1 + a] = np.bincount(flat[own], weights=X[own, a], minlength=nbox)
+        sums_d = torch.from_numpy(sums).to(self.device)
+        dist.all_reduce(sums_d)                                   # every vertex is owned by exactly one rank
+        sums = sums_d.cpu().numpy()
+        used = np.nonzero(sums[:, 0] > 0)[0]                      # drop empty boxes, identically on every rank
+        remap = -np.ones(nbox, dtype=np.int64)
+        remap[used] = np.arange(used.size)
+        agg = remap[flat]
+        assert (agg >= 0).all()
+        cen = sums[used, 1:] / sums[used, :1]
+        xrel = np.ascontiguousarray(X - cen[agg])
+        agg32 = np.ascontiguousarray(agg.astype(np.int32))
+        n_agg = int(used.size)
+        check(lib.skb_dist_coarse_set(self.plan._h, n_agg, ptr(agg32), ptr(xrel), lay.own_lo, lay.own_hi))
+        nc = (6 if dim == 3 else 3) * n_agg
+        z = lambda n: torch.zeros(n, dtype=f64, device=self.device)  # noqa: E731
+        self.coarse = dict(n_agg=n_agg, nc=nc, Ac=z(nc * nc), rc=z(nc), zc=z(nc))
+        return n_agg
+
+    def _coarse_correct(self, r_d, z_d, p_d, s, slot, work, st):
+        """z += P Ainv P^T r (restriction all-reduced); s[slot] = r.z over the owned dofs."""
+        import torch.distributed as dist
+        from ._lib import check, load
+        lib = load()
+        c = self.coarse
+        v0, v1 = self.layout.own_lo, self.layout.own_hi
+        check(lib.skb_dist_coarse_restrict_dev(self.plan._h, r_d.data_ptr(), c["rc"].data_ptr(), st))
+        dist.all_reduce(c["rc"])
+        check(lib.skb_dist_coarse_correct_dev(self.plan._h, v0, v1, c["Ac"].data_ptr(), c["rc"].data_ptr(), c["zc"].data_ptr(),
+                                              r_d.data_ptr(), z_d.data_ptr(), 0 if p_d is None else p_d.data_ptr(),
+                                              s.data_ptr(), slot, work.data_ptr(), st))
+
     def pcg(self, vals_d, diag_d, rhs_d, x_d, rtol=1e-10, max_iter=20000, check_every=10):
         """Block-Jacobi PCG on the distributed matrix (owned rows per rank, complete after the interface exchange).
         Per iteration: halo exchange of p, SpMV + p.q, all-reduce, fused update, all-reduce, direction."""
@@ -316,8 +384,15 @@ class Shard:
         s = w["s"]
         P = lambda t: t.data_ptr()  # noqa: E731
         dp = 0 if diag_d is None else P(diag_d)
+        if self.coarse is not None:
+            # coarse matrix of this system: owned fine blocks per rank, summed over the ranks, inverted by every rank
+            check(lib.skb_dist_coarse_assemble_dev(h, P(vals_d), dp, P(self.coarse["Ac"]), st))
+            dist.all_reduce(self.coarse["Ac"])
+            check(lib.skb_dist_coarse_invert_dev(h, P(self.coarse["Ac"]), st))
         check(lib.skb_dist_pcg_init_dev(h, P(vals_d), dp, v0, v1, P(rhs_d), P(w["dinv"]), P(x_d), P(w["r"]), P(w["z"]),
                                         P(w["p"]), P(s), P(w["work"]), st))
+        if self.coarse is not None:
+            self._coarse_correct(w["r"], w["z"], w["p"], s, 0, w["work"], st)
         dist.all_reduce(s[0:2])
         bb = float(s[1].item())
         it = 0
@@ -331,6 +406,8 @@ class Shard:
                 dist.all_reduce(s[2:3])
                 check(lib.skb_dist_pcg_update_dev(h, v0, v1, P(w["dinv"]), P(w["p"]), P(w["q"]), P(x_d), P(w["r"]),
                                                   P(w["z"]), P(s), P(w["work"]), st))
+                if self.coarse is not None:
+                    self._coarse_correct(w["r"], w["z"], None, s, 3, w["work"], st)
                 dist.all_reduce(s[3:5])
                 check(lib.skb_dist_pcg_direction_dev(h, v0, v1, P(w["z"]), P(w["p"]), P(s), st))
                 it += 1

@@ -106,8 +106,15 @@ def _nccl_worker(rank, world, port, cells, tmp):
     info = shard.newton_step(MAT, xs, x_tilde_d=x_d, mass_d=mass_d, kin_scale=1.0 / h ** 2, fext_d=fext_d, max_iter=3,
                              pcg_rtol=1e-12)
     o0, o1 = lay.own_lo * dim, lay.own_hi * dim
+    # same step with the two-level preconditioner (global aggregates, all-reduced coarse matrix and restriction)
+    n_agg = shard.set_coarse_space(12)
+    xs2 = x_d.clone()
+    info2 = shard.newton_step(MAT, xs2, x_tilde_d=x_d, mass_d=mass_d, kin_scale=1.0 / h ** 2, fext_d=fext_d, max_iter=3,
+                              pcg_rtol=1e-12)
+    shard.set_coarse_space(0)
     np.savez(os.path.join(tmp, "newton%d.npz" % rank), x=xs.cpu().numpy()[o0:o1], lo=lay.v_lo, hi=lay.v_hi,
-             alphas=np.asarray(info["alphas"]), mass=mass_d.cpu().numpy()[o0:o1])
+             alphas=np.asarray(info["alphas"]), mass=mass_d.cpu().numpy()[o0:o1], x2=xs2.cpu().numpy()[o0:o1],
+             alphas2=np.asarray(info2["alphas"]), its=info["pcg_iters"], its2=info2["pcg_iters"], n_agg=n_agg)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -140,3 +147,6 @@ def test_distributed_newton_matches_single_gpu(tmp_path):
         assert rel(d["mass"], mass[lo:hi]) < 1e-13
         assert list(d["alphas"]) == list(info["alphas"])
         assert rel(d["x"], x1.ravel()[lo:hi]) < 1e-8
+        # two-level preconditioner: same iterate, fewer CG iterations
+        assert rel(d["x2"], x1.ravel()[lo:hi]) < 1e-8 and list(d["alphas2"]) == list(info["alphas"])
+        assert 1 < int(d["n_agg"]) <= 16 and int(d["its2"]) < int(d["its"])
