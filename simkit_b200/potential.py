@@ -20,7 +20,10 @@ class ElasticPotential:
     _skb_potential = True
 
     def __init__(self, material, mu, lam, vol=None, plan=None, J=None, X=None, T=None, dim=None, f_ext=None,
-                 pin_k=None, pin_target=None, psd=True):
+                 pin_k=None, pin_target=None, psd=True, coarse="auto"):
+        """``coarse``: vertex aggregates of the two-level PCG preconditioner of the device-resident step
+        (``MeshPlan.set_coarse_space``; needs the rest positions ``X``).  ``"auto"``: about one aggregate per 3,000
+        vertices (8 ... 729) on meshes of 20,000 vertices or more, none below; ``0`` / ``None``: block-Jacobi only."""
         if plan is None:
             if J is not None:
                 plan = plan_from_operator(J, dim if dim is not None else (X.shape[1] if X is not None else 3))
@@ -36,6 +39,10 @@ class ElasticPotential:
         self.pin_k = None if pin_k is None else np.asarray(pin_k, dtype=np.float64).reshape(nd, 1)
         self.pin_target = None if pin_target is None else np.asarray(pin_target, dtype=np.float64).reshape(nd, 1)
         self._materials_set = False
+        if coarse == "auto":
+            coarse = 0 if (X is None or plan.n < 20000) else int(min(729, max(8, plan.n // 3000)))
+        if coarse and X is not None:
+            plan.set_coarse_space(np.asarray(X, dtype=np.float64).reshape(plan.n, plan.dim), int(coarse))
 
     # -- callables (host boundary per call) -----------------------------------------------------
     def energy(self, x):

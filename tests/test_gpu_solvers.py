@@ -297,3 +297,9 @@ def test_two_level_preconditioner(cells):
     xb, ib = plan.newton("stable_neo_hookean", xc, x_tilde=xc, mass=mass, kin_scale=1e4, f_ext=fext, max_iter=2, pcg_rtol=1e-12)
     assert rel(xa, xb) < ITER_TOL and ia["alphas"] == ib["alphas"]
     assert ia["pcg_iters"] < ib["pcg_iters"]
+    # through the drop-in surface: backward_euler with an ElasticPotential that carries the rest positions
+    M = sps.diags(mass)
+    pot = sk.ElasticPotential("stable_neo_hookean", mu, lam, vol, X=X, T=T, f_ext=fext, coarse=n_agg)
+    xe = sk.backward_euler(xc.reshape(-1, 1), xc.reshape(-1, 1), pot.energy, pot.gradient, pot.hessian, M, 1e-2, max_iter=2,
+                           pcg_rtol=1e-12)
+    assert pot.plan.n_agg == n_agg and rel(xe, xb) < ITER_TOL
