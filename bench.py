@@ -416,12 +416,22 @@ def run_ours(args, rank, world, local_rank):
                         "pcg_ms_per_iter": (kms[4] + kms[5]) / max(info["pcg_iters"], 1) / nsteps}
 
         # block-Jacobi alone, then block-Jacobi + rigid-mode coarse correction (csrc/coarse.cuh): same Newton iterate
-        x_bj, newton_bj = newton_leg("3x3 block-Jacobi")
-        n_agg = plan.set_coarse_space(X, args.aggregates)
-        x_tl, newton = newton_leg("3x3 block-Jacobi + rigid-body modes of %d vertex aggregates (two-level, additive)" % n_agg)
-        plan.set_coarse_space(None)
-        newton["block_jacobi_only"] = {k: newton_bj[k] for k in ("steps_per_s", "ms_per_step", "pcg_iters", "pcg_ms_per_iter")}
-        newton["iterate_difference_vs_block_jacobi"] = float(np.abs(x_tl - x_bj).max() / np.abs(x_bj).max())
+        x_bj, newton_bj = newton_leg("%dx%d block-Jacobi" % (dim, dim))
+        # same rule as ElasticPotential(coarse="auto"): the coarse correction is switched on when block-Jacobi needed
+        # more than MeshPlan.COARSE_MIN_ITERS iterations
+        if args.aggregates < 0:
+            want_agg = plan.auto_aggregates() if newton_bj["pcg_iters"] > plan.COARSE_MIN_ITERS else 0
+        else:
+            want_agg = args.aggregates
+        if want_agg:
+            n_agg = plan.set_coarse_space(X, want_agg)
+            x_tl, newton = newton_leg("%dx%d block-Jacobi + rigid-body modes of %d vertex aggregates (two-level, additive)"
+                                      % (dim, dim, n_agg))
+            plan.set_coarse_space(None)
+            newton["block_jacobi_only"] = {k: newton_bj[k] for k in ("steps_per_s", "ms_per_step", "pcg_iters", "pcg_ms_per_iter")}
+            newton["iterate_difference_vs_block_jacobi"] = float(np.abs(x_tl - x_bj).max() / np.abs(x_bj).max())
+        else:
+            newton = newton_bj
     elif args.newton:
         # sharded implicit step: device-resident state, distributed PCG (halo exchange + 2 all-reduces per iteration)
         mass_d = shard.lumped_mass_dofs(rho)
@@ -429,7 +439,7 @@ def run_ours(args, rank, world, local_rank):
         fext_d[:, 1] = -9.8
         fext_d = fext_d.reshape(-1) * mass_d
         nsteps = max(1, min(args.steps, args.newton_steps))
-        n_agg = shard.set_coarse_space(args.aggregates)
+        n_agg = shard.set_coarse_space(min(729, max(8, n_total // 1000)) if args.aggregates < 0 else args.aggregates)
         tt, info = [], None
         for s in range(1 + nsteps):
             xs = x_d.clone()
@@ -528,11 +538,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C5", choices=["C1", "C3", "C4", "C5"])
+    ap.add_argument("--workload", default="C5", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--material", default="stable_neo_hookean", help="constitutive model of the step (default: the headline metric's "
+                    "stable_neo_hookean; BASELINE configs 2 and 3 also name neo_hookean and arap)")
     ap.add_argument("--newton", type=int, default=1, help="also time one backward-Euler Newton step (0 = skip)")
     ap.add_argument("--newton-steps", type=int, default=2)
     ap.add_argument("--pcg-rtol", type=float, default=1e-10)
-    ap.add_argument("--aggregates", type=int, default=729, help="vertex aggregates of the two-level PCG preconditioner")
+    ap.add_argument("--aggregates", type=int, default=-1, help="vertex aggregates of the two-level PCG preconditioner "
+                    "(-1: MeshPlan.auto_aggregates when block-Jacobi needs > 300 iterations, 729 at C5; 0: block-Jacobi only)")
     ap.add_argument("--reduced", type=int, default=0, help="also time the reduced Hessian B^T H B with this many modes (config 4: --workload C4 --reduced 200)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="development only: stop after the device-resident timing")
@@ -540,6 +553,7 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    globals()["MATERIAL"] = args.material
     if args.impl == "reference":
         run_reference(args, rank)
         return

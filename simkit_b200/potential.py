@@ -22,8 +22,10 @@ class ElasticPotential:
     def __init__(self, material, mu, lam, vol=None, plan=None, J=None, X=None, T=None, dim=None, f_ext=None,
                  pin_k=None, pin_target=None, psd=True, coarse="auto"):
         """``coarse``: vertex aggregates of the two-level PCG preconditioner of the device-resident step
-        (``MeshPlan.set_coarse_space``; needs the rest positions ``X``).  ``"auto"``: about one aggregate per 3,000
-        vertices (8 ... 729) on meshes of 20,000 vertices or more, none below; ``0`` / ``None``: block-Jacobi only."""
+        (``MeshPlan.set_coarse_space``; needs the rest positions ``X``).  ``"auto"``: start with block-Jacobi and switch
+        the coarse correction on (``MeshPlan.auto_aggregates`` aggregates) after the first Newton iteration whose
+        PCG needed more than ``MeshPlan.COARSE_MIN_ITERS`` iterations; an integer: that many aggregates from the
+        start; ``0`` / ``None``: block-Jacobi only."""
         if plan is None:
             if J is not None:
                 plan = plan_from_operator(J, dim if dim is not None else (X.shape[1] if X is not None else 3))
@@ -39,10 +41,10 @@ class ElasticPotential:
         self.pin_k = None if pin_k is None else np.asarray(pin_k, dtype=np.float64).reshape(nd, 1)
         self.pin_target = None if pin_target is None else np.asarray(pin_target, dtype=np.float64).reshape(nd, 1)
         self._materials_set = False
-        if coarse == "auto":
-            coarse = 0 if (X is None or plan.n < 20000) else int(min(729, max(8, plan.n // 3000)))
-        if coarse and X is not None:
-            plan.set_coarse_space(np.asarray(X, dtype=np.float64).reshape(plan.n, plan.dim), int(coarse))
+        self._X_rest = None if X is None else np.asarray(X, dtype=np.float64).reshape(plan.n, plan.dim)
+        self._coarse_auto = (coarse == "auto") and self._X_rest is not None
+        if coarse and coarse != "auto" and self._X_rest is not None:
+            plan.set_coarse_space(self._X_rest, int(coarse))
 
     # -- callables (host boundary per call) -----------------------------------------------------
     def energy(self, x):
@@ -82,6 +84,10 @@ class ElasticPotential:
                                    kin_scale=kin_scale, f_ext=self.f_ext, pin_k=self.pin_k,
                                    pin_target=self.pin_target, max_iter=max_iter, do_line_search=do_line_search,
                                    tolerance=tolerance, **kw)
+        if self._coarse_auto and info["pcg_iters"] > self.plan.COARSE_MIN_ITERS * max(1, info["iters"] + 1):
+            # the next steps get the coarse correction (same iterates, fewer CG iterations)
+            self.plan.set_coarse_space(self._X_rest, self.plan.auto_aggregates())
+            self._coarse_auto = False
         return (x, info) if return_info else x
 
     def newton(self, x0, tolerance=1e-6, max_iter=1, do_line_search=True, return_info=False, **kw):

@@ -303,3 +303,13 @@ def test_two_level_preconditioner(cells):
     xe = sk.backward_euler(xc.reshape(-1, 1), xc.reshape(-1, 1), pot.energy, pot.gradient, pot.hessian, M, 1e-2, max_iter=2,
                            pcg_rtol=1e-12)
     assert pot.plan.n_agg == n_agg and rel(xe, xb) < ITER_TOL
+    # "auto": block-Jacobi first, coarse correction switched on once a step needed many CG iterations
+    pot2 = sk.ElasticPotential("stable_neo_hookean", mu, lam, vol, X=X, T=T, f_ext=fext)
+    old = sk.MeshPlan.COARSE_MIN_ITERS
+    try:
+        sk.MeshPlan.COARSE_MIN_ITERS = 5
+        xe2 = sk.backward_euler(xc.reshape(-1, 1), xc.reshape(-1, 1), pot2.energy, pot2.gradient, pot2.hessian, M, 1e-2,
+                                max_iter=2, pcg_rtol=1e-12)
+        assert getattr(pot2.plan, "n_agg", 0) > 0 and rel(xe2, xb) < ITER_TOL
+    finally:
+        sk.MeshPlan.COARSE_MIN_ITERS = old
