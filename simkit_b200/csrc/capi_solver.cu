@@ -130,13 +130,15 @@ static int pcg_run(skb_plan* pl, const double* vals, const double* dadd, const d
   };
   CoarseView cv;
   const bool two_level = pl->coarse != nullptr && pl->coarse->n_agg > 0;
+  bool two_level_ok = two_level;
   if (two_level) {
     int rc = coarse_setup<D>(pl, vals, dadd, st);
-    if (rc) return rc;
-    cv = coarse_view(*pl->coarse, CoarseDim<D>::NC);
+    if (rc == SKB_ENOTSPD) two_level_ok = false;  // degenerate aggregate: block-Jacobi only for this solve
+    else if (rc) return rc;
+    else cv = coarse_view(*pl->coarse, CoarseDim<D>::NC);
   }
   return pcg_loop<D>(pl, p.n, grid, spmv_dot, dinv, rhs, rtol, max_iter, x, raw(pl->w_r), raw(pl->w_z),
-                     raw(pl->w_p), raw(pl->w_q), raw(pl->w_red), iters, relres, st, two_level ? &cv : nullptr);
+                     raw(pl->w_p), raw(pl->w_q), raw(pl->w_red), iters, relres, st, two_level_ok ? &cv : nullptr);
 }
 
 // Builds the plan-side data of the coarse space from the vertex -> aggregate map.

@@ -250,6 +250,8 @@ struct CoarseSpace {
 };
 
 
+#define SKB_ENOTSPD (-5)  // internal: the callers fall back to block-Jacobi for this solve
+
 #define SKB_CUSOLVER(call)                                                                       \
   do {                                                                                           \
     cusolverStatus_t _s = (call);                                                                \
@@ -287,8 +289,8 @@ inline int coarse_invert(skb_plan* pl, double* Ac, int nc, cudaStream_t st) {
   int hinfo[2] = {0, 0};
   SKB_CUDA(cudaMemcpyAsync(hinfo, raw(c.info), 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   SKB_CUDA(cudaStreamSynchronize(st));
-  if (hinfo[0] != 0 || hinfo[1] != 0)
-    return fail(SKB_ECUDA, "coarse matrix of the two-level preconditioner is not positive definite");
+  if (hinfo[0] != 0 || hinfo[1] != 0)  // e.g. an aggregate of collinear vertices: its rotations are dependent
+    return fail(SKB_ENOTSPD, "coarse matrix of the two-level preconditioner is not positive definite");
   coarse_symmetrize_kernel<<<(unsigned)(((size_t)nc * nc + 255) / 256), 256, 0, st>>>(nc, Ac);
   SKB_CUDA(cudaGetLastError());
   return SKB_OK;

@@ -384,14 +384,16 @@ class Shard:
         s = w["s"]
         P = lambda t: t.data_ptr()  # noqa: E731
         dp = 0 if diag_d is None else P(diag_d)
-        if self.coarse is not None:
+        coarse = self.coarse
+        if coarse is not None:
             # coarse matrix of this system: owned fine blocks per rank, summed over the ranks, inverted by every rank
-            check(lib.skb_dist_coarse_assemble_dev(h, P(vals_d), dp, P(self.coarse["Ac"]), st))
-            dist.all_reduce(self.coarse["Ac"])
-            check(lib.skb_dist_coarse_invert_dev(h, P(self.coarse["Ac"]), st))
+            check(lib.skb_dist_coarse_assemble_dev(h, P(vals_d), dp, P(coarse["Ac"]), st))
+            dist.all_reduce(coarse["Ac"])
+            if lib.skb_dist_coarse_invert_dev(h, P(coarse["Ac"]), st) != 0:
+                coarse = None        # degenerate aggregate (same matrix on every rank): block-Jacobi for this solve
         check(lib.skb_dist_pcg_init_dev(h, P(vals_d), dp, v0, v1, P(rhs_d), P(w["dinv"]), P(x_d), P(w["r"]), P(w["z"]),
                                         P(w["p"]), P(s), P(w["work"]), st))
-        if self.coarse is not None:
+        if coarse is not None:
             self._coarse_correct(w["r"], w["z"], w["p"], s, 0, w["work"], st)
         dist.all_reduce(s[0:2])
         bb = float(s[1].item())
@@ -406,7 +408,7 @@ class Shard:
                 dist.all_reduce(s[2:3])
                 check(lib.skb_dist_pcg_update_dev(h, v0, v1, P(w["dinv"]), P(w["p"]), P(w["q"]), P(x_d), P(w["r"]),
                                                   P(w["z"]), P(s), P(w["work"]), st))
-                if self.coarse is not None:
+                if coarse is not None:
                     self._coarse_correct(w["r"], w["z"], None, s, 3, w["work"], st)
                 dist.all_reduce(s[3:5])
                 check(lib.skb_dist_pcg_direction_dev(h, v0, v1, P(w["z"]), P(w["p"]), P(s), st))

@@ -313,3 +313,20 @@ def test_two_level_preconditioner(cells):
         assert getattr(pot2.plan, "n_agg", 0) > 0 and rel(xe2, xb) < ITER_TOL
     finally:
         sk.MeshPlan.COARSE_MIN_ITERS = old
+
+
+def test_two_level_degenerate_aggregates_fall_back():
+    """Aggregates of collinear vertices make the rigid modes dependent (singular coarse matrix): the solve falls
+    back to block-Jacobi instead of failing."""
+    cells = (6, 6, 6)
+    X, T = syn.make_mesh(cells)
+    mu, lam = syn.lame()
+    plan = sk.MeshPlan(X=X, T=T)
+    vol = plan.volume()
+    g, vals = plan.gradient_hessian("stable_neo_hookean", syn.jittered_state(X, cells, (1.0, 1.0, 1.0), sigma=0.1), mu, lam, vol, 1)
+    dadd = np.full(plan.ndof, 10.0)
+    x1, it1, _ = plan.pcg(vals, -g.reshape(-1), diag_add=dadd, rtol=1e-12)
+    n_agg = plan.set_coarse_space(X, 343)          # one vertex per box: 6 modes on 3 dofs
+    assert n_agg == 343
+    x2, it2, _ = plan.pcg(vals, -g.reshape(-1), diag_add=dadd, rtol=1e-12)
+    assert it2 == it1 and np.array_equal(x1, x2)
