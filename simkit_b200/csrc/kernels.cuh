@@ -519,18 +519,25 @@ SKB_HD void block_finalize(const PlanView& p, int item, const double* pblocks, d
   // 2.3 records on average); the summation order stays q0, q0+1, ...
   const double* r0 = pblocks + (size_t)q0 * RS + j;
   const int nq = q1 - q0;
-  const double v0 = (nq > 0) ? r0[0] : 0.0;
-  const double v1 = (nq > 1) ? r0[RS] : 0.0;
-  const double v2 = (nq > 2) ? r0[2 * RS] : 0.0;
-  const double v3 = (nq > 3) ? r0[3 * RS] : 0.0;
+#if defined(SKB_FIN_CS) && defined(__CUDA_ARCH__)  // A/B: streaming (evict-first) accesses, everything is touched once
+#define SKB_FIN_LD(p) __ldcs(p)
+#define SKB_FIN_ST(p, v) __stcs((p), (v))
+#else
+#define SKB_FIN_LD(p) (*(p))
+#define SKB_FIN_ST(p, v) (*(p) = (v))
+#endif
+  const double v0 = (nq > 0) ? SKB_FIN_LD(r0) : 0.0;
+  const double v1 = (nq > 1) ? SKB_FIN_LD(r0 + RS) : 0.0;
+  const double v2 = (nq > 2) ? SKB_FIN_LD(r0 + 2 * RS) : 0.0;
+  const double v3 = (nq > 3) ? SKB_FIN_LD(r0 + 3 * RS) : 0.0;
   acc = v0;
   if (nq > 1) acc += v1;
   if (nq > 2) acc += v2;
   if (nq > 3) acc += v3;
-  for (int q = q0 + 4; q < q1; ++q) acc += pblocks[(size_t)q * RS + j];
+  for (int q = q0 + 4; q < q1; ++q) acc += SKB_FIN_LD(pblocks + (size_t)q * RS + j);
   const int i = j / D, k = j - i * D;
-  vals[(size_t)up.base + (size_t)i * up.stride + k] = acc;
-  if (up.tbase != up.base) vals[(size_t)up.tbase + (size_t)k * up.tstride + i] = acc;
+  SKB_FIN_ST(vals + (size_t)up.base + (size_t)i * up.stride + k, acc);
+  if (up.tbase != up.base) SKB_FIN_ST(vals + (size_t)up.tbase + (size_t)k * up.tstride + i, acc);
 }
 
 template <int D>
@@ -804,6 +811,9 @@ __global__ void SKB_PIPE_BOUNDS(G, E) assemble_pipelined_kernel(PlanView p, Eval
   }
 }
 
+#ifndef SKB_FIN_THREADS
+#define SKB_FIN_THREADS 128
+#endif
 template <int D>
 __global__ void finalize_blocks_kernel(PlanView p, const double* pblocks, double* vals) {
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
