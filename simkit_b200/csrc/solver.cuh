@@ -21,7 +21,10 @@ constexpr int PCG_THREADS = 256;
 #endif
 constexpr int PCG_MAX_GRID = 2048;  // size of each per-CTA partial-sum array
 constexpr int PCG_CTAS_PER_SM = SKB_PCG_CTAS_PER_SM;  // resident CTAs per SM the PCG kernels are compiled and launched for
-constexpr int SPMV_GROUP = 8;  // lanes cooperating on one block row
+#ifndef SKB_SPMV_GROUP
+#define SKB_SPMV_GROUP 16
+#endif
+constexpr int SPMV_GROUP = SKB_SPMV_GROUP;  // lanes cooperating on one block row
 
 // scalars kept on the device between the kernels of an iteration
 struct PcgScalars {
