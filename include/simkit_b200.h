@@ -208,6 +208,9 @@ int skb_svd_rv(int dim, int64_t t, const double* F, double* U, double* S, double
 int skb_polar(int dim, int64_t t, const double* F, double* R, double* SS);
 /* rotation_gradient.py:12-75: dR/dF (t, b, b) */
 int skb_rotation_gradient(int dim, int64_t t, const double* F, double* K);
+/* dS/dF of the polar stretch S = R^T F, (t, d*d, d*d) with rows (m,n) of F and columns (i,j) of S
+ * (stretch_gradient.py:28-54: dR/dF . F + R (x) I). */
+int skb_stretch_gradient(int dim, int64_t t, const double* F, double* dSdF);
 
 /* --------------------------------------------------------- linear solve ----
  * Block-Jacobi preconditioned CG on a matrix in the plan's canonical pattern

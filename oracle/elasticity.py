@@ -180,6 +180,134 @@ def rotation_gradient_F(F):
     return K
 
 
+def stretch_gradient_dF(F):
+    """dS/dF of S = R^T F, (t,d,d,d,d) indexed [m,n,i,j] = dS_ij/dF_mn (stretch_gradient.py:28-54):
+    sum_k dR_ki/dF_mn F_kj + R_mi delta_nj, with dR/dF the symmetric matrix of rotation_gradient_F."""
+    dim = F.shape[-1]
+    R, _ = polar_svd(F)
+    K = rotation_gradient_F(F).reshape(-1, dim, dim, dim, dim)
+    eye = np.eye(dim)
+    return np.einsum("tmnki,tkj->tmnij", K, F) + np.einsum("tmi,nj->tmnij", R, eye)
+
+
+def symmetric_stretch_map(t, dim):
+    """symmetric_stretch_map.py:46-67: diagonal entries first, then the upper triangle row by row; the inverse map
+    averages the two copies of an off-diagonal."""
+    k = dim * (dim + 1) // 2
+    col = {}
+    c = 0
+    for i in range(dim):
+        col[(i, i)] = c
+        c += 1
+    for i in range(dim):
+        for j in range(i + 1, dim):
+            col[(i, j)] = col[(j, i)] = c
+            c += 1
+    S = np.zeros((dim * dim, k))
+    Si = np.zeros((k, dim * dim))
+    for i in range(dim):
+        for j in range(dim):
+            S[i * dim + j, col[(i, j)]] = 1.0
+            Si[col[(i, j)], i * dim + j] = 1.0 if i == j else 0.5
+    return sps.kron(sps.identity(t), sps.csc_matrix(S)), sps.kron(sps.identity(t), sps.csc_matrix(Si))
+
+
+def stretch(F):
+    """stretch.py:9-27: S of F = R S, stacked as a column."""
+    _, S = polar_svd(F)
+    return S.reshape(-1, 1)
+
+
+def stretch_gradient_dz(z, GJB, dim, Ci=None, GJq=None):
+    """stretch_gradient.py:57-131: J^T blockdiag(dS/dF) [Ci^T]."""
+    f = GJB @ np.asarray(z).reshape(-1, 1)
+    if GJq is not None:
+        f = f + GJq
+    F = np.asarray(f).reshape(-1, dim, dim)
+    blocks = stretch_gradient_dF(F).reshape(-1, dim * dim, dim * dim)
+    out = GJB.T @ sps.block_diag(blocks)
+    return out if Ci is None else out @ Ci.T
+
+
+def _compact_embedding(dim):
+    S, _ = symmetric_stretch_map(1, dim)
+    return np.asarray(S.todense())
+
+
+def elastic_S(kind, S, mu, lam, vol, material):
+    """Stretch tier of the dispatcher for Macklin-Mueller NH (energies/elastic.py:327-357, 563-593, 816-846;
+    macklin_mueller_neo_hookean.py:395-478): the F tier at the symmetric stretch, mapped to the compact components
+    by the embedding C0; the Hessian is PSD-projected before the vol weighting."""
+    assert material == "macklin-mueller-neo-hookean"
+    m = "macklin_mueller_neo_hookean"
+    S = np.asarray(S)
+    t, k = S.shape
+    dim = 2 if k == 3 else 3
+    C0 = _compact_embedding(dim)
+    Sf = (S @ C0.T).reshape(t, dim, dim)
+    w = np.asarray(vol, dtype=np.float64).reshape(-1, 1)
+    if kind == "energy":
+        return float((w * energy_element_F(m, Sf, mu, lam)).sum())
+    if kind == "gradient":
+        return (gradient_element_F(m, Sf, mu, lam).reshape(t, dim * dim) @ C0) * w
+    H = np.einsum("ji,tjk,kl->til", C0, hessian_element_F(m, Sf, mu, lam), C0)
+    return psd_project(H) * w.reshape(-1, 1, 1)
+
+
+class _MfemEnergies:
+    @staticmethod
+    def elastic_energy_S(S, mu, lam, vol, material):
+        return elastic_S("energy", S, mu, lam, vol, material)
+
+    @staticmethod
+    def elastic_gradient_S(S, mu, lam, vol, material):
+        return elastic_S("gradient", S, mu, lam, vol, material)
+
+    @staticmethod
+    def elastic_hessian_S(S, mu, lam, vol, material):
+        return elastic_S("hessian", S, mu, lam, vol, material)
+
+
+class MfemSurface:
+    """The part of the simkit surface oracle/mfem_problem.py needs, backed by this oracle."""
+    energies = _MfemEnergies
+    volume = staticmethod(volume)
+    massmatrix = staticmethod(massmatrix)
+    deformation_jacobian = staticmethod(deformation_jacobian)
+    symmetric_stretch_map = staticmethod(symmetric_stretch_map)
+    stretch = staticmethod(stretch)
+    stretch_gradient_dz = staticmethod(stretch_gradient_dz)
+
+    @staticmethod
+    def ympr_to_lame(ym, pr):
+        return ym / (2.0 * (1.0 + pr)), ym * pr / ((1.0 + pr) * (1.0 - 2.0 * pr))
+
+
+def sqp_mfem(p0, energy_func, hess_blocks_func, grad_blocks_func, tolerance=1e-4, max_iter=100, do_line_search=True):
+    """solvers/sqpmfem.py:56-89 with direct solves."""
+    p = p0.copy()
+    for _ in range(max_iter):
+        H_u, H_z, G_u, G_z, G_zi = hess_blocks_func(p)
+        f_u, f_z, f_mu = grad_blocks_func(p)
+        Q = H_u + G_u @ G_zi @ H_z @ G_zi @ G_u.T
+        g_u = -f_u + G_u @ G_zi @ (f_z - H_z @ G_zi @ f_mu)
+        du = spla.spsolve(sps.csc_matrix(Q), g_u) if sps.issparse(Q) else scipy.linalg.solve(Q, g_u)
+        du = np.asarray(du).reshape(-1, 1)
+        dz = G_zi @ (-(f_mu + G_u.T @ du))
+        mu = -G_zi @ (f_z + H_z @ dz)
+        g = np.vstack([f_u + G_u @ mu, f_z + G_z @ mu])
+        dp = np.vstack([du, dz])
+        if do_line_search:
+            alpha, _, _ = backtracking_line_search(lambda q: energy_func(np.vstack([q, mu])), p[:-mu.shape[0]], g, dp)
+        else:
+            alpha = 1.0
+        p[:-mu.shape[0]] += alpha * dp
+        p[-mu.shape[0]:] = mu
+        if float((np.asarray(g_u).T @ du).item()) < tolerance:
+            break
+    return p
+
+
 # --------------------------------------------------------------------------- #
 # element tier                                                                #
 # --------------------------------------------------------------------------- #

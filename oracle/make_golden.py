@@ -25,6 +25,7 @@ from simkit.fast_sandwich_transform_clustered import fast_sandwich_transform_clu
 from simkit.rotation_gradient import rotation_gradient_F as ref_rotgrad  # noqa: E402
 
 from simkit_b200 import synthetic as syn  # noqa: E402
+from oracle.mfem_problem import mfem_problem  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 MATS = {
@@ -200,6 +201,27 @@ def golden_reduced(tag, cells, r, seed):
     print("wrote", tag)
 
 
+def golden_mfem(tag, cells, rho_aug, seed):
+    """MFEM blocks (stretch, dS/dF, ds/dz, symmetric stretch map) and three SQP iterations of the mixed solver."""
+    from simkit.solvers import sqp_mfem as ref_sqp
+    dim = len(cells)
+    X, T = syn.make_mesh(cells)
+    rng = np.random.default_rng(seed)
+    F = np.eye(dim)[None] + 0.35 * rng.standard_normal((60, dim, dim))
+    out = dict(X=X, T=T, dim=dim, rho_aug=rho_aug, F=F, stretch=simkit.stretch(F), dSdF=simkit.stretch_gradient_dF(F))
+    prob = mfem_problem(simkit, X, T, rho_aug)
+    p0 = prob["p0"]
+    u0 = p0[:prob["nz"]]
+    out["dsdz"] = simkit.stretch_gradient_dz(u0, prob["GJB"], Ci=prob["Ci"], dim=dim, GJq=prob["GJq"]).toarray()
+    out["p0"] = p0
+    out["energy0"] = prob["energy"](p0)
+    fb = prob["grad_blocks"](p0)
+    out["f_u0"], out["f_z0"], out["f_mu0"] = (np.asarray(v) for v in fb)
+    out["p3"] = ref_sqp(p0, prob["energy"], prob["hess_blocks"], prob["grad_blocks"], tolerance=1e-12, max_iter=3)
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print("wrote", tag)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     golden_mesh("tet_s01", (3, 2, 2), 0.1, 10)
@@ -210,3 +232,5 @@ if __name__ == "__main__":
     golden_step("step_tri", (6, 5), 21)
     golden_reduced("reduced_tet", (3, 2, 2), 12, 30)
     golden_reduced("reduced_tri", (5, 4), 8, 31)
+    golden_mfem("mfem_tri", (4, 2), 10.0, 40)
+    golden_mfem("mfem_tet", (2, 2, 1), 10.0, 41)

@@ -16,6 +16,8 @@ from .operators import gravity_force, massmatrix, volume, ympr_to_lame  # noqa: 
 from .plan import MeshPlan, plan_from_operator  # noqa: F401
 from .potential import ElasticPotential  # noqa: F401
 from .smallmat import polar_svd, psd_project, rotation_gradient_F, svd_rv  # noqa: F401
-from .solvers import newton_solver  # noqa: F401
+from .solvers import newton_solver, sqp_mfem  # noqa: F401
+from .stretch import (stretch, stretch_gradient, stretch_gradient_dF, stretch_gradient_dx, stretch_gradient_dz,  # noqa: F401
+                      symmetric_stretch_map)
 
 __version__ = "0.1.0"

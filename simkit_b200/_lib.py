@@ -99,6 +99,7 @@ SIGNATURES = {
     "skb_svd_rv": (_int, [_int, _i64, _vp, _vp, _vp, _vp]),
     "skb_polar": (_int, [_int, _i64, _vp, _vp, _vp]),
     "skb_rotation_gradient": (_int, [_int, _i64, _vp, _vp]),
+    "skb_stretch_gradient": (_int, [_int, _i64, _vp, _vp]),
     "skb_pcg": (_int, [_vp, _vp, _vp, _vp, _dbl, _int, _vp, _vp, _vp]),
     "skb_pcg_dev": (_int, [_vp, _vp, _vp, _vp, _dbl, _int, _vp, _vp, _vp, _vp]),
     "skb_csr_pcg": (_int, [_i64, _vp, _vp, _vp, _int, _vp, _dbl, _int, _vp, _vp, _vp]),

@@ -4,7 +4,7 @@
 
 namespace skb {
 
-enum ElemOp { OP_ENERGY = 0, OP_GRADIENT = 1, OP_HESSIAN = 2, OP_SVD = 3, OP_POLAR = 4, OP_ROTGRAD = 5 };
+enum ElemOp { OP_ENERGY = 0, OP_GRADIENT = 1, OP_HESSIAN = 2, OP_SVD = 3, OP_POLAR = 4, OP_ROTGRAD = 5, OP_STRETCHGRAD = 6 };
 
 template <int D>
 __device__ __forceinline__ Mat<D> load_F(const double* F, int64_t e) {
@@ -89,7 +89,22 @@ __global__ void element_kernel(int op, int material, int64_t t, const double* F,
       }
       double H[B * B];
       expand_hessian<D>(h, U, V, H);
-      for (int i = 0; i < B * B; ++i) o0[e * B * B + i] = H[i];
+      if (op == OP_ROTGRAD) {
+        for (int i = 0; i < B * B; ++i) o0[e * B * B + i] = H[i];
+      } else {
+        // OP_STRETCHGRAD: dS/dF of S = R^T F (stretch_gradient.py:28-54),
+        //   out[(m,n),(i,j)] = dS_ij/dF_mn = sum_k (dR_ki/dF_mn) F_kj + R_mi delta_nj,   dR_ki/dF_mn = H[(m,n),(k,i)]
+        const Mat<D> R = matmul_nt(U, V);
+        for (int m = 0; m < D; ++m)
+          for (int n = 0; n < D; ++n)
+            for (int i = 0; i < D; ++i)
+              for (int j = 0; j < D; ++j) {
+                double v = (n == j) ? R.m[m][i] : 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) v = fma(H[(m * D + n) * B + k * D + i], f.m[k][j], v);
+                o0[e * B * B + (m * D + n) * B + i * D + j] = v;
+              }
+      }
     }
   }
 }
@@ -238,6 +253,12 @@ int skb_rotation_gradient(int dim, int64_t t, const double* F, double* K) {
   if (!K) return fail(SKB_EINVAL, "null argument");
   const size_t b = (size_t)dim * dim;
   return run_element(OP_ROTGRAD, 0, dim, t, F, nullptr, 0, nullptr, 0, K, (size_t)t * b * b, nullptr, 0, nullptr, 0);
+}
+
+int skb_stretch_gradient(int dim, int64_t t, const double* F, double* dSdF) {
+  if (!dSdF) return fail(SKB_EINVAL, "null argument");
+  const size_t b = (size_t)dim * dim;
+  return run_element(OP_STRETCHGRAD, 0, dim, t, F, nullptr, 0, nullptr, 0, dSdF, (size_t)t * b * b, nullptr, 0, nullptr, 0);
 }
 
 int skb_psd_project(int64_t t, int b, const double* H, int method, double* out) {
