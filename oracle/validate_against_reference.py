@@ -134,6 +134,25 @@ def main():
             Q = oe.hessian_x(material, U, J, mu_h, lam_h, vol, psd=True, psd_before_vol=True)
             check(f"[{dim}D] elastic_hessian_x {name}", Q.toarray(), Q_ref.toarray(), 1e-11)
 
+        # MFEM blocks (stretch.py, stretch_gradient.py, symmetric_stretch_map.py, the _S tier of the dispatcher)
+        from simkit.stretch_gradient import stretch_gradient_dF as ref_dSdF, stretch_gradient_dz as ref_dsdz
+        from simkit.symmetric_stretch_map import symmetric_stretch_map as ref_ssm
+        Fm = np.asarray(J_ref @ U.reshape(-1, 1)).reshape(-1, dim, dim)
+        check(f"[{dim}D] stretch", oe.stretch(Fm), simkit.stretch(Fm), 1e-13)
+        check(f"[{dim}D] stretch_gradient_dF", oe.stretch_gradient_dF(Fm), ref_dSdF(Fm), 1e-11)
+        Se_r, Sei_r = ref_ssm(t, dim)
+        Se_o, Sei_o = oe.symmetric_stretch_map(t, dim)
+        check(f"[{dim}D] symmetric_stretch_map", np.r_[abs(Se_o - Se_r).max(), abs(Sei_o - Sei_r).max()] + 1.0, np.ones(2), 0.0)
+        dz_r = ref_dsdz(U, sps.csc_matrix(J_ref), dim, Ci=Sei_r)
+        dz_o = oe.stretch_gradient_dz(U, sps.csc_matrix(J), dim, Ci=Sei_o)
+        check(f"[{dim}D] stretch_gradient_dz", dz_o.toarray(), dz_r.toarray(), 1e-11)
+        _, Sm = simkit.polar_svd(Fm)
+        Sc = Sm.reshape(t, dim * dim) @ np.asarray(ref_ssm(1, dim)[1].todense()).T
+        mm = "macklin-mueller-neo-hookean"
+        check(f"[{dim}D] elastic_energy_S (MM)", oe.elastic_S("energy", Sc, mu_h, lam_h, vol, mm), ske.elastic_energy_S(Sc, mu_h, lam_h, vol_ref, mm), 1e-13)
+        check(f"[{dim}D] elastic_gradient_S (MM)", oe.elastic_S("gradient", Sc, mu_h, lam_h, vol, mm), ske.elastic_gradient_S(Sc, mu_h, lam_h, vol_ref, mm))
+        check(f"[{dim}D] elastic_hessian_S (MM)", oe.elastic_S("hessian", Sc, mu_h, lam_h, vol, mm), ske.elastic_hessian_S(Sc, mu_h, lam_h, vol_ref, mm), 1e-11)
+
         # structural pattern is a superset of the canonicalised reference pattern
         mu0, lam0 = syn.lame()
         Q_ref = oe.canonical_csr(ske.stable_neo_hookean_hessian_x(U, J_ref, mu0, lam0, vol_ref))
