@@ -230,6 +230,14 @@ int skb_csr_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const 
  * reduced-space Newton system); A (n, n) row-major.  SKB_EINVAL if singular. */
 int skb_dense_solve(int64_t n, const double* A, const double* b, double* x);
 /* y = (A + diag(diag_add)) x   on device data */
+/* Plane contact springs (energies/contact_springs_plane.py:245-388): E = k/2 sum_{v: n.(x_v - p) < 0} m_v (n.(x_v - p))^2.
+ * X: (nv*dim); weights: (nv) m_v or NULL (1).  Outputs (each may be NULL): energy, grad (nv*dim), blocks (nv*dim*dim,
+ * the Hessian's diagonal blocks k m_v n n^T, zero for vertices above the plane), under (nv, 1 = contacting). */
+int skb_contact_springs_plane(int dim, int64_t nv, const double* X, double k, const double* p, const double* n,
+                              const double* weights, double* energy, double* grad, double* blocks, int32_t* under);
+/* Adds the same term to every following skb_newton on this plan (energy in the line search, gradient, Hessian
+ * blocks straight into the CSR values on the device).  k <= 0 or p == NULL removes it. */
+int skb_newton_set_contact_plane(skb_plan* plan, double k, const double* p, const double* n, const double* weights);
 /* Two-level preconditioner of the plan's PCG (skb_pcg*, skb_newton): block-Jacobi plus a coarse correction on the
  * rigid-body modes of vertex aggregates.  agg: (n) aggregate id of every vertex in [0, n_agg); xrel: (n*dim) vertex
  * position minus the centre of its aggregate.  n_agg = 0 removes it.  The reference solves the Newton system

@@ -212,6 +212,23 @@ def symmetric_stretch_map(t, dim):
     return sps.kron(sps.identity(t), sps.csc_matrix(S)), sps.kron(sps.identity(t), sps.csc_matrix(Si))
 
 
+def contact_springs_plane(X, k, p, n, M=None):
+    """energies/contact_springs_plane.py:245-388: (energy, gradient (n*d,1), Hessian csc, contacting indices) of
+    k/2 sum_{v: n.(x_v - p) < 0} m_v (n.(x_v - p))^2, m = diag(M) (identity by default)."""
+    X = np.asarray(X, dtype=np.float64)
+    nv, dim = X.shape
+    p = np.asarray(p, dtype=np.float64).reshape(-1)
+    n = np.asarray(n, dtype=np.float64).reshape(-1)
+    m = np.ones(nv) if M is None else np.asarray(sps.csr_matrix(M).diagonal())
+    off = (X - p[None, :]) @ n
+    under = off < 0
+    km = np.where(under, k * m, 0.0)
+    E = float((0.5 * km * off * off).sum())
+    g = (km * off)[:, None] * n[None, :]
+    H = sps.block_diag([kmv * np.outer(n, n) for kmv in km], format="csc")
+    return E, g.reshape(-1, 1), H, np.where(under)[0]
+
+
 def stretch(F):
     """stretch.py:9-27: S of F = R S, stacked as a column."""
     _, S = polar_svd(F)

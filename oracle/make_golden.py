@@ -201,6 +201,48 @@ def golden_reduced(tag, cells, r, seed):
     print("wrote", tag)
 
 
+def golden_contact(tag, cells, seed):
+    """Plane contact springs and a backward-Euler step (3 Newton iterations) of stable neo-Hookean + contact."""
+    from simkit.energies.contact_springs_plane import (contact_springs_plane_energy as ce, contact_springs_plane_gradient as cg,
+                                                       contact_springs_plane_hessian as ch)
+    dim = len(cells)
+    X, T = syn.make_mesh(cells)
+    ext = tuple(1.0 for _ in cells)
+    rng = np.random.default_rng(seed)
+    mu, lam = syn.lame()
+    rho, h, k = 1e3, 1e-2, 1e5
+    nrm = np.zeros(dim)
+    nrm[1] = 1.0
+    nrm[0] = 0.3
+    nrm = nrm / np.linalg.norm(nrm)
+    pt = np.full(dim, 0.25)
+    U = syn.jittered_state(X, cells, ext, sigma=0.2, seed=seed)
+    Mv = simkit.massmatrix(X, T, rho)
+    E, inds = ce(U, k, pt, nrm, Mv, return_contact_inds=True)
+    out = dict(X=X, T=T, U=U, dim=dim, k=k, p=pt, n=nrm, mass=Mv.diagonal(), E=E, inds=inds.ravel(),
+               g=cg(U, k, pt, nrm, Mv), H=ch(U, k, pt, nrm, Mv).toarray(), E_noM=ce(U, k, pt, nrm),
+               g_noM=cg(U, k, pt, nrm), E_above=ce(U + 10.0 * nrm, k, pt, nrm, Mv))
+    J = simkit.deformation_jacobian(X, T)
+    vol = simkit.volume(X, T)
+    Md = sps.kron(Mv, sps.identity(dim)).tocsc()
+    fg = simkit.gravity_force(X, T, -9.8, rho).reshape(-1, 1)
+
+    def En(x):
+        return ske.stable_neo_hookean_energy_x(x.reshape(-1, dim), J, mu, lam, vol) - float((fg.T @ x).item()) + ce(x.reshape(-1, dim), k, pt, nrm, Mv)
+
+    def Gr(x):
+        return ske.stable_neo_hookean_gradient_x(x.reshape(-1, dim), J, mu, lam, vol) - fg + cg(x.reshape(-1, dim), k, pt, nrm, Mv)
+
+    def He(x):
+        return ske.stable_neo_hookean_hessian_x(x.reshape(-1, dim), J, mu, lam, vol) + ch(x.reshape(-1, dim), k, pt, nrm, Mv)
+
+    x_curr = U.reshape(-1, 1)
+    x, info = ref_be(x_curr, X.reshape(-1, 1), En, Gr, He, Md, h, max_iter=3, return_info=True)
+    out.update(mu=mu, lam=lam, rho=rho, h=h, fg=fg, be_x=x, be_alphas=np.array(info["alphas"]))
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print("wrote", tag, "contacting", inds.size)
+
+
 def golden_mfem(tag, cells, rho_aug, seed):
     """MFEM blocks (stretch, dS/dF, ds/dz, symmetric stretch map) and three SQP iterations of the mixed solver."""
     from simkit.solvers import sqp_mfem as ref_sqp
@@ -232,5 +274,7 @@ if __name__ == "__main__":
     golden_step("step_tri", (6, 5), 21)
     golden_reduced("reduced_tet", (3, 2, 2), 12, 30)
     golden_reduced("reduced_tri", (5, 4), 8, 31)
+    golden_contact("contact_tet", (3, 3, 2), 50)
+    golden_contact("contact_tri", (6, 5), 51)
     golden_mfem("mfem_tri", (4, 2), 10.0, 40)
     golden_mfem("mfem_tet", (2, 2, 1), 10.0, 41)

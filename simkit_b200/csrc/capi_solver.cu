@@ -253,6 +253,64 @@ int skb_pcg_set_coarse(skb_plan* pl, int64_t n_agg, const int32_t* agg, const do
   SKB_CATCH
 }
 
+int skb_newton_set_contact_plane(skb_plan* pl, double k, const double* p, const double* n, const double* weights) {
+  if (!pl) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  if (!(k > 0.0) || !p || !n) {
+    pl->contact_on = false;
+    pl->contact_w.clear();
+    return SKB_OK;
+  }
+  pl->contact_on = true;
+  pl->contact_k = k;
+  for (int i = 0; i < 3; ++i) {
+    pl->contact_p[i] = i < pl->d.dim ? p[i] : 0.0;
+    pl->contact_n[i] = i < pl->d.dim ? n[i] : 0.0;
+  }
+  if (weights) pl->contact_w.assign(weights, weights + pl->d.n);
+  else pl->contact_w.clear();
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_contact_springs_plane(int dim, int64_t nv, const double* X, double k, const double* p, const double* n,
+                              const double* weights, double* energy, double* grad, double* blocks, int32_t* under) {
+  if (!X || !p || !n) return fail(SKB_EINVAL, "null argument");
+  if (dim != 2 && dim != 3) return fail(SKB_EINVAL, "Only dim == 2 or 3 are supported");
+  if (nv <= 0 || nv >= ((int64_t)1 << 31)) return fail(SKB_EINVAL, "bad vertex count");
+  if (skb_device_count() <= 0) return fail(SKB_ENOGPU, "no CUDA device");
+  SKB_TRY
+  dvec<double> Xd(X, X + nv * dim), gd, bd, wd, part(PCG_MAX_GRID), out(1);
+  dvec<int> ud;
+  ContactPlaneArgs c;
+  c.k = k;
+  for (int i = 0; i < 3; ++i) {
+    c.p[i] = i < dim ? p[i] : 0.0;
+    c.n[i] = i < dim ? n[i] : 0.0;
+  }
+  if (weights) wd.assign(weights, weights + nv);
+  c.w = weights ? raw(wd) : nullptr;
+  if (grad) gd.assign((size_t)nv * dim, 0.0);
+  if (blocks) bd.resize((size_t)nv * dim * dim);
+  if (under) ud.resize(nv);
+  int grid = (int)((nv + PCG_THREADS - 1) / PCG_THREADS);
+  if (grid > 1024) grid = 1024;
+  if (dim == 3)
+    contact_plane_kernel<3><<<grid, PCG_THREADS>>>((int)nv, raw(Xd), c, grad ? raw(gd) : nullptr, blocks ? raw(bd) : nullptr, nullptr, nullptr, raw(part), under ? raw(ud) : nullptr);
+  else
+    contact_plane_kernel<2><<<grid, PCG_THREADS>>>((int)nv, raw(Xd), c, grad ? raw(gd) : nullptr, blocks ? raw(bd) : nullptr, nullptr, nullptr, raw(part), under ? raw(ud) : nullptr);
+  reduce_final_kernel<<<1, PCG_THREADS>>>(raw(part), grid, raw(out));
+  SKB_CUDA(cudaGetLastError());
+  SKB_CUDA(cudaDeviceSynchronize());
+  if (energy) SKB_CUDA(cudaMemcpy(energy, raw(out), sizeof(double), cudaMemcpyDeviceToHost));
+  if (grad) SKB_CUDA(cudaMemcpy(grad, raw(gd), gd.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (blocks) SKB_CUDA(cudaMemcpy(blocks, raw(bd), bd.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (under) SKB_CUDA(cudaMemcpy(under, raw(ud), ud.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  return SKB_OK;
+  SKB_CATCH
+}
+
 int skb_spmv_dev(skb_plan* pl, const double* vals, const double* diag_add, const double* x, double* y,
                  void* stream) {
   if (!pl || !vals || !x || !y) return fail(SKB_EINVAL, "null argument");
@@ -396,8 +454,24 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
   double* part_e = raw(parts);
   double* part_g = part_e + PCG_MAX_GRID;
   double* part_d = part_g + PCG_MAX_GRID;
-  double* red = part_d + PCG_MAX_GRID;  // 3 sums + elastic energy
-  double hred[4];
+  double* red = part_d + PCG_MAX_GRID;  // 3 sums + elastic energy + contact energy
+  double hred[5];
+  ContactPlaneArgs cpa;
+  dvec<double> part_c;
+  dvec<PlanView> pview_d;
+  if (pl->contact_on) {
+    cpa.k = pl->contact_k;
+    for (int i = 0; i < 3; ++i) {
+      cpa.p[i] = pl->contact_p[i];
+      cpa.n[i] = pl->contact_n[i];
+    }
+    cpa.w = pl->contact_w.empty() ? nullptr : raw(pl->contact_w);
+    part_c.resize(PCG_MAX_GRID);
+    const PlanView hv = pl->view();
+    pview_d.assign(&hv, &hv + 1);
+  }
+  const int nverts = pl->d.n;
+  const int dim_ = pl->d.dim;
 
   // total energy at x + s*dx (also leaves the trial point in xtrial)
   auto total_energy = [&](double s, const double* dxp, bool with_gdx, double& e_tot, double& gdx, double& dx2) -> int {
@@ -411,9 +485,17 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
     if (rc) return rc;
     rc = launch_energy(pl, a, red + 3, st);
     if (rc) return rc;
-    SKB_CUDA(cudaMemcpyAsync(hred, red, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    hred[4] = 0.0;
+    if (pl->contact_on) {
+      if (dim_ == 3)
+        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<3><<<vgrid, PCG_THREADS, 0, st>>>(nverts, xtrial, cpa, nullptr, nullptr, nullptr, nullptr, raw(part_c), nullptr));
+      else
+        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<2><<<vgrid, PCG_THREADS, 0, st>>>(nverts, xtrial, cpa, nullptr, nullptr, nullptr, nullptr, raw(part_c), nullptr));
+      SKB_LAUNCH(pl, SKB_K_OTHER, st, reduce_final_kernel<<<1, PCG_THREADS, 0, st>>>(raw(part_c), vgrid, red + 4));
+    }
+    SKB_CUDA(cudaMemcpyAsync(hred, red, (pl->contact_on ? 5 : 4) * sizeof(double), cudaMemcpyDeviceToHost, st));
     SKB_CUDA(cudaStreamSynchronize(st));
-    e_tot = hred[0] + hred[3];
+    e_tot = hred[0] + hred[3] + hred[4];
     gdx = hred[1];
     dx2 = hred[2];
     return SKB_OK;
@@ -429,6 +511,13 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
     if (rc) return rc;
     rc = launch_assemble(pl, a, st);
     if (rc) return rc;
+    if (pl->contact_on) {
+      // contact springs: gradient into g (before rhs = -g is formed), Hessian blocks into the diagonal blocks of vals
+      if (dim_ == 3)
+        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<3><<<vgrid, PCG_THREADS, 0, st>>>(nverts, x, cpa, g, nullptr, raw(pview_d), raw(pl->vals), nullptr, nullptr));
+      else
+        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<2><<<vgrid, PCG_THREADS, 0, st>>>(nverts, x, cpa, g, nullptr, raw(pview_d), raw(pl->vals), nullptr, nullptr));
+    }
     SKB_LAUNCH(pl, SKB_K_OTHER, st,
                newton_gradient_kernel<<<vgrid, PCG_THREADS, 0, st>>>(nd, x, d_f, d_mass, d_xt, kin_scale, d_pk, d_pt, g, rhs,
                                                                      dadd));

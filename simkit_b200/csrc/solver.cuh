@@ -317,6 +317,63 @@ static __global__ void newton_energy_terms_kernel(int n, const double* x, const 
   }
 }
 
+// ---- plane contact springs (energies/contact_springs_plane.py:245-388) --------------------------------------
+// E = k/2 sum_{v under the plane} m_v (n . (x_v - p))^2 ; per contacting vertex: gradient k m_v off n, Hessian block
+// k m_v n n^T.  One thread per vertex; any of the outputs may be null.  `vals` (with the plan view) receives the
+// Hessian blocks straight in the diagonal blocks of the scalar-CSR value array.
+struct ContactPlaneArgs {
+  double k;
+  double p[3];
+  double n[3];
+  const double* w;  // per-vertex weights m_v or nullptr (1)
+};
+
+template <int D>
+__global__ void contact_plane_kernel(int nv, const double* x, ContactPlaneArgs c, double* g_add, double* blocks,
+                                     const PlanView* pv, double* vals, double* part_e, int* under) {
+  __shared__ double sh[32];
+  double e = 0.0;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+    double off = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) off = fma(c.n[i], x[(size_t)v * D + i] - c.p[i], off);
+    const bool in = off < 0.0;
+    if (under) under[v] = in ? 1 : 0;
+    const double m = c.w ? c.w[v] : 1.0;
+    const double km = in ? c.k * m : 0.0;
+    e = fma(0.5 * km * off, off, e);
+    if (g_add) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) g_add[(size_t)v * D + i] += km * off * c.n[i];
+    }
+    if (blocks) {
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) blocks[((size_t)v * D + i) * D + j] = km * c.n[i] * c.n[j];
+    }
+    if (vals && in) {
+      // diagonal block (v, v) of the block row: binary search of v among the sorted block columns
+      const int b0 = pv->bptr[v], b1 = pv->bptr[v + 1];
+      int lo = b0, hi = b1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pv->bcol[mid] < v) lo = mid + 1; else hi = mid;
+      }
+      const int ncol = D * (b1 - b0);
+      double* base = vals + (size_t)b0 * (D * D) + (size_t)D * (lo - b0);
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) base[(size_t)i * ncol + j] += km * c.n[i] * c.n[j];
+    }
+  }
+  if (part_e) {
+    e = block_reduce_sum(e, sh);
+    if (threadIdx.x == 0) part_e[blockIdx.x] = e;
+  }
+}
+
 // out[0..2] = sums of three partial arrays (single CTA)
 static __global__ void reduce3_kernel(const double* a, const double* b, const double* c, int n, double* out) {
   __shared__ double sh[32];

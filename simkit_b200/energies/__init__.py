@@ -9,3 +9,5 @@ from .stable_neo_hookean import *  # noqa: F401,F403
 from .stvk import *  # noqa: F401,F403
 from .neo_hookean import *  # noqa: F401,F403
 from .kinetic import *  # noqa: F401,F403
+from .contact_springs_plane import (contact_springs_plane_energy, contact_springs_plane_gradient,  # noqa: F401
+                                    contact_springs_plane_hessian)

@@ -189,6 +189,22 @@ class MeshPlan:
                          pcg_iters=info.pcg_iters_total, pcg_relres=info.last_pcg_relres,
                          step_norm=info.last_step_norm)
 
+    def set_contact_plane(self, k=0.0, p=None, n=None, weights=None):
+        """Plane contact springs inside the device-resident Newton step (``energies/contact_springs_plane.py``):
+        ``k/2 sum_{v under the plane} m_v (n.(x_v - p))^2`` is added to the energy of the line search, the gradient and
+        (as ``k m_v n n^T`` in the diagonal blocks) the Hessian of every following ``newton``.  ``k = 0`` removes it."""
+        if not k or p is None or n is None:
+            check(self._lib.skb_newton_set_contact_plane(self._h, 0.0, None, None, None))
+            return
+        p = f64(np.asarray(p, dtype=np.float64).reshape(-1))
+        n = f64(np.asarray(n, dtype=np.float64).reshape(-1))
+        if p.size != self.dim or n.size != self.dim:
+            raise ValueError("p and n must have dim entries")
+        w = None if weights is None else f64(np.asarray(weights, dtype=np.float64).reshape(-1))
+        if w is not None and w.size != self.n:
+            raise ValueError("weights must have one entry per vertex")
+        check(self._lib.skb_newton_set_contact_plane(self._h, float(k), ptr(p), ptr(n), ptr(w)))
+
     COARSE_MIN_ITERS = 300   # block-Jacobi iteration count above which the coarse correction pays for itself
 
     def auto_aggregates(self):

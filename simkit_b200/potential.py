@@ -20,12 +20,14 @@ class ElasticPotential:
     _skb_potential = True
 
     def __init__(self, material, mu, lam, vol=None, plan=None, J=None, X=None, T=None, dim=None, f_ext=None,
-                 pin_k=None, pin_target=None, psd=True, coarse="auto"):
+                 pin_k=None, pin_target=None, psd=True, coarse="auto", contact_plane=None):
         """``coarse``: vertex aggregates of the two-level PCG preconditioner of the device-resident step
         (``MeshPlan.set_coarse_space``; needs the rest positions ``X``).  ``"auto"``: start with block-Jacobi and switch
         the coarse correction on (``MeshPlan.auto_aggregates`` aggregates) after the first Newton iteration whose
         PCG needed more than ``MeshPlan.COARSE_MIN_ITERS`` iterations; an integer: that many aggregates from the
-        start; ``0`` / ``None``: block-Jacobi only."""
+        start; ``0`` / ``None``: block-Jacobi only.
+        ``contact_plane``: ``dict(k=, p=, n=[, M=])`` -- penalty springs against a ground plane
+        (``contact_springs_plane_*``), added to the three callables and to the device-resident step."""
         if plan is None:
             if J is not None:
                 plan = plan_from_operator(J, dim if dim is not None else (X.shape[1] if X is not None else 3))
@@ -41,6 +43,13 @@ class ElasticPotential:
         self.pin_k = None if pin_k is None else np.asarray(pin_k, dtype=np.float64).reshape(nd, 1)
         self.pin_target = None if pin_target is None else np.asarray(pin_target, dtype=np.float64).reshape(nd, 1)
         self._materials_set = False
+        self.contact_plane = None
+        if contact_plane is not None:
+            c = dict(contact_plane)
+            M = c.get("M")
+            w = None if M is None else np.asarray(sps.csr_matrix(M).diagonal() if sps.issparse(M) else np.diag(M), dtype=np.float64)
+            self.contact_plane = dict(k=float(c["k"]), p=np.asarray(c["p"], dtype=np.float64).reshape(-1),
+                                      n=np.asarray(c["n"], dtype=np.float64).reshape(-1), w=w)
         self._X_rest = None if X is None else np.asarray(X, dtype=np.float64).reshape(plan.n, plan.dim)
         self._coarse_auto = (coarse == "auto") and self._X_rest is not None
         if coarse and coarse != "auto" and self._X_rest is not None:
@@ -55,7 +64,16 @@ class ElasticPotential:
         if self.pin_k is not None:
             d = xx - self.pin_target
             e += 0.5 * float((self.pin_k * d * d).sum())
+        if self.contact_plane is not None:
+            e += self._contact("energy", xx)
         return e
+
+    def _contact(self, kind, xx):
+        from .energies import contact_springs_plane as cs
+        c = self.contact_plane
+        M = None if c["w"] is None else sps.diags(c["w"])
+        fn = getattr(cs, "contact_springs_plane_" + kind)
+        return fn(xx.reshape(self.plan.n, self.plan.dim), c["k"], c["p"], c["n"], M)
 
     def gradient(self, x):
         xx = np.asarray(x, dtype=np.float64).reshape(-1, 1)
@@ -64,12 +82,16 @@ class ElasticPotential:
             g = g - self.f_ext
         if self.pin_k is not None:
             g = g + self.pin_k * (xx - self.pin_target)
+        if self.contact_plane is not None:
+            g = g + self._contact("gradient", xx)
         return g
 
     def hessian(self, x):
         H = self.plan.hessian(self.material, x, self.mu, self.lam, self.vol, self.psd_mode)
         if self.pin_k is not None:
             H = H + sps.diags(self.pin_k.ravel())
+        if self.contact_plane is not None:
+            H = H + self._contact("hessian", np.asarray(x, dtype=np.float64).reshape(-1, 1))
         return H
 
     # -- device-resident steps -------------------------------------------------------------------
@@ -80,6 +102,11 @@ class ElasticPotential:
 
     def _run(self, x0, x_tilde, mass, kin_scale, tolerance, max_iter, do_line_search, return_info, **kw):
         self.plan.set_materials(self.mu, self.lam, self.vol)
+        c = self.contact_plane
+        if c is not None:
+            self.plan.set_contact_plane(c["k"], c["p"], c["n"], c["w"])
+        else:
+            self.plan.set_contact_plane(0.0)
         x, info = self.plan.newton(self.material, x0, psd_mode=self.psd_mode, x_tilde=x_tilde, mass=mass,
                                    kin_scale=kin_scale, f_ext=self.f_ext, pin_k=self.pin_k,
                                    pin_target=self.pin_target, max_iter=max_iter, do_line_search=do_line_search,
