@@ -235,6 +235,11 @@ int skb_dense_solve(int64_t n, const double* A, const double* b, double* x);
  * the Hessian's diagonal blocks k m_v n n^T, zero for vertices above the plane), under (nv, 1 = contacting). */
 int skb_contact_springs_plane(int dim, int64_t nv, const double* X, double k, const double* p, const double* n,
                               const double* weights, double* energy, double* grad, double* blocks, int32_t* under);
+/* Sphere contact springs (energies/contact_springs_sphere.py:242-360): vertices with |x_v - p| < r, normal
+ * n_v = (x_v - p)/|x_v - p| held fixed in the derivatives, E = k/2 sum m_v (|x_v - p| - r)^2; same outputs. */
+int skb_contact_springs_sphere(int dim, int64_t nv, const double* X, double k, const double* p, double r,
+                               const double* weights, double* energy, double* grad, double* blocks, int32_t* under);
+int skb_newton_set_contact_sphere(skb_plan* plan, double k, const double* p, double r, const double* weights);
 /* Adds the same term to every following skb_newton on this plan (energy in the line search, gradient, Hessian
  * blocks straight into the CSR values on the device).  k <= 0 or p == NULL removes it. */
 int skb_newton_set_contact_plane(skb_plan* plan, double k, const double* p, const double* n, const double* weights);

@@ -229,6 +229,26 @@ def contact_springs_plane(X, k, p, n, M=None):
     return E, g.reshape(-1, 1), H, np.where(under)[0]
 
 
+def contact_springs_sphere(X, k, p, r, M=None):
+    """energies/contact_springs_sphere.py:242-360: vertices with |x_v - p| < r, n_v = (x_v - p)/|x_v - p| held fixed:
+    (energy, gradient (n*d,1), Hessian csc) of k/2 sum m_v (|x_v - p| - r)^2."""
+    X = np.asarray(X, dtype=np.float64)
+    nv, dim = X.shape
+    p = np.asarray(p, dtype=np.float64).reshape(-1)
+    m = np.ones(nv) if M is None else np.asarray(sps.csr_matrix(M).diagonal())
+    d = X - p[None, :]
+    ln = np.linalg.norm(d, axis=1)
+    inside = ln < r
+    with np.errstate(all="ignore"):
+        n = d / ln[:, None]
+    off = ln - r
+    km = np.where(inside, k * m, 0.0)
+    E = float((0.5 * km * off * off).sum())
+    g = np.where(inside[:, None], (km * off)[:, None] * n, 0.0)
+    H = sps.block_diag([kmv * np.outer(nn, nn) if kmv != 0.0 else np.zeros((dim, dim)) for kmv, nn in zip(km, n)], format="csc")
+    return E, g.reshape(-1, 1), H
+
+
 def stretch(F):
     """stretch.py:9-27: S of F = R S, stacked as a column."""
     _, S = polar_svd(F)

@@ -222,10 +222,25 @@ def golden_contact(tag, cells, seed):
     out = dict(X=X, T=T, U=U, dim=dim, k=k, p=pt, n=nrm, mass=Mv.diagonal(), E=E, inds=inds.ravel(),
                g=cg(U, k, pt, nrm, Mv), H=ch(U, k, pt, nrm, Mv).toarray(), E_noM=ce(U, k, pt, nrm),
                g_noM=cg(U, k, pt, nrm), E_above=ce(U + 10.0 * nrm, k, pt, nrm, Mv))
+    from simkit.energies.contact_springs_sphere import (contact_springs_sphere_energy as se, contact_springs_sphere_gradient as sg,
+                                                        contact_springs_sphere_hessian as sh)
+    sc = np.full(dim, 0.55)
+    sr = 0.3
+    out.update(s_p=sc, s_r=sr, s_E=se(U, k, sc, sr, Mv), s_g=sg(U, k, sc, sr, Mv), s_H=sh(U, k, sc, sr, Mv).toarray(),
+               s_E_noM=se(U, k, sc, sr), s_E_far=se(U + 10.0, k, sc, sr, Mv))
     J = simkit.deformation_jacobian(X, T)
     vol = simkit.volume(X, T)
     Md = sps.kron(Mv, sps.identity(dim)).tocsc()
     fg = simkit.gravity_force(X, T, -9.8, rho).reshape(-1, 1)
+
+    def En2(x):
+        return En(x) + se(x.reshape(-1, dim), k, sc, sr, Mv)
+
+    def Gr2(x):
+        return Gr(x) + sg(x.reshape(-1, dim), k, sc, sr, Mv)
+
+    def He2(x):
+        return He(x) + sh(x.reshape(-1, dim), k, sc, sr, Mv)
 
     def En(x):
         return ske.stable_neo_hookean_energy_x(x.reshape(-1, dim), J, mu, lam, vol) - float((fg.T @ x).item()) + ce(x.reshape(-1, dim), k, pt, nrm, Mv)
@@ -239,8 +254,10 @@ def golden_contact(tag, cells, seed):
     x_curr = U.reshape(-1, 1)
     x, info = ref_be(x_curr, X.reshape(-1, 1), En, Gr, He, Md, h, max_iter=3, return_info=True)
     out.update(mu=mu, lam=lam, rho=rho, h=h, fg=fg, be_x=x, be_alphas=np.array(info["alphas"]))
+    x2, info2 = ref_be(x_curr, X.reshape(-1, 1), En2, Gr2, He2, Md, h, max_iter=3, return_info=True)
+    out.update(be2_x=x2, be2_alphas=np.array(info2["alphas"]))
     np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
-    print("wrote", tag, "contacting", inds.size)
+    print("wrote", tag, "contacting", inds.size, "inside sphere", int((np.linalg.norm(U - sc, axis=1) < sr).sum()))
 
 
 def golden_mfem(tag, cells, rho_aug, seed):

@@ -70,6 +70,9 @@ struct skb_plan {
   bool contact_on = false;
   double contact_k = 0.0, contact_p[3] = {0, 0, 0}, contact_n[3] = {0, 0, 0};
   skb::dvec<double> contact_w;
+  bool sphere_on = false;      // skb_newton_set_contact_sphere
+  double sphere_k = 0.0, sphere_p[3] = {0, 0, 0}, sphere_r = 0.0;
+  skb::dvec<double> sphere_w;
   // resident subspace basis of the reduced tier (skb_plan_set_basis)
   skb::dvec<double> basis;
   int64_t basis_r = 0;

@@ -274,9 +274,42 @@ int skb_newton_set_contact_plane(skb_plan* pl, double k, const double* p, const 
   SKB_CATCH
 }
 
+static int contact_eval(int kind, int dim, int64_t nv, const double* X, double k, const double* p, const double* n, double r,
+                        const double* weights, double* energy, double* grad, double* blocks, int32_t* under);
+
 int skb_contact_springs_plane(int dim, int64_t nv, const double* X, double k, const double* p, const double* n,
                               const double* weights, double* energy, double* grad, double* blocks, int32_t* under) {
-  if (!X || !p || !n) return fail(SKB_EINVAL, "null argument");
+  if (!n) return fail(SKB_EINVAL, "null argument");
+  return contact_eval(0, dim, nv, X, k, p, n, 0.0, weights, energy, grad, blocks, under);
+}
+
+int skb_contact_springs_sphere(int dim, int64_t nv, const double* X, double k, const double* p, double r,
+                               const double* weights, double* energy, double* grad, double* blocks, int32_t* under) {
+  return contact_eval(1, dim, nv, X, k, p, nullptr, r, weights, energy, grad, blocks, under);
+}
+
+int skb_newton_set_contact_sphere(skb_plan* pl, double k, const double* p, double r, const double* weights) {
+  if (!pl) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  if (!(k > 0.0) || !p) {
+    pl->sphere_on = false;
+    pl->sphere_w.clear();
+    return SKB_OK;
+  }
+  pl->sphere_on = true;
+  pl->sphere_k = k;
+  pl->sphere_r = r;
+  for (int i = 0; i < 3; ++i) pl->sphere_p[i] = i < pl->d.dim ? p[i] : 0.0;
+  if (weights) pl->sphere_w.assign(weights, weights + pl->d.n);
+  else pl->sphere_w.clear();
+  return SKB_OK;
+  SKB_CATCH
+}
+
+static int contact_eval(int kind, int dim, int64_t nv, const double* X, double k, const double* p, const double* n, double r,
+                        const double* weights, double* energy, double* grad, double* blocks, int32_t* under) {
+  if (!X || !p) return fail(SKB_EINVAL, "null argument");
   if (dim != 2 && dim != 3) return fail(SKB_EINVAL, "Only dim == 2 or 3 are supported");
   if (nv <= 0 || nv >= ((int64_t)1 << 31)) return fail(SKB_EINVAL, "bad vertex count");
   if (skb_device_count() <= 0) return fail(SKB_ENOGPU, "no CUDA device");
@@ -285,9 +318,11 @@ int skb_contact_springs_plane(int dim, int64_t nv, const double* X, double k, co
   dvec<int> ud;
   ContactPlaneArgs c;
   c.k = k;
+  c.kind = kind;
+  c.r = r;
   for (int i = 0; i < 3; ++i) {
     c.p[i] = i < dim ? p[i] : 0.0;
-    c.n[i] = i < dim ? n[i] : 0.0;
+    c.n[i] = (n && i < dim) ? n[i] : 0.0;
   }
   if (weights) wd.assign(weights, weights + nv);
   c.w = weights ? raw(wd) : nullptr;
@@ -454,18 +489,35 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
   double* part_e = raw(parts);
   double* part_g = part_e + PCG_MAX_GRID;
   double* part_d = part_g + PCG_MAX_GRID;
-  double* red = part_d + PCG_MAX_GRID;  // 3 sums + elastic energy + contact energy
-  double hred[5];
-  ContactPlaneArgs cpa;
+  double* red = part_d + PCG_MAX_GRID;  // 3 sums + elastic energy + up to 2 contact energies
+  double hred[6];
+  ContactPlaneArgs contacts[2];
+  int n_contacts = 0;
   dvec<double> part_c;
   dvec<PlanView> pview_d;
   if (pl->contact_on) {
-    cpa.k = pl->contact_k;
+    ContactPlaneArgs& c = contacts[n_contacts++];
+    c.kind = 0;
+    c.r = 0.0;
+    c.k = pl->contact_k;
     for (int i = 0; i < 3; ++i) {
-      cpa.p[i] = pl->contact_p[i];
-      cpa.n[i] = pl->contact_n[i];
+      c.p[i] = pl->contact_p[i];
+      c.n[i] = pl->contact_n[i];
     }
-    cpa.w = pl->contact_w.empty() ? nullptr : raw(pl->contact_w);
+    c.w = pl->contact_w.empty() ? nullptr : raw(pl->contact_w);
+  }
+  if (pl->sphere_on) {
+    ContactPlaneArgs& c = contacts[n_contacts++];
+    c.kind = 1;
+    c.r = pl->sphere_r;
+    c.k = pl->sphere_k;
+    for (int i = 0; i < 3; ++i) {
+      c.p[i] = pl->sphere_p[i];
+      c.n[i] = 0.0;
+    }
+    c.w = pl->sphere_w.empty() ? nullptr : raw(pl->sphere_w);
+  }
+  if (n_contacts) {
     part_c.resize(PCG_MAX_GRID);
     const PlanView hv = pl->view();
     pview_d.assign(&hv, &hv + 1);
@@ -485,17 +537,17 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
     if (rc) return rc;
     rc = launch_energy(pl, a, red + 3, st);
     if (rc) return rc;
-    hred[4] = 0.0;
-    if (pl->contact_on) {
+    hred[4] = hred[5] = 0.0;
+    for (int ci = 0; ci < n_contacts; ++ci) {
       if (dim_ == 3)
-        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<3><<<vgrid, PCG_THREADS, 0, st>>>(nverts, xtrial, cpa, nullptr, nullptr, nullptr, nullptr, raw(part_c), nullptr));
+        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<3><<<vgrid, PCG_THREADS, 0, st>>>(nverts, xtrial, contacts[ci], nullptr, nullptr, nullptr, nullptr, raw(part_c), nullptr));
       else
-        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<2><<<vgrid, PCG_THREADS, 0, st>>>(nverts, xtrial, cpa, nullptr, nullptr, nullptr, nullptr, raw(part_c), nullptr));
-      SKB_LAUNCH(pl, SKB_K_OTHER, st, reduce_final_kernel<<<1, PCG_THREADS, 0, st>>>(raw(part_c), vgrid, red + 4));
+        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<2><<<vgrid, PCG_THREADS, 0, st>>>(nverts, xtrial, contacts[ci], nullptr, nullptr, nullptr, nullptr, raw(part_c), nullptr));
+      SKB_LAUNCH(pl, SKB_K_OTHER, st, reduce_final_kernel<<<1, PCG_THREADS, 0, st>>>(raw(part_c), vgrid, red + 4 + ci));
     }
-    SKB_CUDA(cudaMemcpyAsync(hred, red, (pl->contact_on ? 5 : 4) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SKB_CUDA(cudaMemcpyAsync(hred, red, (4 + n_contacts) * sizeof(double), cudaMemcpyDeviceToHost, st));
     SKB_CUDA(cudaStreamSynchronize(st));
-    e_tot = hred[0] + hred[3] + hred[4];
+    e_tot = hred[0] + hred[3] + hred[4] + hred[5];
     gdx = hred[1];
     dx2 = hred[2];
     return SKB_OK;
@@ -511,12 +563,12 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
     if (rc) return rc;
     rc = launch_assemble(pl, a, st);
     if (rc) return rc;
-    if (pl->contact_on) {
+    for (int ci = 0; ci < n_contacts; ++ci) {
       // contact springs: gradient into g (before rhs = -g is formed), Hessian blocks into the diagonal blocks of vals
       if (dim_ == 3)
-        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<3><<<vgrid, PCG_THREADS, 0, st>>>(nverts, x, cpa, g, nullptr, raw(pview_d), raw(pl->vals), nullptr, nullptr));
+        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<3><<<vgrid, PCG_THREADS, 0, st>>>(nverts, x, contacts[ci], g, nullptr, raw(pview_d), raw(pl->vals), nullptr, nullptr));
       else
-        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<2><<<vgrid, PCG_THREADS, 0, st>>>(nverts, x, cpa, g, nullptr, raw(pview_d), raw(pl->vals), nullptr, nullptr));
+        SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<2><<<vgrid, PCG_THREADS, 0, st>>>(nverts, x, contacts[ci], g, nullptr, raw(pview_d), raw(pl->vals), nullptr, nullptr));
     }
     SKB_LAUNCH(pl, SKB_K_OTHER, st,
                newton_gradient_kernel<<<vgrid, PCG_THREADS, 0, st>>>(nd, x, d_f, d_mass, d_xt, kin_scale, d_pk, d_pt, g, rhs,

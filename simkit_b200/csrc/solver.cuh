@@ -321,11 +321,15 @@ static __global__ void newton_energy_terms_kernel(int n, const double* x, const 
 // E = k/2 sum_{v under the plane} m_v (n . (x_v - p))^2 ; per contacting vertex: gradient k m_v off n, Hessian block
 // k m_v n n^T.  One thread per vertex; any of the outputs may be null.  `vals` (with the plan view) receives the
 // Hessian blocks straight in the diagonal blocks of the scalar-CSR value array.
+// kind 1: sphere (energies/contact_springs_sphere.py:242-360): vertices with |x_v - p| < r, per-vertex outward normal
+// n_v = (x_v - p)/|x_v - p| held fixed in the derivatives, offset |x_v - p| - r; same energy / gradient / block forms.
 struct ContactPlaneArgs {
   double k;
   double p[3];
   double n[3];
   const double* w;  // per-vertex weights m_v or nullptr (1)
+  int kind;         // 0 plane, 1 sphere
+  double r;         // sphere radius
 };
 
 template <int D>
@@ -335,8 +339,25 @@ __global__ void contact_plane_kernel(int nv, const double* x, ContactPlaneArgs c
   double e = 0.0;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
     double off = 0.0;
+    double nv_[D];
+    if (c.kind == 0) {
 #pragma unroll
-    for (int i = 0; i < D; ++i) off = fma(c.n[i], x[(size_t)v * D + i] - c.p[i], off);
+      for (int i = 0; i < D; ++i) {
+        nv_[i] = c.n[i];
+        off = fma(c.n[i], x[(size_t)v * D + i] - c.p[i], off);
+      }
+    } else {
+      double len2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        nv_[i] = x[(size_t)v * D + i] - c.p[i];
+        len2 = fma(nv_[i], nv_[i], len2);
+      }
+      const double len = sqrt(len2);
+#pragma unroll
+      for (int i = 0; i < D; ++i) nv_[i] /= len;
+      off = len - c.r;
+    }
     const bool in = off < 0.0;
     if (under) under[v] = in ? 1 : 0;
     const double m = c.w ? c.w[v] : 1.0;
@@ -344,13 +365,13 @@ __global__ void contact_plane_kernel(int nv, const double* x, ContactPlaneArgs c
     e = fma(0.5 * km * off, off, e);
     if (g_add) {
 #pragma unroll
-      for (int i = 0; i < D; ++i) g_add[(size_t)v * D + i] += km * off * c.n[i];
+      for (int i = 0; i < D; ++i) g_add[(size_t)v * D + i] += km * off * nv_[i];
     }
     if (blocks) {
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
-        for (int j = 0; j < D; ++j) blocks[((size_t)v * D + i) * D + j] = km * c.n[i] * c.n[j];
+        for (int j = 0; j < D; ++j) blocks[((size_t)v * D + i) * D + j] = km * nv_[i] * nv_[j];
     }
     if (vals && in) {
       // diagonal block (v, v) of the block row: binary search of v among the sorted block columns
@@ -365,7 +386,7 @@ __global__ void contact_plane_kernel(int nv, const double* x, ContactPlaneArgs c
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
-        for (int j = 0; j < D; ++j) base[(size_t)i * ncol + j] += km * c.n[i] * c.n[j];
+        for (int j = 0; j < D; ++j) base[(size_t)i * ncol + j] += km * nv_[i] * nv_[j];
     }
   }
   if (part_e) {

@@ -11,3 +11,5 @@ from .neo_hookean import *  # noqa: F401,F403
 from .kinetic import *  # noqa: F401,F403
 from .contact_springs_plane import (contact_springs_plane_energy, contact_springs_plane_gradient,  # noqa: F401
                                     contact_springs_plane_hessian)
+from .contact_springs_sphere import (contact_springs_sphere_energy, contact_springs_sphere_gradient,  # noqa: F401
+                                     contact_springs_sphere_hessian)

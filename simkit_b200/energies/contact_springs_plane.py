@@ -17,20 +17,25 @@ from .. import _lib
 from .._lib import check, f64, ptr
 
 
-def _eval(X, k, p, n, M, want_g, want_h):
+def _eval(X, k, p, n, M, want_g, want_h, r=None):
+    """Shared by the plane (``n`` given) and the sphere (``r`` given) springs."""
     X = f64(X)
     nv, dim = X.shape
     p = f64(np.asarray(p, dtype=np.float64).reshape(-1))
-    nrm = f64(np.asarray(n, dtype=np.float64).reshape(-1))
-    if p.size != dim or nrm.size != dim:
+    nrm = None if n is None else f64(np.asarray(n, dtype=np.float64).reshape(-1))
+    if p.size != dim or (nrm is not None and nrm.size != dim):
         raise ValueError("p and n must have dim entries")
     w = None if M is None else f64(sp.sparse.csr_matrix(M).diagonal() if sp.sparse.issparse(M) else np.diag(np.asarray(M)))
     E = ctypes.c_double(0.0)
     g = np.zeros((nv * dim, 1)) if want_g else None
     blocks = np.empty((nv, dim, dim)) if want_h else None
     under = np.empty(nv, dtype=np.int32)
-    check(_lib.load().skb_contact_springs_plane(dim, nv, ptr(X), float(k), ptr(p), ptr(nrm), ptr(w), ctypes.byref(E), ptr(g),
-                                               ptr(blocks), ptr(under)))
+    if r is None:
+        check(_lib.load().skb_contact_springs_plane(dim, nv, ptr(X), float(k), ptr(p), ptr(nrm), ptr(w), ctypes.byref(E),
+                                                   ptr(g), ptr(blocks), ptr(under)))
+    else:
+        check(_lib.load().skb_contact_springs_sphere(dim, nv, ptr(X), float(k), ptr(p), float(r), ptr(w), ctypes.byref(E),
+                                                    ptr(g), ptr(blocks), ptr(under)))
     inds = np.where(under != 0)[0][:, None] if under.any() else None
     return float(E.value), g, blocks, inds
 

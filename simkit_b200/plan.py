@@ -205,6 +205,20 @@ class MeshPlan:
             raise ValueError("weights must have one entry per vertex")
         check(self._lib.skb_newton_set_contact_plane(self._h, float(k), ptr(p), ptr(n), ptr(w)))
 
+    def set_contact_sphere(self, k=0.0, p=None, r=0.0, weights=None):
+        """Sphere contact springs inside the device-resident Newton step (``energies/contact_springs_sphere.py``);
+        ``k = 0`` removes them.  May be combined with ``set_contact_plane``."""
+        if not k or p is None:
+            check(self._lib.skb_newton_set_contact_sphere(self._h, 0.0, None, 0.0, None))
+            return
+        p = f64(np.asarray(p, dtype=np.float64).reshape(-1))
+        if p.size != self.dim:
+            raise ValueError("p must have dim entries")
+        w = None if weights is None else f64(np.asarray(weights, dtype=np.float64).reshape(-1))
+        if w is not None and w.size != self.n:
+            raise ValueError("weights must have one entry per vertex")
+        check(self._lib.skb_newton_set_contact_sphere(self._h, float(k), ptr(p), float(r), ptr(w)))
+
     COARSE_MIN_ITERS = 300   # block-Jacobi iteration count above which the coarse correction pays for itself
 
     def auto_aggregates(self):

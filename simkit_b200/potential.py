@@ -20,14 +20,15 @@ class ElasticPotential:
     _skb_potential = True
 
     def __init__(self, material, mu, lam, vol=None, plan=None, J=None, X=None, T=None, dim=None, f_ext=None,
-                 pin_k=None, pin_target=None, psd=True, coarse="auto", contact_plane=None):
+                 pin_k=None, pin_target=None, psd=True, coarse="auto", contact_plane=None, contact_sphere=None):
         """``coarse``: vertex aggregates of the two-level PCG preconditioner of the device-resident step
         (``MeshPlan.set_coarse_space``; needs the rest positions ``X``).  ``"auto"``: start with block-Jacobi and switch
         the coarse correction on (``MeshPlan.auto_aggregates`` aggregates) after the first Newton iteration whose
         PCG needed more than ``MeshPlan.COARSE_MIN_ITERS`` iterations; an integer: that many aggregates from the
         start; ``0`` / ``None``: block-Jacobi only.
         ``contact_plane``: ``dict(k=, p=, n=[, M=])`` -- penalty springs against a ground plane
-        (``contact_springs_plane_*``), added to the three callables and to the device-resident step."""
+        (``contact_springs_plane_*``), added to the three callables and to the device-resident step.
+        ``contact_sphere``: ``dict(k=, p=, r=[, M=])`` -- the same against a sphere (``contact_springs_sphere_*``)."""
         if plan is None:
             if J is not None:
                 plan = plan_from_operator(J, dim if dim is not None else (X.shape[1] if X is not None else 3))
@@ -50,6 +51,12 @@ class ElasticPotential:
             w = None if M is None else np.asarray(sps.csr_matrix(M).diagonal() if sps.issparse(M) else np.diag(M), dtype=np.float64)
             self.contact_plane = dict(k=float(c["k"]), p=np.asarray(c["p"], dtype=np.float64).reshape(-1),
                                       n=np.asarray(c["n"], dtype=np.float64).reshape(-1), w=w)
+        self.contact_sphere = None
+        if contact_sphere is not None:
+            c = dict(contact_sphere)
+            M = c.get("M")
+            w = None if M is None else np.asarray(sps.csr_matrix(M).diagonal() if sps.issparse(M) else np.diag(M), dtype=np.float64)
+            self.contact_sphere = dict(k=float(c["k"]), p=np.asarray(c["p"], dtype=np.float64).reshape(-1), r=float(c["r"]), w=w)
         self._X_rest = None if X is None else np.asarray(X, dtype=np.float64).reshape(plan.n, plan.dim)
         self._coarse_auto = (coarse == "auto") and self._X_rest is not None
         if coarse and coarse != "auto" and self._X_rest is not None:
@@ -64,16 +71,24 @@ class ElasticPotential:
         if self.pin_k is not None:
             d = xx - self.pin_target
             e += 0.5 * float((self.pin_k * d * d).sum())
-        if self.contact_plane is not None:
+        if self.contact_plane is not None or self.contact_sphere is not None:
             e += self._contact("energy", xx)
         return e
 
     def _contact(self, kind, xx):
-        from .energies import contact_springs_plane as cs
+        from .energies import contact_springs_plane as cs, contact_springs_sphere as css
+        X = xx.reshape(self.plan.n, self.plan.dim)
+        out = None
         c = self.contact_plane
-        M = None if c["w"] is None else sps.diags(c["w"])
-        fn = getattr(cs, "contact_springs_plane_" + kind)
-        return fn(xx.reshape(self.plan.n, self.plan.dim), c["k"], c["p"], c["n"], M)
+        if c is not None:
+            M = None if c["w"] is None else sps.diags(c["w"])
+            out = getattr(cs, "contact_springs_plane_" + kind)(X, c["k"], c["p"], c["n"], M)
+        c = self.contact_sphere
+        if c is not None:
+            M = None if c["w"] is None else sps.diags(c["w"])
+            o2 = getattr(css, "contact_springs_sphere_" + kind)(X, c["k"], c["p"], c["r"], M)
+            out = o2 if out is None else out + o2
+        return out
 
     def gradient(self, x):
         xx = np.asarray(x, dtype=np.float64).reshape(-1, 1)
@@ -82,7 +97,7 @@ class ElasticPotential:
             g = g - self.f_ext
         if self.pin_k is not None:
             g = g + self.pin_k * (xx - self.pin_target)
-        if self.contact_plane is not None:
+        if self.contact_plane is not None or self.contact_sphere is not None:
             g = g + self._contact("gradient", xx)
         return g
 
@@ -90,7 +105,7 @@ class ElasticPotential:
         H = self.plan.hessian(self.material, x, self.mu, self.lam, self.vol, self.psd_mode)
         if self.pin_k is not None:
             H = H + sps.diags(self.pin_k.ravel())
-        if self.contact_plane is not None:
+        if self.contact_plane is not None or self.contact_sphere is not None:
             H = H + self._contact("hessian", np.asarray(x, dtype=np.float64).reshape(-1, 1))
         return H
 
@@ -107,6 +122,11 @@ class ElasticPotential:
             self.plan.set_contact_plane(c["k"], c["p"], c["n"], c["w"])
         else:
             self.plan.set_contact_plane(0.0)
+        c = self.contact_sphere
+        if c is not None:
+            self.plan.set_contact_sphere(c["k"], c["p"], c["r"], c["w"])
+        else:
+            self.plan.set_contact_sphere(0.0)
         x, info = self.plan.newton(self.material, x0, psd_mode=self.psd_mode, x_tilde=x_tilde, mass=mass,
                                    kin_scale=kin_scale, f_ext=self.f_ext, pin_k=self.pin_k,
                                    pin_target=self.pin_target, max_iter=max_iter, do_line_search=do_line_search,
