@@ -76,11 +76,14 @@ def workload_desc(name, t, n, nnz):
 class ClockSampler:
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index):
+    def __init__(self, index, active=True):
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self._stop = threading.Event()
         self._thr = None
+        self.nv = None
+        if not active:      # N > 1: rank 0 samples its GPU; eight sampler threads only compete with the launch threads
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -110,7 +113,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.02)
 
     def __enter__(self):
         if self.nv is not None:
@@ -270,14 +273,19 @@ def run_ours(args, rank, world, local_rank):
         return float(tt.item())
 
     # ---- device-resident timing -------------------------------------------------------------
+    # everything slow on the host (NVML initialisation of the clock sampler, its thread start) happens BEFORE the
+    # barrier that precedes the first timed launch: a rank that enters the timed loop late makes its neighbours wait
+    # in the interface exchange, and over K short steps that start-up skew would be billed to every step
+    # (scripts/diag_exchange.py: 1.19 ms per step free-running at 8 GPUs)
+    sampler = ClockSampler(local_rank, active=(rank == 0))
     for _ in range(args.warmup):
         step_dev()
     barrier()
     lib.skb_kernel_timing(plan._h, 1)
     l0 = plan.last_launch_count()
-    sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with sampler:
+        barrier()
         e0.record(stream)
         for _ in range(args.steps):
             step_dev()
