@@ -243,6 +243,17 @@ int skb_newton_set_contact_sphere(skb_plan* plan, double k, const double* p, dou
 /* Adds the same term to every following skb_newton on this plan (energy in the line search, gradient, Hessian
  * blocks straight into the CSR values on the device).  k <= 0 or p == NULL removes it. */
 int skb_newton_set_contact_plane(skb_plan* plan, double k, const double* p, const double* n, const double* weights);
+/* energies/quadratic.py:15-70: energy = 1/2 x^T Q x + b^T x (quadratic_energy :15-34), grad = Q x + b
+ * (quadratic_gradient :37-54) for an n x n CSR matrix Q (int32 indptr / indices, host pointers).  b may be NULL (0);
+ * energy or grad may be NULL. */
+int skb_quadratic(int64_t n, const int32_t* indptr, const int32_t* indices, const double* vals, const double* b,
+                  const double* x, double* energy, double* grad);
+/* Adds the same term to every following skb_newton on this plan: energy in the line search, gradient, and the
+ * Hessian Q (quadratic_hessian :57-70) added into the CSR values on the device.  Q: (n*dim)^2 CSR without duplicate
+ * entries, symmetric, every entry inside the mesh's CSR pattern (vertex adjacency (x) dim x dim; SKB_EINVAL
+ * otherwise) -- e.g. dirichlet_penalty.py:65-142, a mass or Laplacian regulariser.  indptr == NULL removes it. */
+int skb_newton_set_quadratic(skb_plan* plan, const int32_t* indptr, const int32_t* indices, const double* vals,
+                             const double* b);
 /* Two-level preconditioner of the plan's PCG (skb_pcg*, skb_newton): block-Jacobi plus a coarse correction on the
  * rigid-body modes of vertex aggregates.  agg: (n) aggregate id of every vertex in [0, n_agg); xrel: (n*dim) vertex
  * position minus the centre of its aggregate.  n_agg = 0 removes it.  The reference solves the Newton system

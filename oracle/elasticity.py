@@ -212,6 +212,40 @@ def symmetric_stretch_map(t, dim):
     return sps.kron(sps.identity(t), sps.csc_matrix(S)), sps.kron(sps.identity(t), sps.csc_matrix(Si))
 
 
+def quadratic_energy(x, Q, b):
+    """energies/quadratic.py:15-34: float(1/2 x^T Q x + b^T x)."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1, 1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1, 1)
+    return float(np.asarray(0.5 * x.T @ (Q @ x) + b.T @ x).item())
+
+
+def quadratic_gradient(x, Q, b):
+    """energies/quadratic.py:37-54: Q x + b, (n, 1)."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1, 1)
+    return np.asarray(Q @ x) + np.asarray(b, dtype=np.float64).reshape(-1, 1)
+
+
+def quadratic_hessian(Q):
+    """energies/quadratic.py:57-70: Q itself."""
+    return Q
+
+
+def dirichlet_penalty(bI, y, nv, gamma):
+    """dirichlet_penalty.py:65-142 (default options): Q = S Gamma S^T, b = -S Gamma y with S the (nv*d, cn*d)
+    selection of the pinned vertices' dofs and Gamma = diag(gamma) (x) I_d."""
+    y = np.asarray(y, dtype=np.float64)
+    assert y.ndim == 2
+    bI = np.asarray(bI).reshape(-1)
+    cn, d = bI.shape[0], y.shape[1]
+    gam = np.ones(cn) * gamma if np.isscalar(gamma) else np.asarray(gamma, dtype=np.float64).reshape(-1)
+    dofs = (bI[:, None] * d + np.arange(d)[None, :]).ravel()
+    w = np.repeat(gam, d)
+    Q = sps.csc_matrix((w, (dofs, dofs)), (nv * d, nv * d))
+    b = np.zeros((nv * d, 1))
+    np.add.at(b[:, 0], dofs, -w * y.reshape(-1))
+    return Q, b
+
+
 def contact_springs_plane(X, k, p, n, M=None):
     """energies/contact_springs_plane.py:245-388: (energy, gradient (n*d,1), Hessian csc, contacting indices) of
     k/2 sum_{v: n.(x_v - p) < 0} m_v (n.(x_v - p))^2, m = diag(M) (identity by default)."""

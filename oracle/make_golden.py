@@ -260,6 +260,69 @@ def golden_contact(tag, cells, seed):
     print("wrote", tag, "contacting", inds.size, "inside sphere", int((np.linalg.norm(U - sc, axis=1) < sr).sum()))
 
 
+def golden_quadratic(tag, cells, seed):
+    """quadratic_* and dirichlet_penalty, and a backward-Euler step (3 Newton iterations) of stable neo-Hookean +
+    gravity + a general sparse quadratic term: pinned vertices (dirichlet_penalty) plus anisotropic springs along the
+    mesh edges (full dim x dim blocks on and off the block diagonal, all inside the mesh's CSR pattern)."""
+    from simkit.energies.quadratic import quadratic_energy as qe, quadratic_gradient as qg, quadratic_hessian as qh
+    from simkit.dirichlet_penalty import dirichlet_penalty as dp
+    dim = len(cells)
+    X, T = syn.make_mesh(cells)
+    ext = tuple(1.0 for _ in cells)
+    rng = np.random.default_rng(seed)
+    nv = X.shape[0]
+    mu, lam = syn.lame()
+    rho, h = 1e3, 1e-2
+    U = syn.jittered_state(X, cells, ext, sigma=0.2, seed=seed)
+    bI = np.where(X[:, 0] == 0.0)[0]
+    y = X[bI] + 0.02 * rng.standard_normal((bI.size, dim))
+    gamma = 1e6 * (1.0 + rng.random(bI.size))
+    Qd, bd = dp(bI, y, nv, gamma)
+    Qs, bs = dp(bI, y, nv, 1e6)
+    edges = set()
+    for el in T:
+        for a in range(dim + 1):
+            for c in range(a + 1, dim + 1):
+                edges.add((min(el[a], el[c]), max(el[a], el[c])))
+    edges = np.array(sorted(edges))[::3]                       # every third edge carries a spring
+    rows, cols, vals = [], [], []
+    for v, w in edges:
+        A = rng.standard_normal((dim, dim))
+        A = 2e3 * (A @ A.T + 0.1 * np.eye(dim))
+        for (r0, c0, sg) in ((v, v, 1.0), (w, w, 1.0), (v, w, -1.0), (w, v, -1.0)):
+            for i in range(dim):
+                for j in range(dim):
+                    rows.append(r0 * dim + i)
+                    cols.append(c0 * dim + j)
+                    vals.append(sg * A[i, j])
+    Qe = sps.csr_matrix((vals, (rows, cols)), (nv * dim, nv * dim))
+    Q = canon(Qe + Qd)
+    b = bd + 5.0 * rng.standard_normal((nv * dim, 1))
+    x = U.reshape(-1, 1)
+    assert qh(Q) is Q
+    out = dict(X=X, T=T, U=U, dim=dim, bI=bI, y=y, gamma=gamma, Qd=Qd.toarray(), bd=bd, Qs=Qs.toarray(), bs=bs,
+               Q_data=Q.data, Q_indices=Q.indices, Q_indptr=Q.indptr, b=b, E=qe(x, Q, b), g=qg(x, Q, b))
+    J = simkit.deformation_jacobian(X, T)
+    vol = simkit.volume(X, T)
+    Mv = simkit.massmatrix(X, T, rho)
+    Md = sps.kron(Mv, sps.identity(dim)).tocsc()
+    fg = simkit.gravity_force(X, T, -9.8, rho).reshape(-1, 1)
+
+    def En(x):
+        return ske.stable_neo_hookean_energy_x(x.reshape(-1, dim), J, mu, lam, vol) - float((fg.T @ x).item()) + qe(x, Q, b)
+
+    def Gr(x):
+        return ske.stable_neo_hookean_gradient_x(x.reshape(-1, dim), J, mu, lam, vol) - fg + qg(x, Q, b)
+
+    def He(x):
+        return ske.stable_neo_hookean_hessian_x(x.reshape(-1, dim), J, mu, lam, vol) + qh(Q)
+
+    xn, info = ref_be(x, X.reshape(-1, 1), En, Gr, He, Md, h, max_iter=3, return_info=True)
+    out.update(mu=mu, lam=lam, rho=rho, h=h, fg=fg, mass=Mv.diagonal(), be_x=xn, be_alphas=np.array(info["alphas"]))
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print("wrote", tag, "pinned", bI.size, "springs", len(edges), "alphas", info["alphas"])
+
+
 def golden_mfem(tag, cells, rho_aug, seed):
     """MFEM blocks (stretch, dS/dF, ds/dz, symmetric stretch map) and three SQP iterations of the mixed solver."""
     from simkit.solvers import sqp_mfem as ref_sqp
@@ -293,5 +356,7 @@ if __name__ == "__main__":
     golden_reduced("reduced_tri", (5, 4), 8, 31)
     golden_contact("contact_tet", (3, 3, 2), 50)
     golden_contact("contact_tri", (6, 5), 51)
+    golden_quadratic("quadratic_tet", (3, 3, 2), 60)
+    golden_quadratic("quadratic_tri", (6, 5), 61)
     golden_mfem("mfem_tri", (4, 2), 10.0, 40)
     golden_mfem("mfem_tet", (2, 2, 1), 10.0, 41)

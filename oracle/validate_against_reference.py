@@ -233,6 +233,23 @@ def main():
         r = rng.standard_normal((nc, dim, dim))
         check(f"[{dim}D] fst eval", oe.fst_eval(ARBs, r, dim), fr(r), 1e-12)
 
+        # quadratic term and Dirichlet penalty
+        from simkit.energies.quadratic import quadratic_energy as rqe, quadratic_gradient as rqg
+        from simkit.dirichlet_penalty import dirichlet_penalty as rdp
+        nvq = X.shape[0]
+        bI = np.sort(rng.choice(nvq, size=5, replace=False))
+        yq = X[bI] + 0.05 * rng.standard_normal((5, dim))
+        for gname, gam in (("scalar", 1e6), ("per vertex", 1e5 * (1.0 + rng.random(5)))):
+            Qr, br = rdp(bI, yq, nvq, gam)
+            Qo, bo = oe.dirichlet_penalty(bI, yq, nvq, gam)
+            check(f"[{dim}D] dirichlet_penalty Q ({gname})", Qo.toarray(), Qr.toarray(), 1e-15)
+            check(f"[{dim}D] dirichlet_penalty b ({gname})", bo, br, 1e-15)
+        Ls = sps.random(nvq * dim, nvq * dim, density=0.02, random_state=3, format="csr")
+        Qs = (Ls + Ls.T + Qr).tocsr()
+        xq = rng.standard_normal((nvq * dim, 1))
+        check(f"[{dim}D] quadratic_energy", oe.quadratic_energy(xq, Qs, br), rqe(xq, Qs, br), 1e-13)
+        check(f"[{dim}D] quadratic_gradient", oe.quadratic_gradient(xq, Qs, br), rqg(xq, Qs, br), 1e-13)
+
     print("FAILED: " + ", ".join(FAIL) if FAIL else "ALL OK")
     return 1 if FAIL else 0
 

@@ -108,6 +108,8 @@ SIGNATURES = {
     "skb_newton_set_contact_plane": (_int, [_vp, _dbl, _vp, _vp, _vp]),
     "skb_contact_springs_sphere": (_int, [_int, _i64, _vp, _dbl, _vp, _dbl, _vp, ctypes.POINTER(_dbl), _vp, _vp, _vp]),
     "skb_newton_set_contact_sphere": (_int, [_vp, _dbl, _vp, _dbl, _vp]),
+    "skb_quadratic": (_int, [_i64, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_dbl), _vp]),
+    "skb_newton_set_quadratic": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "skb_pcg_set_coarse": (_int, [_vp, _i64, _vp, _vp]),
     "skb_spmv_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "skb_newton": (_int, [_vp, ctypes.POINTER(NewtonOpts), _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, ctypes.POINTER(NewtonInfo)]),

@@ -73,6 +73,10 @@ struct skb_plan {
   bool sphere_on = false;      // skb_newton_set_contact_sphere
   double sphere_k = 0.0, sphere_p[3] = {0, 0, 0}, sphere_r = 0.0;
   skb::dvec<double> sphere_w;
+  // general sparse quadratic term of the device-resident Newton step (skb_newton_set_quadratic)
+  bool quad_on = false;
+  skb::dvec<int> quad_ptr, quad_col, quad_pos;
+  skb::dvec<double> quad_val, quad_b;
   // resident subspace basis of the reduced tier (skb_plan_set_basis)
   skb::dvec<double> basis;
   int64_t basis_r = 0;

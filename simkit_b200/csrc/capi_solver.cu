@@ -346,6 +346,87 @@ static int contact_eval(int kind, int dim, int64_t nv, const double* X, double k
   SKB_CATCH
 }
 
+static int quad_grid(int64_t n) {
+  int64_t grid = (n + PCG_THREADS - 1) / PCG_THREADS;
+  if (grid > 1024) grid = 1024;
+  return grid < 1 ? 1 : (int)grid;
+}
+
+int skb_quadratic(int64_t n, const int32_t* indptr, const int32_t* indices, const double* vals, const double* b,
+                  const double* x, double* energy, double* grad) {
+  if (!indptr || !x || (!energy && !grad)) return fail(SKB_EINVAL, "null argument");
+  if (n <= 0 || n >= ((int64_t)1 << 31)) return fail(SKB_EINVAL, "bad size");
+  if (skb_device_count() <= 0) return fail(SKB_ENOGPU, "no CUDA device");
+  const int64_t nnz = indptr[n];
+  if (nnz < 0 || (nnz > 0 && (!indices || !vals))) return fail(SKB_EINVAL, "null argument");
+  SKB_TRY
+  dvec<int> dp(indptr, indptr + n + 1), dc;
+  dvec<double> dv, db, gd, part(PCG_MAX_GRID), out(1);
+  if (nnz > 0) {
+    dc.assign(indices, indices + nnz);
+    dv.assign(vals, vals + nnz);
+  }
+  dvec<double> dx(x, x + n);
+  if (b) db.assign(b, b + n);
+  if (grad) gd.assign((size_t)n, 0.0);
+  const int grid = quad_grid(n);
+  quad_term_kernel<<<grid, PCG_THREADS>>>((int)n, raw(dp), raw(dc), raw(dv), b ? raw(db) : nullptr, raw(dx),
+                                          grad ? raw(gd) : nullptr, raw(part));
+  reduce_final_kernel<<<1, PCG_THREADS>>>(raw(part), grid, raw(out));
+  SKB_CUDA(cudaGetLastError());
+  SKB_CUDA(cudaDeviceSynchronize());
+  if (energy) SKB_CUDA(cudaMemcpy(energy, raw(out), sizeof(double), cudaMemcpyDeviceToHost));
+  if (grad) SKB_CUDA(cudaMemcpy(grad, raw(gd), (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_newton_set_quadratic(skb_plan* pl, const int32_t* indptr, const int32_t* indices, const double* vals,
+                             const double* b) {
+  if (!pl) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  pl->quad_on = false;
+  if (!indptr) {
+    pl->quad_ptr.clear();
+    pl->quad_col.clear();
+    pl->quad_pos.clear();
+    pl->quad_val.clear();
+    pl->quad_b.clear();
+    return SKB_OK;
+  }
+  const int nd = (int)pl->ndof();
+  const int64_t nnz = indptr[nd];
+  if (nnz < 0 || nnz >= ((int64_t)1 << 31) || (nnz > 0 && (!indices || !vals))) return fail(SKB_EINVAL, "bad quadratic term");
+  for (int64_t k = 0; k < nnz; ++k)
+    if (indices[k] < 0 || indices[k] >= nd) return fail(SKB_EINVAL, "quadratic term: column index out of range");
+  pl->quad_ptr.assign(indptr, indptr + nd + 1);
+  pl->quad_pos.assign((size_t)(nnz > 0 ? nnz : 1), 0);
+  if (nnz > 0) {
+    pl->quad_col.assign(indices, indices + nnz);
+    pl->quad_val.assign(vals, vals + nnz);
+  } else {
+    pl->quad_col.assign(1, 0);
+    pl->quad_val.assign(1, 0.0);
+  }
+  if (b) pl->quad_b.assign(b, b + nd);
+  else pl->quad_b.clear();
+  dvec<int> bad(1, 0);
+  const PlanView pv = pl->view();
+  const int grid = (nd + PCG_THREADS - 1) / PCG_THREADS;
+  if (pl->d.dim == 3)
+    quad_positions_kernel<3><<<grid, PCG_THREADS, 0, pl->stream>>>(pv, nd, raw(pl->quad_ptr), raw(pl->quad_col), raw(pl->quad_pos), raw(bad));
+  else
+    quad_positions_kernel<2><<<grid, PCG_THREADS, 0, pl->stream>>>(pv, nd, raw(pl->quad_ptr), raw(pl->quad_col), raw(pl->quad_pos), raw(bad));
+  SKB_CUDA(cudaGetLastError());
+  SKB_CUDA(cudaStreamSynchronize(pl->stream));
+  const int nbad = bad[0];
+  if (nbad != 0) return fail(SKB_EINVAL, "quadratic term: " + std::to_string(nbad) + " entries lie outside the mesh's CSR pattern");
+  pl->quad_on = true;
+  return SKB_OK;
+  SKB_CATCH
+}
+
 int skb_spmv_dev(skb_plan* pl, const double* vals, const double* diag_add, const double* x, double* y,
                  void* stream) {
   if (!pl || !vals || !x || !y) return fail(SKB_EINVAL, "null argument");
@@ -490,7 +571,7 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
   double* part_g = part_e + PCG_MAX_GRID;
   double* part_d = part_g + PCG_MAX_GRID;
   double* red = part_d + PCG_MAX_GRID;  // 3 sums + elastic energy + up to 2 contact energies
-  double hred[6];
+  double hred[7];
   ContactPlaneArgs contacts[2];
   int n_contacts = 0;
   dvec<double> part_c;
@@ -524,6 +605,12 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
   }
   const int nverts = pl->d.n;
   const int dim_ = pl->d.dim;
+  // general sparse quadratic term (skb_newton_set_quadratic)
+  dvec<double> part_q;
+  const int qgrid = quad_grid(nd);
+  const int qnnz = pl->quad_on ? (int)pl->quad_val.size() : 0;
+  const double* quad_b = (pl->quad_on && !pl->quad_b.empty()) ? raw(pl->quad_b) : nullptr;
+  if (pl->quad_on) part_q.resize(PCG_MAX_GRID);
 
   // total energy at x + s*dx (also leaves the trial point in xtrial)
   auto total_energy = [&](double s, const double* dxp, bool with_gdx, double& e_tot, double& gdx, double& dx2) -> int {
@@ -545,9 +632,19 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
         SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<2><<<vgrid, PCG_THREADS, 0, st>>>(nverts, xtrial, contacts[ci], nullptr, nullptr, nullptr, nullptr, raw(part_c), nullptr));
       SKB_LAUNCH(pl, SKB_K_OTHER, st, reduce_final_kernel<<<1, PCG_THREADS, 0, st>>>(raw(part_c), vgrid, red + 4 + ci));
     }
-    SKB_CUDA(cudaMemcpyAsync(hred, red, (4 + n_contacts) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    hred[6] = 0.0;
+    if (pl->quad_on) {
+      SKB_LAUNCH(pl, SKB_K_OTHER, st,
+                 quad_term_kernel<<<qgrid, PCG_THREADS, 0, st>>>(nd, raw(pl->quad_ptr), raw(pl->quad_col), raw(pl->quad_val), quad_b,
+                                                                  xtrial, nullptr, raw(part_q)));
+      SKB_LAUNCH(pl, SKB_K_OTHER, st, reduce_final_kernel<<<1, PCG_THREADS, 0, st>>>(raw(part_q), qgrid, red + 6));
+    }
+    SKB_CUDA(cudaMemcpyAsync(hred, red, (pl->quad_on ? 7 : 4 + n_contacts) * sizeof(double), cudaMemcpyDeviceToHost, st));
     SKB_CUDA(cudaStreamSynchronize(st));
-    e_tot = hred[0] + hred[3] + hred[4] + hred[5];
+    if (!pl->quad_on) hred[6] = 0.0;
+    if (n_contacts < 2) hred[5] = 0.0;
+    if (n_contacts < 1) hred[4] = 0.0;
+    e_tot = hred[0] + hred[3] + hred[4] + hred[5] + hred[6];
     gdx = hred[1];
     dx2 = hred[2];
     return SKB_OK;
@@ -569,6 +666,14 @@ int skb_newton(skb_plan* pl, const skb_newton_opts* o, const double* x0, const d
         SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<3><<<vgrid, PCG_THREADS, 0, st>>>(nverts, x, contacts[ci], g, nullptr, raw(pview_d), raw(pl->vals), nullptr, nullptr));
       else
         SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<2><<<vgrid, PCG_THREADS, 0, st>>>(nverts, x, contacts[ci], g, nullptr, raw(pview_d), raw(pl->vals), nullptr, nullptr));
+    }
+    if (pl->quad_on) {
+      // gradient Q x + b into g, Hessian Q into its slots of the CSR values
+      SKB_LAUNCH(pl, SKB_K_OTHER, st,
+                 quad_term_kernel<<<qgrid, PCG_THREADS, 0, st>>>(nd, raw(pl->quad_ptr), raw(pl->quad_col), raw(pl->quad_val), quad_b,
+                                                                  x, g, nullptr));
+      SKB_LAUNCH(pl, SKB_K_OTHER, st,
+                 add_at_kernel<<<quad_grid(qnnz), PCG_THREADS, 0, st>>>(raw(pl->vals), raw(pl->quad_pos), qnnz, raw(pl->quad_val)));
     }
     SKB_LAUNCH(pl, SKB_K_OTHER, st,
                newton_gradient_kernel<<<vgrid, PCG_THREADS, 0, st>>>(nd, x, d_f, d_mass, d_xt, kin_scale, d_pk, d_pt, g, rhs,

@@ -554,6 +554,23 @@ SKB_HD void vert_finalize(const PlanView& p, int v, const double* pverts, double
   for (int i = 0; i < D; ++i) g[(size_t)v * D + i] = acc[i];
 }
 
+// Index of the scalar entry (row, col) in the canonical CSR value array, or -1 when the block
+// (row / D, col / D) is not in the pattern: the D rows of block row v are contiguous runs of
+// D * (bptr[v+1] - bptr[v]) values, block columns sorted ascending (binary search).
+template <int D>
+SKB_HD int csr_value_position(const int* bptr, const int* bcol, int row, int col) {
+  const int v = row / D, i = row - v * D;
+  const int w = col / D, j = col - w * D;
+  const int b0 = bptr[v], b1 = bptr[v + 1];
+  int lo = b0, hi = b1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (bcol[mid] < w) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= b1 || bcol[lo] != w) return -1;
+  return b0 * (D * D) + i * (D * (b1 - b0)) + D * (lo - b0) + j;
+}
+
 // shared-memory footprint of one assembly CTA (bytes); every region starts 16-byte aligned
 template <int D>
 inline size_t assemble_smem_bytes(const PlanView& p) {

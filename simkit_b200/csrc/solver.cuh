@@ -395,6 +395,46 @@ __global__ void contact_plane_kernel(int nv, const double* x, ContactPlaneArgs c
   }
 }
 
+// ---- general sparse quadratic term 1/2 x^T Q x + b^T x (energies/quadratic.py:15-70) -----------------------
+// One thread per row of the CSR matrix Q (rows of penalty / regulariser matrices are short): y_i = sum_j Q_ij x_j,
+// g_add[i] += y_i + b_i (quadratic_gradient, Q symmetric as the reference assumes), per-CTA partial of
+// x_i (y_i / 2 + b_i) (quadratic_energy).  b, g_add and part_e may be null.  Fixed order => deterministic.
+static __global__ void quad_term_kernel(int n, const int* __restrict__ qptr, const int* __restrict__ qcol,
+                                        const double* __restrict__ qv, const double* __restrict__ b,
+                                        const double* __restrict__ x, double* g_add, double* part_e) {
+  __shared__ double sh[32];
+  double e = 0.0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    double y = 0.0;
+    const int k1 = qptr[r + 1];
+    for (int k = qptr[r]; k < k1; ++k) y = fma(qv[k], x[qcol[k]], y);
+    const double bv = b ? b[r] : 0.0;
+    if (g_add) g_add[r] += y + bv;
+    e = fma(x[r], fma(0.5, y, bv), e);
+  }
+  if (part_e) {
+    e = block_reduce_sum(e, sh);
+    if (threadIdx.x == 0) part_e[blockIdx.x] = e;
+  }
+}
+
+// where every entry of Q sits in the plan's CSR values (quadratic_hessian = Q is then one scatter-add per Newton
+// iteration); *bad counts the entries outside the pattern
+template <int D>
+__global__ void quad_positions_kernel(PlanView p, int n, const int* qptr, const int* qcol, int* pos, int* bad) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int k = qptr[r]; k < qptr[r + 1]; ++k) {
+    const int q = csr_value_position<D>(p.bptr, p.bcol, r, qcol[k]);
+    pos[k] = q < 0 ? 0 : q;
+    if (q < 0) atomicAdd(bad, 1);
+  }
+}
+
+static __global__ void add_at_kernel(double* dst, const int* __restrict__ pos, int n, const double* __restrict__ src) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) dst[pos[k]] += src[k];
+}
+
 // out[0..2] = sums of three partial arrays (single CTA)
 static __global__ void reduce3_kernel(const double* a, const double* b, const double* c, int n, double* out) {
   __shared__ double sh[32];

@@ -13,3 +13,4 @@ from .contact_springs_plane import (contact_springs_plane_energy, contact_spring
                                     contact_springs_plane_hessian)
 from .contact_springs_sphere import (contact_springs_sphere_energy, contact_springs_sphere_gradient,  # noqa: F401
                                      contact_springs_sphere_hessian)
+from .quadratic import quadratic_energy, quadratic_gradient, quadratic_hessian  # noqa: F401

@@ -219,6 +219,25 @@ class MeshPlan:
             raise ValueError("weights must have one entry per vertex")
         check(self._lib.skb_newton_set_contact_sphere(self._h, float(k), ptr(p), float(r), ptr(w)))
 
+    def set_quadratic(self, Q=None, b=None):
+        """General sparse quadratic term ``1/2 x^T Q x + b^T x`` (``energies/quadratic.py``) inside the device-resident
+        Newton step: energy in the line search, gradient ``Q x + b``, Hessian ``Q`` added into the CSR values on the
+        device.  ``Q``: symmetric ``(n*dim, n*dim)`` scipy sparse matrix or ndarray whose entries lie inside the mesh's
+        CSR pattern (``ValueError`` otherwise) -- a ``dirichlet_penalty`` matrix, a mass or Laplacian regulariser;
+        ``Q = None`` removes the term."""
+        self._quad_owner = None   # ElasticPotential's upload cache: any direct call invalidates it
+        self._quad_active = False
+        if Q is None:
+            check(self._lib.skb_newton_set_quadratic(self._h, None, None, None, None))
+            return
+        from .energies.quadratic import _csr
+        indptr, indices, vals = _csr(Q, self.ndof)
+        bb = None if b is None else f64(np.asarray(b, dtype=np.float64).reshape(-1))
+        if bb is not None and bb.size != self.ndof:
+            raise ValueError("b must have n*dim entries")
+        check(self._lib.skb_newton_set_quadratic(self._h, ptr(indptr), ptr(indices), ptr(vals), ptr(bb)))
+        self._quad_active = True
+
     COARSE_MIN_ITERS = 300   # block-Jacobi iteration count above which the coarse correction pays for itself
 
     def auto_aggregates(self):

@@ -20,7 +20,8 @@ class ElasticPotential:
     _skb_potential = True
 
     def __init__(self, material, mu, lam, vol=None, plan=None, J=None, X=None, T=None, dim=None, f_ext=None,
-                 pin_k=None, pin_target=None, psd=True, coarse="auto", contact_plane=None, contact_sphere=None):
+                 pin_k=None, pin_target=None, psd=True, coarse="auto", contact_plane=None, contact_sphere=None,
+                 quadratic=None):
         """``coarse``: vertex aggregates of the two-level PCG preconditioner of the device-resident step
         (``MeshPlan.set_coarse_space``; needs the rest positions ``X``).  ``"auto"``: start with block-Jacobi and switch
         the coarse correction on (``MeshPlan.auto_aggregates`` aggregates) after the first Newton iteration whose
@@ -28,7 +29,9 @@ class ElasticPotential:
         start; ``0`` / ``None``: block-Jacobi only.
         ``contact_plane``: ``dict(k=, p=, n=[, M=])`` -- penalty springs against a ground plane
         (``contact_springs_plane_*``), added to the three callables and to the device-resident step.
-        ``contact_sphere``: ``dict(k=, p=, r=[, M=])`` -- the same against a sphere (``contact_springs_sphere_*``)."""
+        ``contact_sphere``: ``dict(k=, p=, r=[, M=])`` -- the same against a sphere (``contact_springs_sphere_*``).
+        ``quadratic``: ``(Q, b)`` -- a general sparse quadratic term ``1/2 x^T Q x + b^T x`` (``quadratic_*``; e.g. the
+        output of ``dirichlet_penalty``), ``Q`` symmetric and inside the mesh's CSR pattern."""
         if plan is None:
             if J is not None:
                 plan = plan_from_operator(J, dim if dim is not None else (X.shape[1] if X is not None else 3))
@@ -57,6 +60,14 @@ class ElasticPotential:
             M = c.get("M")
             w = None if M is None else np.asarray(sps.csr_matrix(M).diagonal() if sps.issparse(M) else np.diag(M), dtype=np.float64)
             self.contact_sphere = dict(k=float(c["k"]), p=np.asarray(c["p"], dtype=np.float64).reshape(-1), r=float(c["r"]), w=w)
+        self.quadratic = None
+        if quadratic is not None:
+            Q, b = quadratic
+            Q = sps.csr_matrix(Q)
+            if Q.shape != (nd, nd):
+                raise ValueError("quadratic: Q must be (%d, %d)" % (nd, nd))
+            b = np.zeros((nd, 1)) if b is None else np.asarray(b, dtype=np.float64).reshape(nd, 1)
+            self.quadratic = (Q, b)
         self._X_rest = None if X is None else np.asarray(X, dtype=np.float64).reshape(plan.n, plan.dim)
         self._coarse_auto = (coarse == "auto") and self._X_rest is not None
         if coarse and coarse != "auto" and self._X_rest is not None:
@@ -73,6 +84,9 @@ class ElasticPotential:
             e += 0.5 * float((self.pin_k * d * d).sum())
         if self.contact_plane is not None or self.contact_sphere is not None:
             e += self._contact("energy", xx)
+        if self.quadratic is not None:
+            from .energies.quadratic import quadratic_energy
+            e += quadratic_energy(xx, *self.quadratic)
         return e
 
     def _contact(self, kind, xx):
@@ -99,6 +113,9 @@ class ElasticPotential:
             g = g + self.pin_k * (xx - self.pin_target)
         if self.contact_plane is not None or self.contact_sphere is not None:
             g = g + self._contact("gradient", xx)
+        if self.quadratic is not None:
+            from .energies.quadratic import quadratic_gradient
+            g = g + quadratic_gradient(xx, *self.quadratic)
         return g
 
     def hessian(self, x):
@@ -107,6 +124,8 @@ class ElasticPotential:
             H = H + sps.diags(self.pin_k.ravel())
         if self.contact_plane is not None or self.contact_sphere is not None:
             H = H + self._contact("hessian", np.asarray(x, dtype=np.float64).reshape(-1, 1))
+        if self.quadratic is not None:
+            H = H + self.quadratic[0]
         return H
 
     # -- device-resident steps -------------------------------------------------------------------
@@ -127,6 +146,12 @@ class ElasticPotential:
             self.plan.set_contact_sphere(c["k"], c["p"], c["r"], c["w"])
         else:
             self.plan.set_contact_sphere(0.0)
+        if self.quadratic is None:
+            if getattr(self.plan, "_quad_active", False):
+                self.plan.set_quadratic(None)
+        elif getattr(self.plan, "_quad_owner", None) is not self.quadratic:   # uploaded once, not per step
+            self.plan.set_quadratic(*self.quadratic)
+            self.plan._quad_owner = self.quadratic
         x, info = self.plan.newton(self.material, x0, psd_mode=self.psd_mode, x_tilde=x_tilde, mass=mass,
                                    kin_scale=kin_scale, f_ext=self.f_ext, pin_k=self.pin_k,
                                    pin_target=self.pin_target, max_iter=max_iter, do_line_search=do_line_search,

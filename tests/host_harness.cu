@@ -110,6 +110,14 @@ int hs_run(const double* X, const int64_t* T, int64_t n, int64_t t, int64_t t_ac
   return 0;
 }
 
+// csr_value_position (kernels.cuh): where scalar entries (rows[k], cols[k]) sit in the canonical CSR values
+int hs_value_positions(int dim, const int32_t* bptr, const int32_t* bcol, int64_t nq, const int32_t* rows,
+                       const int32_t* cols, int32_t* out) {
+  for (int64_t k = 0; k < nq; ++k)
+    out[k] = dim == 3 ? csr_value_position<3>(bptr, bcol, rows[k], cols[k]) : csr_value_position<2>(bptr, bcol, rows[k], cols[k]);
+  return 0;
+}
+
 // element-level checks of the principal-stretch machinery
 int hs_svd(int dim, int64_t t, const double* F, double* U, double* S, double* V) {
   for (int64_t e = 0; e < t; ++e) {

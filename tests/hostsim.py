@@ -98,6 +98,19 @@ def csr_from_blocks(bptr, bcol, vals, n, dim):
     return sps.csr_matrix((vals, indices, indptr), shape=(n * dim, n * dim))
 
 
+def value_positions(bptr, bcol, rows, cols, dim):
+    """csr_value_position of kernels.cuh for scalar entries (rows[k], cols[k]); -1 = outside the pattern."""
+    lib = load()
+    bptr = np.ascontiguousarray(bptr, dtype=np.int32)
+    bcol = np.ascontiguousarray(bcol, dtype=np.int32)
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    out = np.empty(rows.size, dtype=np.int32)
+    lib.hs_value_positions.argtypes = [ctypes.c_int, _ip, _ip, ctypes.c_int64, _ip, _ip, _ip]
+    lib.hs_value_positions(dim, _p(bptr, _ip), _p(bcol, _ip), rows.size, _p(rows, _ip), _p(cols, _ip), _p(out, _ip))
+    return out
+
+
 def svd(F):
     lib = load()
     F = _c(F)

@@ -1,0 +1,140 @@
+"""General sparse quadratic term and the Dirichlet penalty: oracle and host logic vs the frozen
+reference outputs on the CPU; on the GPU the drop-in ``quadratic_*`` functions and a backward-Euler step of stable
+neo-Hookean + gravity + quadratic term, host-callable and device-resident."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from oracle import elasticity as oe
+
+TAGS = ["quadratic_tet", "quadratic_tri"]
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def load(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    nd = g["X"].shape[0] * int(g["dim"])
+    Q = sps.csr_matrix((g["Q_data"], g["Q_indices"], g["Q_indptr"]), shape=(nd, nd))
+    return g, Q
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_quadratic(golden_dir, tag):
+    g, Q = load(golden_dir, tag)
+    x = g["U"].reshape(-1, 1)
+    assert abs(oe.quadratic_energy(x, Q, g["b"]) - float(g["E"])) <= 1e-13 * abs(float(g["E"]))
+    assert rel(oe.quadratic_gradient(x, Q, g["b"]), g["g"]) < 1e-13
+    assert oe.quadratic_hessian(Q) is Q
+    Qd, bd = oe.dirichlet_penalty(g["bI"], g["y"], g["X"].shape[0], g["gamma"])
+    assert rel(Qd.toarray(), g["Qd"]) == 0.0 and rel(bd, g["bd"]) == 0.0
+    Qs, bs = oe.dirichlet_penalty(g["bI"], g["y"], g["X"].shape[0], 1e6)
+    assert rel(Qs.toarray(), g["Qs"]) == 0.0 and rel(bs, g["bs"]) == 0.0
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_step_with_quadratic(golden_dir, tag):
+    """The oracle's backward Euler with the quadratic term reproduces the reference iterate."""
+    g, Q = load(golden_dir, tag)
+    X, T, dim = g["X"], g["T"], int(g["dim"])
+    mu, lam, h, fg, b = float(g["mu"]), float(g["lam"]), float(g["h"]), g["fg"], g["b"]
+    J = oe.deformation_jacobian(X, T)
+    vol = oe.volume(X, T)
+    Md = sps.kron(sps.diags(g["mass"]), sps.identity(dim)).tocsc()
+
+    def En(x):
+        return oe.energy_x("stable_neo_hookean", x.reshape(-1, dim), J, mu, lam, vol) - float((fg.T @ x).item()) + oe.quadratic_energy(x, Q, b)
+
+    def Gr(x):
+        return oe.gradient_x("stable_neo_hookean", x.reshape(-1, dim), J, mu, lam, vol) - fg + oe.quadratic_gradient(x, Q, b)
+
+    def He(x):
+        return oe.hessian_x("stable_neo_hookean", x.reshape(-1, dim), J, mu, lam, vol, psd=True) + Q
+
+    x1, info = oe.backward_euler(g["U"].reshape(-1, 1), X.reshape(-1, 1), En, Gr, He, Md, h, max_iter=3, return_info=True)
+    assert list(info["alphas"]) == list(g["be_alphas"]) and rel(x1, g["be_x"]) < 1e-10
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_dirichlet_penalty_host(golden_dir, tag):
+    """``simkit_b200.dirichlet_penalty`` is set-up code on the host (no GPU call): same tuples as the reference."""
+    from simkit_b200.dirichlet_penalty import dirichlet_penalty
+    g, _ = load(golden_dir, tag)
+    nv = g["X"].shape[0]
+    Qd, bd = dirichlet_penalty(g["bI"], g["y"], nv, g["gamma"])
+    assert sps.issparse(Qd) and rel(Qd.toarray(), g["Qd"]) == 0.0 and bd.shape == g["bd"].shape and rel(bd, g["bd"]) == 0.0
+    Qs, bs, SG = dirichlet_penalty(g["bI"].reshape(-1, 1), g["y"], nv, 1e6, return_SGamma=True)
+    assert rel(Qs.toarray(), g["Qs"]) == 0.0 and rel(bs, g["bs"]) == 0.0
+    (b_only,) = dirichlet_penalty(g["bI"], g["y"] + 1.0, nv, 1e6, only_b=True, SGamma=SG)
+    assert rel(b_only, -(SG @ (g["y"] + 1.0).reshape(-1, 1))) == 0.0
+    with pytest.raises(AssertionError):
+        dirichlet_penalty(g["bI"], g["y"].reshape(-1), nv, 1e6)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_value_positions_host_replay(golden_dir, tag):
+    """csr_value_position (the map skb_newton_set_quadratic builds on the device) replayed on the host: every entry of
+    Q lands on the entry of the canonical CSR pattern with the same (row, col); entries outside give -1."""
+    import hostsim
+    g, Q = load(golden_dir, tag)
+    X, T, dim = g["X"], g["T"], int(g["dim"])
+    r = hostsim.run(X, T, 0, 1, g["U"], float(g["mu"]), float(g["lam"]))
+    H = hostsim.csr_from_blocks(r["bptr"], r["bcol"], r["vals"], X.shape[0], dim)
+    Qc = Q.tocoo()
+    pos = hostsim.value_positions(r["bptr"], r["bcol"], Qc.row, Qc.col, dim)
+    assert (pos >= 0).all() and np.unique(pos).size == pos.size
+    rows_of = np.repeat(np.arange(H.shape[0]), np.diff(H.indptr))
+    assert np.array_equal(rows_of[pos], Qc.row) and np.array_equal(H.indices[pos], Qc.col)
+    # adding Q through the map == adding the matrices
+    vals = r["vals"].copy()
+    vals[pos] += Qc.data
+    H2 = sps.csr_matrix((vals, H.indices, H.indptr), shape=H.shape)
+    assert rel(H2.toarray(), (H + Q).toarray()) < 1e-15
+    # an entry between two vertices that share no element is outside the pattern
+    Hp = sps.csr_matrix((np.ones_like(H.data), H.indices, H.indptr), shape=H.shape).toarray() > 0
+    out_r, out_c = np.where(~Hp)
+    if out_r.size:
+        assert (hostsim.value_positions(r["bptr"], r["bcol"], out_r[:50], out_c[:50], dim) == -1).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", TAGS)
+def test_gpu_quadratic(golden_dir, tag):
+    import simkit_b200 as sk
+    g, Q = load(golden_dir, tag)
+    X, T, U, dim = g["X"], g["T"], g["U"], int(g["dim"])
+    b = g["b"]
+    x = U.reshape(-1, 1)
+    E = sk.quadratic_energy(x, Q, b)
+    assert isinstance(E, float) and abs(E - float(g["E"])) <= 1e-12 * abs(float(g["E"]))
+    gr = sk.quadratic_gradient(x, Q, b)
+    assert gr.shape == g["g"].shape and rel(gr, g["g"]) < 1e-12
+    assert rel(sk.quadratic_gradient(x, Q.toarray(), b), g["g"]) < 1e-12      # dense Q, as the reference accepts
+    assert sk.quadratic_hessian(Q) is Q
+    # backward Euler with the term: device-resident step (ElasticPotential) and the host-callable path
+    mu, lam, h = float(g["mu"]), float(g["lam"]), float(g["h"])
+    Md = sps.kron(sps.diags(g["mass"]), sps.identity(dim)).tocsc()
+    pot = sk.ElasticPotential("stable_neo_hookean", mu, lam, X=X, T=T, f_ext=g["fg"], quadratic=(Q, b))
+    x_prev = X.reshape(-1, 1)
+    x1, info = sk.backward_euler(x, x_prev, pot.energy, pot.gradient, pot.hessian, Md, h, max_iter=3, return_info=True,
+                                 pcg_rtol=1e-13)
+    assert list(info["alphas"]) == list(g["be_alphas"]) and rel(x1, g["be_x"]) < 1e-8
+    x2 = sk.backward_euler(x, x_prev, lambda v: pot.energy(v), lambda v: pot.gradient(v), lambda v: pot.hessian(v), Md, h,
+                           max_iter=3, pcg_rtol=1e-13)
+    assert rel(x2, g["be_x"]) < 1e-8
+    # a second step reuses the uploaded term
+    x3 = sk.backward_euler(x, x_prev, pot.energy, pot.gradient, pot.hessian, Md, h, max_iter=3, pcg_rtol=1e-13)
+    assert rel(x3, g["be_x"]) < 1e-8
+    # entries outside the mesh's CSR pattern are refused
+    nd = X.shape[0] * dim
+    far = int(np.argmax(np.linalg.norm(X - X[0], axis=1)))
+    Qbad = sps.csr_matrix(([1.0, 1.0], ([0, far * dim], [far * dim, 0])), shape=(nd, nd))
+    with pytest.raises(ValueError):
+        pot.plan.set_quadratic(Qbad, None)
+    pot.plan.set_quadratic(None)
