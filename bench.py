@@ -238,6 +238,8 @@ def run_ours(args, rank, world, local_rank):
     else:
         shard = None
         X, T = syn.make_mesh(args.workload)
+        if args.element_order == "pencil":     # experiment: same mesh, elements listed in spatially compact runs
+            T = np.ascontiguousarray(T[syn.pencil_order(cfg["cells"], cfg["extent"], X, T)])
         plan = sk.MeshPlan(X=X, T=T, device=local_rank)
         U = syn.jittered_state(X, cfg["cells"], cfg["extent"], sigma=0.1)
         t_total, n_total, nnz_total = plan.t, plan.n, plan.nnz
@@ -528,7 +530,8 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": workload_desc(args.workload, t_total, n_total, nnz_total), "material": MATERIAL,
                        "psd": "analytic eigensystem, floor 1e-6 after vol",
                        "l2": "no flush needed: per-step inputs+outputs (>= %.1f GB) exceed the 126 MB L2" % (alg_bytes / 1e9),
-                       "sharding": "none" if world == 1 else "contiguous element slabs, NCCL interface exchange"},
+                       "sharding": "none" if world == 1 else "contiguous element slabs, NCCL interface exchange",
+                       "element_order": args.element_order if world == 1 else "input"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "newton": newton,
         }
@@ -555,6 +558,9 @@ def main():
     ap.add_argument("--aggregates", type=int, default=-1, help="vertex aggregates of the two-level PCG preconditioner "
                     "(-1: MeshPlan.auto_aggregates when block-Jacobi needs > 300 iterations, 729 at C5; 0: block-Jacobi only)")
     ap.add_argument("--reduced", type=int, default=0, help="also time the reduced Hessian B^T H B with this many modes (config 4: --workload C4 --reduced 200)")
+    ap.add_argument("--element-order", default="input", choices=["input", "pencil"],
+                    help="experiment (1 GPU): list the mesh's elements in 3x3-cell pencils (synthetic.pencil_order) instead of the "
+                         "generator's cell-major order; fewer partial records per element")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="development only: stop after the device-resident timing")
     args = ap.parse_args()

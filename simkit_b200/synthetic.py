@@ -124,6 +124,25 @@ def make_mesh(name_or_cells, extent=None):
     return tri_grid(*cells, extent=extent)
 
 
+def pencil_order(cells, extent, X, T, width=None):
+    """Permutation of the elements that makes consecutive runs of 128 elements compact in space: cells are ordered in
+    pencils of ``width x width`` cells (3 x 3 in 3D, 8 in 2D) running along the last axis, so a tile of the assembly kernel
+    covers about 3 x 3 x 2.4 cells (8 x 8 in 2D) instead of a 21-cell line and merges more of its Hessian blocks
+    before they leave the SM (2.33 partial records per tet instead of 3.12; `tests/test_hostsim.py`).  The mesh is
+    the same mesh: only the order in which its elements are listed changes."""
+    dim = len(cells)
+    if width is None:
+        width = 3 if dim == 3 else 8
+    h = np.array([e / c for e, c in zip(extent, cells)])
+    cen = np.asarray(X)[np.asarray(T)].mean(axis=1)
+    ci = np.minimum(np.floor(cen / h[None, :]).astype(np.int64), np.array(cells)[None, :] - 1)
+    if dim == 3:
+        keys = (ci[:, 1] % width, ci[:, 0] % width, ci[:, 2], ci[:, 1] // width, ci[:, 0] // width)
+    else:
+        keys = (ci[:, 0] % width, ci[:, 1], ci[:, 0] // width)
+    return np.lexsort(keys)
+
+
 def cell_size(cells, extent):
     return min(e / c for e, c in zip(extent, cells))
 
