@@ -347,8 +347,15 @@ SKB_HD void element_store(const EvalArgs& a, const ElemState<D>& st, int le, int
     // block (ca, cb), ca <= cb:  K = U M U^T,
     //   M[p][p] = S_pp Wa_p Wb_p + sum_{q != p} a_pq Wa_q Wb_q
     //   M[p][r] = S_pr Wa_p Wb_r + b_pr Wa_r Wb_p
+#if defined(SKB_EXP_SUM0)
+    // A/B experiment: only the pairs among corners 1..D are computed; the pairs of corner 0 follow from the
+    // translation invariance sum_a K_ab = 0 (W[0] = -sum_c W[c]) by reading the element's own staged values back
+    constexpr int CA0 = 1;
+#else
+    constexpr int CA0 = 0;
+#endif
 #pragma unroll
-    for (int ca = 0; ca < K; ++ca)
+    for (int ca = CA0; ca < K; ++ca)
 #pragma unroll
       for (int cb = ca; cb < K; ++cb) {
         Mat<D> M;
@@ -377,6 +384,38 @@ SKB_HD void element_store(const EvalArgs& a, const ElemState<D>& st, int le, int
             sK[stage_idx<D>(ca, cb, i, kk) * E + le] = s;
           }
       }
+#if defined(SKB_EXP_SUM0)
+    {
+      const volatile double* rK = sK;   // real shared-memory loads: forwarding the stores would keep 45 values live
+      double k00[D][D];
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int kk = 0; kk < D; ++kk) k00[i][kk] = 0.0;
+#pragma unroll
+      for (int cb = 1; cb < K; ++cb)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int kk = 0; kk < D; ++kk) {
+            double acc = 0.0;   // K_0b[i][kk] = -sum_{a >= 1} K_ab[i][kk],  K_ab = K_ba^T for a > b
+#pragma unroll
+            for (int ca = 1; ca < K; ++ca) {
+              int idx;
+              if (ca < cb) idx = stage_idx<D>(ca, cb, i, kk);
+              else if (ca > cb) idx = stage_idx<D>(cb, ca, kk, i);
+              else idx = (i <= kk) ? stage_idx<D>(ca, ca, i, kk) : stage_idx<D>(ca, ca, kk, i);
+              acc -= rK[idx * E + le];
+            }
+            sK[stage_idx<D>(0, cb, i, kk) * E + le] = acc;
+            k00[kk][i] -= acc;  // K_00 = -sum_b K_0b^T
+          }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int kk = i; kk < D; ++kk) sK[stage_idx<D>(0, 0, i, kk) * E + le] = k00[i][kk];
+    }
+#endif
   } else {
 #pragma unroll
     for (int ca = 0; ca < K; ++ca)

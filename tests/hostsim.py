@@ -10,7 +10,10 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 BUILD = os.path.join(HERE, "_build")
-LIB = os.path.join(BUILD, "libskb_hostsim.so")
+# SKB_HOSTSIM_FLAGS="-DSKB_EXP_..." replays an A/B kernel variant (same switches as SKB_BUILD_FLAGS in build.py)
+_FLAGS = os.environ.get("SKB_HOSTSIM_FLAGS", "").split()
+_SUFFIX = "".join(c if c.isalnum() else "_" for c in "".join(_FLAGS))
+LIB = os.path.join(BUILD, "libskb_hostsim%s.so" % ("_" + _SUFFIX if _SUFFIX else ""))
 SRC = os.path.join(HERE, "host_harness.cu")
 CSRC = os.path.join(os.path.dirname(HERE), "simkit_b200", "csrc")
 
@@ -32,7 +35,7 @@ def load():
         os.makedirs(BUILD, exist_ok=True)
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         cmd = [nvcc, "-O1", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
-               "-gencode", "arch=compute_100a,code=sm_100a", "-Xcudafe", "--diag_suppress=177",
+               "-gencode", "arch=compute_100a,code=sm_100a", "-Xcudafe", "--diag_suppress=177"] + _FLAGS + [
                "-o", LIB, SRC]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
