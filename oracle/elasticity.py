@@ -212,6 +212,26 @@ def symmetric_stretch_map(t, dim):
     return sps.kron(sps.identity(t), sps.csc_matrix(S)), sps.kron(sps.identity(t), sps.csc_matrix(Si))
 
 
+def dirichlet_laplacian(X, T, mu=1, vector=False):
+    """dirichlet_laplacian.py:16-76: H = J^T diag(vol * mu) J; vector=False averages its dim per-coordinate blocks
+    into the (n, n) vertex Laplacian."""
+    X = np.asarray(X, dtype=np.float64)
+    t = np.asarray(T).shape[0]
+    mu = np.ones((t, 1)) * mu if np.isscalar(mu) else np.asarray(mu, dtype=np.float64).reshape(-1, 1)
+    assert mu.shape[0] == t
+    n, dim = X.shape
+    a = volume(X, T).reshape(-1, 1) * mu
+    J = deformation_jacobian(X, T)
+    H = (J.T @ sps.diags(np.repeat(a.ravel(), dim * dim)) @ J).tocsc()
+    if vector:
+        return H
+    L = sps.csc_matrix((n, n))
+    for i in range(dim):
+        Ii = np.arange(n) * dim + i
+        L = L + H[Ii, :][:, Ii]
+    return sps.csc_matrix(L / dim)
+
+
 def quadratic_energy(x, Q, b):
     """energies/quadratic.py:15-34: float(1/2 x^T Q x + b^T x)."""
     x = np.asarray(x, dtype=np.float64).reshape(-1, 1)

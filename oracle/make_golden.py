@@ -300,6 +300,9 @@ def golden_quadratic(tag, cells, seed):
     b = bd + 5.0 * rng.standard_normal((nv * dim, 1))
     x = U.reshape(-1, 1)
     assert qh(Q) is Q
+    mu_het = 1.0 + rng.random((T.shape[0], 1))
+    lap = dict(mu_het=mu_het, L_het=simkit.dirichlet_laplacian(X, T, mu_het).toarray(),
+               Lv_scalar=simkit.dirichlet_laplacian(X, T, 2.5, vector=True).toarray())
     out = dict(X=X, T=T, U=U, dim=dim, bI=bI, y=y, gamma=gamma, Qd=Qd.toarray(), bd=bd, Qs=Qs.toarray(), bs=bs,
                Q_data=Q.data, Q_indices=Q.indices, Q_indptr=Q.indptr, b=b, E=qe(x, Q, b), g=qg(x, Q, b))
     J = simkit.deformation_jacobian(X, T)
@@ -319,6 +322,7 @@ def golden_quadratic(tag, cells, seed):
 
     xn, info = ref_be(x, X.reshape(-1, 1), En, Gr, He, Md, h, max_iter=3, return_info=True)
     out.update(mu=mu, lam=lam, rho=rho, h=h, fg=fg, mass=Mv.diagonal(), be_x=xn, be_alphas=np.array(info["alphas"]))
+    out.update(lap)
     np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
     print("wrote", tag, "pinned", bI.size, "springs", len(edges), "alphas", info["alphas"])
 

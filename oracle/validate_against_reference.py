@@ -244,6 +244,10 @@ def main():
             Qo, bo = oe.dirichlet_penalty(bI, yq, nvq, gam)
             check(f"[{dim}D] dirichlet_penalty Q ({gname})", Qo.toarray(), Qr.toarray(), 1e-15)
             check(f"[{dim}D] dirichlet_penalty b ({gname})", bo, br, 1e-15)
+        mul = 1.0 + rng.random((T.shape[0], 1))
+        check(f"[{dim}D] dirichlet_laplacian", oe.dirichlet_laplacian(X, T, mul).toarray(), simkit.dirichlet_laplacian(X, T, mul).toarray(), 1e-13)
+        check(f"[{dim}D] dirichlet_laplacian (vector, scalar mu)", oe.dirichlet_laplacian(X, T, 2.5, vector=True).toarray(),
+              simkit.dirichlet_laplacian(X, T, 2.5, vector=True).toarray(), 1e-13)
         Ls = sps.random(nvq * dim, nvq * dim, density=0.02, random_state=3, format="csr")
         Qs = (Ls + Ls.T + Qr).tocsr()
         xq = rng.standard_normal((nvq * dim, 1))

@@ -8,6 +8,7 @@ package does not need a GPU; calling into it does, and fails loudly without one 
 from . import energies, integrators, solvers  # noqa: F401
 from .backtracking_line_search import backtracking_line_search  # noqa: F401
 from .deformation_jacobian import deformation_jacobian  # noqa: F401
+from .dirichlet_laplacian import dirichlet_laplacian  # noqa: F401
 from .dirichlet_penalty import dirichlet_penalty  # noqa: F401
 from .energies import *  # noqa: F401,F403
 from .fast_sandwich_transform_clustered import fast_sandwich_transform_clustered  # noqa: F401

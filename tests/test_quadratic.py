@@ -138,3 +138,44 @@ def test_gpu_quadratic(golden_dir, tag):
     with pytest.raises(ValueError):
         pot.plan.set_quadratic(Qbad, None)
     pot.plan.set_quadratic(None)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_dirichlet_laplacian(golden_dir, tag):
+    g, _ = load(golden_dir, tag)
+    X, T = g["X"], g["T"]
+    assert rel(oe.dirichlet_laplacian(X, T, g["mu_het"]).toarray(), g["L_het"]) < 1e-13
+    assert rel(oe.dirichlet_laplacian(X, T, 2.5, vector=True).toarray(), g["Lv_scalar"]) < 1e-13
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_dirichlet_laplacian_host_replay(golden_dir, tag):
+    """The route ``simkit_b200.dirichlet_laplacian`` takes on the GPU -- the constant linear-elasticity block with
+    ``lam = -mu``, no projection, coordinate blocks averaged -- replayed with the kernel phase functions on the host."""
+    import hostsim
+    g, _ = load(golden_dir, tag)
+    X, T, dim = g["X"], g["T"], int(g["dim"])
+    n = X.shape[0]
+    mu = g["mu_het"]
+    r = hostsim.run(X, T, 4, 0, X, mu, -mu)
+    H = hostsim.csr_from_blocks(r["bptr"], r["bcol"], r["vals"], n, dim).tocsc()
+    L = sum(H[np.arange(n) * dim + i, :][:, np.arange(n) * dim + i] for i in range(dim)) / dim
+    assert rel(L.toarray(), g["L_het"]) < 1e-13
+    # every coordinate block is the Laplacian on its own
+    for i in range(dim):
+        Ii = np.arange(n) * dim + i
+        assert rel(H[Ii, :][:, Ii].toarray(), g["L_het"]) < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", TAGS)
+def test_gpu_dirichlet_laplacian(golden_dir, tag):
+    import simkit_b200 as sk
+    g, _ = load(golden_dir, tag)
+    X, T = g["X"], g["T"]
+    L = sk.dirichlet_laplacian(X, T, g["mu_het"])
+    assert sps.issparse(L) and L.format == "csc" and L.shape == g["L_het"].shape and rel(L.toarray(), g["L_het"]) < 1e-12
+    Lv = sk.dirichlet_laplacian(X, T, 2.5, vector=True)
+    assert Lv.shape == g["Lv_scalar"].shape and rel(Lv.toarray(), g["Lv_scalar"]) < 1e-12
+    with pytest.raises(AssertionError):
+        sk.dirichlet_laplacian(X, T, np.ones(3))
