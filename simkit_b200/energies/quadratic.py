@@ -17,7 +17,7 @@ from .._lib import check, f64, ptr
 
 def _csr(Q, n):
     """(indptr, indices, vals) of ``Q`` as canonical int32 CSR (duplicates summed, sorted columns)."""
-    Qc = sp.sparse.csr_matrix(Q)
+    Qc = sp.sparse.csr_matrix(Q, copy=True)   # canonicalised below: the caller's matrix is left as it is
     if Qc.shape != (n, n):
         raise ValueError("Q must be (%d, %d), got %s" % (n, n, Qc.shape))
     Qc = Qc.astype(np.float64)
