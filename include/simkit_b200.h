@@ -182,6 +182,33 @@ int skb_dist_coarse_restrict_dev(skb_plan* plan, const double* r, double* rc, vo
 int skb_dist_coarse_correct_dev(skb_plan* plan, int v0, int v1, const double* Ainv, double* rc, double* zc,
                                 const double* r, double* z, double* p, double* scalars, int slot, double* work,
                                 void* stream);
+/* ---- opt-in: the distributed PCG driven from C++ with NCCL called directly (csrc/capi_nccl.cu) ----
+ * The sequence of skb_dist_* steps and NCCL calls that simkit_b200/sharding.py (Shard.pcg) issues from Python, as
+ * one C++ loop on the caller's stream: no reference counterpart (the reference solves on one CPU,
+ * solvers/newton.py:52).  NCCL is taken with dlopen from the libnccl.so.2 already in the process; the communicator is
+ * created from an id made on rank 0 (skb_nccl_unique_id, 128 bytes) that the caller broadcasts.  Pointer arrays are
+ * passed as int64 addresses (device pointers of the index lists and pack buffers of every neighbour). */
+int skb_nccl_unique_id(void* out, int64_t nbytes);
+int skb_nccl_init(skb_plan* plan, const void* id_bytes, int64_t nbytes, int rank, int world);
+int skb_nccl_set_halo(skb_plan* plan, int n_peers, const int32_t* peers, const int64_t* send_n, const int64_t* send_idx,
+                      const int64_t* send_buf, const int64_t* recv_n, const int64_t* recv_idx, const int64_t* recv_buf);
+int skb_nccl_finalize(skb_plan* plan);
+typedef struct skb_dist_pcg_args {
+  const double* vals;   /* CSR values of the owned rows (complete after the interface exchange)   */
+  const double* diag;   /* diagonal added to the matrix, or NULL                                  */
+  const double* rhs;
+  double* x;            /* solution (local numbering; owned entries are written)                  */
+  double *dinv, *r, *z, *p, *q;   /* work vectors of Shard._work()                                */
+  double* s;            /* >= 8 device scalars                                                    */
+  double* work;         /* >= 3 * 2048 doubles                                                    */
+  double *Ac, *rc, *zc; /* coarse buffers of Shard.set_coarse_space, or NULL (block-Jacobi only)   */
+  void* stream;
+  double rtol;
+  int32_t v0, v1;       /* owned vertex rows                                                       */
+  int32_t max_iter;
+  int32_t check_every;  /* iterations between host reads of r.r (default 10)                       */
+} skb_dist_pcg_args;
+int skb_dist_pcg_native(skb_plan* plan, const skb_dist_pcg_args* args, int32_t* iters, double* relres);
 /* measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the compute roofline denominator */
 int skb_fp64_peak(int device, double* tflops);
 /* measured FP64 tensor-core throughput (DMMA.8x8x4 = mma.sync.m8n8k4.f64, 512 flops per warp instruction):

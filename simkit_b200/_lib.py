@@ -48,6 +48,17 @@ class NewtonInfo(ctypes.Structure):
     ]
 
 
+class DistPcgArgs(ctypes.Structure):
+    """skb_dist_pcg_args (include/simkit_b200.h)."""
+    _fields_ = [
+        ("vals", _vp), ("diag", _vp), ("rhs", _vp), ("x", _vp),
+        ("dinv", _vp), ("r", _vp), ("z", _vp), ("p", _vp), ("q", _vp),
+        ("s", _vp), ("work", _vp), ("Ac", _vp), ("rc", _vp), ("zc", _vp), ("stream", _vp),
+        ("rtol", _dbl), ("v0", ctypes.c_int32), ("v1", ctypes.c_int32), ("max_iter", ctypes.c_int32),
+        ("check_every", ctypes.c_int32),
+    ]
+
+
 _MAT = [_vp, _i64, _vp, _i64, _vp, _i64]  # mu, mu_n, lam, lam_n, vol, vol_n
 
 SIGNATURES = {
@@ -108,6 +119,11 @@ SIGNATURES = {
     "skb_newton_set_contact_plane": (_int, [_vp, _dbl, _vp, _vp, _vp]),
     "skb_contact_springs_sphere": (_int, [_int, _i64, _vp, _dbl, _vp, _dbl, _vp, ctypes.POINTER(_dbl), _vp, _vp, _vp]),
     "skb_newton_set_contact_sphere": (_int, [_vp, _dbl, _vp, _dbl, _vp]),
+    "skb_nccl_unique_id": (_int, [_vp, _i64]),
+    "skb_nccl_init": (_int, [_vp, _vp, _i64, _int, _int]),
+    "skb_nccl_set_halo": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "skb_nccl_finalize": (_int, [_vp]),
+    "skb_dist_pcg_native": (_int, [_vp, ctypes.POINTER(DistPcgArgs), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_dbl)]),
     "skb_quadratic": (_int, [_i64, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_dbl), _vp]),
     "skb_newton_set_quadratic": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "skb_pcg_set_coarse": (_int, [_vp, _i64, _vp, _vp]),

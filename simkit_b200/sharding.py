@@ -24,6 +24,8 @@ Everything in :class:`ShardLayout` is host-side numpy and is unit-tested on CPU 
 including a world_size-2 gloo run); :class:`Shard` adds the device plan and the NCCL exchange.
 """
 
+import os
+
 import numpy as np
 
 
@@ -292,6 +294,55 @@ class Shard:
         for r, idx in sorted(vrecv.items()):
             check(lib.skb_scatter_dev(v_d.data_ptr(), idx.data_ptr(), idx.numel(), self._vrbuf[r].data_ptr(), st))
 
+    # ------------------------------------------------------------------ native NCCL driving (opt-in)
+    def enable_native_nccl(self):
+        """Drives the distributed PCG from C++ with NCCL called directly (``csrc/capi_nccl.cu``) instead of from this
+        module's Python loop: same kernels, same order -- the iterates agree to rounding (bit for bit at two ranks, where
+        the all-reduce has one summation order) -- without Python and torch.distributed between the steps.  Collective: every rank calls it.  The
+        library creates its own communicator from an id made on rank 0 and broadcast here.  Also switched on by
+        ``SKB_NATIVE_NCCL=1`` in ``make_shard``."""
+        import torch
+        import torch.distributed as dist
+        from ._lib import check, load, ptr
+        lib = load()
+        lay = self.layout
+        idbuf = np.zeros(128, dtype=np.uint8)
+        if lay.rank == 0:
+            check(lib.skb_nccl_unique_id(ptr(idbuf), idbuf.size))
+        t = torch.from_numpy(idbuf).to(self.device)
+        dist.broadcast(t, 0)
+        idbuf = np.ascontiguousarray(t.cpu().numpy())
+        check(lib.skb_nccl_init(self.plan._h, ptr(idbuf), idbuf.size, lay.rank, lay.world))
+        vsend, vrecv = self._vector_lists()
+        peers = sorted(set(vsend) | set(vrecv))
+        i64 = lambda f: np.array([f(r) for r in peers], dtype=np.int64)  # noqa: E731
+        arrs = (np.array(peers, dtype=np.int32),
+                i64(lambda r: vsend[r].numel() if r in vsend else 0),
+                i64(lambda r: vsend[r].data_ptr() if r in vsend else 0),
+                i64(lambda r: self._vsbuf[r].data_ptr() if r in vsend else 0),
+                i64(lambda r: vrecv[r].numel() if r in vrecv else 0),
+                i64(lambda r: vrecv[r].data_ptr() if r in vrecv else 0),
+                i64(lambda r: self._vrbuf[r].data_ptr() if r in vrecv else 0))
+        check(lib.skb_nccl_set_halo(self.plan._h, len(peers), *[ptr(a) for a in arrs]))
+        self._native = True
+
+    def _pcg_native(self, vals_d, diag_d, rhs_d, x_d, rtol, max_iter, check_every):
+        import ctypes
+        import torch
+        from ._lib import DistPcgArgs, check, load
+        lib = load()
+        w = self._work()
+        P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        c = self.coarse
+        a = DistPcgArgs(P(vals_d), P(diag_d), P(rhs_d), P(x_d), P(w["dinv"]), P(w["r"]), P(w["z"]), P(w["p"]), P(w["q"]),
+                        P(w["s"]), P(w["work"]), None if c is None else P(c["Ac"]), None if c is None else P(c["rc"]),
+                        None if c is None else P(c["zc"]), torch.cuda.current_stream().cuda_stream, float(rtol),
+                        int(self.layout.own_lo), int(self.layout.own_hi), int(max_iter), int(check_every))
+        iters = ctypes.c_int32(0)
+        relres = ctypes.c_double(0.0)
+        check(lib.skb_dist_pcg_native(self.plan._h, ctypes.byref(a), ctypes.byref(iters), ctypes.byref(relres)))
+        return int(iters.value), float(relres.value)
+
     # ------------------------------------------------------------------ distributed PCG / Newton
     def _work(self):
         if not hasattr(self, "_w"):
@@ -373,6 +424,8 @@ class Shard:
     def pcg(self, vals_d, diag_d, rhs_d, x_d, rtol=1e-10, max_iter=20000, check_every=10):
         """Block-Jacobi PCG on the distributed matrix (owned rows per rank, complete after the interface exchange).
         Per iteration: halo exchange of p, SpMV + p.q, all-reduce, fused update, all-reduce, direction."""
+        if getattr(self, "_native", False):
+            return self._pcg_native(vals_d, diag_d, rhs_d, x_d, rtol, max_iter, check_every)
         import torch
         import torch.distributed as dist
         from ._lib import check, load
@@ -558,4 +611,6 @@ def make_shard(workload, rank, world, device=0, tile_elems=0, sigma=0.1):
     sh.U_local = syn.jittered_state_rows(cfg["cells"], cfg["extent"], lay.l2g, sigma=sigma)
     sh.t_total, sh.n_total = lay.t_total, lay.n_total
     sh.nnz_total = None
+    if os.environ.get("SKB_NATIVE_NCCL", "") == "1":
+        sh.enable_native_nccl()
     return sh

@@ -102,3 +102,22 @@ def test_host_logic_line_search_and_newton_on_quadratic():
     assert t == 0.0 and x is x0
     with pytest.raises(AssertionError):
         sk.backtracking_line_search(f, x0, g, dx, alpha=0.9)
+
+
+def test_native_nccl_plumbing():
+    """capi_nccl.cu takes NCCL with dlopen(RTLD_NOLOAD) from the process (torch's copy): the argument block has the
+    layout the C side asserts, and an id can be made without a GPU once torch is imported."""
+    import ctypes
+    import numpy as np
+    import torch  # noqa: F401  (loads libnccl.so.2)
+    from simkit_b200 import _lib
+    assert ctypes.sizeof(_lib.DistPcgArgs) == 144
+    lib = _lib.load(require_gpu=False)
+    idbuf = np.zeros(128, dtype=np.uint8)
+    rc = lib.skb_nccl_unique_id(_lib.ptr(idbuf), idbuf.size)
+    if rc != 0:   # a torch build with NCCL linked statically: the native path reports it instead of loading another NCCL
+        assert b"libnccl.so.2" in lib.skb_last_error()
+        return
+    assert idbuf.any()
+    assert lib.skb_nccl_unique_id(_lib.ptr(idbuf), 64) != 0          # buffer too small
+    assert lib.skb_nccl_set_halo(None, 0, None, None, None, None, None, None, None) != 0   # no plan / no communicator

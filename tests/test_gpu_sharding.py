@@ -150,3 +150,61 @@ def test_distributed_newton_matches_single_gpu(tmp_path):
         # two-level preconditioner: same iterate, fewer CG iterations
         assert rel(d["x2"], x1.ravel()[lo:hi]) < 1e-8 and list(d["alphas2"]) == list(info["alphas"])
         assert 1 < int(d["n_agg"]) <= 16 and int(d["its2"]) < int(d["its"])
+
+
+# ------------------------------------------------------------------ 2 GPUs: the same PCG driven natively (capi_nccl.cu)
+def _nccl_native_worker(rank, world, port, cells, tmp):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dim = len(cells)
+    extent = tuple(1.0 for _ in cells)
+    lay = sh.layout_grid_slab(cells, rank, world)
+    shard = sh.Shard(lay, syn.grid_vertices(cells, extent, lay.l2g), device=rank, tile_elems=32)
+    U = syn.jittered_state_rows(cells, extent, lay.l2g, sigma=0.2)
+    mu, lam = syn.lame()
+    shard.set_materials(mu, lam)
+    rho, h = 1e3, 1e-2
+    x_d = torch.from_numpy(U.reshape(-1).copy()).to(dev)
+    mass_d = shard.lumped_mass_dofs(rho)
+    fext_d = torch.zeros(lay.n_local, dim, dtype=torch.float64, device=dev)
+    fext_d[:, 1] = -9.8
+    fext_d = fext_d.reshape(-1) * mass_d
+    kw = dict(x_tilde_d=x_d, mass_d=mass_d, kin_scale=1.0 / h ** 2, fext_d=fext_d, max_iter=3, pcg_rtol=1e-12)
+    out = {}
+    for tag, native, n_agg in (("py", False, 0), ("py_c", False, 12), ("nat", True, 0), ("nat_c", True, 12)):
+        if native and not getattr(shard, "_native", False):
+            shard.enable_native_nccl()
+        shard.set_coarse_space(n_agg)
+        xs = x_d.clone()
+        info = shard.newton_step(MAT, xs, **kw)
+        o0, o1 = lay.own_lo * dim, lay.own_hi * dim
+        out["x_" + tag] = xs.cpu().numpy()[o0:o1]
+        out["its_" + tag] = info["pcg_iters"]
+        out["alphas_" + tag] = np.asarray(info["alphas"])
+    np.savez(os.path.join(tmp, "native%d.npz" % rank), **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_native_nccl_pcg_matches_python_loop(tmp_path):
+    """The C++-driven distributed PCG (own NCCL communicator, no Python between the steps) runs the same kernels in the
+    same order as Shard.pcg: same iteration counts and line-search steps, iterates equal to rounding."""
+    import os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    cells, world = (8, 5, 5), 2
+    port = 29600 + ((os.getpid() + 17) % 1000)
+    mp.spawn(_nccl_native_worker, args=(world, port, cells, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        d = np.load(os.path.join(str(tmp_path), "native%d.npz" % r))
+        for a, b in (("py", "nat"), ("py_c", "nat_c")):
+            assert int(d["its_" + a]) == int(d["its_" + b]) and list(d["alphas_" + a]) == list(d["alphas_" + b])
+            assert rel(d["x_" + b], d["x_" + a]) < 1e-12
