@@ -207,6 +207,8 @@ typedef struct skb_dist_pcg_args {
   int32_t v0, v1;       /* owned vertex rows                                                       */
   int32_t max_iter;
   int32_t check_every;  /* iterations between host reads of r.r (default 10)                       */
+  int32_t use_graph;    /* 1: full chunks of check_every iterations replay one CUDA graph (captured */
+  int32_t reserved;     /*    on the plan's own stream after the first, eager chunk)               */
 } skb_dist_pcg_args;
 int skb_dist_pcg_native(skb_plan* plan, const skb_dist_pcg_args* args, int32_t* iters, double* relres);
 /* measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the compute roofline denominator */

@@ -6,9 +6,11 @@ TAG=${1:-r02b}
 N=${2:-2}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_sharding.py -m gpu -x -q > gpurun_out/${TAG}_pytest_n2.log 2>&1; tail -5 gpurun_out/${TAG}_pytest_n2.log
-for mode in python native; do
-  if [ $mode = native ]; then export SKB_NATIVE_NCCL=1; else unset SKB_NATIVE_NCCL; fi
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+for mode in python native graph; do
+  unset SKB_NATIVE_NCCL
+  [ $mode = native ] && export SKB_NATIVE_NCCL=1
+  [ $mode = graph ] && export SKB_NATIVE_NCCL=2
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
       bench.py --gpus $N --no-cpu > gpurun_out/${TAG}_bench_n${N}_$mode.json 2> gpurun_out/${TAG}_bench_n${N}_$mode.err
   python - <<PY
 import json

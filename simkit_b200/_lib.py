@@ -55,7 +55,7 @@ class DistPcgArgs(ctypes.Structure):
         ("dinv", _vp), ("r", _vp), ("z", _vp), ("p", _vp), ("q", _vp),
         ("s", _vp), ("work", _vp), ("Ac", _vp), ("rc", _vp), ("zc", _vp), ("stream", _vp),
         ("rtol", _dbl), ("v0", ctypes.c_int32), ("v1", ctypes.c_int32), ("max_iter", ctypes.c_int32),
-        ("check_every", ctypes.c_int32),
+        ("check_every", ctypes.c_int32), ("use_graph", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 

@@ -29,7 +29,7 @@
 
 using namespace skb;
 
-static_assert(sizeof(skb_dist_pcg_args) == 144, "skb_dist_pcg_args layout (mirrored by ctypes in simkit_b200/_lib.py)");
+static_assert(sizeof(skb_dist_pcg_args) == 152, "skb_dist_pcg_args layout (mirrored by ctypes in simkit_b200/_lib.py)");
 
 #if defined(SKB_HAVE_NCCL_H)
 namespace {
@@ -233,8 +233,18 @@ int skb_dist_pcg_native(skb_plan* pl, const skb_dist_pcg_args* a, int32_t* iters
     return fail(SKB_EINVAL, "null work vector");
   SKB_CUDA(cudaSetDevice(pl->device));
   SKB_TRY
-  cudaStream_t st = (cudaStream_t)a->stream;
-  void* sp = a->stream;
+  // graph mode: everything runs on the plan's own (capturable, non-default) stream, ordered after the caller's
+  // stream on entry and before it on exit
+  const bool use_graph = a->use_graph != 0;
+  cudaStream_t caller = (cudaStream_t)a->stream;
+  cudaStream_t st = use_graph ? pl->stream : caller;
+  void* sp = (void*)st;
+  cudaEvent_t ev = nullptr;
+  if (use_graph) {
+    SKB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    SKB_CUDA(cudaEventRecord(ev, caller));
+    SKB_CUDA(cudaStreamWaitEvent(st, ev, 0));
+  }
   const int v0 = a->v0, v1 = a->v1;
   double* s = a->s;
   int rc;
@@ -247,6 +257,17 @@ int skb_dist_pcg_native(skb_plan* pl, const skb_dist_pcg_args* a, int32_t* iters
     r2 = all_reduce(d, a->rc, nc, st);
     if (r2) return r2;
     return skb_dist_coarse_correct_dev(pl, v0, v1, a->Ac, a->rc, a->zc, a->r, a->z, pvec, s, slot, a->work, sp);
+  };
+  // one CG iteration: halo exchange of p, SpMV + p.q, all-reduce, fused update, [coarse correction], all-reduce, direction
+  auto iteration = [&]() -> int {
+    int r2;
+    if ((r2 = halo_exchange(d, a->p, st))) return r2;
+    if ((r2 = skb_dist_spmv_dot_dev(pl, a->vals, a->diag, v0, v1, a->p, a->q, s, a->work, sp))) return r2;
+    if ((r2 = all_reduce(d, s + 2, 1, st))) return r2;
+    if ((r2 = skb_dist_pcg_update_dev(pl, v0, v1, a->dinv, a->p, a->q, a->x, a->r, a->z, s, a->work, sp))) return r2;
+    if (coarse && (r2 = coarse_correct(nullptr, 3))) return r2;
+    if ((r2 = all_reduce(d, s + 3, 2, st))) return r2;
+    return skb_dist_pcg_direction_dev(pl, v0, v1, a->z, a->p, s, sp);
   };
   if (coarse) {
     // coarse matrix of this system: owned fine blocks per rank, summed over the ranks, inverted by every rank
@@ -263,27 +284,50 @@ int skb_dist_pcg_native(skb_plan* pl, const skb_dist_pcg_args* a, int32_t* iters
   const double bb = h2[1];
   *iters = 0;
   *relres = 0.0;
-  if (!(bb > 0.0)) return SKB_OK;
   const int every = a->check_every > 0 ? a->check_every : 10;
   int it = 0;
   double rr = bb;
-  while (it < a->max_iter) {
+  cudaGraphExec_t gexec = nullptr;
+  while (bb > 0.0 && it < a->max_iter) {
     const int nrun = (a->max_iter - it) < every ? (a->max_iter - it) : every;
-    for (int k = 0; k < nrun; ++k) {
-      if ((rc = halo_exchange(d, a->p, st))) return rc;
-      if ((rc = skb_dist_spmv_dot_dev(pl, a->vals, a->diag, v0, v1, a->p, a->q, s, a->work, sp))) return rc;
-      if ((rc = all_reduce(d, s + 2, 1, st))) return rc;
-      if ((rc = skb_dist_pcg_update_dev(pl, v0, v1, a->dinv, a->p, a->q, a->x, a->r, a->z, s, a->work, sp))) return rc;
-      if (coarse && (rc = coarse_correct(nullptr, 3))) return rc;
-      if ((rc = all_reduce(d, s + 3, 2, st))) return rc;
-      if ((rc = skb_dist_pcg_direction_dev(pl, v0, v1, a->z, a->p, s, sp))) return rc;
-      ++it;
+    if (use_graph && it > 0 && nrun == every) {
+      // the first chunk ran eagerly (NCCL has set up its peer connections); full chunks from here on replay one graph
+      if (!gexec) {
+        const bool timing = pl->timing;
+        pl->timing = false;   // no event records inside the capture
+        cudaGraph_t graph = nullptr;
+        SKB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        rc = SKB_OK;
+        for (int k = 0; k < nrun && rc == SKB_OK; ++k) rc = iteration();
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);   // always ends the capture, also after a failed step
+        pl->timing = timing;
+        if (rc) {
+          if (graph) cudaGraphDestroy(graph);
+          return rc;
+        }
+        if (ce != cudaSuccess) return fail(SKB_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+        const cudaError_t ci = cudaGraphInstantiate(&gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ci != cudaSuccess) return fail(SKB_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ci));
+      }
+      SKB_CUDA(cudaGraphLaunch(gexec, st));
+    } else {
+      for (int k = 0; k < nrun; ++k)
+        if ((rc = iteration())) return rc;
     }
+    it += nrun;
     SKB_CUDA(cudaMemcpyAsync(h2, s, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     SKB_CUDA(cudaStreamSynchronize(st));
     rr = h2[1];
     if (!(rr > a->rtol * a->rtol * bb)) break;
   }
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (use_graph) {
+    SKB_CUDA(cudaEventRecord(ev, st));
+    SKB_CUDA(cudaStreamWaitEvent(caller, ev, 0));
+    cudaEventDestroy(ev);
+  }
+  if (!(bb > 0.0)) return SKB_OK;
   *iters = it;
   *relres = sqrt(rr / bb);
   return SKB_OK;

@@ -295,12 +295,12 @@ class Shard:
             check(lib.skb_scatter_dev(v_d.data_ptr(), idx.data_ptr(), idx.numel(), self._vrbuf[r].data_ptr(), st))
 
     # ------------------------------------------------------------------ native NCCL driving (opt-in)
-    def enable_native_nccl(self):
+    def enable_native_nccl(self, graph=False):
         """Drives the distributed PCG from C++ with NCCL called directly (``csrc/capi_nccl.cu``) instead of from this
         module's Python loop: same kernels, same order -- the iterates agree to rounding (bit for bit at two ranks, where
         the all-reduce has one summation order) -- without Python and torch.distributed between the steps.  Collective: every rank calls it.  The
         library creates its own communicator from an id made on rank 0 and broadcast here.  Also switched on by
-        ``SKB_NATIVE_NCCL=1`` in ``make_shard``."""
+        ``SKB_NATIVE_NCCL=1`` in ``make_shard`` (``=2`` / ``graph=True``: CUDA-graph replay of the iterations)."""
         import torch
         import torch.distributed as dist
         from ._lib import check, load, ptr
@@ -325,6 +325,7 @@ class Shard:
                 i64(lambda r: self._vrbuf[r].data_ptr() if r in vrecv else 0))
         check(lib.skb_nccl_set_halo(self.plan._h, len(peers), *[ptr(a) for a in arrs]))
         self._native = True
+        self._native_graph = bool(graph)   # full chunks of `check_every` iterations replay one CUDA graph
 
     def _pcg_native(self, vals_d, diag_d, rhs_d, x_d, rtol, max_iter, check_every):
         import ctypes
@@ -337,7 +338,8 @@ class Shard:
         a = DistPcgArgs(P(vals_d), P(diag_d), P(rhs_d), P(x_d), P(w["dinv"]), P(w["r"]), P(w["z"]), P(w["p"]), P(w["q"]),
                         P(w["s"]), P(w["work"]), None if c is None else P(c["Ac"]), None if c is None else P(c["rc"]),
                         None if c is None else P(c["zc"]), torch.cuda.current_stream().cuda_stream, float(rtol),
-                        int(self.layout.own_lo), int(self.layout.own_hi), int(max_iter), int(check_every))
+                        int(self.layout.own_lo), int(self.layout.own_hi), int(max_iter), int(check_every),
+                        1 if getattr(self, "_native_graph", False) else 0, 0)
         iters = ctypes.c_int32(0)
         relres = ctypes.c_double(0.0)
         check(lib.skb_dist_pcg_native(self.plan._h, ctypes.byref(a), ctypes.byref(iters), ctypes.byref(relres)))
@@ -611,6 +613,6 @@ def make_shard(workload, rank, world, device=0, tile_elems=0, sigma=0.1):
     sh.U_local = syn.jittered_state_rows(cfg["cells"], cfg["extent"], lay.l2g, sigma=sigma)
     sh.t_total, sh.n_total = lay.t_total, lay.n_total
     sh.nnz_total = None
-    if os.environ.get("SKB_NATIVE_NCCL", "") == "1":
-        sh.enable_native_nccl()
+    if os.environ.get("SKB_NATIVE_NCCL", "") in ("1", "2"):      # 2: with CUDA-graph replay of the iterations
+        sh.enable_native_nccl(graph=os.environ["SKB_NATIVE_NCCL"] == "2")
     return sh

@@ -111,7 +111,7 @@ def test_native_nccl_plumbing():
     import numpy as np
     import torch  # noqa: F401  (loads libnccl.so.2)
     from simkit_b200 import _lib
-    assert ctypes.sizeof(_lib.DistPcgArgs) == 144
+    assert ctypes.sizeof(_lib.DistPcgArgs) == 152
     lib = _lib.load(require_gpu=False)
     idbuf = np.zeros(128, dtype=np.uint8)
     rc = lib.skb_nccl_unique_id(_lib.ptr(idbuf), idbuf.size)

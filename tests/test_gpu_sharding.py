@@ -177,9 +177,11 @@ def _nccl_native_worker(rank, world, port, cells, tmp):
     fext_d = fext_d.reshape(-1) * mass_d
     kw = dict(x_tilde_d=x_d, mass_d=mass_d, kin_scale=1.0 / h ** 2, fext_d=fext_d, max_iter=3, pcg_rtol=1e-12)
     out = {}
-    for tag, native, n_agg in (("py", False, 0), ("py_c", False, 12), ("nat", True, 0), ("nat_c", True, 12)):
+    for tag, native, n_agg, graph in (("py", False, 0, False), ("py_c", False, 12, False), ("nat", True, 0, False),
+                                      ("nat_c", True, 12, False), ("natg", True, 0, True), ("natg_c", True, 12, True)):
         if native and not getattr(shard, "_native", False):
             shard.enable_native_nccl()
+        shard._native_graph = graph          # full chunks of 10 iterations replay one CUDA graph
         shard.set_coarse_space(n_agg)
         xs = x_d.clone()
         info = shard.newton_step(MAT, xs, **kw)
@@ -205,6 +207,6 @@ def test_native_nccl_pcg_matches_python_loop(tmp_path):
     mp.spawn(_nccl_native_worker, args=(world, port, cells, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         d = np.load(os.path.join(str(tmp_path), "native%d.npz" % r))
-        for a, b in (("py", "nat"), ("py_c", "nat_c")):
+        for a, b in (("py", "nat"), ("py_c", "nat_c"), ("py", "natg"), ("py_c", "natg_c")):
             assert int(d["its_" + a]) == int(d["its_" + b]) and list(d["alphas_" + a]) == list(d["alphas_" + b])
             assert rel(d["x_" + b], d["x_" + a]) < 1e-12
