@@ -20,7 +20,7 @@
 #include <map>
 #include <mutex>
 
-#if defined(__has_include)
+#if defined(__has_include) && !defined(SKB_NO_NCCL)
 #if __has_include(<nccl.h>)
 #include <nccl.h>
 #define SKB_HAVE_NCCL_H 1
