@@ -156,7 +156,7 @@ static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
   }
   if (a.want_hess) {
     SKB_LAUNCH(pl, SKB_K_FINALIZE_BLOCKS, st,
-               finalize_blocks_kernel<D><<<(p.nu * D * D + SKB_FIN_THREADS - 1) / SKB_FIN_THREADS, SKB_FIN_THREADS, 0, st>>>(p, a.pblocks, a.vals));
+               finalize_blocks_kernel<D><<<(p.nu * D * D + SKB_FIN_THREADS * SKB_FIN_PER_THREAD - 1) / (SKB_FIN_THREADS * SKB_FIN_PER_THREAD), SKB_FIN_THREADS, 0, st>>>(p, a.pblocks, a.vals));
   }
   if (a.want_grad) {
     SKB_LAUNCH(pl, SKB_K_FINALIZE_VERTS, st,

@@ -579,6 +579,47 @@ SKB_HD void block_finalize(const PlanView& p, int item, const double* pblocks, d
   if (up.tbase != up.base) SKB_FIN_ST(vals + (size_t)up.tbase + (size_t)k * up.tstride + i, acc);
 }
 
+// A/B experiment (-DSKB_FIN_ITEMS=N): N items per thread, `stride` apart, with the loads of every stage requested
+// for all N items before the first dependent use: level 2 is a chain of dependent round trips (slot pointers and
+// position -> records -> stores) and one item per thread leaves the memory system under-subscribed at 40
+// registers.  Same summation order per item as block_finalize => bit-identical values.
+template <int D, int N>
+SKB_HD void block_finalize_multi(const PlanView& p, int item0, int stride, int n_items, const double* pblocks, double* vals) {
+  constexpr int RS = RecStride<D>::value;
+  int j[N], q0[N], nq[N];
+  UpperPos up[N];
+  bool live[N];
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    const int item = item0 + t * stride;
+    live[t] = item < n_items;
+    const int u = live[t] ? item / (D * D) : 0;
+    j[t] = live[t] ? item - u * (D * D) : 0;
+    q0[t] = p.blocks.sp_ptr[u];
+    nq[t] = live[t] ? p.blocks.sp_ptr[u + 1] - q0[t] : 0;
+    up[t] = p.upos[u];
+  }
+  double v[N][4];
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    const double* r0 = pblocks + (size_t)q0[t] * RS + j[t];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[t][k] = (nq[t] > k) ? r0[k * RS] : 0.0;
+  }
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    if (!live[t]) continue;
+    double acc = v[t][0];
+    if (nq[t] > 1) acc += v[t][1];
+    if (nq[t] > 2) acc += v[t][2];
+    if (nq[t] > 3) acc += v[t][3];
+    for (int q = q0[t] + 4; q < q0[t] + nq[t]; ++q) acc += pblocks[(size_t)q * RS + j[t]];
+    const int i = j[t] / D, k = j[t] - i * D;
+    vals[(size_t)up[t].base + (size_t)i * up[t].stride + k] = acc;
+    if (up[t].tbase != up[t].base) vals[(size_t)up[t].tbase + (size_t)k * up[t].tstride + i] = acc;
+  }
+}
+
 template <int D>
 SKB_HD void vert_finalize(const PlanView& p, int v, const double* pverts, double* g) {
   double acc[D];
@@ -870,10 +911,20 @@ __global__ void SKB_PIPE_BOUNDS(G, E) assemble_pipelined_kernel(PlanView p, Eval
 #ifndef SKB_FIN_THREADS
 #define SKB_FIN_THREADS 128
 #endif
+#if defined(SKB_FIN_ITEMS)
+#define SKB_FIN_PER_THREAD SKB_FIN_ITEMS
+#else
+#define SKB_FIN_PER_THREAD 1
+#endif
 template <int D>
 __global__ void finalize_blocks_kernel(PlanView p, const double* pblocks, double* vals) {
+#if defined(SKB_FIN_ITEMS)
+  block_finalize_multi<D, SKB_FIN_ITEMS>(p, blockIdx.x * (blockDim.x * SKB_FIN_ITEMS) + threadIdx.x, blockDim.x,
+                                         p.nu * (D * D), pblocks, vals);
+#else
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item < p.nu * (D * D)) block_finalize<D>(p, item, pblocks, vals);
+#endif
 }
 
 template <int D>

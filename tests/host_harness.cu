@@ -36,8 +36,17 @@ static void run_assemble(const PlanView& p, const EvalArgs& a, std::vector<doubl
                        a.pverts);
     }
   }
+#if defined(SKB_FIN_ITEMS)
+  if (a.want_hess) {   // the A/B variant's thread grid: blocks of 128 threads, SKB_FIN_ITEMS items per thread
+    const int n_items = p.nu * D * D, T = 128;
+    for (int blk = 0; blk * T * SKB_FIN_ITEMS < n_items; ++blk)
+      for (int th = 0; th < T; ++th)
+        block_finalize_multi<D, SKB_FIN_ITEMS>(p, blk * (T * SKB_FIN_ITEMS) + th, T, n_items, a.pblocks, a.vals);
+  }
+#else
   if (a.want_hess)
     for (int item = 0; item < p.nu * D * D; ++item) block_finalize<D>(p, item, a.pblocks, a.vals);
+#endif
   if (a.want_grad)
     for (int v = 0; v < p.n; ++v) vert_finalize<D>(p, v, a.pverts, a.g);
   double s = 0.0;
