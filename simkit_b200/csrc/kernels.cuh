@@ -461,14 +461,21 @@ SKB_HD void block_phase2(const SchedEntry* ent, const uint16_t* src, int w, int 
   double acc[DD];
   int c = (int)(en.range & 0xffffu);
   const int c1 = (int)(en.range >> 16);
-  if (pair_is_diag<D>((int)(src[c] >> 8))) {
+#if defined(SKB_EXP_SRCBASE)   // the schedule carries (diag flag | staging offset of the pair), see ScatterSrc
+#define SKB_P2_IS_DIAG(sc) (((sc) >> 15) != 0)
+#define SKB_P2_BASE(sc) ((int)(((sc) >> 8) & 0x7fu))
+#else
+#define SKB_P2_IS_DIAG(sc) pair_is_diag<D>((int)((sc) >> 8))
+#define SKB_P2_BASE(sc) pair_base<D>((int)((sc) >> 8))
+#endif
+  if (SKB_P2_IS_DIAG((unsigned)src[c])) {
     double sa[DS];
 #pragma unroll
     for (int k = 0; k < DS; ++k) sa[k] = 0.0;
 #pragma unroll kP2Unroll
     for (; c < c1; ++c) {
       const unsigned sc = src[c];
-      const double* base = sK + pair_base<D>((int)(sc >> 8)) * E + (int)(sc & 0xffu);
+      const double* base = sK + SKB_P2_BASE(sc) * E + (int)(sc & 0xffu);
       double v[DS];
 #pragma unroll
       for (int k = 0; k < DS; ++k) v[k] = base[k * E];
@@ -488,7 +495,7 @@ SKB_HD void block_phase2(const SchedEntry* ent, const uint16_t* src, int w, int 
 #pragma unroll kP2Unroll
     for (; c < c1; ++c) {
       const unsigned sc = src[c];
-      const double* base = sK + pair_base<D>((int)(sc >> 8)) * E + (int)(sc & 0xffu);
+      const double* base = sK + SKB_P2_BASE(sc) * E + (int)(sc & 0xffu);
       double v[DD];
 #pragma unroll
       for (int k = 0; k < DD; ++k) v[k] = base[k * E];

@@ -252,6 +252,10 @@ struct TileQKey {
   }
 };
 // writes the packed source of the i-th contribution (tile-major order) at its fixed-stride position
+#if defined(SKB_EXP_SRCBASE)
+template <int D> SKB_HD int pair_base(int pp);       // kernels.cuh (staging layout)
+template <int D> SKB_HD bool pair_is_diag(int pp);
+#endif
 struct ScatterSrc {
   const int* c;  // contribution ids, tile-major
   uint16_t* tc_src;
@@ -263,7 +267,16 @@ struct ScatterSrc {
     const int rem = c[i] - e * per_elem;
     const int tile = e / tile_elems;
     // every tile before `tile` is full, so position i is tile * tile_stride + local offset
+#if defined(SKB_EXP_SRCBASE)
+    // A/B experiment: block schedules carry the staging offset of the pair (7 bits) and its diagonal flag (bit 15)
+    // instead of the pair index, so phase 2 neither recomputes pair_base nor tests pair_is_diag per contribution
+    int hi = rem;
+    if (per_elem == 10) hi = pair_base<3>(rem) | (pair_is_diag<3>(rem) ? 0x80 : 0);
+    else if (per_elem == 6) hi = pair_base<2>(rem) | (pair_is_diag<2>(rem) ? 0x80 : 0);
+    tc_src[i] = (uint16_t)((hi << 8) | (e - tile * tile_elems));
+#else
     tc_src[i] = (uint16_t)((rem << 8) | (e - tile * tile_elems));
+#endif
     (void)tile_stride;
   }
 };
