@@ -9,7 +9,7 @@
 #    corner-0 pairs by read-back (sum0), elements listed in 3x3-cell pencils (pencil), both together.
 TAG=${1:-r02a}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_quadratic.py tests/test_reference_properties.py -m gpu -q > gpurun_out/${TAG}_pytest_new.log 2>&1; tail -5 gpurun_out/${TAG}_pytest_new.log
+timeout 900 python -m pytest tests/test_zz_quadratic.py tests/test_reference_properties.py -m gpu -q > gpurun_out/${TAG}_pytest_new.log 2>&1; tail -5 gpurun_out/${TAG}_pytest_new.log
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -3 gpurun_out/${TAG}_pytest_gpu.log
 timeout 900 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 1500 gpurun_out/${TAG}_bench.json
 TAGS="main"
