@@ -103,43 +103,6 @@ def test_value_positions_host_replay(golden_dir, tag):
         assert (hostsim.value_positions(r["bptr"], r["bcol"], out_r[:50], out_c[:50], dim) == -1).all()
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("tag", TAGS)
-def test_gpu_quadratic(golden_dir, tag):
-    import simkit_b200 as sk
-    g, Q = load(golden_dir, tag)
-    X, T, U, dim = g["X"], g["T"], g["U"], int(g["dim"])
-    b = g["b"]
-    x = U.reshape(-1, 1)
-    E = sk.quadratic_energy(x, Q, b)
-    assert isinstance(E, float) and abs(E - float(g["E"])) <= 1e-12 * abs(float(g["E"]))
-    gr = sk.quadratic_gradient(x, Q, b)
-    assert gr.shape == g["g"].shape and rel(gr, g["g"]) < 1e-12
-    assert rel(sk.quadratic_gradient(x, Q.toarray(), b), g["g"]) < 1e-12      # dense Q, as the reference accepts
-    assert sk.quadratic_hessian(Q) is Q
-    # backward Euler with the term: device-resident step (ElasticPotential) and the host-callable path
-    mu, lam, h = float(g["mu"]), float(g["lam"]), float(g["h"])
-    Md = sps.kron(sps.diags(g["mass"]), sps.identity(dim)).tocsc()
-    pot = sk.ElasticPotential("stable_neo_hookean", mu, lam, X=X, T=T, f_ext=g["fg"], quadratic=(Q, b))
-    x_prev = X.reshape(-1, 1)
-    x1, info = sk.backward_euler(x, x_prev, pot.energy, pot.gradient, pot.hessian, Md, h, max_iter=3, return_info=True,
-                                 pcg_rtol=1e-13)
-    assert list(info["alphas"]) == list(g["be_alphas"]) and rel(x1, g["be_x"]) < 1e-8
-    x2 = sk.backward_euler(x, x_prev, lambda v: pot.energy(v), lambda v: pot.gradient(v), lambda v: pot.hessian(v), Md, h,
-                           max_iter=3, pcg_rtol=1e-13)
-    assert rel(x2, g["be_x"]) < 1e-8
-    # a second step reuses the uploaded term
-    x3 = sk.backward_euler(x, x_prev, pot.energy, pot.gradient, pot.hessian, Md, h, max_iter=3, pcg_rtol=1e-13)
-    assert rel(x3, g["be_x"]) < 1e-8
-    # entries outside the mesh's CSR pattern are refused
-    nd = X.shape[0] * dim
-    far = int(np.argmax(np.linalg.norm(X - X[0], axis=1)))
-    Qbad = sps.csr_matrix(([1.0, 1.0], ([0, far * dim], [far * dim, 0])), shape=(nd, nd))
-    with pytest.raises(ValueError):
-        pot.plan.set_quadratic(Qbad, None)
-    pot.plan.set_quadratic(None)
-
-
 @pytest.mark.parametrize("tag", TAGS)
 def test_oracle_dirichlet_laplacian(golden_dir, tag):
     g, _ = load(golden_dir, tag)
@@ -179,3 +142,40 @@ def test_gpu_dirichlet_laplacian(golden_dir, tag):
     assert Lv.shape == g["Lv_scalar"].shape and rel(Lv.toarray(), g["Lv_scalar"]) < 1e-12
     with pytest.raises(AssertionError):
         sk.dirichlet_laplacian(X, T, np.ones(3))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", TAGS)
+def test_gpu_quadratic(golden_dir, tag):
+    import simkit_b200 as sk
+    g, Q = load(golden_dir, tag)
+    X, T, U, dim = g["X"], g["T"], g["U"], int(g["dim"])
+    b = g["b"]
+    x = U.reshape(-1, 1)
+    E = sk.quadratic_energy(x, Q, b)
+    assert isinstance(E, float) and abs(E - float(g["E"])) <= 1e-12 * abs(float(g["E"]))
+    gr = sk.quadratic_gradient(x, Q, b)
+    assert gr.shape == g["g"].shape and rel(gr, g["g"]) < 1e-12
+    assert rel(sk.quadratic_gradient(x, Q.toarray(), b), g["g"]) < 1e-12      # dense Q, as the reference accepts
+    assert sk.quadratic_hessian(Q) is Q
+    # backward Euler with the term: device-resident step (ElasticPotential) and the host-callable path
+    mu, lam, h = float(g["mu"]), float(g["lam"]), float(g["h"])
+    Md = sps.kron(sps.diags(g["mass"]), sps.identity(dim)).tocsc()
+    pot = sk.ElasticPotential("stable_neo_hookean", mu, lam, X=X, T=T, f_ext=g["fg"], quadratic=(Q, b))
+    x_prev = X.reshape(-1, 1)
+    x1, info = sk.backward_euler(x, x_prev, pot.energy, pot.gradient, pot.hessian, Md, h, max_iter=3, return_info=True,
+                                 pcg_rtol=1e-13)
+    assert list(info["alphas"]) == list(g["be_alphas"]) and rel(x1, g["be_x"]) < 1e-8
+    x2 = sk.backward_euler(x, x_prev, lambda v: pot.energy(v), lambda v: pot.gradient(v), lambda v: pot.hessian(v), Md, h,
+                           max_iter=3, pcg_rtol=1e-13)
+    assert rel(x2, g["be_x"]) < 1e-8
+    # a second step reuses the uploaded term
+    x3 = sk.backward_euler(x, x_prev, pot.energy, pot.gradient, pot.hessian, Md, h, max_iter=3, pcg_rtol=1e-13)
+    assert rel(x3, g["be_x"]) < 1e-8
+    # entries outside the mesh's CSR pattern are refused
+    nd = X.shape[0] * dim
+    far = int(np.argmax(np.linalg.norm(X - X[0], axis=1)))
+    Qbad = sps.csr_matrix(([1.0, 1.0], ([0, far * dim], [far * dim, 0])), shape=(nd, nd))
+    with pytest.raises(ValueError):
+        pot.plan.set_quadratic(Qbad, None)
+    pot.plan.set_quadratic(None)
