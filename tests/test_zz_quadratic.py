@@ -144,6 +144,45 @@ def test_gpu_dirichlet_laplacian(golden_dir, tag):
         sk.dirichlet_laplacian(X, T, np.ones(3))
 
 
+def test_dirichlet_penalty_pinned_state_is_stationary():
+    """tests/test_dirichlet_penalty.py:10-32 of the reference: shapes, zero gradient and zero energy (up to the dropped
+    constant) at the pinned state -- here for the host drop-in and the oracle."""
+    from simkit_b200.dirichlet_penalty import dirichlet_penalty
+    nv, dim = 4, 2
+    bI = np.array([0, 2])
+    y = np.array([[1.0, 0.0], [0.0, 1.0]])
+    for fn in (dirichlet_penalty, oe.dirichlet_penalty):
+        Q, b = fn(bI, y, nv, 10.0)
+        assert Q.shape == (nv * dim, nv * dim) and b.shape == (nv * dim, 1)
+        x = np.zeros((nv * dim, 1))
+        for k, vi in enumerate(bI):
+            x[vi * dim:(vi + 1) * dim, 0] = y[k]
+        assert np.allclose(Q @ x + b, 0.0, atol=1e-12)
+        assert abs(oe.quadratic_energy(x, Q, b) + 0.5 * 10.0 * (y * y).sum()) < 1e-12    # minus the dropped constant
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mesh", ["triangle", "tet"])
+def test_gpu_laplacian_on_one_element(mesh):
+    """tests/test_dirichlet_laplacian.py:27-60 of the reference on its one-element meshes: csc, symmetric, positive
+    semi-definite, constants in the null space; the vector form has the same properties."""
+    import simkit_b200 as sk
+    if mesh == "triangle":
+        X, T = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]), np.array([[0, 1, 2]])
+    else:
+        X, T = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]]), np.array([[0, 1, 2, 3]])
+    n, dim = X.shape
+    L = sk.dirichlet_laplacian(X, T, mu=1.0, vector=False)
+    assert L.shape == (n, n) and sps.isspmatrix_csc(L)
+    D = L.toarray()
+    assert np.allclose(D, D.T, atol=1e-12) and np.linalg.eigvalsh(D).min() >= -1e-10
+    assert np.allclose(L @ np.ones(n), 0.0, atol=1e-10)
+    assert rel(D, oe.dirichlet_laplacian(X, T, 1.0).toarray()) < 1e-12
+    Lv = sk.dirichlet_laplacian(X, T, mu=1.0, vector=True)
+    Dv = Lv.toarray()
+    assert Lv.shape == (n * dim, n * dim) and np.allclose(Dv, Dv.T, atol=1e-12) and np.linalg.eigvalsh(Dv).min() >= -1e-10
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", TAGS)
 def test_gpu_quadratic(golden_dir, tag):
