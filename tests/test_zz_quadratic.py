@@ -183,6 +183,34 @@ def test_gpu_laplacian_on_one_element(mesh):
     assert Lv.shape == (n * dim, n * dim) and np.allclose(Dv, Dv.T, atol=1e-12) and np.linalg.eigvalsh(Dv).min() >= -1e-10
 
 
+@pytest.mark.parametrize("impl", [pytest.param("oracle", id="oracle"), pytest.param("gpu", id="simkit_b200", marks=pytest.mark.gpu)])
+def test_quadratic_minimiser_and_central_differences(impl):
+    """tests/test_quadratic.py of the reference: for a positive definite dense Q the energy grows away from
+    x* = -Q^-1 b, the gradient matches central differences of the energy (1e-6) and vanishes at x*."""
+    if impl == "gpu":
+        import simkit_b200 as sk
+        qe, qg, qh = sk.quadratic_energy, sk.quadratic_gradient, sk.quadratic_hessian
+    else:
+        qe, qg, qh = oe.quadratic_energy, oe.quadratic_gradient, oe.quadratic_hessian
+    rng = np.random.default_rng(0)
+    n = 6
+    A = rng.standard_normal((n, n))
+    Q = A.T @ A + n * np.eye(n)
+    b = rng.standard_normal((n, 1))
+    x_min = -np.linalg.solve(Q, b)
+    assert qe(x_min + 0.1 * rng.standard_normal((n, 1)), Q, b) > qe(x_min, Q, b)
+    assert np.abs(qg(x_min, Q, b)).max() < 1e-12
+    x = rng.standard_normal((n, 1))
+    g_fd = np.zeros(n)
+    for k in range(n):
+        e = np.zeros((n, 1))
+        e[k] = 1e-6
+        g_fd[k] = (qe(x + e, Q, b) - qe(x - e, Q, b)) / 2e-6
+    g = qg(x, Q, b)
+    assert g.shape == (n, 1) and np.allclose(g.ravel(), g_fd, atol=1e-6)
+    assert qh(Q) is Q
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tag", TAGS)
 def test_gpu_quadratic(golden_dir, tag):
