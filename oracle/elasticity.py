@@ -835,6 +835,50 @@ def block_jacobi_cg(H, rhs, dim, rtol=1e-12, maxiter=20000):
     return x, its[0]
 
 
+def block_jacobi_cg_single_reduction(H, rhs, dim, rtol=1e-10, maxiter=20000):
+    """Prototype (not reference code) of the single-reduction PCG planned for the distributed solve (DESIGN.md
+    section 8, item 5): Chronopoulos-Gear recurrences -- u = M^-1 r, w = A u, then ONE reduction for
+    (r.u, w.u, r.r) per iteration instead of the two of the textbook loop (p.q, then r.z and r.r).  Same
+    block-Jacobi preconditioner as ``block_jacobi_cg``; returns (x, iterations).  In exact arithmetic the iterates are
+    those of standard PCG."""
+    H = sps.csr_matrix(H)
+    n = H.shape[0] // dim
+    Hb = sps.bsr_matrix(H, blocksize=(dim, dim))
+    Hb.sort_indices()
+    diag = np.zeros((n, dim, dim))
+    rows = np.repeat(np.arange(n), np.diff(Hb.indptr))
+    sel = Hb.indices == rows
+    diag[rows[sel]] = Hb.data[sel]
+    inv = np.linalg.inv(diag)
+    prec = lambda v: np.einsum("nij,nj->ni", inv, v.reshape(n, dim)).reshape(-1)  # noqa: E731
+    b = np.asarray(rhs, dtype=np.float64).reshape(-1)
+    x = np.zeros_like(b)
+    r = b.copy()
+    bb = float(b @ b)
+    if not bb > 0.0:
+        return x, 0
+    p = np.zeros_like(b)
+    s = np.zeros_like(b)
+    gamma_old, alpha = 1.0, 1.0
+    for it in range(maxiter):
+        u = prec(r)
+        w = H @ u
+        gamma, delta, rr = float(r @ u), float(w @ u), float(r @ r)     # the one reduction of the iteration
+        if not rr > rtol * rtol * bb:
+            return x, it
+        if it == 0:
+            beta, alpha = 0.0, gamma / delta
+        else:
+            beta = gamma / gamma_old
+            alpha = gamma / (delta - beta * gamma / alpha)
+        p = u + beta * p
+        s = w + beta * s                                                # s = A p without a second SpMV
+        x = x + alpha * p
+        r = r - alpha * s
+        gamma_old = gamma
+    return x, maxiter
+
+
 # --------------------------------------------------------------------------- #
 # reduced operators                                                           #
 # --------------------------------------------------------------------------- #

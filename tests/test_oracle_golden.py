@@ -135,3 +135,25 @@ def test_reduced_and_fst(golden_dir, tag):
     ARBs = oe.fst_precompute(g["fst_A"], g["fst_B"], g["fst_l"], dim)
     assert rel(ARBs, g["fst_ARBs"]) < TOL
     assert rel(oe.fst_eval(ARBs, g["fst_r"], dim), g["fst_out"]) < TOL
+
+
+@pytest.mark.parametrize("cells,h", [((6, 5, 4), 1e-2), ((6, 5, 4), 1.0), ((20, 16), 1e-2)])
+def test_single_reduction_pcg_prototype(cells, h):
+    """The Chronopoulos-Gear (one reduction per iteration) PCG planned for the distributed solve: same iterates as
+    the textbook loop to rounding -- same iteration count (+-2) and the same solution on a backward-Euler system."""
+    import scipy.sparse as sps
+    import scipy.sparse.linalg as spla
+    from simkit_b200 import synthetic as syn
+    dim = len(cells)
+    X, T = syn.make_mesh(cells)
+    U = syn.jittered_state(X, cells, tuple(1.0 for _ in cells), sigma=0.2)
+    mu, lam = syn.lame()
+    J, vol = oe.deformation_jacobian(X, T), oe.volume(X, T)
+    H = oe.hessian_x("stable_neo_hookean", U, J, mu, lam, vol) + sps.kron(oe.massmatrix(X, T, 1e3), sps.identity(dim)) / h ** 2
+    g = oe.gradient_x("stable_neo_hookean", U, J, mu, lam, vol).ravel()
+    x1, i1 = oe.block_jacobi_cg(H, -g, dim, rtol=1e-10)
+    x2, i2 = oe.block_jacobi_cg_single_reduction(H, -g, dim, rtol=1e-10)
+    xd = spla.spsolve(H.tocsc(), -g)
+    scale = np.abs(xd).max()
+    assert abs(i1 - i2) <= 2
+    assert np.abs(x2 - xd).max() <= 10 * max(np.abs(x1 - xd).max(), 1e-12 * scale)
