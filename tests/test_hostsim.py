@@ -115,3 +115,43 @@ def test_pencil_order_merges_more_blocks_per_tile(dim):
     assert b["info"][1] < 0.85 * a["info"][1] and b["info"][2] < 0.85 * a["info"][2]
     assert np.array_equal(a["bptr"], b["bptr"]) and np.array_equal(a["bcol"], b["bcol"])
     assert rel(b["vals"], a["vals"]) < 1e-13 and rel(b["g"], a["g"]) < 1e-13
+
+
+def _odd_meshes(dim):
+    """Edge-case inputs: vertices no element references (at the end and in the middle of the numbering), one element,
+    two disjoint elements, an element listed twice, elements shuffled with rotated corners."""
+    rng = np.random.default_rng(5)
+    cells = (3, 2, 2) if dim == 3 else (5, 4)
+    X, T = syn.make_mesh(cells)
+    U = syn.jittered_state(X, cells, tuple(1.0 for _ in cells), sigma=0.3)
+    out = {"plain": (X, T, U)}
+    out["unreferenced_end"] = (np.vstack([X, rng.random((3, dim))]), T, np.vstack([U, rng.random((3, dim))]))
+    ins = np.insert(np.arange(X.shape[0]), [2, 2, 7], -1)
+    newid = np.full(X.shape[0], -1)
+    newid[ins[ins >= 0]] = np.where(ins >= 0)[0]
+    Xg, Ug = rng.random((ins.size, dim)), rng.random((ins.size, dim))
+    Xg[newid], Ug[newid] = X, U
+    out["unreferenced_middle"] = (Xg, newid[T], Ug)
+    out["one_element"] = (X, T[:1], U)
+    out["two_disjoint"] = (X, T[[0, -1]], U)
+    out["listed_twice"] = (X, np.vstack([T, T[:2]]), U)
+    rot = [1, 2, 0, 3] if dim == 3 else [1, 2, 0]            # even permutation: orientation kept
+    out["shuffled"] = (X, T[rng.permutation(T.shape[0])][:, rot], U)
+    return out
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("case", ["unreferenced_end", "unreferenced_middle", "one_element", "two_disjoint", "listed_twice",
+                                  "shuffled"])
+def test_edge_case_meshes(case, dim):
+    X, T, U = _odd_meshes(dim)[case]
+    n = X.shape[0]
+    mu, lam = syn.heterogeneous_lame(T.shape[0])
+    J, vol = oe.deformation_jacobian(X, T), oe.volume(X, T)
+    g = oe.gradient_x("stable_neo_hookean", U, J, mu, lam, vol).ravel()
+    H = oe.hessian_x("stable_neo_hookean", U, J, mu, lam, vol, psd=True)
+    for tile in (32, 128):
+        r = hostsim.run(X, T, MAT_ID["stable_neo_hookean"], 1, U, mu, lam, vol=vol, tile_elems=tile)
+        Hh = hostsim.csr_from_blocks(r["bptr"], r["bcol"], r["vals"], n, dim)
+        assert rel(r["g"], g) < TOL and abs(Hh - H).max() <= TOL * abs(H).max()
+        assert abs(r["energy"] - oe.energy_x("stable_neo_hookean", U, J, mu, lam, vol)) <= 1e-12 * abs(r["energy"])

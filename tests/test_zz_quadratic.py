@@ -246,3 +246,30 @@ def test_gpu_quadratic(golden_dir, tag):
     with pytest.raises(ValueError):
         pot.plan.set_quadratic(Qbad, None)
     pot.plan.set_quadratic(None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("case", ["unreferenced_end", "unreferenced_middle", "one_element", "two_disjoint", "listed_twice",
+                                  "shuffled"])
+def test_gpu_edge_case_meshes(case, dim):
+    """Edge-case inputs through the drop-in API (the host replay of the same cases is tests/test_hostsim.py): vertices
+    no element references, one element, disjoint elements, an element listed twice, shuffled elements."""
+    import simkit_b200 as sk
+    from simkit_b200 import synthetic as syn
+    from test_hostsim import _odd_meshes
+    X, T, U = _odd_meshes(dim)[case]
+    mu, lam = syn.heterogeneous_lame(T.shape[0])
+    Jo, volo = oe.deformation_jacobian(X, T), oe.volume(X, T)
+    e = oe.energy_x("stable_neo_hookean", U, Jo, mu, lam, volo)
+    g = oe.gradient_x("stable_neo_hookean", U, Jo, mu, lam, volo)
+    H = oe.hessian_x("stable_neo_hookean", U, Jo, mu, lam, volo, psd=True)
+    J, vol = sk.deformation_jacobian(X, T), sk.volume(X, T)
+    assert J.shape == Jo.shape and abs(J - Jo).max() <= 1e-12 * abs(Jo).max() and rel(vol, volo) < 1e-13
+    assert abs(sk.stable_neo_hookean_energy_x(U, J, mu, lam, vol) - e) <= 1e-12 * abs(e)
+    assert rel(sk.stable_neo_hookean_gradient_x(U, J, mu, lam, vol), g) < 1e-10
+    Hs = sk.stable_neo_hookean_hessian_x(U, J, mu, lam, vol)
+    assert Hs.shape == H.shape and abs(Hs - H).max() <= 1e-10 * abs(H).max()
+    # self-contained tier and a plain scipy J (plan recovered from the operator)
+    assert abs(sk.stable_neo_hookean_hessian(X, T, mu, lam, U) - H).max() <= 1e-10 * abs(H).max()
+    assert abs(sk.stable_neo_hookean_hessian_x(U, sps.csc_matrix(Jo), mu, lam, volo) - H).max() <= 1e-10 * abs(H).max()
