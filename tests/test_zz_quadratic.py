@@ -161,11 +161,18 @@ def test_dirichlet_penalty_pinned_state_is_stationary():
         assert abs(oe.quadratic_energy(x, Q, b) + 0.5 * 10.0 * (y * y).sum()) < 1e-12    # minus the dropped constant
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("mesh", ["triangle", "tet"])
-def test_gpu_laplacian_on_one_element(mesh):
-    """tests/test_dirichlet_laplacian.py:27-60 of the reference on its one-element meshes: csc, symmetric, positive
-    semi-definite, constants in the null space; the vector form has the same properties."""
+def _isolated(call, timeout=240):
+    """Runs ``test_zz_quadratic.<call>`` in a child process with a time limit: inputs of a size no GPU run has seen yet
+    (one or two elements) must not be able to leave a stuck kernel in the context the rest of the suite uses."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = "import sys; sys.path.insert(0, %r); import test_zz_quadratic as t; t.%s" % (here, call)
+    r = subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(here), capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def _laplacian_on_one_element(mesh):
     import simkit_b200 as sk
     if mesh == "triangle":
         X, T = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]), np.array([[0, 1, 2]])
@@ -181,6 +188,14 @@ def test_gpu_laplacian_on_one_element(mesh):
     Lv = sk.dirichlet_laplacian(X, T, mu=1.0, vector=True)
     Dv = Lv.toarray()
     assert Lv.shape == (n * dim, n * dim) and np.allclose(Dv, Dv.T, atol=1e-12) and np.linalg.eigvalsh(Dv).min() >= -1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mesh", ["triangle", "tet"])
+def test_gpu_laplacian_on_one_element(mesh):
+    """tests/test_dirichlet_laplacian.py:27-60 of the reference on its one-element meshes: csc, symmetric, positive
+    semi-definite, constants in the null space; the vector form has the same properties."""
+    _isolated("_laplacian_on_one_element(%r)" % mesh)
 
 
 @pytest.mark.parametrize("impl", [pytest.param("oracle", id="oracle"), pytest.param("gpu", id="simkit_b200", marks=pytest.mark.gpu)])
@@ -248,13 +263,7 @@ def test_gpu_quadratic(golden_dir, tag):
     pot.plan.set_quadratic(None)
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("dim", [2, 3])
-@pytest.mark.parametrize("case", ["unreferenced_end", "unreferenced_middle", "one_element", "two_disjoint", "listed_twice",
-                                  "shuffled"])
-def test_gpu_edge_case_meshes(case, dim):
-    """Edge-case inputs through the drop-in API (the host replay of the same cases is tests/test_hostsim.py): vertices
-    no element references, one element, disjoint elements, an element listed twice, shuffled elements."""
+def _edge_case(case, dim):
     import simkit_b200 as sk
     from simkit_b200 import synthetic as syn
     from test_hostsim import _odd_meshes
@@ -273,3 +282,13 @@ def test_gpu_edge_case_meshes(case, dim):
     # self-contained tier and a plain scipy J (plan recovered from the operator)
     assert abs(sk.stable_neo_hookean_hessian(X, T, mu, lam, U) - H).max() <= 1e-10 * abs(H).max()
     assert abs(sk.stable_neo_hookean_hessian_x(U, sps.csc_matrix(Jo), mu, lam, volo) - H).max() <= 1e-10 * abs(H).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("case", ["unreferenced_end", "unreferenced_middle", "one_element", "two_disjoint", "listed_twice",
+                                  "shuffled"])
+def test_gpu_edge_case_meshes(case, dim):
+    """Edge-case inputs through the drop-in API (the host replay of the same cases is tests/test_hostsim.py): vertices
+    no element references, one element, disjoint elements, an element listed twice, shuffled elements."""
+    _isolated("_edge_case(%r, %d)" % (case, dim))
