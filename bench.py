@@ -211,6 +211,42 @@ def load_traffic(kernel_key):
         return None
 
 
+def parity_assembly(workload, g_rows, Q_rows, col_ids, n_layers=2):
+    """Checker (not timed, not part of the product path): gradient rows and Hessian block rows of the first ``n_layers``
+    vertex planes of the workload mesh, as computed on the device, against the oracle on the closed sub-mesh made of
+    the first ``n_layers`` cell layers (the rows of those vertices receive contributions from no other element).
+    ``g_rows``: device gradient of the first rows; ``Q_rows``: scipy CSR of the same rows with local column numbering,
+    ``col_ids`` the global vertex id of every local column vertex.  Returns (max rel gradient, max rel Hessian)."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    import scipy.sparse as sps
+    from oracle import elasticity as oe
+    from simkit_b200 import synthetic as syn
+    cfg = syn.CONFIGS[workload]
+    cells, dim = cfg["cells"], cfg["dim"]
+    Ts = syn.grid_elements(cells, 0, n_layers)
+    nsub = int(Ts.max()) + 1
+    Xs = syn.grid_vertices(cells, cfg["extent"], np.arange(nsub))
+    Us = syn.jittered_state_rows(cells, cfg["extent"], np.arange(nsub), sigma=0.1)
+    mu, lam = syn.lame()
+    Jo, volo = oe.deformation_jacobian(Xs, Ts), oe.volume(Xs, Ts)
+    nfull = n_layers * int(np.prod([c + 1 for c in cells[1:]]))
+    nr = nfull * dim
+    go = np.asarray(oe.gradient_x(MATERIAL, Us, Jo, mu, lam, volo)).ravel()[:nr]
+    Qo = oe.canonical_csr(oe.hessian_x(MATERIAL, Us, Jo, mu, lam, volo, psd=True))[:nr]
+    rel_g = float(np.abs(np.asarray(g_rows).ravel()[:nr] - go).max() / np.abs(go).max())
+    # map the device rows' local columns to global dof ids, then compare on the sub-mesh's columns
+    gdof = (np.asarray(col_ids, dtype=np.int64)[:, None] * dim + np.arange(dim)[None, :]).ravel()
+    Q = sps.csr_matrix(Q_rows)[:nr]
+    Qg = sps.csr_matrix((Q.data, gdof[Q.indices], Q.indptr), shape=(nr, max(int(gdof.max()) + 1, nsub * dim)))
+    d = Qg[:, : nsub * dim] - Qo
+    rel_h = float(abs(d).max() / abs(Qo).max())
+    outside = Qg[:, nsub * dim:]
+    if outside.nnz:
+        rel_h = max(rel_h, float(abs(outside).max() / abs(Qo).max()))
+    return rel_g, rel_h
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -240,8 +276,16 @@ def run_ours(args, rank, world, local_rank):
         X, T = syn.make_mesh(args.workload)
         if args.element_order == "pencil":     # experiment: same mesh, elements listed in spatially compact runs
             T = np.ascontiguousarray(T[syn.pencil_order(cfg["cells"], cfg["extent"], X, T)])
-        plan = sk.MeshPlan(X=X, T=T, device=local_rank)
         U = syn.jittered_state(X, cfg["cells"], cfg["extent"], sigma=0.1)
+        if args.shuffle != "none":             # the caller lists the same mesh in random order
+            rng = np.random.default_rng(17)
+            T = np.ascontiguousarray(T[rng.permutation(T.shape[0])])
+            if args.shuffle == "both":
+                vp = rng.permutation(X.shape[0])
+                inv = np.empty_like(vp)
+                inv[vp] = np.arange(vp.size)
+                X, U, T = np.ascontiguousarray(X[vp]), np.ascontiguousarray(U[vp]), np.ascontiguousarray(inv[T])
+        plan = sk.MeshPlan(X=X, T=T, device=local_rank)
         t_total, n_total, nnz_total = plan.t, plan.n, plan.nnz
     mu, lam = syn.lame()
     vol = plan.volume()
@@ -324,14 +368,22 @@ def run_ours(args, rank, world, local_rank):
     alg_bytes = per_elem * plan.t + 2 * 8 * dim * plan.n + 8 * plan.nnz
     alg_flops = (2600.0 if dim == 3 else 700.0) * plan.t
     k_ms = kms[0] / max(int(kcount[0]), 1)
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     kernel_key = "assemble_pipelined_kernel<%d>" % dim
+    # the algorithmic bytes (366 B/tet at C5) are what the STEP has to move: the CSR values among them are written by
+    # finalize_blocks, not by the assembly kernel, so the fraction is quoted for the chain of kernels that makes up the
+    # step (0.127, not the 0.178 that credited the assembly kernel with bytes it does not move)
+    chain_ms = float(sum(kms[i] / max(int(kcount[i]), 1) for i in range(3)))
+    achieved = alg_bytes / (chain_ms * 1e-3) / 1e9
+    traffic = load_traffic("step") if (world == 1 and args.workload == "C5" and args.shuffle == "none") else None
     roofline = {
-        "kernel": kernel_key, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "kernel": "assembly step = %s + finalize_blocks_kernel + finalize_verts_kernel" % kernel_key,
+        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
         "frac": achieved / hbm_peak, "peak_source": peak_src,
-        "traffic": load_traffic(kernel_key) if (world == 1 and args.workload == "C5") else None,
+        "traffic": traffic,
+        "traffic_source": "profiles/roofline_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of the step's kernels, ncu --set full",
         "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_elem": alg_bytes / plan.t,
-        "kernel_ms": k_ms, "kernel_share_of_step": float(kms[0] / max(kms[:3].sum(), 1e-30)),
+        "kernel_ms": chain_ms, "dominant_kernel": kernel_key, "dominant_kernel_ms": k_ms,
+        "kernel_share_of_step": float(kms[0] / max(kms[:3].sum(), 1e-30)),
         "step_kernels_ms": {"assemble": kms[0] / max(int(kcount[0]), 1), "finalize_blocks": kms[1] / max(int(kcount[1]), 1),
                             "finalize_verts": kms[2] / max(int(kcount[2]), 1)},
         "step_frac_hbm": alg_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak if world == 1 else None,
@@ -389,6 +441,37 @@ def run_ours(args, rank, world, local_rank):
         assert np.array_equal(vals_h, vals_d.cpu().numpy()) and np.array_equal(g_h, g_d.cpu().numpy())
     else:
         assert np.array_equal(vals_h, vals_d[v0:v1].cpu().numpy()) and np.array_equal(g_h, g_d[o0:o1].cpu().numpy())
+
+    # ---- parity of the benched result against the oracle (checker; outside every timed region) ----------------
+    parity = None
+    if not args.no_parity and args.shuffle == "none" and args.element_order == "input":
+        nl = 2
+        rel_g = rel_h = None
+        if rank == 0:
+            cells = cfg["cells"]
+            nfull = nl * int(np.prod([c + 1 for c in cells[1:]]))
+            bptr, bcol = plan.block_pattern()
+            nbr = np.diff(bptr[: nfull + 1]).astype(np.int64)
+            nvals = int(bptr[nfull]) * dim * dim
+            indptr = np.concatenate([[0], np.cumsum(np.repeat(nbr * dim, dim))])
+            indices = np.empty(nvals, dtype=np.int64)
+            pos = 0
+            for v in range(nfull):
+                cols = (bcol[bptr[v]:bptr[v + 1]].astype(np.int64)[:, None] * dim + np.arange(dim)[None, :]).ravel()
+                for _i in range(dim):
+                    indices[pos:pos + cols.size] = cols
+                    pos += cols.size
+            import scipy.sparse as sps
+            Qrows = sps.csr_matrix((vals_d[:nvals].cpu().numpy(), indices, indptr), shape=(nfull * dim, plan.ndof))
+            col_ids = np.arange(plan.n) if shard is None else shard.layout.l2g
+            rel_g, rel_h = parity_assembly(args.workload, g_d[: nfull * dim].cpu().numpy(), Qrows, col_ids, nl)
+        parity = {"assembly": {"what": "gradient rows and Hessian block rows of the first %d vertex planes (rank 0's rows) vs the "
+                                       "oracle on the closed sub-mesh of the first %d cell layers" % (nl, nl),
+                               "max_rel_gradient": rel_g, "max_rel_hessian": rel_h, "tol": 1e-10}}
+        if rank == 0:
+            parity["ok"] = bool(rel_g < 1e-10 and rel_h < 1e-10)
+            assert parity["ok"], "parity check failed: %r" % (parity,)
+    barrier()
 
     # ---- Newton step (assembly + PCG + line search), device-resident -------------------------------
     newton = None
@@ -461,6 +544,39 @@ def run_ours(args, rank, world, local_rank):
             if s > 0:
                 tt.append(time.perf_counter() - t0)
         sec = max_over_ranks(float(np.mean(tt)))
+        if parity is not None:
+            # the same step on ONE GPU (rank 0 builds the whole mesh's plan; the mesh fits) -> every rank compares its
+            # owned rows of x_next; tolerance of north_star for Newton iterates: 1e-8 relative
+            xref = torch.empty(n_total * dim, dtype=f64, device=dev)
+            if rank == 0:
+                Xf, Tf = syn.make_mesh(args.workload)
+                Uf = syn.jittered_state(Xf, cfg["cells"], cfg["extent"], sigma=0.1).reshape(-1)
+                pf = sk.MeshPlan(X=Xf, T=Tf, device=local_rank)
+                pf.set_materials(mu, lam, pf.volume())
+                massf = np.repeat(pf.vertex_masses(rho), dim)
+                fextf = np.zeros((pf.n, dim))
+                fextf[:, 1] = -9.8
+                fextf = fextf.reshape(-1) * massf
+                if n_agg:
+                    pf.set_coarse_space(Xf, n_agg)
+                xn, inf1 = pf.newton(MATERIAL, Uf, x_tilde=Uf, mass=massf, kin_scale=1.0 / h ** 2, f_ext=fextf, max_iter=1,
+                                     pcg_rtol=args.pcg_rtol, pcg_max_iter=20000)
+                xref.copy_(torch.from_numpy(np.ascontiguousarray(xn.reshape(-1))))
+                del pf
+            dist.broadcast(xref, 0)
+            lay = shard.layout
+            o0, o1 = lay.own_lo * dim, lay.own_hi * dim
+            mine = xs[o0:o1]
+            ref = xref[lay.v_lo * dim: lay.v_hi * dim]
+            err = torch.stack([(mine - ref).abs().max(), ref.abs().max()])
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+            rel_x = float(err[0].item() / err[1].item())
+            parity["newton"] = {"what": "x_next of the sharded step (owned rows of every rank) vs the same step on one GPU",
+                                "max_rel": rel_x, "tol": 1e-8}
+            if rank == 0:
+                parity["ok"] = bool(parity["ok"] and rel_x < 1e-8)
+                assert parity["ok"], "parity check failed: %r" % (parity,)
+            del xref
         newton = {"steps_per_s": 1.0 / sec, "ms_per_step": sec * 1e3, "pcg_iters": info["pcg_iters"],
                   "pcg_rtol": args.pcg_rtol, "pcg_relres": info["pcg_relres"], "alpha": info["alphas"][:1],
                   "preconditioner": "3x3 block-Jacobi + rigid-body modes of %d vertex aggregates (two-level, additive)" % n_agg,
@@ -531,9 +647,12 @@ def run_ours(args, rank, world, local_rank):
                        "psd": "analytic eigensystem, floor 1e-6 after vol",
                        "l2": "no flush needed: per-step inputs+outputs (>= %.1f GB) exceed the 126 MB L2" % (alg_bytes / 1e9),
                        "sharding": "none" if world == 1 else "contiguous element slabs, NCCL interface exchange",
-                       "element_order": args.element_order if world == 1 else "input"},
+                       "element_order": "caller: %s%s; plan: internal sort-tile-recursive order (SKB_ELEMENT_ORDER=%s)" % (
+                           args.element_order if world == 1 else "input",
+                           "" if args.shuffle == "none" else ", shuffled " + args.shuffle,
+                           os.environ.get("SKB_ELEMENT_ORDER", "str"))},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "newton": newton,
+            "roofline": roofline, "cpu_baseline": cpu, "newton": newton, "parity_check": parity,
         }
         if reduced is not None:
             line["reduced"] = reduced
@@ -561,6 +680,10 @@ def main():
     ap.add_argument("--element-order", default="input", choices=["input", "pencil"],
                     help="experiment (1 GPU): list the mesh's elements in 3x3-cell pencils (synthetic.pencil_order) instead of the "
                          "generator's cell-major order; fewer partial records per element")
+    ap.add_argument("--shuffle", default="none", choices=["none", "elements", "both"],
+                    help="list the mesh's elements (and vertices) in random order: the plan's internal spatial element order "
+                         "keeps the step within a few percent of the generator's order (1 GPU)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check of the benched result")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="development only: stop after the device-resident timing")
     args = ap.parse_args()

@@ -94,6 +94,11 @@ int skb_plan_slot_map(const skb_plan* plan, int32_t* slot);
 int skb_plan_element_D(const skb_plan* plan, double* D);
 /* vol[e]: signed tet volume / unsigned triangle area  (tetrahedron_volumes.py:26-27, triangle_areas.py:60-79) */
 int skb_plan_volume(const skb_plan* plan, double* vol);
+/* order[i] (int32, t) = the caller's index of the element the plan lists i-th.  The plan keeps its active elements in a
+ * spatial (sort-tile-recursive) order of its own so that the tiles of the assembly kernel are compact (north_star
+ * kernel 1, "spatially sorted"); every per-element array of this ABI is in the CALLER's order.  No reference
+ * counterpart (the reference evaluates elements in the order of T, e.g. energies/stable_neo_hookean.py:531). */
+int skb_plan_element_order(const skb_plan* plan, int32_t* order);
 /* lumped vertex masses m[v] = sum_e rho_e vol_e / (dim+1)   (massmatrix.py:41-49) */
 int skb_plan_vertex_masses(const skb_plan* plan, const double* rho, int64_t rho_n, double* m);
 

@@ -75,6 +75,7 @@ SIGNATURES = {
     "skb_plan_slot_map": (_int, [_vp, _vp]),
     "skb_plan_element_D": (_int, [_vp, _vp]),
     "skb_plan_volume": (_int, [_vp, _vp]),
+    "skb_plan_element_order": (_int, [_vp, _vp]),
     "skb_plan_vertex_masses": (_int, [_vp, _vp, _i64, _vp]),
     "skb_energy": (_int, [_vp, _int, _vp, _vp] + _MAT + [_vp]),
     "skb_gradient": (_int, [_vp, _int, _vp, _vp] + _MAT + [_vp]),

@@ -25,6 +25,7 @@ int make_args(skb_plan* pl, int material, int psd_mode, const double* x, const d
   a.psd_mode = psd_mode;
   a.x = x;
   a.Fbar = fbar;
+  a.eorder = pl->d.eorder.empty() ? nullptr : raw(pl->d.eorder);
   a.mu = raw(pl->mu);
   a.lam = raw(pl->lam);
   a.vol = raw(pl->vol);
@@ -45,31 +46,62 @@ int make_args(skb_plan* pl, int material, int psd_mode, const double* x, const d
   return SKB_OK;
 }
 
+// dst[i] = src[order[i]]: per-element inputs arrive in the caller's element order, the plan keeps them in its own
+__global__ void permute_in_kernel(const double* src, const int* order, int64_t n, double* dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[order[i]];
+}
+// dst[order[i]] = src[i]: the way back, for per-element exports
+__global__ void permute_out_kernel(const double* src, const int* order, int64_t n, double* dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[order[i]] = src[i];
+}
+
+// one per-element (or scalar) input: copied as is when scalar or when the plan keeps the caller's element order,
+// otherwise staged and gathered into the plan's internal element order
+static int upload_per_element(skb_plan* pl, dvec<double>& dst, const double* src, int64_t cnt, bool from_device,
+                              cudaStream_t st) {
+  const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  dst.resize(cnt);
+  if (cnt <= 1 || pl->d.eorder.empty()) {
+    SKB_CUDA(cudaMemcpyAsync(raw(dst), src, cnt * sizeof(double), kind, st));
+    return SKB_OK;
+  }
+  const double* dsrc = src;
+  if (!from_device) {
+    pl->stage_elem.resize(cnt);
+    SKB_CUDA(cudaMemcpyAsync(raw(pl->stage_elem), src, cnt * sizeof(double), kind, st));
+    dsrc = raw(pl->stage_elem);
+  }
+  permute_in_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(dsrc, raw(pl->d.eorder), cnt, raw(dst));
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+}
+
 int upload_materials(skb_plan* pl, const double* mu, int64_t mu_n, const double* lam, int64_t lam_n,
                      const double* vol, int64_t vol_n, bool from_device, cudaStream_t st) {
   const int64_t t = pl->d.t;
   if (!mu || (mu_n != 1 && mu_n != t)) return fail(SKB_EINVAL, "mu must have 1 or t entries");
   if (lam && lam_n != 1 && lam_n != t) return fail(SKB_EINVAL, "lam must have 1 or t entries");
   if (vol && vol_n != 1 && vol_n != t) return fail(SKB_EINVAL, "vol must have 1 or t entries");
-  const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  pl->mu.resize(mu_n);
-  SKB_CUDA(cudaMemcpyAsync(raw(pl->mu), mu, mu_n * sizeof(double), kind, st));
+  int rc = upload_per_element(pl, pl->mu, mu, mu_n, from_device, st);
+  if (rc) return rc;
   pl->mu_n = mu_n;
   if (lam) {
-    pl->lam.resize(lam_n);
-    SKB_CUDA(cudaMemcpyAsync(raw(pl->lam), lam, lam_n * sizeof(double), kind, st));
+    rc = upload_per_element(pl, pl->lam, lam, lam_n, from_device, st);
+    if (rc) return rc;
     pl->lam_n = lam_n;
   } else {
     pl->lam.assign(1, 0.0);
     pl->lam_n = 1;
   }
   if (vol) {
-    pl->vol.resize(vol_n);
-    SKB_CUDA(cudaMemcpyAsync(raw(pl->vol), vol, vol_n * sizeof(double), kind, st));
+    rc = upload_per_element(pl, pl->vol, vol, vol_n, from_device, st);
+    if (rc) return rc;
     pl->vol_n = vol_n;
   } else {
     if (!pl->d.has_vol0) return fail(SKB_EINVAL, "vol is required for a plan built from an operator");
-    pl->vol = pl->d.vol0;
+    pl->vol = pl->d.vol0;  // already in the internal order
     pl->vol_n = t;
   }
   pl->have_materials = true;
@@ -242,10 +274,17 @@ static int plan_create_common(const double* X, const double* Dop, const void* T,
   pl->device = device;
   SKB_CUDA(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
   dvec<int> Td = Th;
+  dvec<double> Xd;
+  if (X) {
+    Xd.assign(X, X + n * dim);
+    // spatial element order of the plan's own (plan.cuh str_element_order); SKB_ELEMENT_ORDER=input keeps the caller's
+    const char* eo = getenv("SKB_ELEMENT_ORDER");
+    if (!(eo && strcmp(eo, "input") == 0) && t > tile_elems)
+      apply_element_order<DeviceBackend>(pl->d, Td, Xd, (int)n, (int)t, dim, tile_elems);
+  }
   if (!build_plan<DeviceBackend>(pl->d, Td, (int)n, (int)t, dim, tile_elems, (int)t_total))
     return fail(SKB_EINVAL, "degenerate element: a vertex is repeated within one element");
   if (X) {
-    dvec<double> Xd(X, X + n * dim);
     set_geometry_from_X<DeviceBackend>(pl->d, Xd);
   } else {
     dvec<double> Dd(Dop, Dop + t * dim * K);
@@ -331,9 +370,11 @@ int skb_plan_slot_map(const skb_plan* pl, int32_t* slot) {
   const int D = pl->d.dim, K = pl->d.K, t = pl->d.t;
   thrust::host_vector<int> bptr = pl->d.bptr, bcol = pl->d.bcol, Ts = pl->d.T32;
   thrust::host_vector<uint8_t> perm = pl->d.perm;
-  for (int e = 0; e < t; ++e) {
+  thrust::host_vector<int> eo = pl->d.eorder;
+  for (int ei = 0; ei < t; ++ei) {
+    const int e = eo.empty() ? ei : eo[ei];  // caller's element index
     int To[4];
-    for (int s = 0; s < K; ++s) To[perm[e * K + s]] = Ts[e * K + s];  // caller's corner order
+    for (int s = 0; s < K; ++s) To[perm[ei * K + s]] = Ts[ei * K + s];  // caller's corner order
     for (int a = 0; a < K; ++a) {
       const int v = To[a];
       const int b0 = bptr[v], nb = bptr[v + 1] - b0;
@@ -357,16 +398,19 @@ int skb_plan_element_D(const skb_plan* pl, double* Dout) {
   const int D = pl->d.dim, K = pl->d.K, t = pl->d.t;
   thrust::host_vector<double> Dm = pl->d.Dm;
   thrust::host_vector<uint8_t> perm = pl->d.perm;
-  for (int e = 0; e < t; ++e)
+  thrust::host_vector<int> eo = pl->d.eorder;
+  for (int ei = 0; ei < t; ++ei) {
+    const int e = eo.empty() ? ei : eo[ei];  // caller's element index
     for (int j = 0; j < D; ++j) {
       double s0 = 0.0;
       for (int s = 1; s < K; ++s) {
-        double v = Dm[(size_t)(j * D + (s - 1)) * t + e];
-        Dout[((size_t)e * D + j) * K + perm[e * K + s]] = v;
+        double v = Dm[(size_t)(j * D + (s - 1)) * t + ei];
+        Dout[((size_t)e * D + j) * K + perm[ei * K + s]] = v;
         s0 -= v;
       }
-      Dout[((size_t)e * D + j) * K + perm[e * K]] = s0;
+      Dout[((size_t)e * D + j) * K + perm[ei * K]] = s0;
     }
+  }
   return SKB_OK;
   SKB_CATCH
 }
@@ -374,8 +418,22 @@ int skb_plan_element_D(const skb_plan* pl, double* Dout) {
 int skb_plan_volume(const skb_plan* pl, double* vol) {
   if (!pl || !vol) return fail(SKB_EINVAL, "null argument");
   SKB_CUDA(cudaSetDevice(pl->device));
-  SKB_CUDA(cudaMemcpy(vol, raw(pl->d.vol0), (size_t)pl->d.t * sizeof(double), cudaMemcpyDeviceToHost));
+  SKB_TRY
+  thrust::host_vector<double> v0 = pl->d.vol0;
+  thrust::host_vector<int> eo = pl->d.eorder;
+  for (int i = 0; i < pl->d.t; ++i) vol[eo.empty() ? i : eo[i]] = v0[i];
   return SKB_OK;
+  SKB_CATCH
+}
+
+int skb_plan_element_order(const skb_plan* pl, int32_t* order) {
+  if (!pl || !order) return fail(SKB_EINVAL, "null argument");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  thrust::host_vector<int> eo = pl->d.eorder;
+  for (int i = 0; i < pl->d.t; ++i) order[i] = eo.empty() ? i : eo[i];
+  return SKB_OK;
+  SKB_CATCH
 }
 
 int skb_plan_vertex_masses(const skb_plan* pl, const double* rho, int64_t rho_n, double* m) {
@@ -386,9 +444,10 @@ int skb_plan_vertex_masses(const skb_plan* pl, const double* rho, int64_t rho_n,
   const int K = pl->d.K, t = pl->d.t, n = pl->d.n;
   thrust::host_vector<double> vol = pl->d.vol0;
   thrust::host_vector<int> T = pl->d.T32;
+  thrust::host_vector<int> eo = pl->d.eorder;
   for (int v = 0; v < n; ++v) m[v] = 0.0;
   for (int e = 0; e < t; ++e) {
-    const double me = vol[e] * rho[rho_n > 1 ? e : 0];
+    const double me = vol[e] * rho[rho_n > 1 ? (eo.empty() ? e : eo[e]) : 0];
     for (int a = 0; a < K; ++a) m[T[e * K + a]] += me;
   }
   for (int v = 0; v < n; ++v) m[v] /= K;

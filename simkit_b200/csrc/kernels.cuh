@@ -19,7 +19,8 @@ struct EvalArgs {
   int material;
   int psd_mode;
   const double* x;     // (n*dim) positions or displacements
-  const double* Fbar;  // (t*dim*dim) per-element offset of the _u tier, or nullptr
+  const double* Fbar;  // (t*dim*dim) per-element offset of the _u tier (CALLER's element order), or nullptr
+  const int* eorder;   // internal element -> caller's element (plan.cuh str_element_order), or nullptr = identity
   const double* mu;
   const double* lam;
   const double* vol;
@@ -118,10 +119,11 @@ SKB_HD void load_raw(const PlanView& p, const EvalArgs& a, int e, const int* Te,
 // F_ij = sum_{a>=1} D[j][a] (x_a[i] - x_0[i])  (+ Fbar)      -- the "J @ x" of the reference
 template <int D>
 SKB_HD void build_F(const EvalArgs& a, int e, const ElemRaw<D>& r, Mat<D>& F) {
+  const size_t ef = (a.Fbar && a.eorder) ? (size_t)a.eorder[e] : (size_t)e;  // Fbar is listed in the caller's order
 #pragma unroll
   for (int i = 0; i < D; ++i)
 #pragma unroll
-    for (int j = 0; j < D; ++j) F.m[i][j] = a.Fbar ? a.Fbar[(size_t)e * D * D + i * D + j] : 0.0;
+    for (int j = 0; j < D; ++j) F.m[i][j] = a.Fbar ? a.Fbar[ef * D * D + i * D + j] : 0.0;
 #pragma unroll
   for (int c = 0; c < D; ++c) {
 #pragma unroll

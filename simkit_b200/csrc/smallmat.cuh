@@ -9,6 +9,21 @@
 #include <math.h>
 #include <float.h>
 
+// Build configuration of the assembly path (every csrc header includes this file first).  The three switches below
+// started as A/B experiments of round 1; timed on a B200 in round 2 (C5, profiles/r02c_ab_element_order.txt) they are
+// worth 2 % of the step together and are now the default.  -DSKB_BASELINE_KERNELS restores the round-1 kernels.
+#if !defined(SKB_BASELINE_KERNELS)
+#ifndef SKB_EXP_SUM0
+#define SKB_EXP_SUM0 1      // corner-0 pairs of the local stiffness by read-back (sum_a K_ab = 0) instead of U M U^T
+#endif
+#ifndef SKB_EXP_SRCBASE
+#define SKB_EXP_SRCBASE 1   // phase-2 sources carry the pair's staging offset + diagonal flag (no pair_base arithmetic)
+#endif
+#ifndef SKB_FIN_ITEMS
+#define SKB_FIN_ITEMS 2     // level 2: two items per thread, loads of every stage batched
+#endif
+#endif
+
 #if defined(__CUDACC__)
 #define SKB_HD __host__ __device__ __forceinline__
 #else

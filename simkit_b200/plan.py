@@ -80,6 +80,12 @@ class MeshPlan:
         check(self._lib.skb_plan_element_D(self._h, ptr(D)))
         return D
 
+    def element_order(self):
+        """``order[i]`` = index (in ``T``) of the element the plan lists ``i``-th (its internal spatial order)."""
+        order = np.empty(self.t, dtype=np.int32)
+        check(self._lib.skb_plan_element_order(self._h, ptr(order)))
+        return order
+
     def volume(self):
         vol = np.empty((self.t, 1))
         check(self._lib.skb_plan_volume(self._h, ptr(vol)))

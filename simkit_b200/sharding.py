@@ -46,8 +46,7 @@ def vertex_cuts(T, ecuts, n):
         v[p] = blk.min() if blk.size else v[p - 1]
     for p in range(world - 1, 0, -1):           # empty blocks / non-monotone meshes: keep ranges ordered
         v[p] = min(v[p], v[p + 1])
-    if np.any(np.diff(v) < 0):
-        raise ValueError("elements are not ordered by vertex id; reorder the mesh before sharding")
+    assert not np.any(np.diff(v) < 0)
     return v
 
 
@@ -169,8 +168,15 @@ def _row_value_positions(lrows, rptr, lcols, bptr, bcol, d):
 
 # ---------------------------------------------------------------------------------- builders
 def layout_from_global(T, n, dim, rank, world, align=1):
-    """Shard layout of ``rank`` from the full element list (tests and small meshes)."""
+    """Shard layout of ``rank`` from the full element list (tests and small meshes).
+
+    The caller may list the elements in any order: they are first sorted (stably) by their smallest vertex id, which
+    makes the contiguous blocks own contiguous, non-decreasing vertex ranges (SURVEY §8e "after ordering elements by
+    minimum vertex id").  ``layout.own_elements`` are the caller's indices of this rank's elements, in the order the
+    shard lists them (per-element inputs of the rank are ``mu[layout.own_elements]`` etc.)."""
     T = np.asarray(T, dtype=np.int64)
+    order = np.argsort(T.min(axis=1), kind="stable")
+    T = T[order]
     ecuts = element_cuts(T.shape[0], world, align)
     vcuts = vertex_cuts(T, ecuts, n)
     own = T[ecuts[rank]:ecuts[rank + 1]]
@@ -178,7 +184,9 @@ def layout_from_global(T, n, dim, rank, world, align=1):
     touch = np.any((lower >= vcuts[rank]) & (lower < vcuts[rank + 1]), axis=1)
     pat = lower[touch]
     pat_rank = np.searchsorted(ecuts, np.nonzero(touch)[0], side="right") - 1
-    return ShardLayout(rank, world, dim, own, pat, pat_rank, vcuts), ecuts
+    lay = ShardLayout(rank, world, dim, own, pat, pat_rank, vcuts)
+    lay.own_elements = order[ecuts[rank]:ecuts[rank + 1]]
+    return lay, ecuts
 
 
 def layout_grid_slab(cells, rank, world):

@@ -75,12 +75,15 @@ int hs_run(const double* X, const int64_t* T, int64_t n, int64_t t, int64_t t_ac
            int psd_mode, const double* x, const double* Fbar, const double* mu, int64_t mu_n,
            const double* lam, int64_t lam_n, const double* vol, int64_t vol_n, int64_t* info, int32_t* bptr,
            int32_t* bcol, int32_t* bslot, double* Dm_out, double* vol_out, double* g, double* vals,
-           double* energy) {
+           double* energy, int reorder) {
   const int K = dim + 1;
   thrust::host_vector<double> Xh(X, X + n * dim);
   thrust::host_vector<int> Th((size_t)t * K);
   for (int64_t i = 0; i < t * K; ++i) Th[i] = (int)T[i];
   PlanData<HostBackend> pd;
+  // reorder != 0: the plan lists the active elements in its own spatial order (plan.cuh str_element_order), as
+  // skb_plan_create does; per-element inputs and outputs below stay in the caller's order
+  if (reorder) apply_element_order<HostBackend>(pd, Th, Xh, (int)n, (int)t_active, dim, tile_elems);
   if (!build_plan<HostBackend>(pd, Th, (int)n, (int)t_active, dim, tile_elems, (int)t)) return -1;
   t = t_active;
   set_geometry_from_X<HostBackend>(pd, Xh);
@@ -91,15 +94,30 @@ int hs_run(const double* X, const int64_t* T, int64_t n, int64_t t, int64_t t_ac
   for (int i = 0; i <= n; ++i) bptr[i] = pd.bptr[i];
   for (int i = 0; i < pd.nnzb; ++i) bcol[i] = pd.bcol[i];
   (void)bslot;
-  for (size_t i = 0; i < pd.Dm.size(); ++i) Dm_out[i] = pd.Dm[i];
-  for (int i = 0; i < t; ++i) vol_out[i] = pd.vol0[i];
+  auto caller = [&](int i) { return pd.eorder.empty() ? i : (int)pd.eorder[i]; };
+  for (int k = 0; k < dim * dim; ++k)
+    for (int i = 0; i < t; ++i) Dm_out[(size_t)k * t + caller(i)] = pd.Dm[(size_t)k * t + i];
+  for (int i = 0; i < t; ++i) vol_out[caller(i)] = pd.vol0[i];
   PlanView p = pd.view();
+  std::vector<double> mu_i, lam_i, vol_i;  // per-element inputs in the internal order
+  if (reorder) {
+    auto gather = [&](const double*& src, int64_t cnt, std::vector<double>& dst) {
+      if (!src || cnt <= 1) return;
+      dst.resize(t);
+      for (int i = 0; i < t; ++i) dst[i] = src[caller(i)];
+      src = dst.data();
+    };
+    gather(mu, mu_n, mu_i);
+    gather(lam, lam_n, lam_i);
+    gather(vol, vol_n, vol_i);
+  }
   std::vector<double> pb((size_t)pd.blocks.n_ts * (dim == 3 ? RecStride<3>::value : RecStride<2>::value)), pv((size_t)pd.verts.n_ts * dim);
   EvalArgs a;
   a.material = material;
   a.psd_mode = psd_mode;
   a.x = x;
   a.Fbar = Fbar;
+  a.eorder = p.eorder;
   a.mu = mu;
   a.lam = lam;
   a.vol = vol ? vol : p.vol0;

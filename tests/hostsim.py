@@ -52,7 +52,7 @@ def _c(a):
 
 
 def run(X, T, material, psd_mode, x, mu, lam, vol=None, Fbar=None, tile_elems=32, want_g=True, want_h=True,
-        t_active=None):
+        t_active=None, reorder=False):
     lib = load()
     X = _c(X)
     T = np.ascontiguousarray(T, dtype=np.int64)
@@ -70,8 +70,8 @@ def run(X, T, material, psd_mode, x, mu, lam, vol=None, Fbar=None, tile_elems=32
             _p(lam), lam.size, _p(vol), 0 if vol is None else vol.size, _p(info, _lp)]
     lib.hs_run.argtypes = [_dp, _lp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                            ctypes.c_int, _dp, _dp, _dp, ctypes.c_int64, _dp, ctypes.c_int64, _dp, ctypes.c_int64,
-                           _lp, _ip, _ip, _ip, _dp, _dp, _dp, _dp, _dp]
-    lib.hs_run(*args, None, None, None, None, None, None, None, None)
+                           _lp, _ip, _ip, _ip, _dp, _dp, _dp, _dp, _dp, ctypes.c_int]
+    lib.hs_run(*args, None, None, None, None, None, None, None, None, int(bool(reorder)))
     nnzb = int(info[0])
     bptr = np.zeros(n + 1, dtype=np.int32)
     bcol = np.zeros(nnzb, dtype=np.int32)
@@ -81,7 +81,8 @@ def run(X, T, material, psd_mode, x, mu, lam, vol=None, Fbar=None, tile_elems=32
     g = np.zeros(n * dim) if want_g else None
     vals = np.zeros(nnzb * dim * dim) if want_h else None
     energy = np.zeros(1)
-    lib.hs_run(*args, _p(bptr, _ip), _p(bcol, _ip), _p(bslot, _ip), _p(Dm), _p(vol0), _p(g), _p(vals), _p(energy))
+    lib.hs_run(*args, _p(bptr, _ip), _p(bcol, _ip), _p(bslot, _ip), _p(Dm), _p(vol0), _p(g), _p(vals), _p(energy),
+               int(bool(reorder)))
     return dict(bptr=bptr, bcol=bcol, bslot=bslot.reshape(t, K, K), Dm=Dm.reshape(dim, dim, t_active), vol0=vol0,
                 g=g, vals=vals, energy=float(energy[0]), info=info)
 

@@ -155,3 +155,32 @@ def test_edge_case_meshes(case, dim):
         Hh = hostsim.csr_from_blocks(r["bptr"], r["bcol"], r["vals"], n, dim)
         assert rel(r["g"], g) < TOL and abs(Hh - H).max() <= TOL * abs(H).max()
         assert abs(r["energy"] - oe.energy_x("stable_neo_hookean", U, J, mu, lam, vol)) <= 1e-12 * abs(r["energy"])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_plan_element_order(dim, shuffle):
+    """The plan's own spatial element order (plan.cuh ``str_element_order``, what ``skb_plan_create`` applies): fewer
+    partial records per element than the generator's order -- also when the caller lists the elements in random order
+    -- with the same pattern and the same assembled values; heterogeneous per-element materials, volumes and the
+    ``_u`` tier's ``Jx_bar`` stay in the caller's order at the boundary."""
+    cells = (18, 18, 18) if dim == 3 else (48, 48)
+    ext = tuple(1.0 for _ in cells)
+    X, T = syn.make_mesh(cells)
+    rng = np.random.default_rng(11)
+    if shuffle:
+        T = T[rng.permutation(T.shape[0])]
+    U = syn.jittered_state(X, cells, ext, sigma=0.1)
+    mu, lam = syn.heterogeneous_lame(T.shape[0])
+    vol = oe.volume(X, T)
+    Fbar = 0.01 * rng.standard_normal((T.shape[0], dim, dim))
+    a = hostsim.run(X, T, 0, 1, U, mu, lam, vol, Fbar=Fbar, tile_elems=128)
+    b = hostsim.run(X, T, 0, 1, U, mu, lam, vol, Fbar=Fbar, tile_elems=128, reorder=True)
+    lexi = hostsim.run(*syn.make_mesh(cells), 0, 1, U, *syn.lame(), tile_elems=128)["info"]
+    assert b["info"][1] < 0.85 * lexi[1] and b["info"][2] < 0.85 * lexi[2]
+    if shuffle:
+        assert b["info"][1] < 0.5 * a["info"][1]
+    assert np.array_equal(a["bptr"], b["bptr"]) and np.array_equal(a["bcol"], b["bcol"])
+    assert rel(b["vals"], a["vals"]) < 1e-13 and rel(b["g"], a["g"]) < 1e-13
+    assert abs(b["energy"] - a["energy"]) <= 1e-13 * abs(a["energy"])
+    assert np.array_equal(a["Dm"], b["Dm"]) and np.array_equal(a["vol0"], b["vol0"])

@@ -44,10 +44,10 @@ def test_slab_layout_matches_general_partition(cells, world):
     assert np.all(owned == 1)                       # every vertex row has exactly one owner
 
 
-def _rank_assembly(lay, X, U, mu, lam):
+def _rank_assembly(lay, X, U, mu, lam, reorder=False):
     """CPU replay of one rank: plan with pattern-only elements, assembly of the own elements only."""
     Xl, Ul = X[lay.l2g], U[lay.l2g]
-    out = hostsim.run(Xl, lay.T_local, MAT_ID, 1, Ul, mu, lam, None, tile_elems=32, t_active=lay.t_own)
+    out = hostsim.run(Xl, lay.T_local, MAT_ID, 1, Ul, mu, lam, None, tile_elems=32, t_active=lay.t_own, reorder=reorder)
     return out
 
 
@@ -88,6 +88,37 @@ def test_sharded_assembly_equals_global_oracle(cells, world):
         ref_rows = Q_ref[gdof[own]]
         assert rel(rows_g.toarray(), ref_rows.toarray()) < 1e-10
         assert rel(o["g"][own], g_ref[gdof[own]]) < 1e-10
+
+
+@pytest.mark.parametrize("cells,world", [((5, 3, 4), 2), ((9, 6), 3)])
+def test_sharding_a_shuffled_element_list(cells, world):
+    """Elements listed in random order: the partitioner orders them by smallest vertex id itself instead
+    of refusing, per-element materials follow through ``own_elements``, every rank's plan applies its own spatial
+    element order on top, and the exchanged result is still the global oracle's."""
+    X, T = syn.make_mesh(cells)
+    dim, n = len(cells), X.shape[0]
+    rng = np.random.default_rng(3)
+    T = T[rng.permutation(T.shape[0])]
+    U = syn.jittered_state(X, cells, tuple(1.0 for _ in cells), sigma=0.3)
+    mu, lam = syn.heterogeneous_lame(T.shape[0])
+    J, vol = oe.deformation_jacobian(X, T), oe.volume(X, T)
+    g_ref = oe.gradient_x(MAT, U, J, mu, lam, vol).ravel()
+    Q_ref = sps.csr_matrix(oe.hessian_x(MAT, U, J, mu, lam, vol, psd=True))
+    lays = [sh.layout_from_global(T, n, dim, r, world)[0] for r in range(world)]
+    assert np.array_equal(np.sort(np.concatenate([l.own_elements for l in lays])), np.arange(T.shape[0]))
+    outs = [_rank_assembly(l, X, U, mu[l.own_elements], lam[l.own_elements], reorder=True) for l in lays]
+    _apply_exchange(lays, outs)
+    owned = np.zeros(n, dtype=int)
+    for lay, o in zip(lays, outs):
+        Ql = hostsim.csr_from_blocks(o["bptr"], o["bcol"], o["vals"], lay.n_local, dim).tocsr()
+        own = np.arange(lay.own_lo * dim, lay.own_hi * dim)
+        gdof = (lay.l2g[:, None] * dim + np.arange(dim)[None, :]).ravel()
+        rows = Ql[own]
+        rows_g = sps.csr_matrix((rows.data, gdof[rows.indices], rows.indptr), shape=(own.size, n * dim))
+        assert rel(rows_g.toarray(), Q_ref[gdof[own]].toarray()) < 1e-10
+        assert rel(o["g"][own], g_ref[gdof[own]]) < 1e-10
+        owned[lay.v_lo:lay.v_hi] += 1
+    assert np.all(owned == 1)
 
 
 # ------------------------------------------------------------------------------ gloo, world size 2
