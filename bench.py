@@ -266,7 +266,7 @@ def run_ours(args, rank, world, local_rank):
     cfg = syn.CONFIGS[args.workload]
     if world > 1:
         from simkit_b200 import sharding
-        shard = sharding.make_shard(args.workload, rank, world, device=local_rank)
+        shard = sharding.make_shard(args.workload, rank, world, device=local_rank, interface=args.interface or None)
         plan, U = shard.plan, shard.U_local
         tt = torch.tensor([shard.nnz_owned], dtype=torch.int64, device=dev)
         dist.all_reduce(tt)
@@ -532,6 +532,8 @@ def run_ours(args, rank, world, local_rank):
         fext_d[:, 1] = -9.8
         fext_d = fext_d.reshape(-1) * mass_d
         nsteps = max(1, min(args.steps, args.newton_steps))
+        if args.dist_solver:
+            shard.solver = args.dist_solver
         n_agg = shard.set_coarse_space(min(729, max(8, n_total // 1000)) if args.aggregates < 0 else args.aggregates)
         tt, info = [], None
         for s in range(1 + nsteps):
@@ -582,6 +584,25 @@ def run_ours(args, rank, world, local_rank):
                   "preconditioner": "3x3 block-Jacobi + rigid-body modes of %d vertex aggregates (two-level, additive)" % n_agg,
                   "includes": "device-resident state per rank; assembly + interface exchange + distributed PCG + line search",
                   "pcg_ms_per_iter": sec * 1e3 / max(info["pcg_iters"], 1)}
+        solver = getattr(shard, "solver", None) or os.environ.get("SKB_DIST_PCG", "peer")
+        if solver.startswith("peer") and not getattr(shard, "_peer", False):
+            solver = "pcg2 (NCCL; peer-memory set-up failed: %s)" % getattr(shard, "_peer_error", "?")
+        nc_ = (6 if dim == 3 else 3) * n_agg
+        newton["solver"] = solver
+        if getattr(shard, "last_solve_ms", None):
+            newton["solve_ms"] = shard.last_solve_ms      # rank 0's host-clock breakdown of the last solve
+        newton["collectives_per_iter"] = (
+            {"all_reduce": 1, "all_reduce_doubles": 4 + nc_, "grouped_send_recv": 1,
+             "note": "single-reduction PCG (csrc/capi_pcg2.cu): gamma, delta, r.r and the restricted vector of the coarse "
+                     "space share one ncclAllReduce; halo of u by one grouped ncclSend/ncclRecv; CUDA-graph replay"}
+            if solver.startswith("pcg2") else
+            {"all_reduce": 0, "grouped_send_recv": 0, "nccl_calls": 0, "peer_store_doubles_reduction": (4 + nc_) * world,
+             "note": "single-reduction PCG over peer memory (csrc/capi_pcg2.cu, transport 1): halo values of u and the 4 + 6 n_agg "
+                     "reduction partials are stored by the producing kernels straight into the other ranks' HBM over NVLink "
+                     "(CUDA IPC mappings, flags); every rank sums the partials itself in rank order; CUDA-graph replay"}
+            if solver.startswith("peer") else
+            {"all_reduce": 3 if n_agg else 2, "all_reduce_doubles": 3 + nc_, "grouped_send_recv": 1,
+             "note": "textbook PCG loop (%s)" % solver})
 
     # ---- reduced (subspace) Hessian B^T H B, BASELINE config 4 (C4 mesh, r = 200) --------------------
     reduced = None
@@ -646,7 +667,12 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": workload_desc(args.workload, t_total, n_total, nnz_total), "material": MATERIAL,
                        "psd": "analytic eigensystem, floor 1e-6 after vol",
                        "l2": "no flush needed: per-step inputs+outputs (>= %.1f GB) exceed the 126 MB L2" % (alg_bytes / 1e9),
-                       "sharding": "none" if world == 1 else "contiguous element slabs, NCCL interface exchange",
+                       "sharding": "none" if world == 1 else (
+                           "contiguous element slabs; interface = %s" % (
+                               "exchange: partial gradient rows and Hessian block-rows of the ghost vertices sent to their owner, "
+                               "one grouped NCCL send/recv per assembly" if shard.interface == "exchange" else
+                               "recompute: every rank also evaluates the one layer of its lower neighbour's elements that touches "
+                               "its rows (ghost elements), no communication in the assembly; NVLink traffic only in the solve")),
                        "element_order": "caller: %s%s; plan: internal sort-tile-recursive order (SKB_ELEMENT_ORDER=%s)" % (
                            args.element_order if world == 1 else "input",
                            "" if args.shuffle == "none" else ", shuffled " + args.shuffle,
@@ -676,6 +702,10 @@ def main():
     ap.add_argument("--pcg-rtol", type=float, default=1e-10)
     ap.add_argument("--aggregates", type=int, default=-1, help="vertex aggregates of the two-level PCG preconditioner "
                     "(-1: MeshPlan.auto_aggregates when block-Jacobi needs > 300 iterations, 729 at C5; 0: block-Jacobi only)")
+    ap.add_argument("--interface", default="", choices=["", "exchange", "recompute"],
+                    help="N > 1: how owned rows get the lower neighbour's interface contributions (Shard docstring); default recompute")
+    ap.add_argument("--dist-solver", default="", choices=["", "python", "native", "native_graph", "pcg2", "pcg2_eager", "peer", "peer_eager"],
+                    help="N > 1: distributed PCG variant (default pcg2: single-reduction, C++-driven, CUDA graph)")
     ap.add_argument("--reduced", type=int, default=0, help="also time the reduced Hessian B^T H B with this many modes (config 4: --workload C4 --reduced 200)")
     ap.add_argument("--element-order", default="input", choices=["input", "pencil"],
                     help="experiment (1 GPU): list the mesh's elements in 3x3-cell pencils (synthetic.pencil_order) instead of the "

@@ -76,9 +76,13 @@ int skb_plan_create_from_operator(const void* T, const double* D, int index_byte
  * reference is single-process).  X, T use the rank's local vertex numbering.  The first t_active
  * elements are this rank's own; the remaining t_total - t_active "pattern-only" elements are the
  * neighbours' elements that touch vertices this rank owns: they are never evaluated, they only reserve
- * CSR slots so that the neighbours' interface block-rows can be added in place. */
+ * CSR slots so that the neighbours' interface block-rows can be added in place.
+ * t_energy (0 = t_active): the first t_energy elements count in the energy and in the plan's internal element
+ * order as one group.  A rank that RE-EVALUATES its lower neighbour's interface elements instead of receiving
+ * their contributions (Shard(interface="recompute"): t_active = t_total = own + neighbour elements) passes its
+ * own element count, so that every element is counted once in the all-reduced energy. */
 int skb_plan_create_sharded(const double* X, const void* T, int index_bytes, int64_t n, int64_t t_active,
-                            int64_t t_total, int dim, int device, int tile_elems, skb_plan** out);
+                            int64_t t_total, int64_t t_energy, int dim, int device, int tile_elems, skb_plan** out);
 void skb_plan_destroy(skb_plan* plan);
 
 /* sizes: n, t, dim, nnzb (block non-zeros), nnz (= nnzb*dim*dim), n_tiles, n_block_partials, n_vertex_partials */
@@ -216,6 +220,38 @@ typedef struct skb_dist_pcg_args {
   int32_t reserved;     /*    on the plan's own stream after the first, eager chunk)               */
 } skb_dist_pcg_args;
 int skb_dist_pcg_native(skb_plan* plan, const skb_dist_pcg_args* args, int32_t* iters, double* relres);
+/* The same solve with ONE collective per iteration (csrc/capi_pcg2.cu): single-reduction (Chronopoulos-Gear) PCG whose
+ * all-reduce carries gamma = r.u, delta = w.u, r.r AND the restricted vector of the two-level preconditioner; 7 kernels,
+ * one grouped ncclSend/ncclRecv (halo of u) and one ncclAllReduce of 4 + 6 n_agg doubles per iteration, chunks of
+ * `check_every` iterations replayed as one CUDA graph.  Work vectors belong to the plan.  Replaces scipy's spsolve of
+ * solvers/newton.py:52 on a sharded mesh; needs skb_nccl_init + skb_nccl_set_halo (and skb_dist_coarse_set for the
+ * two-level preconditioner).  All vectors in the rank's local numbering; x is zeroed, its owned entries are written. */
+typedef struct skb_dist_pcg2_args {
+  const double* vals;   /* CSR values of the owned rows (complete after the interface exchange)   */
+  const double* diag;   /* diagonal added to the matrix, or NULL                                  */
+  const double* rhs;
+  double* x;
+  void* stream;
+  double rtol;
+  int32_t v0, v1;       /* owned vertex rows                                                       */
+  int32_t max_iter;
+  int32_t check_every;  /* iterations per chunk between host reads of the convergence flag (default 25) */
+  int32_t use_graph;    /* 1: full chunks replay one CUDA graph (captured after the first, eager chunk)  */
+  int32_t use_coarse;   /* 1: two-level preconditioner when the plan has a coarse space                 */
+  int32_t transport;    /* 0: NCCL (grouped send/recv + all-reduce); 1: stores into the peers' HBM over NVLink  */
+  int32_t reserved;     /*    through CUDA IPC mappings, flags instead of collective calls (skb_pcg2_peer_*)    */
+} skb_dist_pcg2_args;
+int skb_dist_pcg2(skb_plan* plan, const skb_dist_pcg2_args* args, int32_t* iters, double* relres);
+/* Peer-memory transport of skb_dist_pcg2 (transport = 1): every rank allocates one slab (reduction partials of all
+ * ranks, halo receive area, flags), exports its CUDA IPC handle and maps the slabs of the others; per iteration the
+ * halo values of u and the 4 + 6 n_agg reduction partials are then written straight into the peers' memory by the
+ * kernels that produce them (NVLink stores) and every rank sums the partials itself in rank order.  Collective set-up:
+ * export on every rank, all-gather handle64 (64 bytes) and meta (1 + world int64) in rank order, import on every rank. */
+int skb_pcg2_peer_export(skb_plan* plan, void* handle64, int64_t* meta, int64_t meta_len);
+int skb_pcg2_peer_import(skb_plan* plan, const void* handles, const int64_t* metas);
+/* host-clock breakdown of the plan's last skb_dist_pcg2, ms: set-up (incl. the all-reduce of the coarse matrix), dense
+ * inverse of the coarse matrix (cuSOLVER), iterations, total */
+int skb_dist_pcg2_times(skb_plan* plan, double out[4]);
 /* measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the compute roofline denominator */
 int skb_fp64_peak(int device, double* tflops);
 /* measured FP64 tensor-core throughput (DMMA.8x8x4 = mma.sync.m8n8k4.f64, 512 flops per warp instruction):
@@ -256,6 +292,14 @@ int skb_pcg(skb_plan* plan, const double* vals, const double* diag_add, const do
             double rtol, int max_iter, double* x, int* iters, double* relres);
 int skb_pcg_dev(skb_plan* plan, const double* vals, const double* diag_add, const double* rhs,
                 double rtol, int max_iter, double* x, int* iters, double* relres, void* stream);
+/* skb_pcg on CSR values that are already on the device (a lazy Hessian of simkit_b200/device_csr.py): replaces the
+ * spsolve of solvers/newton.py:52 without the 8*nnz-byte round trip; rhs and x are host pointers. */
+int skb_pcg_vals_dev(skb_plan* plan, const double* vals_dev, const double* diag_add, const double* rhs, double rtol,
+                int max_iter, double* x, int* iters, double* relres);
+/* pos[i] = index of scalar entry (rows[i], cols[i]) in the plan's canonical CSR values, -1 outside the pattern: lets a
+ * sparse term the caller adds to the Hessian (mass / penalty / contact matrices, e.g. integrators/backward_euler.py:84,
+ * examples/interactive_demos/010_interactive_contact_plane_3D.py:104-108) be added on the device. */
+int skb_plan_value_positions(skb_plan* plan, int64_t count, const int32_t* rows, const int32_t* cols, int32_t* pos);
 /* Same solver for ANY sparse SPD matrix in scalar CSR form (what newton_solver receives from user
  * callables, solvers/newton.py:51-52); block = size of the Jacobi blocks (1, 2 or 3; n % block == 0). */
 int skb_csr_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const double* vals, int block,

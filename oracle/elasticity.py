@@ -879,6 +879,99 @@ def block_jacobi_cg_single_reduction(H, rhs, dim, rtol=1e-10, maxiter=20000):
     return x, maxiter
 
 
+def rigid_mode_prolongator(X, agg):
+    """P (n*dim, NC*n_agg) of the two-level preconditioner of simkit_b200/csrc/coarse.cuh (not reference code): the
+    rigid-body modes of vertex aggregates, P_v = [I | -[x_v - c_I]_x] (3 x 6; 2 x 3 in 2D), c_I the aggregate's centroid."""
+    X = np.asarray(X, dtype=np.float64)
+    n, dim = X.shape
+    agg = np.asarray(agg)
+    n_agg = int(agg.max()) + 1
+    NC = 6 if dim == 3 else 3
+    cnt = np.bincount(agg, minlength=n_agg).astype(np.float64)
+    cen = np.stack([np.bincount(agg, weights=X[:, a], minlength=n_agg) / cnt for a in range(dim)], axis=1)
+    xr = X - cen[agg]
+    rows, cols, vals = [], [], []
+    for v in range(n):
+        I = agg[v]
+        for i in range(dim):
+            rows.append(v * dim + i); cols.append(I * NC + i); vals.append(1.0)
+        x = xr[v]
+        if dim == 3:
+            # u + w x x :  out = c[:3] + cross(c[3:], x)
+            ent = [(0, 4, x[2]), (0, 5, -x[1]), (1, 5, x[0]), (1, 3, -x[2]), (2, 3, x[1]), (2, 4, -x[0])]
+        else:
+            ent = [(0, 2, -x[1]), (1, 2, x[0])]
+        for i, a, val in ent:
+            rows.append(v * dim + i); cols.append(I * NC + a); vals.append(val)
+    return sps.csr_matrix((vals, (rows, cols)), shape=(n * dim, NC * n_agg))
+
+
+def two_level_cg_single_reduction(H, rhs, dim, P=None, rtol=1e-10, maxiter=20000):
+    """Prototype (not reference code) of csrc/capi_pcg2.cu, statement for statement: Chronopoulos-Gear PCG with the
+    additive two-level preconditioner M^-1 = D^-1 + P (P^T H P)^-1 P^T, whose restricted residual is carried by the
+    recurrence  P^T r_{k+1} = P^T r_k - alpha (P^T w_k + beta P^T s_{k-1})  so that the one reduction of an iteration
+    (gamma = r.u, delta = w.u, r.r and P^T w) is the only collective.  A bootstrap pass with alpha = beta = 0 produces
+    u_0, w_0 and the first reduction.  ``P=None``: block-Jacobi only.  Returns (x, iterations)."""
+    H = sps.csr_matrix(H)
+    n = H.shape[0] // dim
+    Hb = sps.bsr_matrix(H, blocksize=(dim, dim))
+    Hb.sort_indices()
+    diag = np.zeros((n, dim, dim))
+    rows = np.repeat(np.arange(n), np.diff(Hb.indptr))
+    sel = Hb.indices == rows
+    diag[rows[sel]] = Hb.data[sel]
+    inv = np.linalg.inv(diag)
+    dinv = lambda v: np.einsum("nij,nj->ni", inv, v.reshape(n, dim)).reshape(-1)  # noqa: E731
+    b = np.asarray(rhs, dtype=np.float64).reshape(-1)
+    nd = b.size
+    x, r = np.zeros(nd), b.copy()
+    u, w, p, s = np.zeros(nd), np.zeros(nd), np.zeros(nd), np.zeros(nd)
+    if P is not None:
+        Ainv = np.linalg.inv((P.T @ H @ P).toarray())
+        rc = P.T @ r                       # the one extra reduction of the solve
+        rcs = np.zeros_like(rc)
+        red_c = np.zeros_like(rc)
+    red = np.zeros(3)
+    gamma_old = alpha_old = 1.0
+    bb = rr = 0.0
+    stage = iters = 0
+    for _ in range(maxiter + 1):
+        # --- pcg2_scalars_kernel
+        alpha = beta = 0.0
+        if stage > 0:
+            gamma, delta, rr = red
+            if stage == 1:
+                bb = rr
+            if not bb > 0.0 or not rr > rtol * rtol * bb:
+                break
+            beta = 0.0 if stage == 1 else gamma / gamma_old
+            den = delta if stage == 1 else delta - beta * gamma / alpha_old
+            if not den > 0.0 or not gamma > 0.0:
+                raise RuntimeError("breakdown")
+            alpha = gamma / den
+            gamma_old, alpha_old = gamma, alpha
+            iters += 1
+        stage += 1
+        if P is not None:
+            rcs = red_c + beta * rcs
+            rc = rc - alpha * rcs
+            zc = Ainv @ rc                 # --- pcg2_gemv_kernel
+        # --- pcg2_update_kernel
+        p = u + beta * p
+        s = w + beta * s
+        x = x + alpha * p
+        r = r - alpha * s
+        u = dinv(r)
+        if P is not None:
+            u = u + P @ zc
+        # --- halo exchange of u, pcg2_spmv_kernel, pcg2_restrict_kernel, the all-reduce
+        w = H @ u
+        red = np.array([r @ u, w @ u, r @ r])
+        if P is not None:
+            red_c = P.T @ w
+    return x, iters
+
+
 # --------------------------------------------------------------------------- #
 # reduced operators                                                           #
 # --------------------------------------------------------------------------- #

@@ -12,7 +12,7 @@ from .dirichlet_laplacian import dirichlet_laplacian  # noqa: F401
 from .dirichlet_penalty import dirichlet_penalty  # noqa: F401
 from .energies import *  # noqa: F401,F403
 from .fast_sandwich_transform_clustered import fast_sandwich_transform_clustered  # noqa: F401
-from .integrators import backward_euler, bdf2  # noqa: F401
+from .integrators import backward_euler, bdf2, forward_euler  # noqa: F401
 from .linear_solve import solve_dense, solve_sparse  # noqa: F401
 from .operators import gravity_force, massmatrix, volume, ympr_to_lame  # noqa: F401
 from .plan import MeshPlan, plan_from_operator  # noqa: F401

@@ -59,6 +59,16 @@ class DistPcgArgs(ctypes.Structure):
     ]
 
 
+class DistPcg2Args(ctypes.Structure):
+    """skb_dist_pcg2_args (include/simkit_b200.h)."""
+    _fields_ = [
+        ("vals", _vp), ("diag", _vp), ("rhs", _vp), ("x", _vp), ("stream", _vp), ("rtol", _dbl),
+        ("v0", ctypes.c_int32), ("v1", ctypes.c_int32), ("max_iter", ctypes.c_int32), ("check_every", ctypes.c_int32),
+        ("use_graph", ctypes.c_int32), ("use_coarse", ctypes.c_int32), ("transport", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
 _MAT = [_vp, _i64, _vp, _i64, _vp, _i64]  # mu, mu_n, lam, lam_n, vol, vol_n
 
 SIGNATURES = {
@@ -67,7 +77,7 @@ SIGNATURES = {
     "skb_version": (ctypes.c_char_p, []),
     "skb_plan_create": (_int, [_vp, _vp, _int, _i64, _i64, _int, _int, _int, ctypes.POINTER(_vp)]),
     "skb_plan_create_from_operator": (_int, [_vp, _vp, _int, _i64, _i64, _int, _int, _int, ctypes.POINTER(_vp)]),
-    "skb_plan_create_sharded": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _int, _int, _int, ctypes.POINTER(_vp)]),
+    "skb_plan_create_sharded": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _i64, _int, _int, _int, ctypes.POINTER(_vp)]),
     "skb_plan_destroy": (None, [_vp]),
     "skb_plan_info": (_int, [_vp, _vp]),
     "skb_plan_csr_pattern": (_int, [_vp, _vp, _vp]),
@@ -125,8 +135,14 @@ SIGNATURES = {
     "skb_nccl_set_halo": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "skb_nccl_finalize": (_int, [_vp]),
     "skb_dist_pcg_native": (_int, [_vp, ctypes.POINTER(DistPcgArgs), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_dbl)]),
+    "skb_dist_pcg2": (_int, [_vp, ctypes.POINTER(DistPcg2Args), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_dbl)]),
+    "skb_dist_pcg2_times": (_int, [_vp, _vp]),
+    "skb_pcg2_peer_export": (_int, [_vp, _vp, _vp, _i64]),
+    "skb_pcg2_peer_import": (_int, [_vp, _vp, _vp]),
     "skb_quadratic": (_int, [_i64, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_dbl), _vp]),
     "skb_newton_set_quadratic": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "skb_pcg_vals_dev": (_int, [_vp, _vp, _vp, _vp, _dbl, _int, _vp, ctypes.POINTER(_int), ctypes.POINTER(_dbl)]),
+    "skb_plan_value_positions": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "skb_pcg_set_coarse": (_int, [_vp, _i64, _vp, _vp]),
     "skb_spmv_dev": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "skb_newton": (_int, [_vp, ctypes.POINTER(NewtonOpts), _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, ctypes.POINTER(NewtonInfo)]),

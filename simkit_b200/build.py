@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 _TAG = os.environ.get("SKB_BUILD_TAG", "")
 OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(HERE, "libsimkit_b200" + ("_" + _TAG if _TAG else "") + ".so")
-SOURCES = ["capi.cu", "capi_elements.cu", "capi_solver.cu", "capi_reduced.cu", "capi_dist.cu", "capi_nccl.cu"]
+SOURCES = ["capi.cu", "capi_elements.cu", "capi_solver.cu", "capi_reduced.cu", "capi_dist.cu", "capi_nccl.cu", "capi_pcg2.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -67,7 +67,7 @@ def build(force=False, verbose=False, ptxas_info=False):
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
         return obj, r.stderr
 
-    with ThreadPoolExecutor(max_workers=min(6, len(srcs))) as ex:
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         results = list(ex.map(compile_one, srcs))
     objs = [o for o, _ in results]
     if verbose or ptxas_info:

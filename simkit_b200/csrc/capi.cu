@@ -204,12 +204,13 @@ int launch_assemble(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
 
 int launch_energy(skb_plan* pl, const EvalArgs& a, double* out_dev, cudaStream_t st) {
   const PlanView p = pl->view();
-  const int nb = (p.t + 255) / 256;
+  const int count = pl->d.t_energy;   // a shard that re-evaluates its neighbour's interface elements counts only its own
+  const int nb = (count + 255) / 256;
   if (pl->esums.size() < (size_t)nb) pl->esums.resize(nb);
   if (p.dim == 3)
-    SKB_LAUNCH(pl, SKB_K_ENERGY, st, energy_kernel<3><<<nb, 256, 0, st>>>(p, a, raw(pl->esums)));
+    SKB_LAUNCH(pl, SKB_K_ENERGY, st, energy_kernel<3><<<nb, 256, 0, st>>>(p, a, count, raw(pl->esums)));
   else
-    SKB_LAUNCH(pl, SKB_K_ENERGY, st, energy_kernel<2><<<nb, 256, 0, st>>>(p, a, raw(pl->esums)));
+    SKB_LAUNCH(pl, SKB_K_ENERGY, st, energy_kernel<2><<<nb, 256, 0, st>>>(p, a, count, raw(pl->esums)));
   SKB_LAUNCH(pl, SKB_K_OTHER, st, reduce_final_kernel<<<1, 1024, 0, st>>>(raw(pl->esums), nb, out_dev));
   SKB_CUDA(cudaGetLastError());
   return SKB_OK;
@@ -250,8 +251,10 @@ int skb_device_count(void) {
 }
 
 static int plan_create_common(const double* X, const double* Dop, const void* T, int index_bytes, int64_t n,
-                              int64_t t, int dim, int device, int tile_elems, skb_plan** out, int64_t t_total = -1) {
+                              int64_t t, int dim, int device, int tile_elems, skb_plan** out, int64_t t_total = -1,
+                              int64_t t_energy = 0) {
   if (t_total < t) t_total = t;
+  if (t_energy <= 0 || t_energy > t) t_energy = t;
   if ((!X && !Dop) || !T || !out) return fail(SKB_EINVAL, "null argument");
   if (dim != 2 && dim != 3) return fail(SKB_EINVAL, "Only dim == 2 or 3 are supported");
   if (index_bytes != 4 && index_bytes != 8) return fail(SKB_EINVAL, "index_bytes must be 4 or 8");
@@ -280,8 +283,9 @@ static int plan_create_common(const double* X, const double* Dop, const void* T,
     // spatial element order of the plan's own (plan.cuh str_element_order); SKB_ELEMENT_ORDER=input keeps the caller's
     const char* eo = getenv("SKB_ELEMENT_ORDER");
     if (!(eo && strcmp(eo, "input") == 0) && t > tile_elems)
-      apply_element_order<DeviceBackend>(pl->d, Td, Xd, (int)n, (int)t, dim, tile_elems);
+      apply_element_order<DeviceBackend>(pl->d, Td, Xd, (int)n, (int)t, dim, tile_elems, (int)t_energy);
   }
+  pl->d.t_energy = (int)t_energy;
   if (!build_plan<DeviceBackend>(pl->d, Td, (int)n, (int)t, dim, tile_elems, (int)t_total))
     return fail(SKB_EINVAL, "degenerate element: a vertex is repeated within one element");
   if (X) {
@@ -304,10 +308,11 @@ int skb_plan_create(const double* X, const void* T, int index_bytes, int64_t n, 
 }
 
 int skb_plan_create_sharded(const double* X, const void* T, int index_bytes, int64_t n, int64_t t_active,
-                            int64_t t_total, int dim, int device, int tile_elems, skb_plan** out) {
+                            int64_t t_total, int64_t t_energy, int dim, int device, int tile_elems, skb_plan** out) {
   if (!X) return fail(SKB_EINVAL, "null X");
   if (t_total < t_active) return fail(SKB_EINVAL, "t_total must be >= t_active");
-  return plan_create_common(X, nullptr, T, index_bytes, n, t_active, dim, device, tile_elems, out, t_total);
+  if (t_energy < 0 || t_energy > t_active) return fail(SKB_EINVAL, "t_energy must be in [0, t_active]");
+  return plan_create_common(X, nullptr, T, index_bytes, n, t_active, dim, device, tile_elems, out, t_total, t_energy);
 }
 
 int skb_plan_create_from_operator(const void* T, const double* D, int index_bytes, int64_t n, int64_t t,
@@ -319,6 +324,7 @@ int skb_plan_create_from_operator(const void* T, const double* D, int index_byte
 void skb_plan_destroy(skb_plan* plan) {
   if (!plan) return;
   cudaSetDevice(plan->device);
+  skb_nccl_finalize(plan);
   if (plan->stream) cudaStreamDestroy(plan->stream);
   if (plan->coarse) skb::coarse_destroy(plan->coarse);
   delete plan;

@@ -67,6 +67,7 @@ struct skb_plan {
   // PCG / Newton work vectors (allocated on first use)
   skb::dvec<double> w_r, w_z, w_p, w_q, w_dx, w_xt, w_x, w_xtrial, w_dinv, w_diag, w_mass, w_fext, w_xtilde, w_red;
   skb::CoarseSpace* coarse = nullptr;  // skb_pcg_set_coarse
+  void* dist = nullptr;                // skb::DistNative (nccl_api.cuh): communicator, halo lists, solver state; skb_nccl_init
   // plane contact springs of the device-resident Newton step (skb_newton_set_contact_plane)
   bool contact_on = false;
   double contact_k = 0.0, contact_p[3] = {0, 0, 0}, contact_n[3] = {0, 0, 0};

@@ -11,45 +11,19 @@
 // already in the process (the one torch loaded), so the default library has no NCCL dependency and two NCCL
 // versions can never meet in one process.  The communicator is this library's own (ncclCommInitRank with an id that the
 // Python side broadcasts through torch.distributed).
-#include "capi_common.cuh"
+#include "nccl_api.cuh"
 #include "solver.cuh"
 #include "coarse.cuh"
-
-#include <dlfcn.h>
-
-#include <map>
-#include <mutex>
-
-#if defined(__has_include) && !defined(SKB_NO_NCCL)
-#if __has_include(<nccl.h>)
-#include <nccl.h>
-#define SKB_HAVE_NCCL_H 1
-#endif
-#endif
 
 using namespace skb;
 
 static_assert(sizeof(skb_dist_pcg_args) == 152, "skb_dist_pcg_args layout (mirrored by ctypes in simkit_b200/_lib.py)");
 
 #if defined(SKB_HAVE_NCCL_H)
-namespace {
-
-struct NcclApi {
-  void* handle = nullptr;
-  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
-  ncclResult_t (*GroupStart)() = nullptr;
-  ncclResult_t (*GroupEnd)() = nullptr;
-  const char* (*GetErrorString)(ncclResult_t) = nullptr;
-  bool ok = false;
-  std::string why;
-};
+namespace skb {
 
 NcclApi& nccl() {
+
   static NcclApi a;
   static std::mutex mu;
   std::lock_guard<std::mutex> lk(mu);
@@ -85,34 +59,6 @@ NcclApi& nccl() {
   return a;
 }
 
-#define SKB_NCCL(call)                                                                                  \
-  do {                                                                                                  \
-    ncclResult_t _r = (call);                                                                           \
-    if (_r != ncclSuccess) return fail(SKB_ECUDA, std::string(#call) + ": " + nccl().GetErrorString(_r)); \
-  } while (0)
-
-struct Halo {
-  int peer;
-  int64_t ns, nr;
-  const int32_t *sidx, *ridx;
-  double *sbuf, *rbuf;
-};
-
-struct DistNative {
-  ncclComm_t comm = nullptr;
-  int rank = 0, world = 1;
-  std::vector<Halo> halo;
-};
-
-std::mutex g_mu;
-std::map<skb_plan*, DistNative> g_state;
-
-DistNative* state_of(skb_plan* pl) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_state.find(pl);
-  return it == g_state.end() ? nullptr : &it->second;
-}
-
 // refreshes the non-owned copies of v from their owners (Shard.halo_exchange): pack, one grouped send/recv, unpack
 int halo_exchange(DistNative& d, double* v, cudaStream_t st) {
   NcclApi& n = nccl();
@@ -140,7 +86,7 @@ int all_reduce(DistNative& d, double* buf, size_t count, cudaStream_t st) {
   return SKB_OK;
 }
 
-}  // namespace
+}  // namespace skb
 #endif  // SKB_HAVE_NCCL_H
 
 extern "C" {
@@ -173,8 +119,8 @@ int skb_nccl_init(skb_plan* pl, const void* id_bytes, int64_t nbytes, int rank, 
   memcpy(&id, id_bytes, sizeof(id));
   ncclComm_t comm = nullptr;
   SKB_NCCL(nccl().CommInitRank(&comm, world, id, rank));
-  std::lock_guard<std::mutex> lk(g_mu);
-  DistNative& d = g_state[pl];
+  if (!pl->dist) pl->dist = new DistNative();
+  DistNative& d = *state_of(pl);
   if (d.comm) nccl().CommDestroy(d.comm);
   d.comm = comm;
   d.rank = rank;
@@ -212,11 +158,14 @@ int skb_nccl_set_halo(skb_plan* pl, int n_peers, const int32_t* peers, const int
 
 int skb_nccl_finalize(skb_plan* pl) {
 #if defined(SKB_HAVE_NCCL_H)
-  std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_state.find(pl);
-  if (it != g_state.end()) {
-    if (it->second.comm && nccl().ok) nccl().CommDestroy(it->second.comm);
-    g_state.erase(it);
+  // called by skb_plan_destroy as well: the communicator, the halo lists (raw pointers into the caller's tensors) and
+  // the solver state can never outlive the plan or be inherited by another plan allocated at the same address
+  DistNative* d = state_of(pl);
+  if (d) {
+    if (d->pcg2) pcg2_destroy(d->pcg2);
+    if (d->comm && nccl().ok) nccl().CommDestroy(d->comm);
+    delete d;
+    pl->dist = nullptr;
   }
 #endif
   return SKB_OK;
@@ -240,6 +189,22 @@ int skb_dist_pcg_native(skb_plan* pl, const skb_dist_pcg_args* a, int32_t* iters
   cudaStream_t st = use_graph ? pl->stream : caller;
   void* sp = (void*)st;
   cudaEvent_t ev = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  // every exit path (also the early `return rc` ones) re-joins the caller's stream and releases the event and the graph
+  struct Guard {
+    cudaEvent_t& ev;
+    cudaGraphExec_t& gexec;
+    cudaStream_t st, caller;
+    bool use_graph;
+    ~Guard() {
+      if (gexec) cudaGraphExecDestroy(gexec);
+      if (use_graph && ev) {
+        cudaEventRecord(ev, st);
+        cudaStreamWaitEvent(caller, ev, 0);
+      }
+      if (ev) cudaEventDestroy(ev);
+    }
+  } guard{ev, gexec, st, caller, use_graph};
   if (use_graph) {
     SKB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     SKB_CUDA(cudaEventRecord(ev, caller));
@@ -287,7 +252,6 @@ int skb_dist_pcg_native(skb_plan* pl, const skb_dist_pcg_args* a, int32_t* iters
   const int every = a->check_every > 0 ? a->check_every : 10;
   int it = 0;
   double rr = bb;
-  cudaGraphExec_t gexec = nullptr;
   while (bb > 0.0 && it < a->max_iter) {
     const int nrun = (a->max_iter - it) < every ? (a->max_iter - it) : every;
     if (use_graph && it > 0 && nrun == every) {
@@ -320,12 +284,6 @@ int skb_dist_pcg_native(skb_plan* pl, const skb_dist_pcg_args* a, int32_t* iters
     SKB_CUDA(cudaStreamSynchronize(st));
     rr = h2[1];
     if (!(rr > a->rtol * a->rtol * bb)) break;
-  }
-  if (gexec) cudaGraphExecDestroy(gexec);
-  if (use_graph) {
-    SKB_CUDA(cudaEventRecord(ev, st));
-    SKB_CUDA(cudaStreamWaitEvent(caller, ev, 0));
-    cudaEventDestroy(ev);
   }
   if (!(bb > 0.0)) return SKB_OK;
   *iters = it;

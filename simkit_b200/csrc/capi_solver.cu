@@ -480,6 +480,64 @@ int skb_pcg(skb_plan* pl, const double* vals, const double* diag_add, const doub
   SKB_CATCH
 }
 
+// The same solve on CSR values that are already resident on the device (the lazy Hessian the drop-in `*_hessian_x`
+// functions return, simkit_b200/device_csr.py): nothing but the right-hand side and the solution cross PCIe.
+int skb_pcg_vals_dev(skb_plan* pl, const double* vals_dev, const double* diag_add, const double* rhs, double rtol,
+                int max_iter, double* x, int* iters, double* relres) {
+  if (!pl || !vals_dev || !rhs || !x) return fail(SKB_EINVAL, "null argument");
+  if (!(rtol >= 0.0) || max_iter < 0) return fail(SKB_EINVAL, "bad tolerance / max_iter");
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  pl->launches = 0;
+  const size_t nd = pl->ndof();
+  ensure(pl->w_dx, nd);
+  ensure(pl->g, nd);
+  SKB_CUDA(cudaMemcpyAsync(raw(pl->g), rhs, nd * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+  const double* dadd = nullptr;
+  if (diag_add) {
+    ensure(pl->w_diag, nd);
+    SKB_CUDA(cudaMemcpyAsync(raw(pl->w_diag), diag_add, nd * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+    dadd = raw(pl->w_diag);
+  }
+  int rc = pcg_solve(pl, vals_dev, dadd, raw(pl->g), rtol, max_iter, raw(pl->w_dx), iters, relres, pl->stream);
+  if (rc) return rc;
+  SKB_CUDA(cudaMemcpyAsync(x, raw(pl->w_dx), nd * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+  SKB_CUDA(cudaStreamSynchronize(pl->stream));
+  return SKB_OK;
+  SKB_CATCH
+}
+
+}  // extern "C"
+
+template <int D>
+static __global__ void value_positions_kernel(const int* bptr, const int* bcol, int64_t count, const int32_t* rows,
+                                              const int32_t* cols, int32_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = csr_value_position<D>(bptr, bcol, rows[i], cols[i]);
+}
+
+extern "C" {
+
+// pos[i] = index of the scalar entry (rows[i], cols[i]) in the plan's canonical CSR value array, -1 if the entry is
+// outside the pattern (device binary search over the block columns; host arrays in and out)
+int skb_plan_value_positions(skb_plan* pl, int64_t count, const int32_t* rows, const int32_t* cols, int32_t* pos) {
+  if (!pl || (count > 0 && (!rows || !cols || !pos))) return fail(SKB_EINVAL, "null argument");
+  if (count <= 0) return SKB_OK;
+  SKB_CUDA(cudaSetDevice(pl->device));
+  SKB_TRY
+  dvec<int32_t> r(rows, rows + count), c(cols, cols + count), o(count);
+  const unsigned grid = (unsigned)((count + 255) / 256);
+  if (pl->d.dim == 3)
+    value_positions_kernel<3><<<grid, 256, 0, pl->stream>>>(raw(pl->d.bptr), raw(pl->d.bcol), count, raw(r), raw(c), raw(o));
+  else
+    value_positions_kernel<2><<<grid, 256, 0, pl->stream>>>(raw(pl->d.bptr), raw(pl->d.bcol), count, raw(r), raw(c), raw(o));
+  SKB_CUDA(cudaGetLastError());
+  SKB_CUDA(cudaMemcpyAsync(pos, raw(o), count * sizeof(int32_t), cudaMemcpyDeviceToHost, pl->stream));
+  SKB_CUDA(cudaStreamSynchronize(pl->stream));
+  return SKB_OK;
+  SKB_CATCH
+}
+
 int skb_csr_pcg(int64_t n, const int32_t* indptr, const int32_t* indices, const double* vals, int block,
                 const double* rhs, double rtol, int max_iter, double* x, int* iters, double* relres) {
   if (!indptr || !indices || !vals || !rhs || !x) return fail(SKB_EINVAL, "null argument");

@@ -959,11 +959,13 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* sh) {
   return v;  // valid in thread 0
 }
 
+// count <= p.t: the elements that take part in the sum (a shard that also evaluates its lower neighbour's interface
+// elements counts only its own, which the plan lists first)
 template <int D>
-__global__ void energy_kernel(PlanView p, EvalArgs a, double* block_sums) {
+__global__ void energy_kernel(PlanView p, EvalArgs a, int count, double* block_sums) {
   __shared__ double sh[32];
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  double v = (e < p.t) ? energy_element<D>(p, a, e) : 0.0;
+  double v = (e < count) ? energy_element<D>(p, a, e) : 0.0;
   v = block_reduce_sum(v, sh);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = v;
 }

@@ -133,6 +133,8 @@ struct PlanView {
 template <class B>
 struct PlanData {
   int dim = 0, K = 0, n = 0, t = 0, tile_elems = 0, n_tiles = 0, nnzb = 0, nu = 0;
+  int t_energy = 0;  // elements [0, t_energy) count in energies and other sums over elements (== t unless a shard also
+                     // evaluates its lower neighbour's interface elements, which then follow its own)
   bool has_vol0 = false;
   typename B::template vec<int> T32, bptr, bcol, brow;
   typename B::template vec<int> eorder;    // [t] internal element i is the caller's element eorder[i]; empty = identity
@@ -550,14 +552,31 @@ void str_element_order(const typename B::template vec<double>& X, const typename
   }
 }
 
-// Reorders the first t (active) rows of T into the internal order and records it in p.eorder.
+struct AddOffset {
+  int off;
+  SKB_HD int operator()(int x) const { return x + off; }
+};
+
+// Reorders the first t (active) rows of T into the internal order and records it in p.eorder.  t_split in (0, t)
+// orders the ranges [0, t_split) and [t_split, t) separately (a shard that also evaluates its lower neighbour's
+// interface elements keeps its own elements first: the energy sums over those only).
 template <class B>
 void apply_element_order(PlanData<B>& p, typename B::template vec<int>& T, const typename B::template vec<double>& X, int n,
-                         int t, int dim, int tile_elems) {
+                         int t, int dim, int tile_elems, int t_split = 0) {
   auto pol = B::policy();
   const int K = dim + 1;
-  str_element_order<B>(X, T, n, t, dim, tile_elems, p.eorder);
-  typename B::template vec<int> Tn(T);  // pattern-only rows (>= t) stay where they are
+  using IV = typename B::template vec<int>;
+  p.eorder.resize(t);
+  int bounds[3] = {0, (t_split > 0 && t_split < t) ? t_split : t, t};
+  for (int part = 0; part < 2; ++part) {
+    const int a = bounds[part], b = bounds[part + 1];
+    if (b <= a) continue;
+    IV Tsub(T.begin() + (size_t)a * K, T.begin() + (size_t)b * K);
+    IV ord;
+    str_element_order<B>(X, Tsub, n, b - a, dim, tile_elems, ord);
+    thrust::transform(pol, ord.begin(), ord.end(), p.eorder.begin() + a, AddOffset{a});
+  }
+  IV Tn(T);  // pattern-only rows (>= t) stay where they are
   thrust::counting_iterator<int> it0(0);
   thrust::for_each(pol, it0, it0 + t,
                    PermuteRows{thrust::raw_pointer_cast(T.data()), thrust::raw_pointer_cast(p.eorder.data()),
@@ -721,6 +740,7 @@ bool build_plan(PlanData<B>& p, const typename B::template vec<int>& T, int n, i
   const int K = dim + 1;
   const int NP = K * (K + 1) / 2;
   p.dim = dim; p.K = K; p.n = n; p.t = t;
+  if (p.t_energy <= 0 || p.t_energy > t) p.t_energy = t;
   p.tile_elems = tile_elems;
   p.n_tiles = (t + tile_elems - 1) / tile_elems;
   thrust::counting_iterator<int> it0(0);

@@ -63,3 +63,20 @@ def kinetic_gradient_bdf2(x, x_curr, x_prev, x_prev2, x_prev3, M, h):
 
 def kinetic_hessian_bdf2(M, h):
     return kinetic_hessian(M, h, _BDF2_COEFF)
+
+
+# displacement (`_u`) tier: x = x_bar + u  (kinetic.py:291-407)
+def kinetic_energy_be_u(u, x_curr, x_prev, M, h, x_bar):
+    return kinetic_energy_be(x_bar + u, x_curr, x_prev, M, h)
+
+
+def kinetic_gradient_be_u(u, x_curr, x_prev, M, h, x_bar):
+    return kinetic_gradient_be(x_bar + u, x_curr, x_prev, M, h)
+
+
+def kinetic_energy_bdf2_u(u, x_curr, x_prev, x_prev2, x_prev3, M, h, x_bar):
+    return kinetic_energy_bdf2(x_bar + u, x_curr, x_prev, x_prev2, x_prev3, M, h)
+
+
+def kinetic_gradient_bdf2_u(u, x_curr, x_prev, x_prev2, x_prev3, M, h, x_bar):
+    return kinetic_gradient_bdf2(x_bar + u, x_curr, x_prev, x_prev2, x_prev3, M, h)

@@ -17,7 +17,7 @@ from ._lib import MATERIAL_IDS, check, f64, material_arg, ptr
 
 
 class MeshPlan:
-    def __init__(self, X=None, T=None, dim=None, n=None, D=None, device=0, tile_elems=0, t_active=None):
+    def __init__(self, X=None, T=None, dim=None, n=None, D=None, device=0, tile_elems=0, t_active=None, t_energy=None):
         lib = _lib.load()
         T = np.ascontiguousarray(T)
         if T.dtype not in (np.int64, np.int32):
@@ -29,10 +29,13 @@ class MeshPlan:
             self.n, self.dim = int(X.shape[0]), int(X.shape[1])
             if T.shape[1] != self.dim + 1:
                 raise ValueError("Only dim == 2 or 3 simplices (dim+1 corners) are supported")
-            if t_active is not None and t_active != self.t:
-                # one rank of a sharded mesh: trailing elements only reserve pattern slots
-                t_total, self.t = self.t, int(t_active)
-                check(lib.skb_plan_create_sharded(ptr(X), ptr(T), T.dtype.itemsize, self.n, self.t, t_total, self.dim,
+            if (t_active is not None and t_active != self.t) or t_energy is not None:
+                # one rank of a sharded mesh: trailing elements only reserve pattern slots (t_active < t), or are the
+                # lower neighbour's interface elements evaluated here as well (t_energy < t_active = t)
+                t_total = self.t
+                self.t = t_total if t_active is None else int(t_active)
+                check(lib.skb_plan_create_sharded(ptr(X), ptr(T), T.dtype.itemsize, self.n, self.t, t_total,
+                                                  0 if t_energy is None else int(t_energy), self.dim,
                                                   device, tile_elems, ctypes.byref(handle)))
             else:
                 check(lib.skb_plan_create(ptr(X), ptr(T), T.dtype.itemsize, self.n, self.t, self.dim, device,

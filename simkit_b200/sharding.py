@@ -221,14 +221,32 @@ def layout_grid_slab(cells, rank, world):
 class Shard:
     """One rank's device plan + NCCL interface exchange (needs a GPU and an initialised process group)."""
 
-    def __init__(self, layout, X_local, device=0, tile_elems=0):
+    def __init__(self, layout, X_local, device=0, tile_elems=0, interface=None):
+        """``interface``: how the rows this rank owns get the contributions of the lower neighbour's interface elements
+        (the one layer of elements that touches them):
+
+        * ``"exchange"``  -- north_star's scheme: the neighbour evaluates them, packs the partial gradient rows and
+          Hessian block-rows of its ghost vertices and sends them over NVLink (one grouped NCCL send/recv per
+          assembly); they are added here in rank order;
+        * ``"recompute"`` -- this rank evaluates that layer itself (ghost elements: +1 plane of cells, 5.8 % more
+          elements at 8 ranks of the 139^3 grid) and the assembly needs no communication at all; the energy still
+          sums every element once (``t_energy``).  Same owned rows to rounding (another summation order).
+
+        Default: ``SKB_SHARD_INTERFACE`` or ``"recompute"`` (faster at every rank count measured)."""
         import torch
         from .plan import MeshPlan
         self.layout = layout
         self.X_local = np.ascontiguousarray(X_local, dtype=np.float64)
         self.coarse = None
-        self.plan = MeshPlan(X=X_local, T=layout.T_local, device=device, tile_elems=tile_elems,
-                             t_active=layout.t_own)
+        self.interface = interface or os.environ.get("SKB_SHARD_INTERFACE", "recompute")
+        if self.interface not in ("exchange", "recompute"):
+            raise ValueError("interface must be 'exchange' or 'recompute'")
+        if self.interface == "recompute":
+            self.plan = MeshPlan(X=X_local, T=layout.T_local, device=device, tile_elems=tile_elems,
+                                 t_energy=layout.t_own)
+        else:
+            self.plan = MeshPlan(X=X_local, T=layout.T_local, device=device, tile_elems=tile_elems,
+                                 t_active=layout.t_own)
         bptr, bcol = self.plan.block_pattern()
         send, recv = layout.exchange_maps(bptr, bcol)
         dev = torch.device("cuda", device)
@@ -239,8 +257,8 @@ class Shard:
         f64 = torch.float64
         self.sbuf = {r: torch.empty(g.numel() + h.numel(), dtype=f64, device=dev) for r, (g, h) in self.send.items()}
         self.rbuf = {r: torch.empty(g.numel() + h.numel(), dtype=f64, device=dev) for r, (g, h) in self.recv.items()}
-        self.exchange_launches = 2 * (len(self.send) + len(self.recv))
-        self.exchange_bytes = 8 * sum(b.numel() for b in self.sbuf.values())
+        self.exchange_launches = 2 * (len(self.send) + len(self.recv)) if self.interface == "exchange" else 0
+        self.exchange_bytes = 8 * sum(b.numel() for b in self.sbuf.values()) if self.interface == "exchange" else 0
         d = layout.dim
         self.nnz_owned = int(bptr[layout.own_hi] - bptr[layout.own_lo]) * d * d
 
@@ -250,6 +268,8 @@ class Shard:
         import torch
         import torch.distributed as dist
         from ._lib import check, load
+        if self.interface == "recompute":      # the owned rows are complete: this rank evaluated every element they see
+            return
         lib = load()
         st = torch.cuda.current_stream().cuda_stream
         ops = []
@@ -334,6 +354,59 @@ class Shard:
         check(lib.skb_nccl_set_halo(self.plan._h, len(peers), *[ptr(a) for a in arrs]))
         self._native = True
         self._native_graph = bool(graph)   # full chunks of `check_every` iterations replay one CUDA graph
+
+    def enable_peer_transport(self):
+        """Maps every rank's solver slab into every other rank (CUDA IPC over NVLink/NVSwitch) so that the per-iteration
+        halo exchange and the reduction of ``skb_dist_pcg2`` become stores into the peers' memory issued by the
+        producing kernels (``csrc/capi_pcg2.cu``, transport 1) instead of NCCL calls.  Collective.  Returns whether
+        ALL ranks succeeded (decided together, so every rank takes the same branch afterwards)."""
+        import torch
+        import torch.distributed as dist
+        from ._lib import load, ptr
+        lib = load()
+        if not getattr(self, "_native", False):
+            self.enable_native_nccl()
+        world = self.layout.world
+        h = np.zeros(64, dtype=np.uint8)
+        meta = np.zeros(1 + world, dtype=np.int64)
+        ok = lib.skb_pcg2_peer_export(self.plan._h, ptr(h), ptr(meta), meta.size) == 0
+        blob = np.concatenate([h, meta.view(np.uint8)])
+        t = torch.from_numpy(blob).to(self.device)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            blobs = [o.cpu().numpy() for o in out]
+            handles = np.ascontiguousarray(np.concatenate([b[:64] for b in blobs]))
+            metas = np.ascontiguousarray(np.concatenate([b[64:] for b in blobs]).view(np.int64))
+            ok = lib.skb_pcg2_peer_import(self.plan._h, ptr(handles), ptr(metas)) == 0
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self._peer = int(flag.item()) == 1
+        if not self._peer:
+            self._peer_error = lib.skb_last_error().decode()
+        return self._peer
+
+    def _pcg2(self, vals_d, diag_d, rhs_d, x_d, rtol, max_iter, check_every=25, graph=True, transport=0):
+        """Single-reduction PCG with the coarse restriction folded into its one all-reduce (``csrc/capi_pcg2.cu``):
+        per iteration 7 kernels, one grouped NCCL send/recv and one NCCL all-reduce, replayed as a CUDA graph."""
+        import ctypes
+        import torch
+        from ._lib import DistPcg2Args, check, load
+        lib = load()
+        P = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        a = DistPcg2Args(P(vals_d), P(diag_d), P(rhs_d), P(x_d), torch.cuda.current_stream().cuda_stream, float(rtol),
+                         int(self.layout.own_lo), int(self.layout.own_hi), int(max_iter), int(check_every),
+                         1 if graph else 0, 1 if self.coarse is not None else 0, int(transport), 0)
+        iters = ctypes.c_int32(0)
+        relres = ctypes.c_double(0.0)
+        check(lib.skb_dist_pcg2(self.plan._h, ctypes.byref(a), ctypes.byref(iters), ctypes.byref(relres)))
+        tm = np.zeros(4)
+        check(lib.skb_dist_pcg2_times(self.plan._h, tm.ctypes.data_as(ctypes.c_void_p)))
+        self.last_solve_ms = dict(setup=float(tm[0]), coarse_inverse=float(tm[1]), iterations=float(tm[2]), total=float(tm[3]),
+                                  per_iteration=float(tm[2]) / max(int(iters.value), 1))
+        return int(iters.value), float(relres.value)
 
     def _pcg_native(self, vals_d, diag_d, rhs_d, x_d, rtol, max_iter, check_every):
         import ctypes
@@ -434,8 +507,27 @@ class Shard:
     def pcg(self, vals_d, diag_d, rhs_d, x_d, rtol=1e-10, max_iter=20000, check_every=10):
         """Block-Jacobi PCG on the distributed matrix (owned rows per rank, complete after the interface exchange).
         Per iteration: halo exchange of p, SpMV + p.q, all-reduce, fused update, all-reduce, direction."""
-        if getattr(self, "_native", False):
+        mode = getattr(self, "solver", None) or os.environ.get("SKB_DIST_PCG", "peer")
+        if mode in ("peer", "peer_eager"):
+            # default: the C++-driven single-reduction solve whose exchanges are NVLink stores into the peers' memory;
+            # NCCL transport if the IPC mappings cannot be set up.  Collective: every rank takes the same branch.
+            if not hasattr(self, "_peer"):
+                self.enable_peer_transport()
+            if self._peer:
+                return self._pcg2(vals_d, diag_d, rhs_d, x_d, rtol, max_iter, graph=(mode == "peer"), transport=1)
+            mode = "pcg2" if mode == "peer" else "pcg2_eager"
+        if mode in ("pcg2", "pcg2_eager"):
+            # the same solve over NCCL (grouped send/recv + one all-reduce per iteration)
+            if not getattr(self, "_native", False):
+                self.enable_native_nccl()
+            return self._pcg2(vals_d, diag_d, rhs_d, x_d, rtol, max_iter, graph=(mode == "pcg2"))
+        if mode in ("native", "native_graph"):            # the textbook loop below, issued from C++ (capi_nccl.cu)
+            if not getattr(self, "_native", False):
+                self.enable_native_nccl()
+            self._native_graph = (mode == "native_graph")
             return self._pcg_native(vals_d, diag_d, rhs_d, x_d, rtol, max_iter, check_every)
+        if mode != "python":
+            raise ValueError("unknown distributed solver %r" % (mode,))
         import torch
         import torch.distributed as dist
         from ._lib import check, load
@@ -611,16 +703,16 @@ class Shard:
         return sps.csr_matrix((vals_owned, cols, ip - ip[0]), shape=(r1 - r0, n_total * d))
 
 
-def make_shard(workload, rank, world, device=0, tile_elems=0, sigma=0.1):
+def make_shard(workload, rank, world, device=0, tile_elems=0, sigma=0.1, interface=None):
     """Shard of a named synthetic config with its jittered state (bench.py, N > 1)."""
     from . import synthetic as syn
     cfg = syn.CONFIGS[workload]
     lay = layout_grid_slab(cfg["cells"], rank, world)
     X_local = syn.grid_vertices(cfg["cells"], cfg["extent"], lay.l2g)
-    sh = Shard(lay, X_local, device=device, tile_elems=tile_elems)
+    sh = Shard(lay, X_local, device=device, tile_elems=tile_elems, interface=interface)
     sh.U_local = syn.jittered_state_rows(cfg["cells"], cfg["extent"], lay.l2g, sigma=sigma)
     sh.t_total, sh.n_total = lay.t_total, lay.n_total
     sh.nnz_total = None
-    if os.environ.get("SKB_NATIVE_NCCL", "") in ("1", "2"):      # 2: with CUDA-graph replay of the iterations
-        sh.enable_native_nccl(graph=os.environ["SKB_NATIVE_NCCL"] == "2")
+    if os.environ.get("SKB_NATIVE_NCCL", "") in ("1", "2"):      # the textbook loop driven from C++ (2: graph replay)
+        sh.solver = "native_graph" if os.environ["SKB_NATIVE_NCCL"] == "2" else "native"
     return sh

@@ -79,8 +79,54 @@ def test_sharded_device_assembly(cells, world):
         assert np.array_equal(np.diff(indptr)[own], ref_nnz)
 
 
+@pytest.mark.parametrize("cells,world", [((6, 4, 5), 2), ((9, 4, 4), 4), ((12, 7), 3)])
+def test_sharded_device_assembly_recompute(cells, world):
+    """``Shard(interface="recompute")`` on the device: every rank evaluates its lower neighbour's interface elements
+    itself (plan with ``t_energy`` = own elements), so its owned rows are complete without any exchange, and the
+    per-rank energies -- own elements only -- add up to the global energy."""
+    import ctypes
+    import torch
+    import simkit_b200 as sk
+    from simkit_b200._lib import MATERIAL_IDS, PSD_AFTER_VOL, check, load
+    lib = load()
+    dev = torch.device("cuda", 0)
+    X, T = syn.make_mesh(cells)
+    dim, n = len(cells), X.shape[0]
+    U = syn.jittered_state(X, cells, tuple(1.0 for _ in cells), sigma=0.3)
+    mu, lam = syn.lame()
+    J, vol = oe.deformation_jacobian(X, T), oe.volume(X, T)
+    g_ref = oe.gradient_x(MAT, U, J, mu, lam, vol).ravel()
+    Q_ref = sps.csr_matrix(oe.hessian_x(MAT, U, J, mu, lam, vol, psd=True))
+    E_ref = oe.energy_x(MAT, U, J, mu, lam, vol)
+    st = torch.cuda.current_stream().cuda_stream
+    E_sum = 0.0
+    for r in range(world):
+        lay = sh.layout_grid_slab(cells, r, world)
+        plan = sk.MeshPlan(X=X[lay.l2g], T=lay.T_local, tile_elems=32, t_energy=lay.t_own)
+        assert plan.t == lay.t_own + lay.t_pattern
+        plan.set_materials(mu, lam, plan.volume())
+        x_d = torch.from_numpy(U[lay.l2g].reshape(-1).copy()).to(dev)
+        g_d = torch.empty(plan.ndof, dtype=torch.float64, device=dev)
+        v_d = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
+        e_d = torch.zeros(1, dtype=torch.float64, device=dev)
+        check(lib.skb_gradient_hessian_dev(plan._h, MATERIAL_IDS[MAT], PSD_AFTER_VOL, x_d.data_ptr(), None,
+                                           g_d.data_ptr(), v_d.data_ptr(), st))
+        check(lib.skb_energy_dev(plan._h, MATERIAL_IDS[MAT], x_d.data_ptr(), None, e_d.data_ptr(), st))
+        torch.cuda.synchronize()
+        E_sum += float(e_d.item())
+        indptr, indices = plan.csr_pattern()
+        Ql = sps.csr_matrix((v_d.cpu().numpy(), indices, indptr), shape=(plan.ndof, plan.ndof))
+        own = np.arange(lay.own_lo * dim, lay.own_hi * dim)
+        gdof = (lay.l2g[:, None] * dim + np.arange(dim)[None, :]).ravel()
+        rows = Ql[own]
+        rows_g = sps.csr_matrix((rows.data, gdof[rows.indices], rows.indptr), shape=(own.size, n * dim))
+        assert rel(rows_g.toarray(), Q_ref[gdof[own]].toarray()) < 1e-10
+        assert rel(g_d.cpu().numpy()[own], g_ref[gdof[own]]) < 1e-10
+    assert abs(E_sum - E_ref) <= 1e-12 * abs(E_ref)
+
+
 # ------------------------------------------------------------------ 2 GPUs: NCCL exchange + distributed Newton
-def _nccl_worker(rank, world, port, cells, tmp):
+def _nccl_worker(rank, world, port, cells, tmp, interface="recompute"):
     import os
     import torch
     import torch.distributed as dist
@@ -92,7 +138,7 @@ def _nccl_worker(rank, world, port, cells, tmp):
     dim = len(cells)
     extent = tuple(1.0 for _ in cells)
     lay = sh.layout_grid_slab(cells, rank, world)
-    shard = sh.Shard(lay, syn.grid_vertices(cells, extent, lay.l2g), device=rank, tile_elems=32)
+    shard = sh.Shard(lay, syn.grid_vertices(cells, extent, lay.l2g), device=rank, tile_elems=32, interface=interface)
     U = syn.jittered_state_rows(cells, extent, lay.l2g, sigma=0.2)
     mu, lam = syn.lame()
     shard.set_materials(mu, lam)
@@ -119,7 +165,8 @@ def _nccl_worker(rank, world, port, cells, tmp):
     dist.destroy_process_group()
 
 
-def test_distributed_newton_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("interface", ["recompute", "exchange"])
+def test_distributed_newton_matches_single_gpu(tmp_path, interface):
     import os
     import torch
     if torch.cuda.device_count() < 2:
@@ -127,8 +174,8 @@ def test_distributed_newton_matches_single_gpu(tmp_path):
     import torch.multiprocessing as mp
     import simkit_b200 as sk
     cells, world = (8, 5, 5), 2
-    port = 29600 + (os.getpid() % 1000)
-    mp.spawn(_nccl_worker, args=(world, port, cells, str(tmp_path)), nprocs=world, join=True)
+    port = 29600 + ((os.getpid() + (0 if interface == "recompute" else 31)) % 1000)
+    mp.spawn(_nccl_worker, args=(world, port, cells, str(tmp_path), interface), nprocs=world, join=True)
     X, T = syn.make_mesh(cells)
     U = syn.jittered_state(X, cells, (1.0, 1.0, 1.0), sigma=0.2)
     mu, lam = syn.lame()
@@ -177,11 +224,12 @@ def _nccl_native_worker(rank, world, port, cells, tmp):
     fext_d = fext_d.reshape(-1) * mass_d
     kw = dict(x_tilde_d=x_d, mass_d=mass_d, kin_scale=1.0 / h ** 2, fext_d=fext_d, max_iter=3, pcg_rtol=1e-12)
     out = {}
-    for tag, native, n_agg, graph in (("py", False, 0, False), ("py_c", False, 12, False), ("nat", True, 0, False),
-                                      ("nat_c", True, 12, False), ("natg", True, 0, True), ("natg_c", True, 12, True)):
-        if native and not getattr(shard, "_native", False):
-            shard.enable_native_nccl()
-        shard._native_graph = graph          # full chunks of 10 iterations replay one CUDA graph
+    for tag, solver, n_agg in (("py", "python", 0), ("py_c", "python", 12), ("nat", "native", 0), ("nat_c", "native", 12),
+                               ("natg", "native_graph", 0), ("natg_c", "native_graph", 12), ("p2e", "pcg2_eager", 0),
+                               ("p2e_c", "pcg2_eager", 12), ("p2", "pcg2", 0), ("p2_c", "pcg2", 12),
+                               ("pe", "peer_eager", 0), ("pe_c", "peer_eager", 12), ("pp", "peer", 0), ("pp_c", "peer", 12),
+                               ("pp2", "peer", 0)):
+        shard.solver = solver
         shard.set_coarse_space(n_agg)
         xs = x_d.clone()
         info = shard.newton_step(MAT, xs, **kw)
@@ -189,6 +237,7 @@ def _nccl_native_worker(rank, world, port, cells, tmp):
         out["x_" + tag] = xs.cpu().numpy()[o0:o1]
         out["its_" + tag] = info["pcg_iters"]
         out["alphas_" + tag] = np.asarray(info["alphas"])
+    out["peer_ok"] = int(getattr(shard, "_peer", False))
     np.savez(os.path.join(tmp, "native%d.npz" % rank), **out)
     dist.barrier()
     dist.destroy_process_group()
@@ -210,3 +259,18 @@ def test_native_nccl_pcg_matches_python_loop(tmp_path):
         for a, b in (("py", "nat"), ("py_c", "nat_c"), ("py", "natg"), ("py_c", "natg_c")):
             assert int(d["its_" + a]) == int(d["its_" + b]) and list(d["alphas_" + a]) == list(d["alphas_" + b])
             assert rel(d["x_" + b], d["x_" + a]) < 1e-12
+        # the single-reduction solve (capi_pcg2.cu): other recurrences, same Krylov iterates to rounding -> same
+        # line-search steps, iteration counts within a few, Newton iterates equal to the solver tolerance
+        for a, b in (("py", "p2e"), ("py_c", "p2e_c"), ("py", "p2"), ("py_c", "p2_c")):
+            assert list(d["alphas_" + a]) == list(d["alphas_" + b])
+            assert abs(int(d["its_" + a]) - int(d["its_" + b])) <= 3 + int(d["its_" + a]) // 8
+            assert rel(d["x_" + b], d["x_" + a]) < 1e-9
+        assert np.array_equal(d["x_p2"], d["x_p2e"]) and np.array_equal(d["x_p2_c"], d["x_p2e_c"])   # graph replay = eager
+        # peer-memory transport (NVLink stores + flags instead of NCCL calls): the same recurrences; the reduction sums
+        # the ranks' partials in rank order instead of NCCL's order -> equal to rounding; reproducible run to run
+        assert int(d["peer_ok"]) == 1
+        for a, b in (("p2", "pe"), ("p2_c", "pe_c"), ("p2", "pp"), ("p2_c", "pp_c")):
+            assert list(d["alphas_" + a]) == list(d["alphas_" + b])
+            assert abs(int(d["its_" + a]) - int(d["its_" + b])) <= 2
+            assert rel(d["x_" + b], d["x_" + a]) < 1e-10
+        assert np.array_equal(d["x_pp"], d["x_pe"]) and np.array_equal(d["x_pp"], d["x_pp2"])

@@ -121,6 +121,29 @@ def test_sharding_a_shuffled_element_list(cells, world):
     assert np.all(owned == 1)
 
 
+@pytest.mark.parametrize("cells,world", [((5, 3, 4), 2), ((6, 3, 3), 3), ((9, 6), 3)])
+def test_recomputed_interface_needs_no_exchange(cells, world):
+    """``Shard(interface="recompute")``: a rank that also evaluates its lower neighbour's interface elements (the
+    pattern-only elements made active) has complete owned rows without any exchange."""
+    X, T = syn.make_mesh(cells)
+    dim, n = len(cells), X.shape[0]
+    U = syn.jittered_state(X, cells, tuple(1.0 for _ in cells), sigma=0.3)
+    mu, lam = syn.lame()
+    J, vol = oe.deformation_jacobian(X, T), oe.volume(X, T)
+    g_ref = oe.gradient_x(MAT, U, J, mu, lam, vol).ravel()
+    Q_ref = sps.csr_matrix(oe.hessian_x(MAT, U, J, mu, lam, vol, psd=True))
+    for r in range(world):
+        lay = sh.layout_grid_slab(cells, r, world)
+        o = hostsim.run(X[lay.l2g], lay.T_local, MAT_ID, 1, U[lay.l2g], mu, lam, None, tile_elems=32, reorder=True)
+        Ql = hostsim.csr_from_blocks(o["bptr"], o["bcol"], o["vals"], lay.n_local, dim).tocsr()
+        own = np.arange(lay.own_lo * dim, lay.own_hi * dim)
+        gdof = (lay.l2g[:, None] * dim + np.arange(dim)[None, :]).ravel()
+        rows = Ql[own]
+        rows_g = sps.csr_matrix((rows.data, gdof[rows.indices], rows.indptr), shape=(own.size, n * dim))
+        assert rel(rows_g.toarray(), Q_ref[gdof[own]].toarray()) < 1e-10
+        assert rel(o["g"][own], g_ref[gdof[own]]) < 1e-10
+
+
 # ------------------------------------------------------------------------------ gloo, world size 2
 def _gloo_worker(rank, world, port, cells, tmp):
     import torch
