@@ -285,7 +285,10 @@ def run_ours(args, rank, world, local_rank):
                 inv = np.empty_like(vp)
                 inv[vp] = np.arange(vp.size)
                 X, U, T = np.ascontiguousarray(X[vp]), np.ascontiguousarray(U[vp]), np.ascontiguousarray(inv[T])
-        plan = sk.MeshPlan(X=X, T=T, device=local_rank)
+        # the reference's own set-up call (deformation_jacobian.py:9-87); the drop-in builds the device plan and hands it
+        # on through J, the way every `*_x` function of the reference receives its mesh
+        Jop = sk.deformation_jacobian(X, T)
+        plan = Jop._skb_plan
         t_total, n_total, nnz_total = plan.t, plan.n, plan.nnz
     mu, lam = syn.lame()
     vol = plan.volume()
@@ -403,12 +406,20 @@ def run_ours(args, rank, world, local_rank):
     x_h, vol_h = pinned(plan.ndof), pinned(plan.t)
     x_h[:] = U.reshape(-1)
     vol_h[:] = vol.reshape(-1)
+    e2e_out = {}
     if shard is None:
-        g_h, vals_h = pinned(plan.ndof), pinned(plan.nnz)
-        api = "MeshPlan.gradient_hessian -> skb_gradient_hessian (host pointers, pinned buffers)"
+        # the reference's call pattern (energies/stable_neo_hookean.py:477-538): two calls with host arrays, a host
+        # gradient and a host scipy matrix back.  `.data` forces the values of the lazy Hessian onto the host.
+        grad_x, hess_x = getattr(sk, MATERIAL + "_gradient_x"), getattr(sk, MATERIAL + "_hessian_x")
+        margs = (mu,) if MATERIAL == "arap" else (mu, lam)
+        U_h = x_h.reshape(-1, dim)
+        api = "sk.%s_gradient_x(U, J, mu, lam, vol) + sk.%s_hessian_x(U, J, mu, lam, vol).data (host arrays in, host ndarray + host csr_matrix out)" % (MATERIAL, MATERIAL)
 
-        def step_e2e():
-            plan.gradient_hessian(MATERIAL, x_h, mu, lam, vol_h, PSD_AFTER_VOL, g_out=g_h.reshape(-1, 1), vals_out=vals_h)
+        def step_e2e(touch=True):
+            e2e_out["g"] = grad_x(U_h, Jop, *margs, vol_h)
+            H = hess_x(U_h, Jop, *margs, vol_h)
+            e2e_out["vals"] = H.data if touch else None
+            e2e_out["H"] = H
     else:
         v0, v1 = shard.owned_value_range()
         o0, o1 = shard.layout.own_lo * dim, shard.layout.own_hi * dim
@@ -428,7 +439,11 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         dt = time.perf_counter() - t0
     dt = max_over_ranks(dt)
-    h2d = 8 * (plan.ndof + plan.t + 2)
+    if shard is None:
+        g_h, vals_h = e2e_out["g"].ravel(), e2e_out["vals"]
+        h2d = 2 * 8 * (plan.ndof + plan.t + 2)       # each of the two calls uploads the state and the per-element weights
+    else:
+        h2d = 8 * (plan.ndof + plan.t + 2)
     d2h = 8 * (g_h.size + vals_h.size)
     if world > 1:
         tt = torch.tensor([h2d, d2h], dtype=torch.int64, device=dev)
@@ -436,6 +451,15 @@ def run_ours(args, rank, world, local_rank):
         h2d, d2h = int(tt[0].item()), int(tt[1].item())
     e2e = {"value": t_total / (dt / e2e_steps), "unit": "tets/s", "ms_per_step": dt / e2e_steps * 1e3,
            "steps": e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "api": api}
+    if shard is None:
+        # the same two calls when the caller does not look at the values on the host (what a Newton loop does: the lazy
+        # Hessian goes into `H + M/h**2` and the solve on the device); reported beside the contract number, not as it
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e(touch=False)
+        torch.cuda.synchronize()
+        e2e["values_left_on_device_ms_per_step"] = (time.perf_counter() - t0) / e2e_steps * 1e3
+        e2e_out.clear()
     if shard is None:
         # the e2e and device-resident paths must agree bit for bit (same kernels, same reduction order)
         assert np.array_equal(vals_h, vals_d.cpu().numpy()) and np.array_equal(g_h, g_d.cpu().numpy())
@@ -525,6 +549,40 @@ def run_ours(args, rank, world, local_rank):
             newton["iterate_difference_vs_block_jacobi"] = float(np.abs(x_tl - x_bj).max() / np.abs(x_bj).max())
         else:
             newton = newton_bj
+        if not args.no_closures:
+            # the same step through the reference's own call pattern: energy / gradient / Hessian closures around the
+            # `*_x` functions plus gravity, handed to backward_euler (examples/interactive_demos/010_..._3D.py:81-116,
+            # integrators/backward_euler.py:27-91).  The Hessian stays on the device through `H + M/h**2` and the solve.
+            import scipy.sparse as sps
+            Mv = sps.diags(mass).tocsc()
+            fg = fext.reshape(-1, 1)
+            e_x = getattr(sk, MATERIAL + "_energy_x")
+
+            def E_cl(x):
+                return e_x(x.reshape(-1, dim), Jop, *margs, vol_h) - float((fg.T @ x.reshape(-1, 1)).item())
+
+            def G_cl(x):
+                return grad_x(x.reshape(-1, dim), Jop, *margs, vol_h) - fg
+
+            def H_cl(x):
+                return hess_x(x.reshape(-1, dim), Jop, *margs, vol_h)
+
+            x0c = np.ascontiguousarray(xc.reshape(-1, 1))
+            tcl, xcl, icl = [], None, None
+            for s in range(2 + nsteps):          # the first solve runs block-Jacobi and switches the coarse space on
+                t0 = time.perf_counter()
+                xcl, icl = sk.backward_euler(x0c, x0c, E_cl, G_cl, H_cl, Mv, h, max_iter=1, return_info=True,
+                                             pcg_rtol=args.pcg_rtol)
+                if s > 1:
+                    tcl.append(time.perf_counter() - t0)
+            plan.set_coarse_space(None)
+            sec_cl = float(np.mean(tcl))
+            xref = x_tl if want_agg else x_bj
+            newton["through_reference_closures"] = {
+                "api": "sk.backward_euler(x, x_prev, E, G, H, M, h) with E/G/H closures around sk.%s_{energy,gradient,hessian}_x - gravity" % MATERIAL,
+                "steps_per_s": 1.0 / sec_cl, "ms_per_step": sec_cl * 1e3, "alpha": [float(a_) for a_ in icl["alphas"][:1]],
+                "vs_device_resident_step": sec_cl * 1e3 / newton["ms_per_step"],
+                "iterate_difference_vs_device_resident_step": float(np.abs(xcl.ravel() - xref.ravel()).max() / np.abs(xref).max())}
     elif args.newton:
         # sharded implicit step: device-resident state, distributed PCG (halo exchange + 2 all-reduces per iteration)
         mass_d = shard.lumped_mass_dofs(rho)
@@ -648,6 +706,35 @@ def run_ours(args, rank, world, local_rank):
                                   "the symmetric kernel computes (rows padded to the DMMA k = 4)",
                    "hr_symmetry_defect": float(np.abs(Hr - Hr.T).max() / np.abs(Hr).max())}
 
+    if args.reduced and shard is not None:
+        # sharded reduced Hessian: every rank contracts its own elements, one all-reduce of 1 + r + r^2 doubles
+        r = args.reduced
+        ext = np.asarray(cfg["extent"], dtype=np.float64)
+        Bl = syn.cos_modes(shard.X_local, r, seed=2, lo=np.zeros(dim), hi=ext, n_total=n_total)
+        z = 0.02 * np.random.default_rng(3).standard_normal(r)
+        plan.set_basis(Bl)
+        x0l = shard.X_local.reshape(-1)
+        tt_r, times = [], np.zeros(3)
+        for s_ in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            Er, gr_, Hr = shard.reduced(MATERIAL, None, z, x0_local=x0l, psd_mode=PSD_AFTER_VOL)
+            barrier()
+            if s_ > 0:
+                tt_r.append(time.perf_counter() - t0)
+            check(lib.skb_reduced_last_times(ptr(times)))
+        plan.set_basis(None)
+        sec_r = max_over_ranks(min(tt_r))
+        contr = max_over_ranks(float(times[1]))
+        b = dim * dim
+        flops = (2.0 * b * b * r + 2.0 * b * r * r) * t_total
+        reduced = {"r": r, "elements": t_total, "api_resident_basis_ms": sec_r * 1e3, "contraction_ms_max_over_ranks": contr,
+                   "contraction_tflops_all_ranks": flops / (contr * 1e-3) / 1e12, "algorithmic_flops": flops,
+                   "all_reduce_bytes": shard.reduced_allreduce_bytes,
+                   "hr_symmetry_defect": float(np.abs(Hr - Hr.T).max() / np.abs(Hr).max()),
+                   "what": "Shard.reduced: per-rank B^T H B over the rank's own elements (basis rows of its local vertices "
+                           "resident), one all-reduce of 1 + r + r^2 doubles"}
+
     # ---- CPU baseline (rank 0, N = 1) -----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -714,6 +801,7 @@ def main():
                     help="list the mesh's elements (and vertices) in random order: the plan's internal spatial element order "
                          "keeps the step within a few percent of the generator's order (1 GPU)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check of the benched result")
+    ap.add_argument("--no-closures", action="store_true", help="skip the Newton step through reference-style closures")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="development only: stop after the device-resident timing")
     args = ap.parse_args()

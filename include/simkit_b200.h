@@ -292,6 +292,27 @@ int skb_pcg(skb_plan* plan, const double* vals, const double* diag_add, const do
             double rtol, int max_iter, double* x, int* iters, double* relres);
 int skb_pcg_dev(skb_plan* plan, const double* vals, const double* diag_add, const double* rhs,
                 double rtol, int max_iter, double* x, int* iters, double* relres, void* stream);
+/* ---- device-resident CSR values (the lazy Hessian of simkit_b200/device_csr.py; csrc/capi_buffers.cu) ----------
+ * The reference's `*_hessian_x` return a host scipy matrix (energies/stable_neo_hookean.py:506-538) that the caller
+ * sums with its mass / penalty / contact matrices (integrators/backward_euler.py:84) and passes to spsolve
+ * (solvers/newton.py:52).  These entry points keep the 8*nnz bytes of values in HBM through that chain. */
+int skb_buf_alloc(int device, int64_t n, double** out);            /* n doubles of device memory          */
+void skb_buf_free(int device, double* buf);
+int skb_buf_copy(int device, double* dst, const double* src, int64_t n);
+int skb_buf_axpy(int device, double* dst, double a, const double* src, int64_t n);     /* dst += a * src    */
+int skb_buf_scale(int device, double* dst, double a, int64_t n);                       /* dst *= a          */
+/* dst[pos[i]] += a * vals[i]; pos (int32, distinct, -1 = skip) and vals are HOST arrays of `count` entries */
+int skb_buf_index_add(int device, double* dst, const int32_t* pos, const double* vals, int64_t count, double a);
+/* vals_dev (the plan's CSR value layout) += a * diag(d), d a host vector of n*dim entries (lumped mass / penalty) */
+int skb_buf_add_diagonal(skb_plan* plan, double* vals_dev, const double* diag, double a);
+int skb_buf_download(int device, const double* src, int64_t n, double* host);
+/* page-locked host memory for that download (pooled by the Python side) */
+int skb_host_alloc(int64_t nbytes, void** out);
+void skb_host_free(void* p);
+/* skb_gradient_hessian with the CSR values left on the device in vals_dev (nnz doubles); g (host, optional) */
+int skb_gradient_hessian_resident(skb_plan* plan, int material, int psd_mode, const double* x, const double* Fbar,
+                                  const double* mu, int64_t mu_n, const double* lam, int64_t lam_n, const double* vol,
+                                  int64_t vol_n, double* g, double* vals_dev);
 /* skb_pcg on CSR values that are already on the device (a lazy Hessian of simkit_b200/device_csr.py): replaces the
  * spsolve of solvers/newton.py:52 without the 8*nnz-byte round trip; rhs and x are host pointers. */
 int skb_pcg_vals_dev(skb_plan* plan, const double* vals_dev, const double* diag_add, const double* rhs, double rtol,

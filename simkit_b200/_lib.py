@@ -141,6 +141,17 @@ SIGNATURES = {
     "skb_pcg2_peer_import": (_int, [_vp, _vp, _vp]),
     "skb_quadratic": (_int, [_i64, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_dbl), _vp]),
     "skb_newton_set_quadratic": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "skb_buf_alloc": (_int, [_int, _i64, ctypes.POINTER(_vp)]),
+    "skb_buf_free": (None, [_int, _vp]),
+    "skb_buf_copy": (_int, [_int, _vp, _vp, _i64]),
+    "skb_buf_axpy": (_int, [_int, _vp, _dbl, _vp, _i64]),
+    "skb_buf_scale": (_int, [_int, _vp, _dbl, _i64]),
+    "skb_buf_index_add": (_int, [_int, _vp, _vp, _vp, _i64, _dbl]),
+    "skb_buf_add_diagonal": (_int, [_vp, _vp, _vp, _dbl]),
+    "skb_buf_download": (_int, [_int, _vp, _i64, _vp]),
+    "skb_host_alloc": (_int, [_i64, ctypes.POINTER(_vp)]),
+    "skb_host_free": (None, [_vp]),
+    "skb_gradient_hessian_resident": (_int, [_vp, _int, _int, _vp, _vp] + _MAT + [_vp, _vp]),
     "skb_pcg_vals_dev": (_int, [_vp, _vp, _vp, _vp, _dbl, _int, _vp, ctypes.POINTER(_int), ctypes.POINTER(_dbl)]),
     "skb_plan_value_positions": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "skb_pcg_set_coarse": (_int, [_vp, _i64, _vp, _vp]),

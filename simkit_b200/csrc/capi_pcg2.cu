@@ -218,29 +218,36 @@ static __global__ void pcg2_gemv_kernel(const Pcg2Scalars* sc, int nc, const dou
   const int lane = threadIdx.x & 31;
   if (row >= nc) return;
   const double* a = Ainv + (size_t)row * nc;
-  double s0 = 0.0, s1 = 0.0;
+  // four independent 256-byte requests per warp in flight (the kernel streams nc^2 doubles once: bandwidth-bound)
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int k = lane;
-  for (; k + 32 < nc; k += 64) {
-    s0 = fma(a[k], rc[k], s0);
-    s1 = fma(a[k + 32], rc[k + 32], s1);
+  for (; k + 96 < nc; k += 128) {
+    const double a0 = a[k], a1 = a[k + 32], a2 = a[k + 64], a3 = a[k + 96];
+    s0 = fma(a0, rc[k], s0);
+    s1 = fma(a1, rc[k + 32], s1);
+    s2 = fma(a2, rc[k + 64], s2);
+    s3 = fma(a3, rc[k + 96], s3);
   }
-  if (k < nc) s0 = fma(a[k], rc[k], s0);
-  double s = s0 + s1;
+  for (; k < nc; k += 32) s0 = fma(a[k], rc[k], s0);
+  double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
   if (lane == 0) zc[row] = s;
 }
 
 // p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;  u = Dinv r [+ P zc]      (owned vertices)
+// and the per-CTA partial sums of r.u and r.r of the NEW r, u (part[0..grid), part[2 grid..3 grid); w.u comes from the SpMV)
 template <int D, bool COARSE>
-__global__ void __launch_bounds__(PCG_THREADS, PCG_CTAS_PER_SM)
+__global__ void __launch_bounds__(PCG_THREADS, 5)
 pcg2_update_kernel(const Pcg2Scalars* sc, int v0, int v1, const double* __restrict__ dinv, const int* __restrict__ agg,
                    const double* __restrict__ xrel, const double* __restrict__ zc, const double* __restrict__ w,
                    double* __restrict__ u, double* __restrict__ p, double* __restrict__ s, double* __restrict__ x,
-                   double* __restrict__ r) {
+                   double* __restrict__ r, double* part) {
+  __shared__ double sh[32];
   if (sc->done) return;
   constexpr int NC = CoarseDim<D>::NC;
   const double alpha = sc->alpha, beta = sc->beta;
+  double ru = 0.0, rr = 0.0;
   for (int v = v0 + blockIdx.x * blockDim.x + threadIdx.x; v < v1; v += gridDim.x * blockDim.x) {
     double rl[D], ul[D];
 #pragma unroll
@@ -267,7 +274,17 @@ pcg2_update_kernel(const Pcg2Scalars* sc, int v0, int v1, const double* __restri
       for (int i = 0; i < D; ++i) ul[i] += o[i];
     }
 #pragma unroll
-    for (int i = 0; i < D; ++i) u[(size_t)v * D + i] = ul[i];
+    for (int i = 0; i < D; ++i) {
+      u[(size_t)v * D + i] = ul[i];
+      ru = fma(rl[i], ul[i], ru);
+      rr = fma(rl[i], rl[i], rr);
+    }
+  }
+  ru = block_reduce_sum(ru, sh);
+  rr = block_reduce_sum(rr, sh);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = ru;
+    part[2 * gridDim.x + blockIdx.x] = rr;
   }
 }
 
@@ -284,12 +301,11 @@ static __global__ void pcg2_unpack_kernel(const Pcg2Scalars* sc, double* __restr
   if (i < n) v[idx[i]] = buf[i];
 }
 
-// w = (A + diag) u on the owned block rows; per-CTA partial sums of r.u, w.u, r.r
+// w = (A + diag) u on the owned block rows; per-CTA partial sums of w.u (part[grid..2 grid))
 template <int D>
 __global__ void __launch_bounds__(PCG_THREADS, PCG_CTAS_PER_SM)
 pcg2_spmv_kernel(const Pcg2Scalars* sc, PlanView p, const double* __restrict__ vals, const double* __restrict__ dadd,
-                 const double* __restrict__ u, const double* __restrict__ r, double* __restrict__ w, int v0, int v1,
-                 double* part) {
+                 const double* __restrict__ u, double* __restrict__ w, int v0, int v1, double* part) {
   __shared__ double sh[32];
   if (sc->done) return;
   constexpr int GW = 32 / SPMV_GROUP;
@@ -297,7 +313,7 @@ pcg2_spmv_kernel(const Pcg2Scalars* sc, PlanView p, const double* __restrict__ v
   const int gw = (threadIdx.x & 31) / SPMV_GROUP;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  double ru = 0.0, wu = 0.0, rr = 0.0;
+  double wu = 0.0;
   for (int vb = v0 + warp * GW; vb < v1; vb += nwarps * GW) {
     const int v = vb + gw;
     const bool valid = v < v1;
@@ -324,24 +340,16 @@ pcg2_spmv_kernel(const Pcg2Scalars* sc, PlanView p, const double* __restrict__ v
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         const size_t k = (size_t)v * D + i;
-        const double ui = u[k], ri = r[k];
+        const double ui = u[k];
         double wi = acc[i];
         if (dadd) wi = fma(dadd[k], ui, wi);
         w[k] = wi;
-        ru = fma(ri, ui, ru);
         wu = fma(wi, ui, wu);
-        rr = fma(ri, ri, rr);
       }
     }
   }
-  ru = block_reduce_sum(ru, sh);
   wu = block_reduce_sum(wu, sh);
-  rr = block_reduce_sum(rr, sh);
-  if (threadIdx.x == 0) {
-    part[blockIdx.x] = ru;
-    part[gridDim.x + blockIdx.x] = wu;
-    part[2 * gridDim.x + blockIdx.x] = rr;
-  }
+  if (threadIdx.x == 0) part[gridDim.x + blockIdx.x] = wu;
 }
 
 // CTAs [0, n_agg): red[4 + I*NC + a] = sum over the OWNED vertices of aggregate I of (P_v^T w_v)_a  (fixed order);
@@ -724,14 +732,14 @@ int skb_dist_pcg2(skb_plan* pl, const skb_dist_pcg2_args* a, int32_t* iters, dou
     const double* xrel = coarse ? raw(cs->xrel) : nullptr;
     if (D == 3) {
       if (coarse)
-        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<3, true><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r));
+        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<3, true><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r, raw(S.part)));
       else
-        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<3, false><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r));
+        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<3, false><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r, raw(S.part)));
     } else {
       if (coarse)
-        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<2, true><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r));
+        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<2, true><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r, raw(S.part)));
       else
-        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<2, false><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r));
+        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<2, false><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r, raw(S.part)));
     }
     // halo of u
     if (peer) {
@@ -756,9 +764,9 @@ int skb_dist_pcg2(skb_plan* pl, const skb_dist_pcg2_args* a, int32_t* iters, dou
         SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg2_unpack_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(sc, u, raw(S.ridx), nr, raw(S.rbuf)));
     }
     if (D == 3)
-      SKB_LAUNCH(pl, SKB_K_SPMV, st, pcg2_spmv_kernel<3><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, pv, a->vals, a->diag, u, r, w, v0, v1, raw(S.part)));
+      SKB_LAUNCH(pl, SKB_K_SPMV, st, pcg2_spmv_kernel<3><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, pv, a->vals, a->diag, u, w, v0, v1, raw(S.part)));
     else
-      SKB_LAUNCH(pl, SKB_K_SPMV, st, pcg2_spmv_kernel<2><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, pv, a->vals, a->diag, u, r, w, v0, v1, raw(S.part)));
+      SKB_LAUNCH(pl, SKB_K_SPMV, st, pcg2_spmv_kernel<2><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, pv, a->vals, a->diag, u, w, v0, v1, raw(S.part)));
     const int* vord = coarse ? raw(cs->vord) : nullptr;
     const int* aptr = coarse ? raw(cs->aptr) : nullptr;
     const int ngrid_r = n_agg * (coarse ? 1 : 0) + 1;

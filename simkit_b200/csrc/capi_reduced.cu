@@ -758,8 +758,11 @@ int skb_reduced_hessian_from_basis(skb_plan* pl, int material, int psd_mode, int
   if (!B && (pl->basis_r != r || pl->basis_r == 0))
     return fail(SKB_EINVAL, "B is NULL and the plan holds no resident basis of this dimension (skb_plan_set_basis)");
   SKB_CUDA(cudaSetDevice(pl->device));
-  return pl->d.dim == 3 ? reduced_run<3>(pl, material, psd_mode, pl->d.t, r, nullptr, nullptr, B, x0, z, nullptr, 0, nullptr, 0, nullptr, 0, energy, gr, Hr)
-                        : reduced_run<2>(pl, material, psd_mode, pl->d.t, r, nullptr, nullptr, B, x0, z, nullptr, 0, nullptr, 0, nullptr, 0, energy, gr, Hr);
+  // the elements that count in sums over elements: all of them, or a shard's own (which the plan lists first) when it
+  // also evaluates its lower neighbour's interface elements -- every element then enters the all-reduced sums once
+  const int64_t t = pl->d.t_energy;
+  return pl->d.dim == 3 ? reduced_run<3>(pl, material, psd_mode, t, r, nullptr, nullptr, B, x0, z, nullptr, 0, nullptr, 0, nullptr, 0, energy, gr, Hr)
+                        : reduced_run<2>(pl, material, psd_mode, t, r, nullptr, nullptr, B, x0, z, nullptr, 0, nullptr, 0, nullptr, 0, energy, gr, Hr);
 }
 
 int skb_fst_precompute(int dim, int64_t t, int64_t m1, int64_t m2, int64_t ncl, const double* A, const double* B,

@@ -80,3 +80,32 @@ def kinetic_energy_bdf2_u(u, x_curr, x_prev, x_prev2, x_prev3, M, h, x_bar):
 
 def kinetic_gradient_bdf2_u(u, x_curr, x_prev, x_prev2, x_prev3, M, h, x_bar):
     return kinetic_gradient_bdf2(x_bar + u, x_curr, x_prev, x_prev2, x_prev3, M, h)
+
+
+def kinetic_closures(x_tilde, M, h, c):
+    """``(energy(x), gradient(x), hessian())`` of ``0.5 c / h^2 |x - x_tilde|_M^2`` for a FIXED inertial target, as the
+    integrators use them inside one step (integrators/backward_euler.py:73-85 recompute the target and go through a
+    sparse mat-vec on every evaluation; at 8 M dofs that host arithmetic costs more than the GPU side of the step).
+    A diagonal ``M`` (the lumped mass every example uses) takes an element-wise path: same value to rounding."""
+    from ..device_csr import diagonal_of
+    s = c / (h ** 2)
+    xt = np.asarray(x_tilde, dtype=np.float64).reshape(-1, 1)
+    diag = diagonal_of(M) if sp.sparse.issparse(M) else None
+    if diag is not None:
+        md = diag.reshape(-1, 1) * s
+
+        def energy(x):
+            d = x.reshape(-1, 1) - xt
+            return 0.5 * float(np.vdot(d, md * d))
+
+        def gradient(x):
+            return md * (x.reshape(-1, 1) - xt)
+    else:
+        def energy(x):
+            return kinetic_energy(x.reshape(-1, 1) - xt, M, h, c)
+
+        def gradient(x):
+            return kinetic_gradient(x.reshape(-1, 1) - xt, M, h, c)
+
+    Hk = kinetic_hessian(M, h, c)
+    return energy, gradient, (lambda: Hk)

@@ -1,6 +1,6 @@
 """Backward Euler: drop-in for simkit/integrators/backward_euler.py:27-91."""
 
-from ..energies.kinetic import be_target, kinetic_energy_be, kinetic_gradient_be, kinetic_hessian_be
+from ..energies.kinetic import be_target, kinetic_closures
 from ..solvers.newton import newton_solver
 
 
@@ -14,15 +14,17 @@ def backward_euler(x_curr, x_prev, energy_func, gradient_func, hessian_func, M, 
                                  max_iter=max_iter, do_line_search=do_line_search, return_info=return_info,
                                  **solver_kw)
 
+    x0 = be_target(x_curr, x_prev, h)
+    k_e, k_g, k_h = kinetic_closures(x0, M, h, 1.0)      # kinetic.py:125-194 with the target evaluated once
+
     def energy(x):
-        return energy_func(x) + kinetic_energy_be(x, x_curr, x_prev, M, h)
+        return energy_func(x) + k_e(x)
 
     def gradient(x):
-        return gradient_func(x) + kinetic_gradient_be(x, x_curr, x_prev, M, h)
+        return gradient_func(x) + k_g(x)
 
     def hessian(x):
-        return hessian_func(x) + kinetic_hessian_be(M, h)
+        return hessian_func(x) + k_h()
 
-    x0 = be_target(x_curr, x_prev, h)
     return newton_solver(x0, energy, gradient, hessian, tolerance=tolerance, max_iter=max_iter,
                          do_line_search=do_line_search, return_info=return_info, **solver_kw)

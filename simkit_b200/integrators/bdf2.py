@@ -1,6 +1,6 @@
 """BDF2: drop-in for simkit/integrators/bdf2.py:31-101 (kinetic coefficient 9/4)."""
 
-from ..energies.kinetic import bdf2_target, kinetic_energy_bdf2, kinetic_gradient_bdf2, kinetic_hessian_bdf2
+from ..energies.kinetic import bdf2_target, kinetic_closures
 from ..solvers.newton import newton_solver
 
 
@@ -14,15 +14,17 @@ def bdf2(x_curr, x_prev, x_prev2, x_prev3, energy_func, gradient_func, hessian_f
                                  tolerance=tolerance, max_iter=max_iter, do_line_search=do_line_search,
                                  return_info=return_info, **solver_kw)
 
+    x0 = bdf2_target(x_curr, x_prev, x_prev2, x_prev3, h)
+    k_e, k_g, k_h = kinetic_closures(x0, M, h, 9.0 / 4.0)   # kinetic.py:200-279 with the target evaluated once
+
     def energy(x):
-        return energy_func(x) + kinetic_energy_bdf2(x, x_curr, x_prev, x_prev2, x_prev3, M, h)
+        return energy_func(x) + k_e(x)
 
     def gradient(x):
-        return gradient_func(x) + kinetic_gradient_bdf2(x, x_curr, x_prev, x_prev2, x_prev3, M, h)
+        return gradient_func(x) + k_g(x)
 
     def hessian(x):
-        return hessian_func(x) + kinetic_hessian_bdf2(M, h)
+        return hessian_func(x) + k_h()
 
-    x0 = bdf2_target(x_curr, x_prev, x_prev2, x_prev3, h)
     return newton_solver(x0, energy, gradient, hessian, tolerance=tolerance, max_iter=max_iter,
                          do_line_search=do_line_search, return_info=return_info, **solver_kw)

@@ -47,6 +47,10 @@ class MeshPlan:
                                                     device, tile_elems, ctypes.byref(handle)))
         self._lib = lib
         self._h = handle
+        self.device = int(device)
+        self.n_agg = 0
+        # rest positions kept for the automatic two-level preconditioner of solves on lazy Hessians (device_csr.py)
+        self._X_rest = None if X is None or t_active is not None or t_energy is not None else X
         self.T = T
         info = np.zeros(8, dtype=np.int64)
         check(lib.skb_plan_info(self._h, ptr(info)))
@@ -150,7 +154,25 @@ class MeshPlan:
         return vals
 
     def hessian(self, material, x, mu, lam, vol, psd_mode, Fbar=None):
-        return self.csr_matrix(self.hessian_values(material, x, mu, lam, vol, psd_mode, Fbar))
+        """The assembled Hessian as a :class:`simkit_b200.device_csr.DeviceCSR`: a ``scipy.sparse.csr_matrix`` whose
+        values stay in HBM until something on the host touches them (SKB_LAZY_HESSIAN=0: plain host matrix)."""
+        import os
+        if os.environ.get("SKB_LAZY_HESSIAN", "1") == "0":
+            return self.csr_matrix(self.hessian_values(material, x, mu, lam, vol, psd_mode, Fbar))
+        from .device_csr import DeviceCSR, _Buffer
+        x = self._x(x)
+        Fbar = self._fbar(Fbar)
+        keep, margs = self._mats(mu, lam, vol)
+        buf = _Buffer(self.device, self.nnz)
+        check(self._lib.skb_gradient_hessian_resident(self._h, MATERIAL_IDS[material], int(psd_mode), ptr(x), ptr(Fbar),
+                                                      *margs, None, buf.ptr))
+        return DeviceCSR(_plan=self, _buf=buf)
+
+    def value_positions_of(self, S):
+        """``(pos, vals)`` of the stored entries of the scipy sparse ``S`` inside this mesh's CSR values, or
+        ``(None, None)`` if ``S`` has a non-zero outside the pattern (``device_csr.value_positions_of``)."""
+        from .device_csr import value_positions_of
+        return value_positions_of(self, S)
 
     def gradient_hessian(self, material, x, mu, lam, vol, psd_mode, Fbar=None, g_out=None, vals_out=None):
         x = self._x(x)
@@ -193,6 +215,11 @@ class MeshPlan:
         out = np.empty((self.ndof, 1))
         check(self._lib.skb_newton(self._h, ctypes.byref(opts), ptr(x0), ptr(opt[0]), ptr(opt[1]), float(kin_scale),
                                    ptr(opt[2]), ptr(opt[3]), ptr(opt[4]), ptr(out), ctypes.byref(info)))
+        if not np.isfinite(info.last_pcg_relres) or not np.isfinite(info.last_step_norm):
+            raise _lib.SimkitB200Error(
+                "Newton step failed: the linear solve produced a non-finite residual (relres %r). The Newton system must be "
+                "symmetric positive definite: project the Hessian (psd=True) or add inertia / penalty terms; NaN in the "
+                "state (inverted elements under neo_hookean) propagates as in the reference." % (info.last_pcg_relres,))
         n_it = info.iters + 1
         return out, dict(iters=info.iters, alphas=[info.alphas[i] for i in range(min(n_it, 64))],
                          pcg_iters=info.pcg_iters_total, pcg_relres=info.last_pcg_relres,

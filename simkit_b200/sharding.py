@@ -608,6 +608,10 @@ class Shard:
             check(lib.skb_dist_newton_rhs_dev(h, v0, v1, P(x_d), P(fext_d), P(mass_d), P(x_tilde_d), float(kin_scale), 0, 0,
                                               P(w["g"]), P(w["rhs"]), P(w["diag"]), st))
             pit, relres = self.pcg(w["vals"], w["diag"], w["rhs"], w["dx"], rtol=pcg_rtol, max_iter=pcg_max_iter)
+            if not np.isfinite(relres):
+                from ._lib import SimkitB200Error
+                raise SimkitB200Error("distributed Newton step: the linear solve produced a non-finite residual; the system "
+                                      "must be symmetric positive definite")
             alpha = 1.0
             if do_line_search:
                 e0, gdx, dx2 = total_energy(0.0, True)
@@ -632,6 +636,29 @@ class Shard:
             if step < tolerance:
                 break
         return info
+
+    # ------------------------------------------------------------------ reduced (subspace) tier
+    def reduced(self, material, B_local, z, x0_local=None, psd_mode=1, want=("E", "g", "H")):
+        """Reduced energy / gradient / Hessian ``B^T g``, ``B^T H B`` of the GLOBAL mesh (``elastic_*_z``,
+        energies/elastic.py:749-782): every rank contracts its own elements against the rows of the basis that belong to
+        its local vertices (``B_local``: ``(n_local*dim, r)``; ``None``: the basis set with ``plan.set_basis``), then ONE
+        all-reduce sums the ``1 + r + r*r`` numbers over the ranks (320 KB at r = 200).  Collective."""
+        import torch
+        import torch.distributed as dist
+        E, g, H = self.plan.reduced(material, B_local, z, x0=x0_local, psd_mode=psd_mode, want=want)
+        r = int(np.asarray(z).size)
+        buf = np.zeros(1 + r + r * r)
+        buf[0] = E
+        if g is not None:
+            buf[1:1 + r] = g.ravel()
+        if H is not None:
+            buf[1 + r:] = H.ravel()
+        t = torch.from_numpy(buf).to(self.device)
+        dist.all_reduce(t)
+        buf = t.cpu().numpy()
+        self.reduced_allreduce_bytes = buf.nbytes
+        return (float(buf[0]), None if g is None else buf[1:1 + r].reshape(r, 1).copy(),
+                None if H is None else buf[1 + r:].reshape(r, r).copy())
 
     def lumped_mass_dofs(self, rho=1.0):
         """Device vector (local dofs) of the lumped masses ``massmatrix.py:41-49`` of the GLOBAL mesh on this rank's

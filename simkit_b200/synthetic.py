@@ -167,6 +167,27 @@ def heterogeneous_lame(t, ym=1e5, pr=0.45, seed=1):
     return lame(yme, pr)
 
 
+def cos_modes(X, r, seed=2, lo=None, hi=None, n_total=None):
+    """The same family of smooth modes as ``smooth_modes`` WITHOUT the QR, as a pure function of the vertex position:
+    rows can be generated for any subset of the vertices (one rank of a sharded mesh passes the global bounding box
+    ``lo, hi`` and vertex count ``n_total``) and agree with the rows of the global basis.  Columns are scaled by
+    ``1/sqrt(n_total)`` (about unit norm)."""
+    rng = np.random.default_rng(seed)
+    n, dim = X.shape
+    lo = X.min(0) if lo is None else np.asarray(lo, dtype=np.float64)
+    hi = X.max(0) if hi is None else np.asarray(hi, dtype=np.float64)
+    n_total = n if n_total is None else int(n_total)
+    Xn = (X - lo) / (hi - lo)
+    B = np.empty((n * dim, r))
+    for j in range(r):
+        k = rng.integers(0, 4, size=dim)
+        phase = rng.uniform(0, np.pi, size=dim)
+        f = np.prod(np.cos(np.pi * k[None, :] * Xn + phase[None, :]), axis=1)
+        w = rng.standard_normal(dim)
+        B[:, j] = (f[:, None] * w[None, :]).reshape(-1) / np.sqrt(n_total)
+    return B
+
+
 def smooth_modes(X, r, seed=2):
     """Dense random smooth basis ``B (n*dim, r)`` for the reduced config (C4).
 

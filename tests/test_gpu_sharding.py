@@ -274,3 +274,60 @@ def test_native_nccl_pcg_matches_python_loop(tmp_path):
             assert abs(int(d["its_" + a]) - int(d["its_" + b])) <= 2
             assert rel(d["x_" + b], d["x_" + a]) < 1e-10
         assert np.array_equal(d["x_pp"], d["x_pe"]) and np.array_equal(d["x_pp"], d["x_pp2"])
+
+
+# ------------------------------------------------------------------ 2 GPUs: sharded reduced Hessian + r x r all-reduce
+def _reduced_worker(rank, world, port, cells, tmp, interface):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    extent = tuple(1.0 for _ in cells)
+    lay = sh.layout_grid_slab(cells, rank, world)
+    Xl = syn.grid_vertices(cells, extent, lay.l2g)
+    shard = sh.Shard(lay, Xl, device=rank, tile_elems=32, interface=interface)
+    mu, lam = syn.lame()
+    shard.set_materials(mu, lam)
+    r = 24
+    Bl = syn.cos_modes(Xl, r, seed=9, lo=np.zeros(len(cells)), hi=np.ones(len(cells)), n_total=lay.n_total)
+    z = 0.05 * np.random.default_rng(5).standard_normal(r)
+    E, g, H = shard.reduced(MAT, Bl, z, x0_local=Xl.reshape(-1))
+    if rank == 0:
+        np.savez(os.path.join(tmp, "reduced_%s.npz" % interface), E=E, g=g, H=H, nbytes=shard.reduced_allreduce_bytes)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("interface", ["recompute", "exchange"])
+def test_sharded_reduced_hessian_matches_single_gpu(tmp_path, interface):
+    """north_star: "... and allreduces the small r x r reduced Hessian" -- every rank contracts its own elements, one
+    all-reduce of 1 + r + r^2 doubles; equal to the single-GPU reduced tier on the whole mesh and to B^T Q B of the oracle."""
+    import os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    import simkit_b200 as sk
+    cells, world = (8, 5, 5), 2
+    port = 29600 + ((os.getpid() + (53 if interface == "recompute" else 71)) % 1000)
+    mp.spawn(_reduced_worker, args=(world, port, cells, str(tmp_path), interface), nprocs=world, join=True)
+    d = np.load(os.path.join(str(tmp_path), "reduced_%s.npz" % interface))
+    X, T = syn.make_mesh(cells)
+    mu, lam = syn.lame()
+    r = 24
+    B = syn.cos_modes(X, r, seed=9, lo=np.zeros(3), hi=np.ones(3), n_total=X.shape[0])
+    z = 0.05 * np.random.default_rng(5).standard_normal(r)
+    plan = sk.MeshPlan(X=X, T=T, tile_elems=32)
+    plan.set_materials(mu, lam, plan.volume())
+    E1, g1, H1 = plan.reduced(MAT, B, z, x0=X.reshape(-1))
+    assert abs(float(d["E"]) - E1) <= 1e-12 * abs(E1)
+    assert rel(d["g"], g1) < 1e-10 and rel(d["H"], H1) < 1e-10
+    Jo, volo = oe.deformation_jacobian(X, T), oe.volume(X, T)
+    x = (B @ z).reshape(-1, 3) + X
+    Qo = oe.hessian_x(MAT, x, Jo, mu, lam, volo)
+    assert rel(d["H"], B.T @ (Qo @ B)) < 1e-10
+    assert int(d["nbytes"]) == 8 * (1 + r + r * r)
