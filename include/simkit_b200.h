@@ -176,6 +176,12 @@ int skb_dist_pcg_direction_dev(skb_plan* plan, int v0, int v1, const double* z, 
 int skb_dist_newton_rhs_dev(skb_plan* plan, int v0, int v1, const double* x, const double* f_ext, const double* mass,
                             const double* x_tilde, double kin_scale, const double* pin_k, const double* pin_t, double* g,
                             double* rhs, double* diag, void* stream);
+/* contact springs on the owned vertices of a shard (energies/contact_springs_plane.py:245-388,
+ * contact_springs_sphere.py): kind 0 plane (p, nrm), 1 sphere (p, r); gradient into g and k m_v n n^T into the diagonal
+ * blocks of vals when given; this rank's share of the energy into energy_out (device) when given */
+int skb_dist_contact_dev(skb_plan* plan, int v0, int v1, const double* x, int kind, double k, const double* p,
+                         const double* nrm, double r, const double* w, double* g, double* vals, double* energy_out,
+                         double* work, void* stream);
 int skb_dist_newton_terms_dev(skb_plan* plan, int v0, int v1, const double* x, const double* dx, double s,
                               const double* f_ext, const double* mass, const double* x_tilde, double kin_scale,
                               const double* pin_k, const double* pin_t, const double* g, double* xtrial, double* out,
@@ -435,6 +441,13 @@ int skb_fst_precompute(int dim, int64_t t, int64_t m1, int64_t m2, int64_t n_clu
                        const double* A, const double* B, const int32_t* l, double* ARBs);
 int skb_fst_eval(int dim, int64_t m1, int64_t m2, int64_t n_clusters, const double* ARBs,
                  const double* r, double* out);
+
+/* ---- subspace construction (csrc/capi_subspace.cu) ---------------------------------------------
+ * Thin Householder QR of a row-major (n x r) matrix as numpy.linalg.qr returns it (orthonormalize.py:42), and
+ * G = A^T diag(w) B (row-major r x s; w may be NULL) for B^T M B / B^T M y of project_into_subspace.py:49-53.
+ * Host pointers; cuSOLVER geqrf + orgqr and cuBLAS gemm (plain library calls on a one-off set-up step). */
+int skb_qr_thin(int64_t n, int64_t r, const double* A, double* Q, double* R);
+int skb_weighted_gram(int64_t n, int64_t r, int64_t s, const double* A, const double* w, const double* B, double* G);
 
 #ifdef __cplusplus
 }

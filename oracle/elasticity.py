@@ -879,6 +879,30 @@ def block_jacobi_cg_single_reduction(H, rhs, dim, rtol=1e-10, maxiter=20000):
     return x, maxiter
 
 
+def orthonormalize(B, M=None, threshold=1e-16):
+    """orthonormalize.py:9-49."""
+    if M is None:
+        M = sps.identity(B.shape[0])
+    msqrt = np.sqrt(M.diagonal())
+    Bm = sps.diags(msqrt, 0) @ B
+    Q, R = np.linalg.qr(Bm.toarray() if sps.issparse(Bm) else Bm)
+    nonsing = np.abs(R).sum(axis=1) > threshold
+    return sps.diags(1.0 / msqrt, 0) @ Q[:, nonsing]
+
+
+def project_into_subspace(y, B, M=None, BMB=None, BMy=None):
+    """project_into_subspace.py:9-59."""
+    if M is None:
+        M = sps.identity(y.shape[0])
+    if BMy is None:
+        BMy = B.T @ M @ y
+    if BMB is None:
+        BMB = B.T @ M @ B
+    if sps.issparse(BMB):
+        return spla.spsolve(BMB, BMy).reshape(-1, 1)
+    return np.linalg.solve(BMB, BMy).reshape(-1, 1)
+
+
 def rigid_mode_prolongator(X, agg):
     """P (n*dim, NC*n_agg) of the two-level preconditioner of simkit_b200/csrc/coarse.cuh (not reference code): the
     rigid-body modes of vertex aggregates, P_v = [I | -[x_v - c_I]_x] (3 x 6; 2 x 3 in 2D), c_I the aggregate's centroid."""

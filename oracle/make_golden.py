@@ -348,8 +348,32 @@ def golden_mfem(tag, cells, rho_aug, seed):
     print("wrote", tag)
 
 
+def golden_subspace(tag, cells, seed):
+    """orthonormalize / project_into_subspace of the reference on a small basis with a dependent column."""
+    from simkit.orthonormalize import orthonormalize
+    from simkit.project_into_subspace import project_into_subspace
+    import scipy.sparse as sps
+    rng = np.random.default_rng(seed)
+    X, T = syn.make_mesh(cells)
+    dim = X.shape[1]
+    nd = X.size
+    M = sps.kron(simkit.massmatrix(X, T, 1e3), sps.identity(dim)).tocsc()
+    B = rng.standard_normal((nd, 9))
+    B[:, 6] = B[:, 2] - 0.5 * B[:, 4]
+    y = rng.standard_normal((nd, 1))
+    out = dict(X=X, T=T, dim=dim, B=B, y=y, mass_diag=M.diagonal(),
+               ortho_mass=np.asarray(orthonormalize(B, M, 1e-8)), ortho_id=np.asarray(orthonormalize(B[:, :6])),
+               z_mass=project_into_subspace(y, B[:, :6], M), z_id=project_into_subspace(y, B[:, :6]))
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print("wrote", tag)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "subspace":      # add the newer fixtures without rewriting the old ones
+        golden_subspace("subspace_tet", (3, 2, 2), 70)
+        golden_subspace("subspace_tri", (5, 4), 71)
+        sys.exit(0)
     golden_mesh("tet_s01", (3, 2, 2), 0.1, 10)
     golden_mesh("tet_s04", (3, 2, 2), 0.4, 11)
     golden_mesh("tri_s01", (5, 4), 0.1, 12)

@@ -254,6 +254,19 @@ def main():
         check(f"[{dim}D] quadratic_energy", oe.quadratic_energy(xq, Qs, br), rqe(xq, Qs, br), 1e-13)
         check(f"[{dim}D] quadratic_gradient", oe.quadratic_gradient(xq, Qs, br), rqg(xq, Qs, br), 1e-13)
 
+        # subspace construction helpers
+        from simkit.orthonormalize import orthonormalize as ref_on
+        from simkit.project_into_subspace import project_into_subspace as ref_pis
+        nd = X.shape[0] * dim
+        Bs = rng.standard_normal((nd, 7))
+        Bs[:, 5] = Bs[:, 1] * 2.0                     # a dependent column: dropped by the threshold test
+        Md = sps.diags(1.0 + rng.random(nd))
+        check(f"[{dim}D] orthonormalize (mass)", oe.orthonormalize(Bs, Md, 1e-10), ref_on(Bs, Md, 1e-10), 1e-12)
+        check(f"[{dim}D] orthonormalize (identity)", oe.orthonormalize(Bs[:, :5]), ref_on(Bs[:, :5]), 1e-12)
+        yv = rng.standard_normal((nd, 1))
+        check(f"[{dim}D] project_into_subspace (mass)", oe.project_into_subspace(yv, Bs[:, :5], Md), ref_pis(yv, Bs[:, :5], Md), 1e-12)
+        check(f"[{dim}D] project_into_subspace (identity)", oe.project_into_subspace(yv, Bs[:, :5]), ref_pis(yv, Bs[:, :5]), 1e-12)
+
     print("FAILED: " + ", ".join(FAIL) if FAIL else "ALL OK")
     return 1 if FAIL else 0
 

@@ -14,6 +14,8 @@ from .energies import *  # noqa: F401,F403
 from .fast_sandwich_transform_clustered import fast_sandwich_transform_clustered  # noqa: F401
 from .integrators import backward_euler, bdf2, forward_euler  # noqa: F401
 from .linear_solve import solve_dense, solve_sparse  # noqa: F401
+from .orthonormalize import orthonormalize  # noqa: F401
+from .project_into_subspace import project_into_subspace  # noqa: F401
 from .operators import gravity_force, massmatrix, volume, ympr_to_lame  # noqa: F401
 from .plan import MeshPlan, plan_from_operator  # noqa: F401
 from .potential import ElasticPotential  # noqa: F401

@@ -135,6 +135,7 @@ SIGNATURES = {
     "skb_nccl_set_halo": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "skb_nccl_finalize": (_int, [_vp]),
     "skb_dist_pcg_native": (_int, [_vp, ctypes.POINTER(DistPcgArgs), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_dbl)]),
+    "skb_dist_contact_dev": (_int, [_vp, _int, _int, _vp, _int, _dbl, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
     "skb_dist_pcg2": (_int, [_vp, ctypes.POINTER(DistPcg2Args), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_dbl)]),
     "skb_dist_pcg2_times": (_int, [_vp, _vp]),
     "skb_pcg2_peer_export": (_int, [_vp, _vp, _vp, _i64]),
@@ -152,6 +153,8 @@ SIGNATURES = {
     "skb_host_alloc": (_int, [_i64, ctypes.POINTER(_vp)]),
     "skb_host_free": (None, [_vp]),
     "skb_gradient_hessian_resident": (_int, [_vp, _int, _int, _vp, _vp] + _MAT + [_vp, _vp]),
+    "skb_qr_thin": (_int, [_i64, _i64, _vp, _vp, _vp]),
+    "skb_weighted_gram": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "skb_pcg_vals_dev": (_int, [_vp, _vp, _vp, _vp, _dbl, _int, _vp, ctypes.POINTER(_int), ctypes.POINTER(_dbl)]),
     "skb_plan_value_positions": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "skb_pcg_set_coarse": (_int, [_vp, _i64, _vp, _vp]),

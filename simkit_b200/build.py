@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 _TAG = os.environ.get("SKB_BUILD_TAG", "")
 OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(HERE, "libsimkit_b200" + ("_" + _TAG if _TAG else "") + ".so")
-SOURCES = ["capi.cu", "capi_elements.cu", "capi_solver.cu", "capi_reduced.cu", "capi_dist.cu", "capi_nccl.cu", "capi_pcg2.cu", "capi_buffers.cu"]
+SOURCES = ["capi.cu", "capi_elements.cu", "capi_solver.cu", "capi_reduced.cu", "capi_dist.cu", "capi_nccl.cu", "capi_pcg2.cu", "capi_buffers.cu", "capi_subspace.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -76,7 +76,7 @@ def build(force=False, verbose=False, ptxas_info=False):
                 print(log)
     # cuSOLVER: dense Cholesky inverse of the coarse system of the two-level PCG preconditioner (csrc/coarse.cuh)
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(nvcc)), "lib64")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcusolver", "-ldl", "-Xlinker", "-rpath=" + cuda_lib]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcusolver", "-lcublas", "-ldl", "-Xlinker", "-rpath=" + cuda_lib]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -59,6 +59,7 @@ struct skb_plan {
   cudaStream_t stream = nullptr;  // stream of the host-pointer entry points
   // device staging of the host-pointer entry points / resident materials
   skb::dvec<double> x, fbar, mu, lam, vol, g, vals;
+  skb::dvec<skb::PlanView> pview_dev;  // device copy of view() for kernels that take it by pointer
   skb::dvec<double> stage_elem;  // staging of a per-element host array before it is permuted into the plan's order
   int64_t mu_n = 0, lam_n = 0, vol_n = 0;
   bool have_materials = false;

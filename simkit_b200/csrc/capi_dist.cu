@@ -342,6 +342,44 @@ int skb_dist_newton_rhs_dev(skb_plan* pl, int v0, int v1, const double* x, const
   return SKB_OK;
 }
 
+// Contact springs (energies/contact_springs_plane.py:245-388, contact_springs_sphere.py) on the owned vertices [v0, v1):
+// kind 0 = plane (point p, normal nrm), 1 = sphere (centre p, radius r); w = per-vertex weights (device, local
+// numbering) or NULL.  g / vals non-NULL: gradient added into g, k m_v n n^T into the diagonal blocks of vals.
+// energy_out non-NULL: this rank's part of the energy (the caller all-reduces it).
+int skb_dist_contact_dev(skb_plan* pl, int v0, int v1, const double* x, int kind, double k, const double* p, const double* nrm,
+                         double r, const double* w, double* g, double* vals, double* energy_out, double* work, void* stream) {
+  DIST_CHECK(pl)
+  if (!x || !p || (kind == 0 && !nrm) || (energy_out && !work)) return fail(SKB_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  SKB_TRY
+  const int D = pl->d.dim;
+  ContactPlaneArgs c;
+  memset(&c, 0, sizeof(c));
+  c.k = k;
+  for (int i = 0; i < D; ++i) {
+    c.p[i] = p[i];
+    c.n[i] = nrm ? nrm[i] : 0.0;
+  }
+  c.w = w;
+  c.kind = kind;
+  c.r = r;
+  const PlanView* pvd = nullptr;
+  if (vals) {
+    if (pl->pview_dev.size() != 1) pl->pview_dev.resize(1);
+    const PlanView hv = pl->view();
+    SKB_CUDA(cudaMemcpyAsync(raw(pl->pview_dev), &hv, sizeof(PlanView), cudaMemcpyHostToDevice, st));
+    pvd = raw(pl->pview_dev);
+  }
+  if (D == 3)
+    SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<3><<<DIST_GRID, PCG_THREADS, 0, st>>>(v1, x, c, g, nullptr, pvd, vals, energy_out ? work : nullptr, nullptr, v0));
+  else
+    SKB_LAUNCH(pl, SKB_K_OTHER, st, contact_plane_kernel<2><<<DIST_GRID, PCG_THREADS, 0, st>>>(v1, x, c, g, nullptr, pvd, vals, energy_out ? work : nullptr, nullptr, v0));
+  if (energy_out) SKB_LAUNCH(pl, SKB_K_OTHER, st, dist_reduce_kernel<<<1, PCG_THREADS, 0, st>>>(work, DIST_GRID, energy_out, 0, -1));
+  SKB_CUDA(cudaGetLastError());
+  return SKB_OK;
+  SKB_CATCH
+}
+
 int skb_dist_newton_terms_dev(skb_plan* pl, int v0, int v1, const double* x, const double* dx, double s,
                               const double* f_ext, const double* mass, const double* x_tilde, double kin_scale,
                               const double* pin_k, const double* pin_t, const double* g, double* xtrial, double* out,

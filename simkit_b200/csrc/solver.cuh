@@ -332,12 +332,13 @@ struct ContactPlaneArgs {
   double r;         // sphere radius
 };
 
+// vertices [vbeg, nv): a shard passes its owned range (every vertex is then handled by exactly one rank)
 template <int D>
 __global__ void contact_plane_kernel(int nv, const double* x, ContactPlaneArgs c, double* g_add, double* blocks,
-                                     const PlanView* pv, double* vals, double* part_e, int* under) {
+                                     const PlanView* pv, double* vals, double* part_e, int* under, int vbeg = 0) {
   __shared__ double sh[32];
   double e = 0.0;
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
+  for (int v = vbeg + blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) {
     double off = 0.0;
     double nv_[D];
     if (c.kind == 0) {

@@ -435,7 +435,7 @@ class Shard:
             z = lambda n: torch.zeros(n, dtype=f64, device=self.device)  # noqa: E731
             self._w = dict(r=z(nd), z=z(nd), p=z(nd), q=z(nd), dx=z(nd), rhs=z(nd), diag=z(nd), g=z(nd), xtrial=z(nd),
                            dinv=z(self.plan.n * self.layout.dim ** 2), vals=z(self.plan.nnz), s=z(8), work=z(3 * 2048),
-                           ls=z(4))
+                           ls=z(6))
         return self._w
 
     def set_coarse_space(self, n_agg_target=729):
@@ -575,10 +575,18 @@ class Shard:
 
     def newton_step(self, material, x_d, x_tilde_d=None, mass_d=None, kin_scale=0.0, fext_d=None, psd_mode=1,
                     max_iter=1, do_line_search=True, tolerance=1e-6, ls_alpha=0.01, ls_beta=0.5, ls_max_iter=100,
-                    ls_threshold=1e-12, pcg_rtol=1e-10, pcg_max_iter=20000):
+                    ls_threshold=1e-12, pcg_rtol=1e-10, pcg_max_iter=20000, pin_k_d=None, pin_target_d=None,
+                    contact_plane=None, contact_sphere=None):
         """One implicit step on the sharded mesh (same loop as ``skb_newton`` / solvers/newton.py:42-70): assembly +
         interface exchange, distributed PCG, Armijo backtracking on the all-reduced total energy.  ``x_d`` (local
-        numbering, all local vertices) is updated in place; materials must have been set."""
+        numbering, all local vertices) is updated in place; materials must have been set.
+
+        The per-vertex terms every reference caller adds before the solve act on the OWNED vertices of
+        each rank: ``pin_k_d`` / ``pin_target_d`` -- device vectors (local dofs) of a Dirichlet penalty
+        ``1/2 sum k_i (x_i - t_i)^2`` (``dirichlet_penalty.py:65-142`` with a diagonal ``SGamma``); ``contact_plane`` =
+        ``dict(k=, p=, n=[, w_d=])`` and ``contact_sphere`` = ``dict(k=, p=, r=[, w_d=])`` -- penalty springs against a
+        plane / sphere (``energies/contact_springs_plane.py``, ``contact_springs_sphere.py``), ``w_d`` the per-vertex
+        weights (device, local vertices; default 1).  Their energies join the all-reduce of the line search."""
         import torch
         import torch.distributed as dist
         from ._lib import MATERIAL_IDS, check, load
@@ -591,22 +599,41 @@ class Shard:
         mat = MATERIAL_IDS[material]
         info = dict(iters=-1, alphas=[], pcg_iters=0, pcg_relres=0.0, step_norm=0.0)
         ls = w["ls"]
+        dim = self.layout.dim
+        contacts = []
+        for kind, c in ((0, contact_plane), (1, contact_sphere)):
+            if c is not None and c.get("k"):
+                from ._lib import f64, ptr
+                pp = f64(np.asarray(c["p"], dtype=np.float64).reshape(-1))
+                nn = f64(np.asarray(c.get("n", np.zeros(dim)), dtype=np.float64).reshape(-1))
+                if pp.size != dim or nn.size != dim:
+                    raise ValueError("contact: p and n must have dim entries")
+                contacts.append((kind, float(c["k"]), pp, nn, float(c.get("r", 0.0)), c.get("w_d")))
+
+        def contact(xv_d, g_d, vals_d, e_slot):
+            from ._lib import ptr
+            for ci, (kind, k, pp, nn, r, w_d) in enumerate(contacts):
+                check(lib.skb_dist_contact_dev(h, v0, v1, P(xv_d), kind, k, ptr(pp), ptr(nn), r, P(w_d), P(g_d), P(vals_d),
+                                               0 if e_slot is None else P(ls) + 8 * (e_slot + ci), P(w["work"]), st))
 
         def total_energy(sstep, with_g):
+            ls.zero_()
             check(lib.skb_dist_newton_terms_dev(h, v0, v1, P(x_d), P(w["dx"]), float(sstep), P(fext_d), P(mass_d),
-                                                P(x_tilde_d), float(kin_scale), 0, 0, P(w["g"]) if with_g else 0,
-                                                P(w["xtrial"]), P(ls), P(w["work"]), st))
+                                                P(x_tilde_d), float(kin_scale), P(pin_k_d), P(pin_target_d),
+                                                P(w["g"]) if with_g else 0, P(w["xtrial"]), P(ls), P(w["work"]), st))
             self.halo_exchange(w["xtrial"])
             check(lib.skb_energy_dev(h, mat, P(w["xtrial"]), 0, P(ls) + 24, st))
+            contact(w["xtrial"], None, None, 4)
             dist.all_reduce(ls)
             e = ls.cpu().numpy()
-            return float(e[0] + e[3]), float(e[1]), float(e[2])
+            return float(e[0] + e[3] + e[4] + e[5]), float(e[1]), float(e[2])
 
         self.halo_exchange(x_d)
         for it in range(max_iter):
             self.gradient_hessian_dev(material, psd_mode, x_d, w["g"], w["vals"])
-            check(lib.skb_dist_newton_rhs_dev(h, v0, v1, P(x_d), P(fext_d), P(mass_d), P(x_tilde_d), float(kin_scale), 0, 0,
-                                              P(w["g"]), P(w["rhs"]), P(w["diag"]), st))
+            contact(x_d, w["g"], w["vals"], None)       # gradient rows and diagonal blocks of the owned vertices
+            check(lib.skb_dist_newton_rhs_dev(h, v0, v1, P(x_d), P(fext_d), P(mass_d), P(x_tilde_d), float(kin_scale),
+                                              P(pin_k_d), P(pin_target_d), P(w["g"]), P(w["rhs"]), P(w["diag"]), st))
             pit, relres = self.pcg(w["vals"], w["diag"], w["rhs"], w["dx"], rtol=pcg_rtol, max_iter=pcg_max_iter)
             if not np.isfinite(relres):
                 from ._lib import SimkitB200Error

@@ -158,9 +158,22 @@ def _nccl_worker(rank, world, port, cells, tmp, interface="recompute"):
     info2 = shard.newton_step(MAT, xs2, x_tilde_d=x_d, mass_d=mass_d, kin_scale=1.0 / h ** 2, fext_d=fext_d, max_iter=3,
                               pcg_rtol=1e-12)
     shard.set_coarse_space(0)
+    # per-vertex terms on a sharded mesh: face x = 0 pinned with a penalty, plane and sphere contact
+    Xl = syn.grid_vertices(cells, extent, lay.l2g)
+    pin_k = np.zeros((lay.n_local, dim))
+    pin_k[Xl[:, 0] == 0.0] = 1e6
+    pin_k_d = torch.from_numpy(pin_k.reshape(-1)).to(dev)
+    pin_t_d = torch.from_numpy(Xl.reshape(-1).copy()).to(dev)
+    wv_d = mass_d.reshape(-1, dim)[:, 0].contiguous()
+    xs3 = x_d.clone()
+    info3 = shard.newton_step(MAT, xs3, x_tilde_d=x_d, mass_d=mass_d, kin_scale=1.0 / h ** 2, fext_d=fext_d, max_iter=3,
+                              pcg_rtol=1e-12, pin_k_d=pin_k_d, pin_target_d=pin_t_d,
+                              contact_plane=dict(k=1e5, p=[0.0, 0.2, 0.0], n=[0.0, 1.0, 0.0], w_d=wv_d),
+                              contact_sphere=dict(k=1e5, p=[0.5, 0.5, 0.5], r=0.3, w_d=wv_d))
     np.savez(os.path.join(tmp, "newton%d.npz" % rank), x=xs.cpu().numpy()[o0:o1], lo=lay.v_lo, hi=lay.v_hi,
              alphas=np.asarray(info["alphas"]), mass=mass_d.cpu().numpy()[o0:o1], x2=xs2.cpu().numpy()[o0:o1],
-             alphas2=np.asarray(info2["alphas"]), its=info["pcg_iters"], its2=info2["pcg_iters"], n_agg=n_agg)
+             alphas2=np.asarray(info2["alphas"]), its=info["pcg_iters"], its2=info2["pcg_iters"], n_agg=n_agg,
+             x3=xs3.cpu().numpy()[o0:o1], alphas3=np.asarray(info3["alphas"]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -188,10 +201,20 @@ def test_distributed_newton_matches_single_gpu(tmp_path, interface):
     fext = fext.reshape(-1) * mass
     x1, info = plan.newton(MAT, U.reshape(-1), x_tilde=U.reshape(-1), mass=mass, kin_scale=1.0 / h ** 2, f_ext=fext,
                            max_iter=3, pcg_rtol=1e-12)
+    pin_k = np.zeros_like(X)
+    pin_k[X[:, 0] == 0.0] = 1e6
+    plan.set_contact_plane(1e5, [0.0, 0.2, 0.0], [0.0, 1.0, 0.0], mass[::3])
+    plan.set_contact_sphere(1e5, [0.5, 0.5, 0.5], 0.3, mass[::3])
+    x3, info3 = plan.newton(MAT, U.reshape(-1), x_tilde=U.reshape(-1), mass=mass, kin_scale=1.0 / h ** 2, f_ext=fext,
+                            pin_k=pin_k.reshape(-1), pin_target=X.reshape(-1), max_iter=3, pcg_rtol=1e-12)
+    plan.set_contact_plane(0.0)
+    plan.set_contact_sphere(0.0)
+    assert np.abs(x3 - x1).max() > 1e-6 * np.abs(x1).max()          # the extra terms do change the step
     for r in range(world):
         d = np.load(os.path.join(str(tmp_path), "newton%d.npz" % r))
         lo, hi = int(d["lo"]) * 3, int(d["hi"]) * 3
         assert rel(d["mass"], mass[lo:hi]) < 1e-13
+        assert list(d["alphas3"]) == list(info3["alphas"]) and rel(d["x3"], x3.ravel()[lo:hi]) < 1e-8
         assert list(d["alphas"]) == list(info["alphas"])
         assert rel(d["x"], x1.ravel()[lo:hi]) < 1e-8
         # two-level preconditioner: same iterate, fewer CG iterations
