@@ -359,7 +359,7 @@ def golden_subspace(tag, cells, seed):
     nd = X.size
     M = sps.kron(simkit.massmatrix(X, T, 1e3), sps.identity(dim)).tocsc()
     B = rng.standard_normal((nd, 9))
-    B[:, 6] = B[:, 2] - 0.5 * B[:, 4]
+    B[:, 8] = B[:, 2] - 0.5 * B[:, 4]      # dependent LAST column: its row of R vanishes and the reference drops it
     y = rng.standard_normal((nd, 1))
     out = dict(X=X, T=T, dim=dim, B=B, y=y, mass_diag=M.diagonal(),
                ortho_mass=np.asarray(orthonormalize(B, M, 1e-8)), ortho_id=np.asarray(orthonormalize(B[:, :6])),
