@@ -57,13 +57,15 @@ constexpr int PEER_RED_CAP = 4 + 6 * 2048 + 4;   // 12296 doubles: 4 scalars + t
 constexpr long long PEER_SPIN_LIMIT = 6000000000ll;   // clock64 ticks (~3 s) before a wait gives up and flags an error
 
 struct PeerSlabLayout {
-  size_t off_G, off_fred, off_fhalo, off_rbuf, bytes;
+  size_t off_G, off_fred, off_fhalo, off_zc, off_fzc, off_rbuf, bytes;
   __host__ __device__ static PeerSlabLayout make(int world, int64_t nr) {
     PeerSlabLayout L;
     L.off_G = 0;
     L.off_fred = (size_t)2 * world * PEER_RED_CAP * sizeof(double);
     L.off_fhalo = L.off_fred + (size_t)PEER_MAXW * sizeof(unsigned long long);
-    L.off_rbuf = L.off_fhalo + (size_t)PEER_MAXW * sizeof(unsigned long long) + 256;
+    L.off_zc = L.off_fhalo + (size_t)PEER_MAXW * sizeof(unsigned long long) + 256;   // zc: the coarse solution, every rank
+    L.off_fzc = L.off_zc + (size_t)PEER_RED_CAP * sizeof(double);                    // writes its slice into every slab
+    L.off_rbuf = L.off_fzc + (size_t)PEER_MAXW * sizeof(unsigned long long) + 256;
     L.bytes = L.off_rbuf + (size_t)(nr > 0 ? nr : 1) * sizeof(double) + 256;
     return L;
   }
@@ -73,6 +75,11 @@ struct PeerRedTable {      // kernel argument: where my partials go on every ran
   int world, me;
   double* G[PEER_MAXW];                 // base of rank q's G array
   unsigned long long* fred[PEER_MAXW];  // rank q's fred array
+};
+struct PeerZcTable {       // kernel argument: where my slice of the coarse solution goes on every rank
+  int world, me;
+  double* zc[PEER_MAXW];
+  unsigned long long* fzc[PEER_MAXW];
 };
 struct PeerHaloTable {     // kernel argument: where my halo values go
   int np;
@@ -89,29 +96,6 @@ __device__ __forceinline__ bool peer_wait(const volatile unsigned long long* fla
     __nanosleep(20);
   }
   return true;
-}
-
-// the reduction partials of the previous pass arrive from every rank -> red[k] = sum over ranks in rank order
-static __global__ void pcg3_gather_kernel(Pcg2Scalars* sc, int world, int nred, const double* G,
-                                          const volatile unsigned long long* fred, double* red) {
-  __shared__ int ok;
-  if (sc->done || sc->stage == 0) return;   // bootstrap pass: nothing was reduced yet (red is zero)
-  const unsigned long long seq = sc->seq;
-  if (threadIdx.x == 0) ok = 1;
-  __syncthreads();
-  if ((int)threadIdx.x < world && !peer_wait(fred + threadIdx.x, seq)) ok = 0;
-  __syncthreads();
-  if (!ok) {
-    if (threadIdx.x == 0) sc->done = 5;
-    return;
-  }
-  __threadfence_system();
-  const double* Gp = G + (size_t)(seq & 1ull) * world * PEER_RED_CAP;
-  for (int k = threadIdx.x; k < nred; k += blockDim.x) {
-    double acc = 0.0;
-    for (int q = 0; q < world; ++q) acc += __ldcg(Gp + (size_t)q * PEER_RED_CAP + k);
-    red[k] = acc;
-  }
 }
 
 // halo of u: my owned values the neighbours need go straight into their receive areas; the last CTA raises the flags
@@ -159,9 +143,33 @@ static __global__ void pcg3_wait_unpack_kernel(Pcg2Scalars* sc, double* __restri
 // ---- iteration kernels ------------------------------------------------------------------------------------------
 // scalars of the iteration from the reduced sums red = [gamma, delta, rr, -, P^T w ...], then the coarse recurrences
 //   rcs = P^T w + beta rcs,   rc -= alpha rcs      (one CTA; nc <= 12288 values)
-static __global__ void pcg2_scalars_kernel(Pcg2Scalars* sc, const double* red, int nc, double* rc, double* rcs) {
+// With the peer-memory transport (G != NULL) the kernel first waits for the partials of the previous pass from every
+// rank and sums them into `red` in rank order (what the all-reduce does for the NCCL transport).
+static __global__ void pcg2_scalars_kernel(Pcg2Scalars* sc, double* red, int nc, double* rc, double* rcs, int world,
+                                           const double* G, const volatile unsigned long long* fred) {
   __shared__ double sab[2];
   __shared__ int sdone;
+  __shared__ int ok;
+  if (G && !sc->done && sc->stage > 0) {      // bootstrap pass: nothing was reduced yet (red is zero)
+    const unsigned long long seq = sc->seq;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    if ((int)threadIdx.x < world && !peer_wait(fred + threadIdx.x, seq)) ok = 0;
+    __syncthreads();
+    if (!ok) {
+      if (threadIdx.x == 0) sc->done = 5;
+    } else {
+      __threadfence_system();
+      const double* Gp = G + (size_t)(seq & 1ull) * world * PEER_RED_CAP;
+      for (int k = threadIdx.x; k < 4 + nc; k += blockDim.x) {
+        double acc = 0.0;
+        for (int q = 0; q < world; ++q) acc += __ldcg(Gp + (size_t)q * PEER_RED_CAP + k);
+        red[k] = acc;
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     Pcg2Scalars s = *sc;
     double alpha = 0.0, beta = 0.0;
@@ -235,6 +243,45 @@ static __global__ void pcg2_gemv_kernel(const Pcg2Scalars* sc, int nc, const dou
   if (lane == 0) zc[row] = s;
 }
 
+// Peer-memory transport: every rank holds only ITS columns [c0, c0 + w) of the inverse of the coarse matrix (Xs, nc x w
+// column-major, from potrf + potrs with unit right-hand sides) and computes that slice of zc = Ainv rc -- one warp per
+// column -- storing it into the zc area of EVERY rank's slab; the last CTA raises this rank's flag on every rank.  The
+// dense apply per iteration shrinks by the rank count, and so does the O(nc^3) inverse (potrf only, no potri).
+static __global__ void pcg3_gemv_push_kernel(const Pcg2Scalars* sc, int nc, int c0, int w, const double* __restrict__ Xs,
+                                             const double* __restrict__ rc, PeerZcTable t, unsigned int* counter) {
+  __shared__ int last;
+  if (sc->done) return;
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (col < w) {
+    const double* a = Xs + (size_t)col * nc;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = lane;
+    for (; k + 96 < nc; k += 128) {
+      const double a0 = a[k], a1 = a[k + 32], a2 = a[k + 64], a3 = a[k + 96];
+      s0 = fma(a0, rc[k], s0);
+      s1 = fma(a1, rc[k + 32], s1);
+      s2 = fma(a2, rc[k + 64], s2);
+      s3 = fma(a3, rc[k + 96], s3);
+    }
+    for (; k < nc; k += 32) s0 = fma(a[k], rc[k], s0);
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0)
+      for (int q = 0; q < t.world; ++q) t.zc[q][c0 + col] = s;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) *counter = 0;
+    __threadfence_system();
+    if ((int)threadIdx.x < t.world) *(volatile unsigned long long*)(t.fzc[threadIdx.x] + t.me) = sc->seq;
+  }
+}
+
 // p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;  u = Dinv r [+ P zc]      (owned vertices)
 // and the per-CTA partial sums of r.u and r.r of the NEW r, u (part[0..grid), part[2 grid..3 grid); w.u comes from the SpMV)
 template <int D, bool COARSE>
@@ -242,10 +289,25 @@ __global__ void __launch_bounds__(PCG_THREADS, 5)
 pcg2_update_kernel(const Pcg2Scalars* sc, int v0, int v1, const double* __restrict__ dinv, const int* __restrict__ agg,
                    const double* __restrict__ xrel, const double* __restrict__ zc, const double* __restrict__ w,
                    double* __restrict__ u, double* __restrict__ p, double* __restrict__ s, double* __restrict__ x,
-                   double* __restrict__ r, double* part) {
+                   double* __restrict__ r, double* part, int zc_world, const volatile unsigned long long* fzc,
+                   Pcg2Scalars* sc_w) {
   __shared__ double sh[32];
+  __shared__ int ok;
   if (sc->done) return;
   constexpr int NC = CoarseDim<D>::NC;
+  if (COARSE && zc_world > 0) {
+    // zc arrives in slices from all ranks (pcg3_gemv_push_kernel): wait for this pass's slices
+    const unsigned long long seq = sc->seq;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    if ((int)threadIdx.x < zc_world && !peer_wait(fzc + threadIdx.x, seq)) ok = 0;
+    __syncthreads();
+    if (!ok) {
+      if (threadIdx.x == 0 && blockIdx.x == 0) sc_w->done = 5;
+      return;
+    }
+    __threadfence_system();
+  }
   const double alpha = sc->alpha, beta = sc->beta;
   double ru = 0.0, rr = 0.0;
   for (int v = v0 + blockIdx.x * blockDim.x + threadIdx.x; v < v1; v += gridDim.x * blockDim.x) {
@@ -268,7 +330,7 @@ pcg2_update_kernel(const Pcg2Scalars* sc, int v0, int v1, const double* __restri
 #pragma unroll
       for (int i = 0; i < D; ++i) xr[i] = xrel[(size_t)v * D + i];
 #pragma unroll
-      for (int a = 0; a < NC; ++a) cc[a] = zc[I * NC + a];
+      for (int a = 0; a < NC; ++a) cc[a] = __ldcg(zc + I * NC + a);
       coarse_P<D>(xr, cc, o);
 #pragma unroll
       for (int i = 0; i < D; ++i) ul[i] += o[i];
@@ -467,6 +529,9 @@ struct Pcg2State {
   bool peer_ready = false;
   PeerRedTable red_tab{};
   PeerHaloTable halo_tab{};
+  PeerZcTable zc_tab{};
+  dvec<double> Xs;                   // my columns of the inverse of the coarse matrix (nc x zc_w, column-major)
+  int zc_c0 = 0, zc_w = 0;
   dvec<unsigned int> counters;       // [2] last-CTA counters of the two pushing kernels
   int g_transport = -1;
 };
@@ -532,7 +597,7 @@ int skb_pcg2_peer_export(skb_plan* pl, void* handle64, int64_t* meta, int64_t me
     SKB_CUDA(cudaMalloc(&S.slab, S.lay.bytes));
     SKB_CUDA(cudaMemset(S.slab, 0, S.lay.bytes));
     SKB_CUDA(cudaDeviceSynchronize());
-    S.counters.assign(2, 0u);
+    S.counters.assign(4, 0u);
   }
   cudaIpcMemHandle_t h;
   SKB_CUDA(cudaIpcGetMemHandle(&h, S.slab));
@@ -577,6 +642,13 @@ int skb_pcg2_peer_import(skb_plan* pl, const void* handles, const int64_t* metas
     const PeerSlabLayout L = PeerSlabLayout::make(W, metas[(size_t)q * (1 + W)]);
     S.red_tab.G[q] = reinterpret_cast<double*>((char*)S.peer_base[q] + L.off_G);
     S.red_tab.fred[q] = reinterpret_cast<unsigned long long*>((char*)S.peer_base[q] + L.off_fred);
+  }
+  S.zc_tab.world = W;
+  S.zc_tab.me = me;
+  for (int q = 0; q < W; ++q) {
+    const PeerSlabLayout L = PeerSlabLayout::make(W, metas[(size_t)q * (1 + W)]);
+    S.zc_tab.zc[q] = reinterpret_cast<double*>((char*)S.peer_base[q] + L.off_zc);
+    S.zc_tab.fzc[q] = reinterpret_cast<unsigned long long*>((char*)S.peer_base[q] + L.off_fzc);
   }
   S.halo_tab.np = (int)d.halo.size();
   for (size_t i = 0; i <= d.halo.size(); ++i) S.halo_tab.soff[i] = S.soff[i];
@@ -657,6 +729,10 @@ int skb_dist_pcg2(skb_plan* pl, const skb_dist_pcg2_args* a, int32_t* iters, dou
   }
   int rc_;
   if ((rc_ = pcg2_prepare_halo(d, S, st))) return rc_;
+  // transport of the per-iteration exchanges: 1 = stores into the other ranks' HBM over NVLink (CUDA IPC mappings,
+  // flags instead of collective calls), 0 = NCCL (grouped send/recv + all-reduce)
+  const bool peer = a->transport == 1 && S.peer_ready && 4 + nc <= PEER_RED_CAP;
+  if (a->transport == 1 && !peer) return fail(SKB_EINVAL, "peer-memory transport requested but not set up (skb_pcg2_peer_export / _import)");
   Pcg2Scalars* sc = raw(S.sc);
   double *r = raw(S.r), *u = raw(S.u), *w = raw(S.w), *p = raw(S.p), *s = raw(S.s), *x = a->x, *red = raw(S.red);
   const int64_t ns = S.soff.back(), nr = S.roff.back();
@@ -684,7 +760,16 @@ int skb_dist_pcg2(skb_plan* pl, const skb_dist_pcg2_args* a, int32_t* iters, dou
     if ((rc_ = all_reduce(d, raw(S.Ainv), (size_t)nc * nc, st))) return rc_;
     SKB_CUDA(cudaStreamSynchronize(st));
     t_inv0 = now();
-    if (coarse_invert(pl, raw(S.Ainv), nc, st) != 0) coarse = false;   // degenerate aggregate: block-Jacobi for this solve
+    if (peer) {
+      // every rank factors the (identical) coarse matrix and keeps only ITS columns of the inverse
+      const int W = d.world;
+      S.zc_c0 = (int)((int64_t)nc * d.rank / W);
+      S.zc_w = (int)((int64_t)nc * (d.rank + 1) / W) - S.zc_c0;
+      if (S.Xs.size() < (size_t)nc * (S.zc_w > 0 ? S.zc_w : 1)) S.Xs.resize((size_t)nc * (S.zc_w > 0 ? S.zc_w : 1));
+      if (coarse_factor_slice(pl, raw(S.Ainv), nc, S.zc_c0, S.zc_w, raw(S.Xs), st) != 0) coarse = false;
+    } else if (coarse_invert(pl, raw(S.Ainv), nc, st) != 0) {
+      coarse = false;   // degenerate aggregate: block-Jacobi for this solve
+    }
     SKB_CUDA(cudaStreamSynchronize(st));
     t_inv1 = now();
   }
@@ -710,36 +795,38 @@ int skb_dist_pcg2(skb_plan* pl, const skb_dist_pcg2_args* a, int32_t* iters, dou
     if ((rc_ = all_reduce(d, raw(S.rc), nc, st))) return rc_;
   }
   const int nc_it = coarse ? nc : 0;
-  // transport of the two per-iteration exchanges: 1 = stores into the neighbours' HBM over NVLink (CUDA IPC mappings,
-  // flags instead of collective calls), 0 = NCCL (grouped send/recv + all-reduce)
-  const bool peer = a->transport == 1 && S.peer_ready && 4 + nc_it <= PEER_RED_CAP;
-  if (a->transport == 1 && !peer) return fail(SKB_EINVAL, "peer-memory transport requested but not set up (skb_pcg2_peer_export / _import)");
   const PeerSlabLayout& L = S.lay;
   const double* myG = peer ? reinterpret_cast<const double*>((char*)S.slab + L.off_G) : nullptr;
   const unsigned long long* my_fred = peer ? reinterpret_cast<const unsigned long long*>((char*)S.slab + L.off_fred) : nullptr;
   const unsigned long long* my_fhalo = peer ? reinterpret_cast<const unsigned long long*>((char*)S.slab + L.off_fhalo) : nullptr;
   const double* my_rbuf = peer ? reinterpret_cast<const double*>((char*)S.slab + L.off_rbuf) : nullptr;
+  const double* my_zc = peer ? reinterpret_cast<const double*>((char*)S.slab + L.off_zc) : nullptr;
+  const unsigned long long* my_fzc = peer ? reinterpret_cast<const unsigned long long*>((char*)S.slab + L.off_fzc) : nullptr;
+  const double* zc_use = (peer && coarse) ? my_zc : raw(S.zc);
+  const int zc_world = (peer && coarse) ? d.world : 0;
   SKB_CUDA(cudaStreamSynchronize(st));
   const double t_iter0 = now();
 
   auto iteration = [&]() -> int {
-    if (peer)
-      SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg3_gather_kernel<<<1, 1024, 0, st>>>(sc, d.world, 4 + nc_it, myG, my_fred, red));
-    SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg2_scalars_kernel<<<1, 1024, 0, st>>>(sc, red, nc_it, raw(S.rc), raw(S.rcs)));
-    if (coarse)
+    SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg2_scalars_kernel<<<1, 1024, 0, st>>>(sc, red, nc_it, raw(S.rc), raw(S.rcs), d.world,
+                                                                           peer ? myG : nullptr, my_fred));
+    if (coarse && peer)
+      SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg3_gemv_push_kernel<<<(S.zc_w * 32 + 255) / 256 > 0 ? (S.zc_w * 32 + 255) / 256 : 1, 256, 0, st>>>(
+                     sc, nc, S.zc_c0, S.zc_w, raw(S.Xs), raw(S.rc), S.zc_tab, raw(S.counters) + 2));
+    else if (coarse)
       SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_gemv_kernel<<<(nc * 32 + 255) / 256, 256, 0, st>>>(sc, nc, raw(S.Ainv), raw(S.rc), raw(S.zc)));
     const int* agg = coarse ? raw(cs->agg) : nullptr;
     const double* xrel = coarse ? raw(cs->xrel) : nullptr;
     if (D == 3) {
       if (coarse)
-        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<3, true><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r, raw(S.part)));
+        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<3, true><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, zc_use, w, u, p, s, x, r, raw(S.part), zc_world, my_fzc, sc));
       else
-        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<3, false><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r, raw(S.part)));
+        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<3, false><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, zc_use, w, u, p, s, x, r, raw(S.part), zc_world, my_fzc, sc));
     } else {
       if (coarse)
-        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<2, true><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r, raw(S.part)));
+        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<2, true><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, zc_use, w, u, p, s, x, r, raw(S.part), zc_world, my_fzc, sc));
       else
-        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<2, false><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, raw(S.zc), w, u, p, s, x, r, raw(S.part)));
+        SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<2, false><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, zc_use, w, u, p, s, x, r, raw(S.part), zc_world, my_fzc, sc));
     }
     // halo of u
     if (peer) {

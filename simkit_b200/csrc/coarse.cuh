@@ -296,4 +296,34 @@ inline int coarse_invert(skb_plan* pl, double* Ac, int nc, cudaStream_t st) {
   return SKB_OK;
 }
 
+// unit columns c0 .. c0 + w of the identity, column-major nc x w
+static __global__ void coarse_unit_columns_kernel(int nc, int c0, int w, double* X) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)nc * w) return;
+  const int col = (int)(idx / nc), row = (int)(idx - (size_t)col * nc);
+  X[idx] = (row == c0 + col) ? 1.0 : 0.0;
+}
+
+// Cholesky factor of Ac in place (potrf) and the columns [c0, c0 + w) of its inverse into Xs (nc x w, column-major;
+// potrs with unit right-hand sides): what ONE rank of a sharded solve needs of the dense inverse.  No potri.
+inline int coarse_factor_slice(skb_plan* pl, double* Ac, int nc, int c0, int w, double* Xs, cudaStream_t st) {
+  CoarseSpace& c = *pl->coarse;
+  if (!c.handle) SKB_CUSOLVER(cusolverDnCreate(&c.handle));
+  SKB_CUSOLVER(cusolverDnSetStream(c.handle, st));
+  int lw = 0;
+  SKB_CUSOLVER(cusolverDnDpotrf_bufferSize(c.handle, CUBLAS_FILL_MODE_LOWER, nc, Ac, nc, &lw));
+  if ((int)c.work.size() < lw) c.work.resize(lw);
+  if (c.info.size() < 2) c.info.resize(2);
+  SKB_CUSOLVER(cusolverDnDpotrf(c.handle, CUBLAS_FILL_MODE_LOWER, nc, Ac, nc, raw(c.work), lw, raw(c.info)));
+  coarse_unit_columns_kernel<<<(unsigned)(((size_t)nc * w + 255) / 256), 256, 0, st>>>(nc, c0, w, Xs);
+  SKB_CUDA(cudaGetLastError());
+  SKB_CUSOLVER(cusolverDnDpotrs(c.handle, CUBLAS_FILL_MODE_LOWER, nc, w, Ac, nc, Xs, nc, raw(c.info) + 1));
+  int hinfo[2] = {0, 0};
+  SKB_CUDA(cudaMemcpyAsync(hinfo, raw(c.info), 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SKB_CUDA(cudaStreamSynchronize(st));
+  if (hinfo[0] != 0 || hinfo[1] != 0)
+    return fail(SKB_ENOTSPD, "coarse matrix of the two-level preconditioner is not positive definite");
+  return SKB_OK;
+}
+
 }  // namespace skb

@@ -210,6 +210,15 @@ def test_reduced_against_golden(golden_dir, tag):
     assert rel(f.ARBs, g["fst_ARBs"]) < 1e-12
     assert rel(f(g["fst_r"]), g["fst_out"]) < 1e-12
     assert rel(f.eval(2 * g["fst_r"]), 2 * g["fst_out"]) < 1e-12      # linearity in r
+    # sparse operators densified in chunks of elements (tiny chunk budget forces several chunks): same ARBs
+    cls = sk.fast_sandwich_transform_clustered
+    old = cls.CHUNK_BYTES
+    cls.CHUNK_BYTES = 8 * dim * dim * (g["fst_A"].shape[0] + g["fst_B"].shape[1]) * 3     # three elements per chunk
+    try:
+        f2 = cls(sps.csc_matrix(g["fst_A"]), sps.csr_matrix(g["fst_B"]), g["fst_l"], dim=dim)
+    finally:
+        cls.CHUNK_BYTES = old
+    assert rel(f2.ARBs, g["fst_ARBs"]) < 1e-12
 
 
 def test_reduced_r200_against_oracle():
