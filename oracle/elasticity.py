@@ -903,6 +903,34 @@ def project_into_subspace(y, B, M=None, BMB=None, BMy=None):
     return np.linalg.solve(BMB, BMy).reshape(-1, 1)
 
 
+def lbs_jacobian(V, W):
+    """lbs_jacobian.py:12-47."""
+    n, d = V.shape
+    k = W.shape[1]
+    V1 = np.hstack((V, np.ones((n, 1))))
+    Wexp = np.kron(W, np.ones((1, d + 1)))
+    V1exp = np.kron(np.ones((1, k)), V1)
+    return np.kron(Wexp * V1exp, np.identity(d))
+
+
+def skinning_eigenmodes(X, T, k, mu=1, bI=None):
+    """skinning_eigenmodes.py:19-84 with the shift-invert ARPACK call of eigs.py:96-103.  The reference's inverse
+    operator is a UMFPACK LU (cvxopt, absent here: PARITY UNPINNED for this function -- the reference itself cannot be
+    run); this restatement lets scipy factor ``L + eps M`` with SuperLU, the same tiny regularisation the product uses."""
+    M = sps.csc_matrix(massmatrix(X, T))
+    L = sps.csc_matrix(dirichlet_laplacian(X, T, mu))
+    Ii = np.arange(X.shape[0]) if bI is None else np.setdiff1d(np.arange(X.shape[0]), bI)
+    Lf = L[Ii, :][:, Ii]
+    Mf = sps.diags(M.diagonal()[Ii]).tocsc()
+    eps = 1e-10 * Lf.diagonal().sum() / Mf.diagonal().sum()
+    lu = spla.splu((Lf + eps * Mf).tocsc())
+    op = spla.LinearOperator(Lf.shape, matvec=lu.solve, dtype=np.float64)
+    E, Wi = spla.eigsh(Lf, M=Mf, k=k, sigma=0, which="LM", OPinv=op, v0=np.ones(Lf.shape[0]))
+    W = np.zeros((X.shape[0], k))
+    W[Ii] = Wi
+    return W, E - eps, lbs_jacobian(X, W)
+
+
 def rigid_mode_prolongator(X, agg):
     """P (n*dim, NC*n_agg) of the two-level preconditioner of simkit_b200/csrc/coarse.cuh (not reference code): the
     rigid-body modes of vertex aggregates, P_v = [I | -[x_v - c_I]_x] (3 x 6; 2 x 3 in 2D), c_I the aggregate's centroid."""

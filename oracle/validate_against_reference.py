@@ -263,6 +263,9 @@ def main():
         Md = sps.diags(1.0 + rng.random(nd))
         check(f"[{dim}D] orthonormalize (mass)", oe.orthonormalize(Bs, Md, 1e-10), ref_on(Bs, Md, 1e-10), 1e-12)
         check(f"[{dim}D] orthonormalize (identity)", oe.orthonormalize(Bs[:, :5]), ref_on(Bs[:, :5]), 1e-12)
+        from simkit.lbs_jacobian import lbs_jacobian as ref_lbs
+        Ww = rng.standard_normal((X.shape[0], 4))
+        check(f"[{dim}D] lbs_jacobian", oe.lbs_jacobian(X, Ww), ref_lbs(X, Ww), 1e-15)
         yv = rng.standard_normal((nd, 1))
         check(f"[{dim}D] project_into_subspace (mass)", oe.project_into_subspace(yv, Bs[:, :5], Md), ref_pis(yv, Bs[:, :5], Md), 1e-12)
         check(f"[{dim}D] project_into_subspace (identity)", oe.project_into_subspace(yv, Bs[:, :5]), ref_pis(yv, Bs[:, :5]), 1e-12)

@@ -13,6 +13,8 @@ from .dirichlet_penalty import dirichlet_penalty  # noqa: F401
 from .energies import *  # noqa: F401,F403
 from .fast_sandwich_transform_clustered import fast_sandwich_transform_clustered  # noqa: F401
 from .integrators import backward_euler, bdf2, forward_euler  # noqa: F401
+from .lbs_jacobian import lbs_jacobian  # noqa: F401
+from .skinning_eigenmodes import skinning_eigenmodes  # noqa: F401
 from .linear_solve import solve_dense, solve_sparse  # noqa: F401
 from .orthonormalize import orthonormalize  # noqa: F401
 from .project_into_subspace import project_into_subspace  # noqa: F401

@@ -98,6 +98,20 @@ __device__ __forceinline__ bool peer_wait(const volatile unsigned long long* fla
   return true;
 }
 
+// Waits until the first n flags (n <= 32) reach this pass's sequence number.  ONE small CTA polls: when every CTA of a
+// large kernel polled the same flag line, the reads saturated that L2 slice and delayed the very store they were waiting
+// for (8 GPUs: +15 us per synchronisation point); the consumer kernel that follows in the stream needs no wait of its own.
+static __global__ void pcg3_wait_kernel(Pcg2Scalars* sc, const volatile unsigned long long* flags, int n, int use_peer_index,
+                                        PeerHaloTable t) {
+  if (sc->done) return;
+  const unsigned long long seq = sc->seq;
+  if ((int)threadIdx.x < n) {
+    const volatile unsigned long long* f = use_peer_index ? flags + t.peer[threadIdx.x] : flags + threadIdx.x;
+    if (!peer_wait(f, seq)) sc->done = 5;
+  }
+  __threadfence_system();
+}
+
 // halo of u: my owned values the neighbours need go straight into their receive areas; the last CTA raises the flags
 static __global__ void pcg3_pack_push_kernel(const Pcg2Scalars* sc, const double* __restrict__ v,
                                              const int32_t* __restrict__ idx, PeerHaloTable t, unsigned int* counter) {
@@ -120,22 +134,10 @@ static __global__ void pcg3_pack_push_kernel(const Pcg2Scalars* sc, const double
   }
 }
 
-// waits for the neighbours' halo values of this pass, then copies them into the non-owned entries of u
-static __global__ void pcg3_wait_unpack_kernel(Pcg2Scalars* sc, double* __restrict__ v, const int32_t* __restrict__ idx,
-                                               int64_t n, const double* rbuf, PeerHaloTable t,
-                                               const volatile unsigned long long* my_fhalo) {
-  __shared__ int ok;
+// copies the neighbours' halo values of this pass (already waited for by pcg3_wait_kernel) into the non-owned entries of u
+static __global__ void pcg3_unpack_kernel(const Pcg2Scalars* sc, double* __restrict__ v, const int32_t* __restrict__ idx,
+                                          int64_t n, const double* rbuf) {
   if (sc->done) return;
-  const unsigned long long seq = sc->seq;
-  if (threadIdx.x == 0) ok = 1;
-  __syncthreads();
-  if ((int)threadIdx.x < t.np && !peer_wait(my_fhalo + t.peer[threadIdx.x], seq)) ok = 0;
-  __syncthreads();
-  if (!ok) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) sc->done = 5;
-    return;
-  }
-  __threadfence_system();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     v[idx[i]] = __ldcg(rbuf + i);
 }
@@ -292,22 +294,9 @@ pcg2_update_kernel(const Pcg2Scalars* sc, int v0, int v1, const double* __restri
                    double* __restrict__ r, double* part, int zc_world, const volatile unsigned long long* fzc,
                    Pcg2Scalars* sc_w) {
   __shared__ double sh[32];
-  __shared__ int ok;
   if (sc->done) return;
   constexpr int NC = CoarseDim<D>::NC;
-  if (COARSE && zc_world > 0) {
-    // zc arrives in slices from all ranks (pcg3_gemv_push_kernel): wait for this pass's slices
-    const unsigned long long seq = sc->seq;
-    if (threadIdx.x == 0) ok = 1;
-    __syncthreads();
-    if ((int)threadIdx.x < zc_world && !peer_wait(fzc + threadIdx.x, seq)) ok = 0;
-    __syncthreads();
-    if (!ok) {
-      if (threadIdx.x == 0 && blockIdx.x == 0) sc_w->done = 5;
-      return;
-    }
-    __threadfence_system();
-  }
+  (void)zc_world; (void)fzc; (void)sc_w;   // the slices of zc were waited for by pcg3_wait_kernel
   const double alpha = sc->alpha, beta = sc->beta;
   double ru = 0.0, rr = 0.0;
   for (int v = v0 + blockIdx.x * blockDim.x + threadIdx.x; v < v1; v += gridDim.x * blockDim.x) {
@@ -817,6 +806,8 @@ int skb_dist_pcg2(skb_plan* pl, const skb_dist_pcg2_args* a, int32_t* iters, dou
       SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_gemv_kernel<<<(nc * 32 + 255) / 256, 256, 0, st>>>(sc, nc, raw(S.Ainv), raw(S.rc), raw(S.zc)));
     const int* agg = coarse ? raw(cs->agg) : nullptr;
     const double* xrel = coarse ? raw(cs->xrel) : nullptr;
+    if (coarse && peer)   // the slices of zc from all ranks
+      SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg3_wait_kernel<<<1, 32, 0, st>>>(sc, my_fzc, d.world, 0, S.halo_tab));
     if (D == 3) {
       if (coarse)
         SKB_LAUNCH(pl, SKB_K_PCG_VECTOR, st, pcg2_update_kernel<3, true><<<PCG2_GRID, PCG_THREADS, 0, st>>>(sc, v0, v1, raw(S.dinv), agg, xrel, zc_use, w, u, p, s, x, r, raw(S.part), zc_world, my_fzc, sc));
@@ -833,8 +824,10 @@ int skb_dist_pcg2(skb_plan* pl, const skb_dist_pcg2_args* a, int32_t* iters, dou
       // stores into the neighbours' receive areas + flags; then wait for theirs and unpack
       if (ns > 0)
         SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg3_pack_push_kernel<<<(unsigned)((ns + 255) / 256 < 296 ? (ns + 255) / 256 : 296), 256, 0, st>>>(sc, u, raw(S.sidx), S.halo_tab, raw(S.counters)));
-      if (nr > 0)
-        SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg3_wait_unpack_kernel<<<(unsigned)((nr + 255) / 256 < 296 ? (nr + 255) / 256 : 296), 256, 0, st>>>(sc, u, raw(S.ridx), nr, my_rbuf, S.halo_tab, my_fhalo));
+      if (nr > 0) {
+        SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg3_wait_kernel<<<1, 32, 0, st>>>(sc, my_fhalo, S.halo_tab.np, 1, S.halo_tab));
+        SKB_LAUNCH(pl, SKB_K_OTHER, st, pcg3_unpack_kernel<<<(unsigned)((nr + 255) / 256 < 296 ? (nr + 255) / 256 : 296), 256, 0, st>>>(sc, u, raw(S.ridx), nr, my_rbuf));
+      }
     } else {
       // pack, one grouped send/recv, unpack
       if (ns > 0)

@@ -57,3 +57,48 @@ def test_gpu_subspace_helpers(golden_dir, tag):
     assert rel(sk.project_into_subspace(g["y"], g["B"][:, :6], Mg), zr) < 1e-10
     Bs = sps.csc_matrix(g["B"][:, :6])
     assert rel(sk.project_into_subspace(g["y"], Bs, Mg), zr) < 1e-9
+
+
+def _jittered(cells, seed=2):
+    from simkit_b200 import synthetic as syn
+    X, T = syn.make_mesh(cells)
+    rng = np.random.default_rng(seed)
+    return X + 0.25 * syn.cell_size(cells, tuple(1.0 for _ in cells)) * rng.standard_normal(X.shape), T
+
+
+@pytest.mark.parametrize("cells", [(6, 5, 4), (12, 9)])
+def test_oracle_skinning_eigenmodes(cells):
+    """The restated ARPACK shift-invert call: M-orthonormal modes that satisfy L w = lambda M w, a (near) zero constant
+    mode without pins, strictly positive spectrum with pins, and the LBS Jacobian layout."""
+    X, T = _jittered(cells)
+    n, dim = X.shape
+    L, M = oe.dirichlet_laplacian(X, T, 1), oe.massmatrix(X, T)
+    W, E, B = oe.skinning_eigenmodes(X, T, 5)
+    assert W.shape == (n, 5) and E.shape == (5,) and B.shape == (n * dim, n * 0 + 5 * (dim + 1) * dim)
+    assert abs(E[0]) < 1e-8 * E[1] and np.all(np.diff(E) > 0)
+    assert np.abs(L @ W - (M @ W) * E).max() < 1e-9 * np.abs(L @ W).max()
+    assert rel(W.T @ (M @ W), np.eye(5)) < 1e-9
+    bI = np.where(X[:, 0] < 0.08)[0]
+    Wp, Ep, _ = oe.skinning_eigenmodes(X, T, 4, bI=bI)
+    assert np.all(Ep > 0) and np.abs(Wp[bI]).max() == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells", [(6, 5, 4), (12, 9)])
+def test_gpu_skinning_eigenmodes(cells):
+    """Same ARPACK recurrence with the inverse applied by the GPU PCG: eigenvalues to 1e-8, modes equal up to sign
+    (simple spectrum on a jittered mesh), LBS Jacobian from them; with and without pinned vertices."""
+    import simkit_b200 as sk
+    X, T = _jittered(cells)
+    for bI in (None, np.where(X[:, 0] < 0.08)[0]):
+        k = 6
+        Wo, Eo, Bo = oe.skinning_eigenmodes(X, T, k, bI=bI)
+        W, E, B = sk.skinning_eigenmodes(X, T, k, bI=bI)
+        assert W.shape == Wo.shape and B.shape == Bo.shape
+        assert np.abs(E - Eo).max() <= 1e-8 * np.abs(Eo).max()
+        sgn = np.sign(np.sum(W * Wo, axis=0))
+        assert rel(W * sgn, Wo) < 1e-6
+        assert rel(B, oe.lbs_jacobian(X, W)) < 1e-14
+    assert rel(sk.lbs_jacobian(X, Wo), oe.lbs_jacobian(X, Wo)) == 0.0
+    with pytest.raises(ValueError):
+        sk.skinning_eigenmodes(X, T, 3, Aeq=sps.identity(X.shape[0]).tocsr()[:2])
