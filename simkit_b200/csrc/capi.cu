@@ -119,6 +119,10 @@ int upload_materials(skb_plan* pl, const double* mu, int64_t mu_n, const double*
 #ifndef SKB_PIPE_NBUF
 #define SKB_PIPE_NBUF 2
 #endif
+// default assembly kernel when SKB_ASSEMBLE is not set: 1 = pipelined, 2 = warp-specialised
+#ifndef SKB_ASSEMBLE_DEFAULT
+#define SKB_ASSEMBLE_DEFAULT 1
+#endif
 
 template <int D, int G, int NBUF, int MAT>
 static int launch_pipelined(skb_plan* pl, const PlanView& p, const EvalArgs& a, size_t psmem, int grid, cudaStream_t st) {
@@ -130,6 +134,18 @@ static int launch_pipelined(skb_plan* pl, const PlanView& p, const EvalArgs& a, 
     attr_set = true;
   }
   SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_pipelined_kernel<D, G, NBUF, MAT, E><<<grid, G * E, psmem, st>>>(p, a));
+  return SKB_OK;
+}
+
+// warp-specialised persistent kernel (kernels.cuh assemble_ws_kernel): 2 compute + 2 reducer warpgroups per CTA
+template <int D, int MAT>
+static int launch_ws(skb_plan* pl, const PlanView& p, const EvalArgs& a, size_t wsmem, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SKB_CUDA(cudaFuncSetAttribute(assemble_ws_kernel<D, MAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_ws_kernel<D, MAT><<<grid, 512, wsmem, st>>>(p, a));
   return SKB_OK;
 }
 
@@ -146,16 +162,39 @@ static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
   static int use_pipe_env = -1;
   if (use_pipe_env < 0) {
     const char* ev = getenv("SKB_ASSEMBLE");
-    use_pipe_env = (ev && strcmp(ev, "tile") == 0) ? 0 : 1;
+    use_pipe_env = (ev && strcmp(ev, "tile") == 0) ? 0 : (ev && strcmp(ev, "ws") == 0) ? 2 : (ev && strcmp(ev, "pipe") == 0) ? 1 : SKB_ASSEMBLE_DEFAULT;
   }
-  const bool pipe = use_pipe_env && E == SKB_PIPE_E && psmem <= 227 * 1024 && p.n_tiles >= 2 * G;
+  const size_t wsmem = WsSmem<D>::total(p);
+  const bool ws = use_pipe_env == 2 && E == 128 && wsmem <= 227 * 1024 && p.n_tiles >= 2 * WsSmem<D>::P;
+  const bool pipe = !ws && use_pipe_env && E == SKB_PIPE_E && psmem <= 227 * 1024 && p.n_tiles >= 2 * G;
   static bool told = false;
   if (!told && getenv("SKB_VERBOSE")) {
     told = true;
-    fprintf(stderr, "simkit_b200: assembly %s, tile %d elements, %d groups, %d buffers, %zu B shared (pipelined) / %zu B (tile)\n",
-            pipe ? "pipelined" : "one CTA per tile", E, G, NBUF, psmem, smem);
+    fprintf(stderr, "simkit_b200: assembly %s, tile %d elements, %d groups, %d buffers, %zu B shared (pipelined) / %zu B (tile) / %zu B (warp-specialised)\n",
+            ws ? "warp-specialised" : pipe ? "pipelined" : "one CTA per tile", E, G, NBUF, psmem, smem, wsmem);
   }
-  if (pipe) {
+  if (ws) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+    constexpr int P = WsSmem<D>::P;
+    int grid = sms;
+    if (grid * P > p.n_tiles) grid = (p.n_tiles + P - 1) / P;
+    int rc = SKB_OK;
+    if (D == 3) {
+      switch (a.material) {
+        case MAT_STABLE_NEO_HOOKEAN: rc = launch_ws<3, MAT_STABLE_NEO_HOOKEAN>(pl, p, a, wsmem, grid, st); break;
+        case MAT_NEO_HOOKEAN: rc = launch_ws<3, MAT_NEO_HOOKEAN>(pl, p, a, wsmem, grid, st); break;
+        case MAT_ARAP: rc = launch_ws<3, MAT_ARAP>(pl, p, a, wsmem, grid, st); break;
+        case MAT_STVK: rc = launch_ws<3, MAT_STVK>(pl, p, a, wsmem, grid, st); break;
+        case MAT_FCR: rc = launch_ws<3, MAT_FCR>(pl, p, a, wsmem, grid, st); break;
+        case MAT_MACKLIN_MUELLER_NEO_HOOKEAN: rc = launch_ws<3, MAT_MACKLIN_MUELLER_NEO_HOOKEAN>(pl, p, a, wsmem, grid, st); break;
+        default: rc = launch_ws<3, MAT_LINEAR_ELASTICITY>(pl, p, a, wsmem, grid, st); break;
+      }
+    } else {
+      rc = launch_ws<2, -1>(pl, p, a, wsmem, grid, st);
+    }
+    if (rc) return rc;
+  } else if (pipe) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
     int grid = sms;
@@ -187,8 +226,12 @@ static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
     SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_tile_kernel<D><<<p.n_tiles, E, smem, st>>>(p, a));
   }
   if (a.want_hess) {
-    SKB_LAUNCH(pl, SKB_K_FINALIZE_BLOCKS, st,
-               finalize_blocks_kernel<D><<<(p.nu * D * D + SKB_FIN_THREADS * SKB_FIN_PER_THREAD - 1) / (SKB_FIN_THREADS * SKB_FIN_PER_THREAD), SKB_FIN_THREADS, 0, st>>>(p, a.pblocks, a.vals));
+#if defined(SKB_FIN_SLOT)   // one thread per upper slot
+    const int fin_grid = (p.nu + SKB_FIN_THREADS - 1) / SKB_FIN_THREADS;
+#else
+    const int fin_grid = (p.nu * D * D + SKB_FIN_THREADS * SKB_FIN_PER_THREAD - 1) / (SKB_FIN_THREADS * SKB_FIN_PER_THREAD);
+#endif
+    SKB_LAUNCH(pl, SKB_K_FINALIZE_BLOCKS, st, finalize_blocks_kernel<D><<<fin_grid, SKB_FIN_THREADS, 0, st>>>(p, a.pblocks, a.vals));
   }
   if (a.want_grad) {
     SKB_LAUNCH(pl, SKB_K_FINALIZE_VERTS, st,

@@ -175,20 +175,57 @@ struct ElemState {
 // to its staging area sG [value][le]; everything the stiffness blocks need stays in `st`.
 // MAT >= 0 fixes the material at compile time (dead constitutive branches vanish, fewer live
 // registers); MAT = -1 reads it from the arguments.
-template <int D, int MAT = -1>
-SKB_HD void element_math(const EvalArgs& a, int e, const ElemRaw<D>& raw, int le, int E, double* sG, ElemState<D>& st) {
+struct NoHook {
+  SKB_HD void operator()() const {}
+};
+
+// `before_staging` is called exactly once, by every thread, after the register-only part that never touches shared
+// memory (F, SVD) and before the first store to the gradient staging area: the warp-specialised kernel waits there for
+// the reducer warps to release the pair's staging memory.
+//
+// SCRATCH: the element operator D, the material and the weight of element `le` sit in a per-thread column of shared
+// memory sS ([D*D + 3][E]: D row-major, mu, lam, vol; filled by cp.async one tile ahead) and are read twice -- for F
+// and again after the hook -- instead of staying in 24 registers across the SVD, where ptxas would spill them right
+// behind their loads and stall on the load latency (profiles/r02p: STL behind LDG = 7 % of the warp time).
+template <int D>
+SKB_HD void scratch_read(const double* sS, int le, int E, ElemRaw<D>& r) {
+#pragma unroll
+  for (int j = 0; j < D; ++j)
+#pragma unroll
+    for (int c = 0; c < D; ++c) r.Dm[j][c] = sS[(j * D + c) * E + le];
+  r.mu = sS[(D * D) * E + le];
+  r.lam = sS[(D * D + 1) * E + le];
+  r.vol = sS[(D * D + 2) * E + le];
+}
+
+// LATE: the hook is called at the END of the register-only part instead (the local gradient waits in 2 K D registers),
+// so that the reducers have the whole of phase 1a to finish the previous tile.
+SKB_HD void compiler_memory_barrier() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" ::: "memory");
+#endif
+}
+
+template <int D, int MAT = -1, class Hook = NoHook, bool SCRATCH = false, bool LATE = false>
+SKB_HD void element_math(const EvalArgs& a, int e, ElemRaw<D>& raw, int le, int E, double* sG, ElemState<D>& st,
+                         Hook before_staging = Hook(), const double* sS = nullptr) {
   constexpr int K = D + 1;
   const int material = (MAT >= 0) ? MAT : a.material;
   Mat<D> F;
+  if (SCRATCH) scratch_read<D>(sS, le, E, raw);
   build_F<D>(a, e, raw, F);
-  const double mu = raw.mu, lam = raw.lam, vol = raw.vol;
-  const double (&Dm)[D][D] = raw.Dm;
 
   Mat<D> V;
   Vec<D> sig;
   const bool iso = (material != MAT_LINEAR_ELASTICITY);
   const bool need_svd = (a.want_hess && iso) || (a.want_grad && material_uses_rotation(material));
   if (need_svd) svd_rv(F, st.U, sig, V);
+  if (!LATE) before_staging();
+  else compiler_memory_barrier();
+  if (SCRATCH) scratch_read<D>(sS, le, E, raw);  // behind a memory clobber: real loads again
+  const double mu = raw.mu, lam = raw.lam, vol = raw.vol;
+  const double (&Dm)[D][D] = raw.Dm;
+  double gl[LATE ? K * D : 1];
 
   if (a.want_grad) {
     Mat<D> P;
@@ -220,13 +257,24 @@ SKB_HD void element_math(const EvalArgs& a, int e, const ElemRaw<D>& raw, int le
 #pragma unroll
         for (int j = 0; j < D; ++j) s = fma(P.m[i][j], Dm[j][c], s);
         s *= vol;
-        sG[((c + 1) * D + i) * E + le] = s;
+        if (LATE) gl[(c + 1) * D + i] = s;
+        else sG[((c + 1) * D + i) * E + le] = s;
         s0 -= s;
       }
-      sG[i * E + le] = s0;
+      if (LATE) gl[i] = s0;
+      else sG[i * E + le] = s0;
     }
   }
-  if (!a.want_hess) return;
+  if (!a.want_hess) {
+    if (LATE) {
+      before_staging();
+      if (a.want_grad) {
+#pragma unroll
+        for (int k = 0; k < K * D; ++k) sG[k * E + le] = gl[k];
+      }
+    }
+    return;
+  }
 
   if (iso) {
     st.h = principal_hessian<D>(material, sig, mu, lam);
@@ -277,6 +325,13 @@ SKB_HD void element_math(const EvalArgs& a, int e, const ElemRaw<D>& raw, int le
     st.cI = 0.5 * (w_sym + w_skew);
     st.cT = 0.5 * (w_sym - w_skew);
     st.cR = (w_tr - w_sym) / D;
+  }
+  if (LATE) {
+    before_staging();
+    if (a.want_grad) {
+#pragma unroll
+      for (int k = 0; k < K * D; ++k) sG[k * E + le] = gl[k];
+    }
   }
 }
 
@@ -629,6 +684,62 @@ SKB_HD void block_finalize_multi(const PlanView& p, int item0, int stride, int n
   }
 }
 
+// A/B experiment (-DSKB_FIN_SLOT): one thread per upper slot.  The thread reads the slot's whole partial records
+// (RS doubles each, consecutive in memory) with 256-bit loads, two records requested before the first add, so that
+// ~200 bytes per thread are in flight instead of 32; the sums run in the same order per entry (q0, q0+1, ...) =>
+// bit-identical values.  Neighbouring threads own neighbouring slots: the record stream is read as whole sectors.
+template <int D>
+SKB_HD void load_record(const double* r, double (&v)[RecStride<D>::value]) {
+  constexpr int RS = RecStride<D>::value;
+#pragma unroll
+  for (int k = 0; k < RS; k += 4) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[k]), "=d"(v[k + 1]), "=d"(v[k + 2]), "=d"(v[k + 3]) : "l"(r + k));
+#else
+    v[k] = r[k]; v[k + 1] = r[k + 1]; v[k + 2] = r[k + 2]; v[k + 3] = r[k + 3];
+#endif
+  }
+}
+
+template <int D>
+SKB_HD void block_finalize_slot(const PlanView& p, int u, const double* pblocks, double* vals) {
+  constexpr int DD = D * D, RS = RecStride<D>::value;
+  const int q0 = p.blocks.sp_ptr[u];
+  const int nq = p.blocks.sp_ptr[u + 1] - q0;
+  const UpperPos up = p.upos[u];
+  const double* r = pblocks + (size_t)q0 * RS;
+  double acc[RS], b[RS];
+#pragma unroll
+  for (int k = 0; k < RS; ++k) acc[k] = 0.0;
+  if (nq > 0) load_record<D>(r, acc);
+  if (nq > 1) {
+    load_record<D>(r + RS, b);
+#pragma unroll
+    for (int k = 0; k < DD; ++k) acc[k] += b[k];
+  }
+  for (int q = 2; q < nq; q += 2) {
+    double c[RS];
+    load_record<D>(r + (size_t)q * RS, b);
+    if (q + 1 < nq) load_record<D>(r + (size_t)(q + 1) * RS, c);
+#pragma unroll
+    for (int k = 0; k < DD; ++k) acc[k] += b[k];
+    if (q + 1 < nq) {
+#pragma unroll
+      for (int k = 0; k < DD; ++k) acc[k] += c[k];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int k = 0; k < D; ++k) vals[(size_t)up.base + (size_t)i * up.stride + k] = acc[i * D + k];
+  if (up.tbase != up.base) {
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+      for (int i = 0; i < D; ++i) vals[(size_t)up.tbase + (size_t)k * up.tstride + i] = acc[i * D + k];
+  }
+}
+
 template <int D>
 SKB_HD void vert_finalize(const PlanView& p, int v, const double* pverts, double* g) {
   double acc[D];
@@ -917,6 +1028,261 @@ __global__ void SKB_PIPE_BOUNDS(G, E) assemble_pipelined_kernel(PlanView p, Eval
   }
 }
 
+// ------------------------------------------------------------ warp-specialised --
+// The pipelined kernel above is latency-bound with the register file full: its 12 warps hold 168 registers each
+// through phase 2 (a shared-memory reduction that needs 50) and through the waits for a staging buffer, so only
+// ~43 % of the warp time is math (profiles/r02p_assemble_ncu_summary.txt).  Here the roles are split the Blackwell
+// way: a CTA is four warpgroups, two COMPUTE groups that only ever run the per-element math (phase 1a + 1b) at
+// 200 registers (setmaxnreg.inc; the ILP ptxas wants and no spills), and two REDUCER groups at 56 registers
+// (setmaxnreg.dec) that run phase 2 and the TMA prefetch of the reduction schedule.  Compute group c and reducer
+// group c form a pair around one staging area (packed stiffness + gradient) and hand it back and forth with two named
+// barriers (bar.arrive / bar.sync, the PTX producer-consumer idiom): FULL (compute arrives, reducer waits) and EMPTY
+// (reducer arrives, compute waits -- inside element_math, after the SVD and before its first staging store, so the
+// wait is normally over before it is reached).  The schedule of the reducer's NEXT tile is double-buffered and
+// requested one tile ahead.  2 x 128 x 200 + 2 x 128 x 56 = 65,536 registers: the whole file.
+// Same per-tile schedule and summation order as the other two kernels => bitwise identical results.
+template <int D>
+struct WsSmem {
+  static constexpr int P = 2;  // (compute, reducer) pairs per CTA
+  // per compute group: [D*D + 3][E] doubles (element operator, mu, lam, vol) + [K][E] corner indices of the NEXT tile
+  SKB_HD static size_t scratch_bytes(const PlanView& p) {
+    return (size_t)p.tile_elems * ((D * D + 3) * sizeof(double) + (D + 1) * sizeof(int));
+  }
+  SKB_HD static size_t pair_bytes(const PlanView& p) {
+    return PipeSmem<D>::buffer_bytes(p) + PipeSmem<D>::grad_bytes(p) + PipeSmem<D>::sched_bytes(p) + scratch_bytes(p);
+  }
+  SKB_HD static size_t total(const PlanView& p) { return P * pair_bytes(p) + 8 * (size_t)P + 4 * (size_t)P + 32; }
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+// Ampere-style asynchronous copies global -> shared (SASS LDGSTS): no register is involved, so nothing can be spilled
+// behind the load
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+#ifndef SKB_WS_COMPUTE_REGS
+#define SKB_WS_COMPUTE_REGS 200
+#endif
+#ifndef SKB_WS_REDUCER_REGS
+#define SKB_WS_REDUCER_REGS 56
+#endif
+#ifndef SKB_WS_POOLED   // 1: both reducer groups work on every tile (half the phase-2 latency per tile); 0: reducer group c serves compute group c
+#define SKB_WS_POOLED 1
+#endif
+#ifndef SKB_WS_LATE     // 1: the compute groups wait for the staging area at the end of phase 1a (element_math LATE)
+#define SKB_WS_LATE 0
+#endif
+
+template <int D, int MAT>
+__global__ void __launch_bounds__(512, 1) assemble_ws_kernel(PlanView p, EvalArgs a) {
+  constexpr int K = D + 1;
+  constexpr int NP = K * (K + 1) / 2;
+  constexpr int DD = D * D;
+  constexpr int E = 128;  // a warpgroup = one tile
+  constexpr int P = WsSmem<D>::P;
+  constexpr int BAR_FULL = 1, BAR_EMPTY = 1 + P, BAR_RG = 1 + 2 * P;  // named barriers 1 .. 3P (0 = __syncthreads)
+  constexpr bool POOL = SKB_WS_POOLED != 0;
+  constexpr int RT = POOL ? P * E : E;  // reducer threads that work on one tile
+  constexpr int HAND = E + RT;          // threads on a FULL / EMPTY barrier: one compute group + its reducers
+  extern __shared__ __align__(16) double smem[];
+  const int wg = threadIdx.x >> 7;
+  const int gt = threadIdx.x & 127;
+  const bool is_compute = wg < P;
+  const int pair = is_compute ? wg : wg - P;
+  unsigned char* base = reinterpret_cast<unsigned char*>(smem);
+  const size_t bufB = PipeSmem<D>::buffer_bytes(p), gradB = PipeSmem<D>::grad_bytes(p), schB = PipeSmem<D>::sched_bytes(p);
+  unsigned char* pb = base + (size_t)pair * WsSmem<D>::pair_bytes(p);
+  double* sK = reinterpret_cast<double*>(pb);
+  double* sG = reinterpret_cast<double*>(pb + bufB);
+  unsigned char* sched = pb + bufB + gradB;
+  double* sS = reinterpret_cast<double*>(pb + bufB + gradB + schB);  // [DD + 3][E]
+  int* sT = reinterpret_cast<int*>(sS + (DD + 3) * E);                // [K][E]
+  unsigned char* tail = base + (size_t)P * WsSmem<D>::pair_bytes(p);
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(tail);  // [P] mbarriers of the schedule copies
+  int* sNext = reinterpret_cast<int*>(sBar + P);                           // [P] next phase-2 chunk
+
+  if (threadIdx.x < P) {
+    mbar_init(smem_u32(sBar + threadIdx.x), 1);
+    sNext[threadIdx.x] = 0;
+  }
+  __syncthreads();
+
+  const int tstep = gridDim.x * P;
+  int tile = blockIdx.x * P + pair;
+
+  if (is_compute) {
+    reg_alloc<SKB_WS_COMPUTE_REGS>();
+    // Threads past the end of the mesh run the math on the last element (no divergence around the barriers); their
+    // staging column is not referenced by the tile's schedule.
+    const int last = p.t - 1;
+    auto prefetch_T = [&](int en) {  // corner indices -> sT
+#pragma unroll
+      for (int c = 0; c < K; ++c) cp_async4(sT + c * E + gt, p.T32 + (size_t)en * K + c);
+      cp_async_commit();
+    };
+    auto prefetch_S = [&](int en) {  // element operator, material, weight -> sS
+#pragma unroll
+      for (int j = 0; j < DD; ++j) cp_async8(sS + j * E + gt, p.Dm + (size_t)j * p.t + en);
+      cp_async8(sS + DD * E + gt, a.mu + (size_t)en * a.mu_stride);
+      if (a.lam) cp_async8(sS + (DD + 1) * E + gt, a.lam + (size_t)en * a.lam_stride);
+      else sS[(DD + 1) * E + gt] = 0.0;
+      cp_async8(sS + (DD + 2) * E + gt, a.vol + (size_t)en * a.vol_stride);
+      cp_async_commit();
+    };
+    ElemRaw<D> raw;
+    auto gather_x = [&]() {  // the only indirect loads; 2 D (D + 1) registers in flight during the K-block math
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const int v = sT[c * E + gt];
+#pragma unroll
+        for (int i = 0; i < D; ++i) raw.xs[c][i] = a.x[(size_t)v * D + i];
+      }
+    };
+    if (tile < p.n_tiles) {
+      const int e0 = min(tile * E + gt, last);
+      prefetch_T(e0);
+      prefetch_S(e0);
+      cp_async_wait<0>();
+      gather_x();
+    }
+    for (; tile < p.n_tiles; tile += tstep) {
+      const int e = min(tile * E + gt, last);
+      const bool have_next = tile + tstep < p.n_tiles;
+      const int en = min((tile + tstep) * E + gt, last);
+      if (have_next) {
+        prefetch_T(en);
+        cp_async_wait<1>();  // everything but the copy group just committed: this tile's sS
+      } else {
+        cp_async_wait<0>();
+      }
+      ElemState<D> st;
+      auto wait_empty = [&]() { named_bar_sync(BAR_EMPTY + pair, HAND); };
+#if defined(SKB_WS_NOMATH)  // timing experiment only (wrong results): the reducers alone
+      wait_empty();
+#else
+      element_math<D, MAT, decltype(wait_empty), true, SKB_WS_LATE != 0>(a, e, raw, gt, E, sG, st, wait_empty, sS);
+#endif
+      if (have_next) {
+        cp_async_wait<0>();  // the next tile's corner indices (requested before the math)
+        gather_x();          // in flight during the K-block math
+        prefetch_S(en);      // this tile's sS was last read right after the hook
+      }
+#if !defined(SKB_WS_NOMATH)
+      element_store<D, MAT>(a, st, gt, E, sK);
+#endif
+      __threadfence_block();
+      named_bar_arrive(BAR_FULL + pair, HAND);
+    }
+  } else {
+    reg_dealloc<SKB_WS_REDUCER_REGS>();
+    // Pooled: all P * E reducer threads walk the CTA's tiles in order (pair 0, pair 1, pair 0, ...); otherwise reducer
+    // group c walks the tiles of compute group c.
+    const int rt = POOL ? (int)threadIdx.x - P * E : gt;
+    const int rg = POOL ? 0 : pair;  // reducer-group barrier / chunk counter
+    unsigned parbits = 0;
+    auto issue = [&](int tl, int pr) {  // one thread: the tile's reduction schedule -> pair pr's schedule area (TMA unit)
+      unsigned char* sc = base + (size_t)pr * WsSmem<D>::pair_bytes(p) + bufB + gradB;
+      const unsigned mb = smem_u32(sBar + pr);
+      const int nbe = a.want_hess ? p.blocks.tl_ptr[tl + 1] - p.blocks.tl_ptr[tl] : 0;
+      const int nve = a.want_grad ? p.verts.tl_ptr[tl + 1] - p.verts.tl_ptr[tl] : 0;
+      unsigned bytes = 0;
+      if (nbe) bytes += nbe * (unsigned)sizeof(SchedEntry) + E * NP * (unsigned)sizeof(uint16_t);
+      if (nve) bytes += nve * (unsigned)sizeof(SchedEntry) + E * K * (unsigned)sizeof(uint16_t);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the generic-proxy reads of the last tile are done
+      mbar_expect_tx(mb, bytes);
+      unsigned char* q = sc;
+      if (nbe) tma_bulk_g2s(smem_u32(q), p.blocks.tl_ent + p.blocks.tl_ptr[tl], nbe * (unsigned)sizeof(SchedEntry), mb);
+      q += (size_t)p.blocks.max_entries * sizeof(SchedEntry);
+      if (nbe) tma_bulk_g2s(smem_u32(q), p.blocks.tc_src + (size_t)tl * E * NP, E * NP * (unsigned)sizeof(uint16_t), mb);
+      q += (size_t)E * NP * sizeof(uint16_t);
+      if (nve) tma_bulk_g2s(smem_u32(q), p.verts.tl_ent + p.verts.tl_ptr[tl], nve * (unsigned)sizeof(SchedEntry), mb);
+      q += (size_t)p.verts.max_entries * sizeof(SchedEntry);
+      if (nve) tma_bulk_g2s(smem_u32(q), p.verts.tc_src + (size_t)tl * E * K, E * K * (unsigned)sizeof(uint16_t), mb);
+    };
+    // every staging area starts empty; its first schedule is requested right away
+#pragma unroll
+    for (int pr = 0; pr < P; ++pr) {
+      if (!POOL && pr != pair) continue;
+      const int t0 = blockIdx.x * P + pr;
+      if (t0 < p.n_tiles) {
+        if (rt == 0) issue(t0, pr);
+        named_bar_arrive(BAR_EMPTY + pr, HAND);
+      }
+    }
+    for (int s = 0;; ++s) {
+      const int pr = POOL ? s % P : pair;
+      const int tl = blockIdx.x * P + pr + (POOL ? s / P : s) * tstep;  // increasing in s
+      if (tl >= p.n_tiles) break;
+      const bool have_next = tl + tstep < p.n_tiles;
+      const int nbe = a.want_hess ? p.blocks.tl_ptr[tl + 1] - p.blocks.tl_ptr[tl] : 0;
+      const int nve = a.want_grad ? p.verts.tl_ptr[tl + 1] - p.verts.tl_ptr[tl] : 0;
+      unsigned char* ppb = base + (size_t)pr * WsSmem<D>::pair_bytes(p);
+      const double* rK = reinterpret_cast<const double*>(ppb);
+      const double* rG = reinterpret_cast<const double*>(ppb + bufB);
+      const unsigned char* sc = ppb + bufB + gradB;
+      const SchedEntry* sBE = reinterpret_cast<const SchedEntry*>(sc);
+      sc += (size_t)p.blocks.max_entries * sizeof(SchedEntry);
+      const uint16_t* sBS = reinterpret_cast<const uint16_t*>(sc);
+      sc += (size_t)E * NP * sizeof(uint16_t);
+      const SchedEntry* sVE = reinterpret_cast<const SchedEntry*>(sc);
+      sc += (size_t)p.verts.max_entries * sizeof(SchedEntry);
+      const uint16_t* sVS = reinterpret_cast<const uint16_t*>(sc);
+      named_bar_sync(BAR_FULL + pr, HAND);                         // compute group pr has staged the tile
+      mbar_wait(smem_u32(sBar + pr), (parbits >> pr) & 1u);       // its schedule has landed (requested a tile ago)
+      parbits ^= 1u << pr;
+#if !defined(SKB_WS_NOP2)  // (timing experiment only when defined: the compute groups alone)
+      {
+        // greedy longest-first chunks of 32 entries from a shared counter, as in the pipelined kernel
+        const int lane = rt & 31;
+        const int nbc = (nbe + 31) >> 5, nvc = (nve + 31) >> 5;
+        const int nb_first = nbc < 4 ? nbc : 4;
+        for (;;) {
+          int ch = 0;
+          if (lane == 0) ch = atomicAdd(&sNext[rg], 1);
+          ch = __shfl_sync(0xffffffffu, ch, 0);
+          if (ch >= nbc + nvc) break;
+          if (ch >= nb_first && ch < nb_first + nvc) {
+            const int w = ((ch - nb_first) << 5) + lane;
+            if (w < nve) vert_phase2<D>(sVE, sVS, w, E, rG, a.pverts);
+          } else {
+            const int w = ((ch < nb_first ? ch : ch - nvc) << 5) + lane;
+            if (w < nbe) block_phase2<D>(sBE, sBS, w, E, rK, a.pblocks);
+          }
+        }
+      }
+#endif
+      named_bar_sync(BAR_RG + rg, RT);  // every reducer thread is done with the staging area and the schedule
+      if (rt == 0) {
+        sNext[rg] = 0;
+        if (have_next) issue(tl + tstep, pr);
+      }
+      if (have_next) named_bar_arrive(BAR_EMPTY + pr, HAND);
+    }
+  }
+}
+
 #ifndef SKB_FIN_THREADS
 #define SKB_FIN_THREADS 128
 #endif
@@ -927,7 +1293,10 @@ __global__ void SKB_PIPE_BOUNDS(G, E) assemble_pipelined_kernel(PlanView p, Eval
 #endif
 template <int D>
 __global__ void finalize_blocks_kernel(PlanView p, const double* pblocks, double* vals) {
-#if defined(SKB_FIN_ITEMS)
+#if defined(SKB_FIN_SLOT)
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < p.nu) block_finalize_slot<D>(p, u, pblocks, vals);
+#elif defined(SKB_FIN_ITEMS)
   block_finalize_multi<D, SKB_FIN_ITEMS>(p, blockIdx.x * (blockDim.x * SKB_FIN_ITEMS) + threadIdx.x, blockDim.x,
                                          p.nu * (D * D), pblocks, vals);
 #else

@@ -1,0 +1,73 @@
+"""The assembly kernels (one CTA per tile, pipelined persistent, warp-specialised persistent: csrc/kernels.cuh) run the
+same per-tile schedule in the same summation order.  The two persistent kernels instantiate the same per-material phase
+functions, so their results agree to rounding (bit for bit
+wherever the compiler contracted the arithmetic the same way), and two runs of one kernel are bit-identical.  The kernel is chosen once per process
+(SKB_ASSEMBLE), so each one runs in a child process (with a time limit: the warp-specialised kernel synchronises its
+warpgroups with named barriers) and the parent compares the arrays."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CHILD = r"""
+import sys, numpy as np
+import simkit_b200 as sk
+from simkit_b200 import synthetic as syn
+from simkit_b200._lib import MATERIAL_IDS
+out = sys.argv[1]
+res = {}
+for cells in ((9, 8, 7), (37, 29), (3, 3, 2)):
+    dim = len(cells)
+    X, T = syn.make_mesh(cells)
+    rng = np.random.default_rng(5)
+    U = X + 0.2 * syn.cell_size(cells, tuple(1.0 for _ in cells)) * rng.standard_normal(X.shape)
+    mu, lam = syn.heterogeneous_lame(T.shape[0])
+    plan = sk.MeshPlan(X=X, T=T)
+    vol = plan.volume()
+    for mat in sorted(MATERIAL_IDS):
+        for psd in (0, 1):
+            g, v = plan.gradient_hessian(mat, U, mu, lam, vol, psd)
+            res["%s_%d_%s_g_%d" % (mat, psd, "x".join(map(str, cells)), dim)] = g
+            res["%s_%d_%s_v_%d" % (mat, psd, "x".join(map(str, cells)), dim)] = v
+    # gradient-only and Hessian-only calls, and the _u tier's per-element offset
+    res["gonly_%d" % dim] = plan.gradient("stable_neo_hookean", U, mu, lam, vol)
+    res["honly_%d" % dim] = plan.hessian_values("arap", U, mu, lam, vol, 1)
+    Fbar = 0.05 * rng.standard_normal((T.shape[0], dim, dim)) + np.eye(dim)
+    g, v = plan.gradient_hessian("neo_hookean", U - X, mu, lam, vol, 1, Fbar=Fbar)
+    res["fbar_g_%d" % dim], res["fbar_v_%d" % dim] = g, v
+np.savez(out, **res)
+"""
+
+
+def _run(kernel, tmp_path):
+    out = str(tmp_path / ("vals_%s.npz" % kernel))
+    env = dict(os.environ, SKB_ASSEMBLE=kernel)
+    r = subprocess.run([sys.executable, "-c", CHILD, out], cwd=os.path.dirname(HERE), env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return np.load(out)
+
+
+def test_assembly_kernels_agree(tmp_path):
+    tile, pipe, ws = (_run(k, tmp_path) for k in ("tile", "pipe", "ws"))
+    ws2 = _run("ws", tmp_path)
+    assert sorted(pipe.files) == sorted(ws.files) == sorted(tile.files)
+    worst = 0.0
+    for k in pipe.files:
+        assert np.all(np.isfinite(ws[k])), k
+        # no atomics, fixed summation order: two runs of the warp-specialised kernel are bit-identical (a race in the
+        # warpgroup hand-over would show here)
+        assert np.array_equal(ws[k], ws2[k]), "%s differs between two runs of the warp-specialised kernel" % k
+        scale = max(np.abs(pipe[k]).max(), 1e-300)
+        # same schedule and summation order; the compiler may contract a*b+c differently in the two kernel bodies
+        d = np.abs(pipe[k] - ws[k]).max() / scale
+        worst = max(worst, d)
+        assert d <= 1e-12, "%s: pipelined vs warp-specialised kernel, %g" % (k, d)
+        assert np.abs(tile[k] - pipe[k]).max() <= 1e-12 * scale, "%s: tile kernel vs pipelined kernel" % k
+    print("largest pipelined / warp-specialised difference: %g" % worst)
