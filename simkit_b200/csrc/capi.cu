@@ -119,9 +119,10 @@ int upload_materials(skb_plan* pl, const double* mu, int64_t mu_n, const double*
 #ifndef SKB_PIPE_NBUF
 #define SKB_PIPE_NBUF 2
 #endif
-// default assembly kernel when SKB_ASSEMBLE is not set: 1 = pipelined, 2 = warp-specialised
+// default assembly kernel when SKB_ASSEMBLE is not set: 1 = pipelined, 2 = warp-specialised (falls back to the
+// pipelined kernel, then to one CTA per tile, when the tile size or the schedule does not fit)
 #ifndef SKB_ASSEMBLE_DEFAULT
-#define SKB_ASSEMBLE_DEFAULT 1
+#define SKB_ASSEMBLE_DEFAULT 2
 #endif
 
 template <int D, int G, int NBUF, int MAT>
@@ -226,11 +227,7 @@ static int launch_assemble_t(skb_plan* pl, const EvalArgs& a, cudaStream_t st) {
     SKB_LAUNCH(pl, SKB_K_ASSEMBLE, st, assemble_tile_kernel<D><<<p.n_tiles, E, smem, st>>>(p, a));
   }
   if (a.want_hess) {
-#if defined(SKB_FIN_SLOT)   // one thread per upper slot
-    const int fin_grid = (p.nu + SKB_FIN_THREADS - 1) / SKB_FIN_THREADS;
-#else
     const int fin_grid = (p.nu * D * D + SKB_FIN_THREADS * SKB_FIN_PER_THREAD - 1) / (SKB_FIN_THREADS * SKB_FIN_PER_THREAD);
-#endif
     SKB_LAUNCH(pl, SKB_K_FINALIZE_BLOCKS, st, finalize_blocks_kernel<D><<<fin_grid, SKB_FIN_THREADS, 0, st>>>(p, a.pblocks, a.vals));
   }
   if (a.want_grad) {

@@ -198,15 +198,7 @@ SKB_HD void scratch_read(const double* sS, int le, int E, ElemRaw<D>& r) {
   r.vol = sS[(D * D + 2) * E + le];
 }
 
-// LATE: the hook is called at the END of the register-only part instead (the local gradient waits in 2 K D registers),
-// so that the reducers have the whole of phase 1a to finish the previous tile.
-SKB_HD void compiler_memory_barrier() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("" ::: "memory");
-#endif
-}
-
-template <int D, int MAT = -1, class Hook = NoHook, bool SCRATCH = false, bool LATE = false>
+template <int D, int MAT = -1, class Hook = NoHook, bool SCRATCH = false>
 SKB_HD void element_math(const EvalArgs& a, int e, ElemRaw<D>& raw, int le, int E, double* sG, ElemState<D>& st,
                          Hook before_staging = Hook(), const double* sS = nullptr) {
   constexpr int K = D + 1;
@@ -220,12 +212,10 @@ SKB_HD void element_math(const EvalArgs& a, int e, ElemRaw<D>& raw, int le, int 
   const bool iso = (material != MAT_LINEAR_ELASTICITY);
   const bool need_svd = (a.want_hess && iso) || (a.want_grad && material_uses_rotation(material));
   if (need_svd) svd_rv(F, st.U, sig, V);
-  if (!LATE) before_staging();
-  else compiler_memory_barrier();
-  if (SCRATCH) scratch_read<D>(sS, le, E, raw);  // behind a memory clobber: real loads again
+  before_staging();
+  if (SCRATCH) scratch_read<D>(sS, le, E, raw);  // the hook is a barrier with a memory clobber: real loads again
   const double mu = raw.mu, lam = raw.lam, vol = raw.vol;
   const double (&Dm)[D][D] = raw.Dm;
-  double gl[LATE ? K * D : 1];
 
   if (a.want_grad) {
     Mat<D> P;
@@ -257,24 +247,13 @@ SKB_HD void element_math(const EvalArgs& a, int e, ElemRaw<D>& raw, int le, int 
 #pragma unroll
         for (int j = 0; j < D; ++j) s = fma(P.m[i][j], Dm[j][c], s);
         s *= vol;
-        if (LATE) gl[(c + 1) * D + i] = s;
-        else sG[((c + 1) * D + i) * E + le] = s;
+        sG[((c + 1) * D + i) * E + le] = s;
         s0 -= s;
       }
-      if (LATE) gl[i] = s0;
-      else sG[i * E + le] = s0;
+      sG[i * E + le] = s0;
     }
   }
-  if (!a.want_hess) {
-    if (LATE) {
-      before_staging();
-      if (a.want_grad) {
-#pragma unroll
-        for (int k = 0; k < K * D; ++k) sG[k * E + le] = gl[k];
-      }
-    }
-    return;
-  }
+  if (!a.want_hess) return;
 
   if (iso) {
     st.h = principal_hessian<D>(material, sig, mu, lam);
@@ -325,13 +304,6 @@ SKB_HD void element_math(const EvalArgs& a, int e, ElemRaw<D>& raw, int le, int 
     st.cI = 0.5 * (w_sym + w_skew);
     st.cT = 0.5 * (w_sym - w_skew);
     st.cR = (w_tr - w_sym) / D;
-  }
-  if (LATE) {
-    before_staging();
-    if (a.want_grad) {
-#pragma unroll
-      for (int k = 0; k < K * D; ++k) sG[k * E + le] = gl[k];
-    }
   }
 }
 
@@ -385,6 +357,44 @@ SKB_HD Mat<D> local_block(const ElemState<D>& st, int ca, int cb) {
       }
   }
   return Kb;
+}
+
+// Corner-0 pairs of the local stiffness from the translation invariance sum_a K_ab = 0 (W[0] = -sum_c W[c]): reads
+// the element's own staged pairs among corners 1..D back and writes K_0b = -sum_{a>=1} K_ab and K_00 = -sum_b K_0b^T.
+// One thread per element, conflict-free columns.
+template <int D>
+SKB_HD void element_sum0(int le, int E, double* sK) {
+  constexpr int K = D + 1;
+  {
+      const volatile double* rK = sK;   // real shared-memory loads: forwarding the stores would keep 45 values live
+      double k00[D][D];
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int kk = 0; kk < D; ++kk) k00[i][kk] = 0.0;
+#pragma unroll
+      for (int cb = 1; cb < K; ++cb)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int kk = 0; kk < D; ++kk) {
+            double acc = 0.0;   // K_0b[i][kk] = -sum_{a >= 1} K_ab[i][kk],  K_ab = K_ba^T for a > b
+#pragma unroll
+            for (int ca = 1; ca < K; ++ca) {
+              int idx;
+              if (ca < cb) idx = stage_idx<D>(ca, cb, i, kk);
+              else if (ca > cb) idx = stage_idx<D>(cb, ca, kk, i);
+              else idx = (i <= kk) ? stage_idx<D>(ca, ca, i, kk) : stage_idx<D>(ca, ca, kk, i);
+              acc -= rK[idx * E + le];
+            }
+            sK[stage_idx<D>(0, cb, i, kk) * E + le] = acc;
+            k00[kk][i] -= acc;  // K_00 = -sum_b K_0b^T
+          }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int kk = i; kk < D; ++kk) sK[stage_idx<D>(0, 0, i, kk) * E + le] = k00[i][kk];
+    }
 }
 
 // Phase 1b: writes the element's packed (K*D)x(K*D) local stiffness and its local gradient to
@@ -442,36 +452,7 @@ SKB_HD void element_store(const EvalArgs& a, const ElemState<D>& st, int le, int
           }
       }
 #if defined(SKB_EXP_SUM0)
-    {
-      const volatile double* rK = sK;   // real shared-memory loads: forwarding the stores would keep 45 values live
-      double k00[D][D];
-#pragma unroll
-      for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int kk = 0; kk < D; ++kk) k00[i][kk] = 0.0;
-#pragma unroll
-      for (int cb = 1; cb < K; ++cb)
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-          for (int kk = 0; kk < D; ++kk) {
-            double acc = 0.0;   // K_0b[i][kk] = -sum_{a >= 1} K_ab[i][kk],  K_ab = K_ba^T for a > b
-#pragma unroll
-            for (int ca = 1; ca < K; ++ca) {
-              int idx;
-              if (ca < cb) idx = stage_idx<D>(ca, cb, i, kk);
-              else if (ca > cb) idx = stage_idx<D>(cb, ca, kk, i);
-              else idx = (i <= kk) ? stage_idx<D>(ca, ca, i, kk) : stage_idx<D>(ca, ca, kk, i);
-              acc -= rK[idx * E + le];
-            }
-            sK[stage_idx<D>(0, cb, i, kk) * E + le] = acc;
-            k00[kk][i] -= acc;  // K_00 = -sum_b K_0b^T
-          }
-#pragma unroll
-      for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int kk = i; kk < D; ++kk) sK[stage_idx<D>(0, 0, i, kk) * E + le] = k00[i][kk];
-    }
+    element_sum0<D>(le, E, sK);
 #endif
   } else {
 #pragma unroll
@@ -681,62 +662,6 @@ SKB_HD void block_finalize_multi(const PlanView& p, int item0, int stride, int n
     const int i = j[t] / D, k = j[t] - i * D;
     vals[(size_t)up[t].base + (size_t)i * up[t].stride + k] = acc;
     if (up[t].tbase != up[t].base) vals[(size_t)up[t].tbase + (size_t)k * up[t].tstride + i] = acc;
-  }
-}
-
-// A/B experiment (-DSKB_FIN_SLOT): one thread per upper slot.  The thread reads the slot's whole partial records
-// (RS doubles each, consecutive in memory) with 256-bit loads, two records requested before the first add, so that
-// ~200 bytes per thread are in flight instead of 32; the sums run in the same order per entry (q0, q0+1, ...) =>
-// bit-identical values.  Neighbouring threads own neighbouring slots: the record stream is read as whole sectors.
-template <int D>
-SKB_HD void load_record(const double* r, double (&v)[RecStride<D>::value]) {
-  constexpr int RS = RecStride<D>::value;
-#pragma unroll
-  for (int k = 0; k < RS; k += 4) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v[k]), "=d"(v[k + 1]), "=d"(v[k + 2]), "=d"(v[k + 3]) : "l"(r + k));
-#else
-    v[k] = r[k]; v[k + 1] = r[k + 1]; v[k + 2] = r[k + 2]; v[k + 3] = r[k + 3];
-#endif
-  }
-}
-
-template <int D>
-SKB_HD void block_finalize_slot(const PlanView& p, int u, const double* pblocks, double* vals) {
-  constexpr int DD = D * D, RS = RecStride<D>::value;
-  const int q0 = p.blocks.sp_ptr[u];
-  const int nq = p.blocks.sp_ptr[u + 1] - q0;
-  const UpperPos up = p.upos[u];
-  const double* r = pblocks + (size_t)q0 * RS;
-  double acc[RS], b[RS];
-#pragma unroll
-  for (int k = 0; k < RS; ++k) acc[k] = 0.0;
-  if (nq > 0) load_record<D>(r, acc);
-  if (nq > 1) {
-    load_record<D>(r + RS, b);
-#pragma unroll
-    for (int k = 0; k < DD; ++k) acc[k] += b[k];
-  }
-  for (int q = 2; q < nq; q += 2) {
-    double c[RS];
-    load_record<D>(r + (size_t)q * RS, b);
-    if (q + 1 < nq) load_record<D>(r + (size_t)(q + 1) * RS, c);
-#pragma unroll
-    for (int k = 0; k < DD; ++k) acc[k] += b[k];
-    if (q + 1 < nq) {
-#pragma unroll
-      for (int k = 0; k < DD; ++k) acc[k] += c[k];
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < D; ++i)
-#pragma unroll
-    for (int k = 0; k < D; ++k) vals[(size_t)up.base + (size_t)i * up.stride + k] = acc[i * D + k];
-  if (up.tbase != up.base) {
-#pragma unroll
-    for (int k = 0; k < D; ++k)
-#pragma unroll
-      for (int i = 0; i < D; ++i) vals[(size_t)up.tbase + (size_t)k * up.tstride + i] = acc[i * D + k];
   }
 }
 
@@ -1030,17 +955,27 @@ __global__ void SKB_PIPE_BOUNDS(G, E) assemble_pipelined_kernel(PlanView p, Eval
 
 // ------------------------------------------------------------ warp-specialised --
 // The pipelined kernel above is latency-bound with the register file full: its 12 warps hold 168 registers each
-// through phase 2 (a shared-memory reduction that needs 50) and through the waits for a staging buffer, so only
-// ~43 % of the warp time is math (profiles/r02p_assemble_ncu_summary.txt).  Here the roles are split the Blackwell
-// way: a CTA is four warpgroups, two COMPUTE groups that only ever run the per-element math (phase 1a + 1b) at
-// 200 registers (setmaxnreg.inc; the ILP ptxas wants and no spills), and two REDUCER groups at 56 registers
-// (setmaxnreg.dec) that run phase 2 and the TMA prefetch of the reduction schedule.  Compute group c and reducer
-// group c form a pair around one staging area (packed stiffness + gradient) and hand it back and forth with two named
-// barriers (bar.arrive / bar.sync, the PTX producer-consumer idiom): FULL (compute arrives, reducer waits) and EMPTY
-// (reducer arrives, compute waits -- inside element_math, after the SVD and before its first staging store, so the
-// wait is normally over before it is reached).  The schedule of the reducer's NEXT tile is double-buffered and
-// requested one tile ahead.  2 x 128 x 200 + 2 x 128 x 56 = 65,536 registers: the whole file.
-// Same per-tile schedule and summation order as the other two kernels => bitwise identical results.
+// through phase 2 (a shared-memory reduction that needs 50) and through the waits for a staging buffer, ptxas spills
+// the next tile's prefetched inputs right behind their loads (a stall of a full DRAM latency per tile), and only ~43 %
+// of the warp time is math (profiles/r02p_assemble_ncu_summary.txt).  Here the roles are split the Blackwell way:
+// a CTA is four warpgroups, two COMPUTE groups that only ever run the per-element math (phase 1a + 1b) at 200
+// registers (setmaxnreg.inc: no spills), and two REDUCER groups at 56 registers (setmaxnreg.dec) that run phase 2 and
+// the TMA prefetch of the reduction schedule.  2 x 128 x 200 + 2 x 128 x 56 = 65,536 registers: the whole file.
+//   * Each compute group owns one staging area (packed stiffness + gradient) and hands it to the reducers and back
+//     with two named barriers (bar.arrive / bar.sync, the PTX producer-consumer idiom): FULL (compute arrives, reducers
+//     wait) and EMPTY (reducers arrive, compute waits -- inside element_math, after the SVD and before its first
+//     staging store, so the wait is normally over before it is reached).
+//   * The reducers are POOLED: all 256 reducer threads work on one tile at a time, alternating between the two
+//     compute groups' areas, which halves the time an area stays with the reducers (4.46 -> 4.21 ms at C5).
+//   * Inputs of a compute group's NEXT tile never pass through long-lived registers: the corner indices, the element
+//     operator, material and weight are copied global -> shared with cp.async (LDGSTS) one tile ahead; only the 12
+//     gathered coordinates (the indirect loads) sit in registers, and only during the K-block math.  The operator is
+//     read from that scratch twice (for F and after the SVD) instead of living across the SVD.
+//   * The schedule of a group's next tile is requested (TMA bulk copies on an mbarrier) as soon as its last phase 2 ends.
+// Same per-tile schedule and summation order as the other two kernels: results agree to the compiler's FMA contraction
+// and are bit-identical run to run (tests/test_gpu_kernel_variants.py).  Measured at C5 (profiles/r02t_*): pipelined
+// 4.79 ms, this kernel 3.79 ms; compute groups alone 3.26 ms, reducers alone 2.62 ms (before the sweep loops of the
+// SVD / eigen-solve were re-rolled, which cut the instruction footprint from 99 KB to 52 KB and the kernel by 10 %).
 template <int D>
 struct WsSmem {
   static constexpr int P = 2;  // (compute, reducer) pairs per CTA
@@ -1088,11 +1023,8 @@ __device__ __forceinline__ void cp_async_wait() {
 #ifndef SKB_WS_REDUCER_REGS
 #define SKB_WS_REDUCER_REGS 56
 #endif
-#ifndef SKB_WS_POOLED   // 1: both reducer groups work on every tile (half the phase-2 latency per tile); 0: reducer group c serves compute group c
+#ifndef SKB_WS_POOLED   // 1: both reducer groups work on every tile; 0 (A/B): reducer group c serves compute group c
 #define SKB_WS_POOLED 1
-#endif
-#ifndef SKB_WS_LATE     // 1: the compute groups wait for the staging area at the end of phase 1a (element_math LATE)
-#define SKB_WS_LATE 0
 #endif
 
 template <int D, int MAT>
@@ -1182,7 +1114,7 @@ __global__ void __launch_bounds__(512, 1) assemble_ws_kernel(PlanView p, EvalArg
 #if defined(SKB_WS_NOMATH)  // timing experiment only (wrong results): the reducers alone
       wait_empty();
 #else
-      element_math<D, MAT, decltype(wait_empty), true, SKB_WS_LATE != 0>(a, e, raw, gt, E, sG, st, wait_empty, sS);
+      element_math<D, MAT, decltype(wait_empty), true>(a, e, raw, gt, E, sG, st, wait_empty, sS);
 #endif
       if (have_next) {
         cp_async_wait<0>();  // the next tile's corner indices (requested before the math)
@@ -1293,10 +1225,7 @@ __global__ void __launch_bounds__(512, 1) assemble_ws_kernel(PlanView p, EvalArg
 #endif
 template <int D>
 __global__ void finalize_blocks_kernel(PlanView p, const double* pblocks, double* vals) {
-#if defined(SKB_FIN_SLOT)
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u < p.nu) block_finalize_slot<D>(p, u, pblocks, vals);
-#elif defined(SKB_FIN_ITEMS)
+#if defined(SKB_FIN_ITEMS)
   block_finalize_multi<D, SKB_FIN_ITEMS>(p, blockIdx.x * (blockDim.x * SKB_FIN_ITEMS) + threadIdx.x, blockDim.x,
                                          p.nu * (D * D), pblocks, vals);
 #else

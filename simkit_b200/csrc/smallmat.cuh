@@ -201,6 +201,8 @@ SKB_HD void sym_schur2_fast(double app, double aqq, double apq, double& c, doubl
 template <int N>
 SKB_HD void jacobi_eig(Mat<N> a, Vec<N>& w, Mat<N>& V, int max_sweeps = 12, double tol2 = 1e-32) {
   V = identity<N>();
+  // sweeps stay a loop (1-3 run; unrolled, the 12 copies of the sweep body were 40 KB of never-executed instructions)
+#pragma unroll 1
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     double off = 0.0, diag = 0.0;
 #pragma unroll
@@ -407,6 +409,7 @@ SKB_HD void jacobi_warm_f32(const Mat<3>& F, float V[3][3]) {
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0f : 0.0f;
+#pragma unroll 1
   for (int sweep = 0; sweep < 6; ++sweep) {
     const float off = fmaf(a[0][1], a[0][1], fmaf(a[0][2], a[0][2], a[1][2] * a[1][2]));
     const float dg = fmaf(a[0][0], a[0][0], fmaf(a[1][1], a[1][1], a[2][2] * a[2][2]));
@@ -528,9 +531,11 @@ SKB_HD void svd_rv(const Mat<3>& F, Mat<3>& U, Vec<3>& sig, Mat<3>& V) {
     V.m[2][2] = v0[0] * v1[1] - v0[1] * v1[0];
   }
   Mat<3> A = matmul(F, V);
-  hestenes_sweep_thr<3>(A, V, 1e-34);
-  for (int it = 0; it < 12; ++it)
-    if (!hestenes_sweep_thr<3>(A, V, 1e-26)) break;
+  // the first sweep always rotates (threshold 1e-34), later ones only what is left above 1e-13 relative; ONE copy of
+  // the sweep body in the instruction stream (the per-element code is ~100 KB: instruction fetch shows in the profile)
+#pragma unroll 1
+  for (int it = 0; it < 13; ++it)
+    if (!hestenes_sweep_thr<3>(A, V, it == 0 ? 1e-34 : 1e-26) && it > 0) break;
 #endif
   Vec<3> n2;  // squared column norms; square roots are taken once, through rsqrt
 #pragma unroll

@@ -36,10 +36,7 @@ static void run_assemble(const PlanView& p, const EvalArgs& a, std::vector<doubl
                        a.pverts);
     }
   }
-#if defined(SKB_FIN_SLOT)
-  if (a.want_hess)
-    for (int u = 0; u < p.nu; ++u) block_finalize_slot<D>(p, u, a.pblocks, a.vals);
-#elif defined(SKB_FIN_ITEMS)
+#if defined(SKB_FIN_ITEMS)
   if (a.want_hess) {   // the A/B variant's thread grid: blocks of 128 threads, SKB_FIN_ITEMS items per thread
     const int n_items = p.nu * D * D, T = 128;
     for (int blk = 0; blk * T * SKB_FIN_ITEMS < n_items; ++blk)

@@ -22,7 +22,7 @@ from simkit_b200 import synthetic as syn
 from simkit_b200._lib import MATERIAL_IDS
 out = sys.argv[1]
 res = {}
-for cells in ((9, 8, 7), (37, 29), (3, 3, 2)):
+for cells in ((9, 8, 7), (37, 29), (3, 3, 2), (24, 20, 18)):
     dim = len(cells)
     X, T = syn.make_mesh(cells)
     rng = np.random.default_rng(5)
@@ -30,8 +30,9 @@ for cells in ((9, 8, 7), (37, 29), (3, 3, 2)):
     mu, lam = syn.heterogeneous_lame(T.shape[0])
     plan = sk.MeshPlan(X=X, T=T)
     vol = plan.volume()
-    for mat in sorted(MATERIAL_IDS):
-        for psd in (0, 1):
+    big = T.shape[0] > 10000   # many tiles per CTA and many level-2 pieces: one material is enough
+    for mat in (["stable_neo_hookean"] if big else sorted(MATERIAL_IDS)):
+        for psd in ((1,) if big else (0, 1)):
             g, v = plan.gradient_hessian(mat, U, mu, lam, vol, psd)
             res["%s_%d_%s_g_%d" % (mat, psd, "x".join(map(str, cells)), dim)] = g
             res["%s_%d_%s_v_%d" % (mat, psd, "x".join(map(str, cells)), dim)] = v
@@ -39,14 +40,14 @@ for cells in ((9, 8, 7), (37, 29), (3, 3, 2)):
     res["gonly_%d" % dim] = plan.gradient("stable_neo_hookean", U, mu, lam, vol)
     res["honly_%d" % dim] = plan.hessian_values("arap", U, mu, lam, vol, 1)
     Fbar = 0.05 * rng.standard_normal((T.shape[0], dim, dim)) + np.eye(dim)
-    g, v = plan.gradient_hessian("neo_hookean", U - X, mu, lam, vol, 1, Fbar=Fbar)
+    g, v = plan.gradient_hessian("stable_neo_hookean", U - X, mu, lam, vol, 1, Fbar=Fbar)
     res["fbar_g_%d" % dim], res["fbar_v_%d" % dim] = g, v
 np.savez(out, **res)
 """
 
 
-def _run(kernel, tmp_path):
-    out = str(tmp_path / ("vals_%s.npz" % kernel))
+def _run(kernel, tmp_path, tag=""):
+    out = str(tmp_path / ("vals_%s%s.npz" % (kernel, tag)))
     env = dict(os.environ, SKB_ASSEMBLE=kernel)
     r = subprocess.run([sys.executable, "-c", CHILD, out], cwd=os.path.dirname(HERE), env=env, capture_output=True, text=True,
                        timeout=600)
@@ -56,18 +57,22 @@ def _run(kernel, tmp_path):
 
 def test_assembly_kernels_agree(tmp_path):
     tile, pipe, ws = (_run(k, tmp_path) for k in ("tile", "pipe", "ws"))
-    ws2 = _run("ws", tmp_path)
+    ws2 = _run("ws", tmp_path, tag="_again")
     assert sorted(pipe.files) == sorted(ws.files) == sorted(tile.files)
     worst = 0.0
     for k in pipe.files:
-        assert np.all(np.isfinite(ws[k])), k
         # no atomics, fixed summation order: two runs of the warp-specialised kernel are bit-identical (a race in the
-        # warpgroup hand-over would show here)
-        assert np.array_equal(ws[k], ws2[k]), "%s differs between two runs of the warp-specialised kernel" % k
-        scale = max(np.abs(pipe[k]).max(), 1e-300)
+        # warpgroup hand-over would show here).  Plain neo-Hookean is NaN on inverted elements (log J), like the
+        # reference: the NaNs must sit in the same places in every kernel.
+        assert np.array_equal(ws[k], ws2[k], equal_nan=True), "%s differs between two runs of the warp-specialised kernel" % k
+        ok = np.isfinite(pipe[k])
+        assert np.array_equal(ok, np.isfinite(ws[k])) and np.array_equal(ok, np.isfinite(tile[k])), k
+        if "neo_hookean" not in k or "stable" in k:
+            assert ok.all(), k
+        scale = max(np.abs(pipe[k][ok]).max(), 1e-300)
         # same schedule and summation order; the compiler may contract a*b+c differently in the two kernel bodies
-        d = np.abs(pipe[k] - ws[k]).max() / scale
+        d = np.abs(pipe[k][ok] - ws[k][ok]).max() / scale
         worst = max(worst, d)
         assert d <= 1e-12, "%s: pipelined vs warp-specialised kernel, %g" % (k, d)
-        assert np.abs(tile[k] - pipe[k]).max() <= 1e-12 * scale, "%s: tile kernel vs pipelined kernel" % k
+        assert np.abs(tile[k][ok] - pipe[k][ok]).max() <= 1e-12 * scale, "%s: tile kernel vs pipelined kernel" % k
     print("largest pipelined / warp-specialised difference: %g" % worst)
