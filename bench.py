@@ -10,7 +10,7 @@ neo-Hookean gradient + PSD-projected Hessian + CSR assembly of every element of 
   value     tets/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e       same metric through the public host-pointer API (pinned host buffers, H2D of the state and
             D2H of gradient + CSR values inside the timed region)
-  roofline  dominant kernel (assemble_pipelined_kernel) against the measured HBM peak; algorithmic bytes per
+  roofline  dominant kernel (assemble_ws_kernel) against the measured HBM peak; algorithmic bytes per
             tet from SURVEY.md §8(d); the FP64 fraction is reported beside it
   cpu_baseline  the numpy/scipy oracle (a port of the reference CPU path) on a bounded sample
   newton    one backward-Euler Newton step (assembly + block-Jacobi PCG + line search), steps/s
@@ -371,13 +371,17 @@ def run_ours(args, rank, world, local_rank):
     alg_bytes = per_elem * plan.t + 2 * 8 * dim * plan.n + 8 * plan.nnz
     alg_flops = (2600.0 if dim == 3 else 700.0) * plan.t
     k_ms = kms[0] / max(int(kcount[0]), 1)
-    kernel_key = "assemble_pipelined_kernel<%d>" % dim
+    # the library picks the assembly kernel (csrc/capi.cu launch_assemble_t): warp-specialised persistent kernel by
+    # default, SKB_ASSEMBLE=pipe|tile for the round-1 kernels
+    which = os.environ.get("SKB_ASSEMBLE", "ws")
+    kernel_key = {"pipe": "assemble_pipelined_kernel<%d>", "tile": "assemble_tile_kernel<%d>"}.get(which, "assemble_ws_kernel<%d>") % dim
     # the algorithmic bytes (366 B/tet at C5) are what the STEP has to move: the CSR values among them are written by
     # finalize_blocks, not by the assembly kernel, so the fraction is quoted for the chain of kernels that makes up the
     # step (0.127, not the 0.178 that credited the assembly kernel with bytes it does not move)
     chain_ms = float(sum(kms[i] / max(int(kcount[i]), 1) for i in range(3)))
     achieved = alg_bytes / (chain_ms * 1e-3) / 1e9
-    traffic = load_traffic("step") if (world == 1 and args.workload == "C5" and args.shuffle == "none") else None
+    traffic = (load_traffic("step_ws" if which not in ("pipe", "tile") else "step")
+               if (world == 1 and args.workload == "C5" and args.shuffle == "none") else None)
     roofline = {
         "kernel": "assembly step = %s + finalize_blocks_kernel + finalize_verts_kernel" % kernel_key,
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

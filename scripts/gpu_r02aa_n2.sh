@@ -1,0 +1,23 @@
+#!/bin/bash
+# r02aa (2 GPUs): sharding tests (pins / contacts on shards, sharded reduced, peer transport with the sliced coarse solve);
+# bench at N with the default configuration
+N=${1:-2}
+mkdir -p gpurun_out
+timeout 700 python -m pytest tests/test_gpu_sharding.py -m gpu -x -q > gpurun_out/r02aa_pytest_n2.log 2>&1; tail -6 gpurun_out/r02aa_pytest_n2.log
+run() {  # tag, extra args
+  tag=$1; shift
+  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $N --no-cpu "$@" > gpurun_out/r02aa_bench_n${N}_$tag.json 2> gpurun_out/r02aa_bench_n${N}_$tag.err
+  echo "$tag rc=$?"
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/r02aa_bench_n${N}_$tag.json")); nw = d.get("newton", {})
+    print("$tag", "step %.3f ms" % d["ms_per_step"], "newton %.2f steps/s, %s PCG iterations, %.3f ms per iteration" % (
+        nw.get("steps_per_s", float("nan")), nw.get("pcg_iters"), nw.get("pcg_ms_per_iter", float("nan"))), nw.get("solver"), nw.get("solve_ms"), (d.get("parity_check") or {}).get("ok"), (d.get("parity_check") or {}).get("newton"))
+except Exception as ex:
+    print("$tag", "FAILED", ex)
+PY
+  tail -2 gpurun_out/r02aa_bench_n${N}_$tag.err | cut -c1-300
+}
+run default

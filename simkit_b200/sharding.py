@@ -6,13 +6,14 @@ range of vertex rows ``[v_p, v_{p+1})`` with ``v_p`` = smallest vertex id its el
 vertex an element touches is owned by its own rank or a HIGHER one.  For rank ``q``:
 
 * own elements                 evaluated here;
-* ghost vertices               referenced by own elements, owned by a higher rank: the partial gradient rows
-                               and Hessian block-rows computed here travel to the owner (one NCCL send per
-                               neighbour per assembly) and are added there, in rank order -> deterministic;
-* pattern-only elements        lower ranks' elements that touch vertices owned here.  They are never
-                               evaluated: they only reserve CSR slots (``skb_plan_create_sharded``), so the
-                               rows this rank owns have the full global pattern (columns reaching into the
-                               lower neighbour = "halo" vertices);
+* ghost vertices               referenced by own elements, owned by a higher rank.  ``interface="exchange"``: the
+                               partial gradient rows and Hessian block-rows computed here travel to the owner
+                               (one NCCL send per neighbour per assembly) and are added there, in rank order;
+* pattern-only elements        lower ranks' elements that touch vertices owned here.  ``interface="recompute"``
+                               (default): this rank evaluates them too, so its owned rows are complete without any
+                               communication; ``"exchange"``: they are never evaluated and only reserve CSR slots
+                               (``skb_plan_create_sharded``).  Either way the rows this rank owns have the full
+                               global pattern (columns reaching into the lower neighbour = "halo" vertices);
 * local vertex numbering       sorted global ids of (halo | owned | ghost) -- monotone, so sorted local
                                patterns are sorted global patterns.
 
