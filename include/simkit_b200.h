@@ -449,6 +449,22 @@ int skb_fst_eval(int dim, int64_t m1, int64_t m2, int64_t n_clusters, const doub
 int skb_qr_thin(int64_t n, int64_t r, const double* A, double* Q, double* R);
 int skb_weighted_gram(int64_t n, int64_t r, int64_t s, const double* A, const double* w, const double* B, double* G);
 
+/* ---- spectral clustering / cubature (csrc/capi_cluster.cu) --------------------------------------
+ * skb_average_onto_simplex: At (t x p) = mean over the K corners T (t x K, int32) of the per-vertex rows A (n x p)
+ *   (average_onto_simplex.py:8-37).
+ * skb_kmeans2_pp: scipy.cluster.vq.kmeans2(data, k, iter, minit="++") as spectral_clustering.py:46 calls it: `first` is
+ *   the uniformly drawn first centre row and `uniforms` the k - 1 numbers in [0, 1) of the k-means++ draws, taken by the
+ *   caller from scipy's own generator in scipy's order; centroids (k x p), labels (n, int32: from the LAST assignment,
+ *   i.e. before the last centre update, as scipy returns them); n_empty counts empty clusters met (scipy warns).
+ * skb_cubature_pick: lI[j] = first row of data nearest to centroid j, mc[j] = sum of vol over the rows labelled j
+ *   (spectral_cubature.py:63-66: pairwise_distance + argmin, bincount).
+ * Host pointers, row-major. */
+int skb_average_onto_simplex(int64_t n, int64_t p, int64_t t, int K, const double* A, const int32_t* T, double* At);
+int skb_kmeans2_pp(int64_t n, int64_t p, int64_t k, int iters, int64_t first, const double* uniforms, const double* data,
+                   double* centroids, int32_t* labels, int32_t* n_empty);
+int skb_cubature_pick(int64_t n, int64_t p, int64_t k, const double* data, const double* centroids, const int32_t* labels,
+                      const double* vol, int64_t* lI, double* mc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -903,6 +903,29 @@ def project_into_subspace(y, B, M=None, BMB=None, BMy=None):
     return np.linalg.solve(BMB, BMy).reshape(-1, 1)
 
 
+def average_onto_simplex(A, T):
+    """average_onto_simplex.py:8-37."""
+    A = np.asarray(A, dtype=np.float64)
+    return sum(A[T[:, c], :] / T.shape[1] for c in range(T.shape[1]))
+
+
+def spectral_clustering(W, k, D=None, seed=0):
+    """spectral_clustering.py:9-48: scipy's kmeans2 with k-means++ seeding on the weighted rows (scipy IS the
+    reference's algorithm here; simkit_b200 restates it on the GPU)."""
+    from scipy.cluster.vq import kmeans2
+    B = np.asarray(W, dtype=np.float64) * (np.ones((W.shape[0], 1)) if D is None else D)
+    c, l = kmeans2(B, k, seed=seed, minit="++")
+    return l, c
+
+
+def spectral_cubature(X, T, W, k):
+    """spectral_cubature.py:18-74 -> (lI, mc, labels, centroids)."""
+    Wt = average_onto_simplex(W, T)
+    labels, centroids = spectral_clustering(Wt, k)
+    D = np.linalg.norm(centroids[:, None, :] - Wt[None, :, :], axis=2)
+    return np.argmin(D, axis=1), np.bincount(labels, volume(X, T).flatten()), labels, centroids
+
+
 def lbs_jacobian(V, W):
     """lbs_jacobian.py:12-47."""
     n, d = V.shape

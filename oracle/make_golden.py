@@ -368,8 +368,28 @@ def golden_subspace(tag, cells, seed):
     print("wrote", tag)
 
 
+def golden_cubature(tag, cells, p, k, seed):
+    """spectral_cubature of the reference (scipy kmeans2 with k-means++ seeding, seed 0) on smooth modes."""
+    from simkit.spectral_cubature import spectral_cubature
+    from simkit.spectral_clustering import spectral_clustering
+    rng = np.random.default_rng(seed)
+    X, T = syn.make_mesh(cells)
+    X = X + 0.2 * syn.cell_size(cells, tuple(1.0 for _ in cells)) * rng.standard_normal(X.shape)
+    W = np.cos(X @ (2.0 * np.pi * rng.standard_normal((X.shape[1], p))) + rng.random((1, p)))   # smooth per-vertex modes (n, p)
+    lI, mc, labels, cen = spectral_cubature(X, T, W, k, return_labels=True, return_centroids=True)
+    Dw = 0.5 + rng.random((X.shape[0], 1))
+    l2, c2 = spectral_clustering(W, k, D=Dw, seed=3)
+    out = dict(X=X, T=T, W=W, k=k, lI=lI, mc=mc, labels=labels, centroids=cen, Dw=Dw, labels_w=l2, centroids_w=c2)
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print("wrote", tag)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "cubature":
+        golden_cubature("cubature_tet", (7, 6, 5), 8, 12, 80)
+        golden_cubature("cubature_tri", (24, 19), 6, 9, 81)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "subspace":      # add the newer fixtures without rewriting the old ones
         golden_subspace("subspace_tet", (3, 2, 2), 70)
         golden_subspace("subspace_tri", (5, 4), 71)

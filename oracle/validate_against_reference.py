@@ -263,6 +263,14 @@ def main():
         Md = sps.diags(1.0 + rng.random(nd))
         check(f"[{dim}D] orthonormalize (mass)", oe.orthonormalize(Bs, Md, 1e-10), ref_on(Bs, Md, 1e-10), 1e-12)
         check(f"[{dim}D] orthonormalize (identity)", oe.orthonormalize(Bs[:, :5]), ref_on(Bs[:, :5]), 1e-12)
+        from simkit.spectral_cubature import spectral_cubature as ref_sc
+        from simkit.average_onto_simplex import average_onto_simplex as ref_avg
+        Wm = rng.standard_normal((X.shape[0], 6)) * np.array([3.0, 2.0, 1.5, 1.0, 0.7, 0.5])
+        check(f"[{dim}D] average_onto_simplex", oe.average_onto_simplex(Wm, T), ref_avg(Wm, T), 1e-15)
+        rl = ref_sc(X, T, Wm, 5, return_labels=True, return_centroids=True)
+        ol = oe.spectral_cubature(X, T, Wm, 5)
+        for nm, a, b in zip(("lI", "mc", "labels", "centroids"), ol, rl):
+            check(f"[{dim}D] spectral_cubature {nm}", np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), 1e-13)
         from simkit.lbs_jacobian import lbs_jacobian as ref_lbs
         Ww = rng.standard_normal((X.shape[0], 4))
         check(f"[{dim}D] lbs_jacobian", oe.lbs_jacobian(X, Ww), ref_lbs(X, Ww), 1e-15)

@@ -18,6 +18,9 @@ from .skinning_eigenmodes import skinning_eigenmodes  # noqa: F401
 from .linear_solve import solve_dense, solve_sparse  # noqa: F401
 from .orthonormalize import orthonormalize  # noqa: F401
 from .project_into_subspace import project_into_subspace  # noqa: F401
+from .average_onto_simplex import average_onto_simplex  # noqa: F401
+from .spectral_clustering import spectral_clustering  # noqa: F401
+from .spectral_cubature import spectral_cubature  # noqa: F401
 from .operators import gravity_force, massmatrix, volume, ympr_to_lame  # noqa: F401
 from .plan import MeshPlan, plan_from_operator  # noqa: F401
 from .potential import ElasticPotential  # noqa: F401

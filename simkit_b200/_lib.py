@@ -155,6 +155,9 @@ SIGNATURES = {
     "skb_gradient_hessian_resident": (_int, [_vp, _int, _int, _vp, _vp] + _MAT + [_vp, _vp]),
     "skb_qr_thin": (_int, [_i64, _i64, _vp, _vp, _vp]),
     "skb_weighted_gram": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "skb_average_onto_simplex": (_int, [_i64, _i64, _i64, _int, _vp, _vp, _vp]),
+    "skb_kmeans2_pp": (_int, [_i64, _i64, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "skb_cubature_pick": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "skb_pcg_vals_dev": (_int, [_vp, _vp, _vp, _vp, _dbl, _int, _vp, ctypes.POINTER(_int), ctypes.POINTER(_dbl)]),
     "skb_plan_value_positions": (_int, [_vp, _i64, _vp, _vp, _vp]),
     "skb_pcg_set_coarse": (_int, [_vp, _i64, _vp, _vp]),

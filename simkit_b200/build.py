@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 _TAG = os.environ.get("SKB_BUILD_TAG", "")
 OBJ = os.path.join(HERE, "csrc", "_obj" + ("_" + _TAG if _TAG else ""))
 LIB = os.path.join(HERE, "libsimkit_b200" + ("_" + _TAG if _TAG else "") + ".so")
-SOURCES = ["capi.cu", "capi_elements.cu", "capi_solver.cu", "capi_reduced.cu", "capi_dist.cu", "capi_nccl.cu", "capi_pcg2.cu", "capi_buffers.cu", "capi_subspace.cu"]
+SOURCES = ["capi.cu", "capi_elements.cu", "capi_solver.cu", "capi_reduced.cu", "capi_dist.cu", "capi_nccl.cu", "capi_pcg2.cu", "capi_buffers.cu", "capi_subspace.cu", "capi_cluster.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -102,3 +102,73 @@ def test_gpu_skinning_eigenmodes(cells):
     assert rel(sk.lbs_jacobian(X, Wo), oe.lbs_jacobian(X, Wo)) == 0.0
     with pytest.raises(ValueError):
         sk.skinning_eigenmodes(X, T, 3, Aeq=sps.identity(X.shape[0]).tocsr()[:2])
+
+
+# ------------------------------------------------------------------------------------------ spectral clustering / cubature
+def _kmeans2_pp_numpy(B, k, seed, iters=10):
+    """The algorithm csrc/capi_cluster.cu runs, step for step, in numpy: k-means++ seeding from the host-drawn numbers
+    (simkit_b200.spectral_clustering._scipy_draws) with a running minimum and `target = u * total` in place of scipy's
+    normalised cumulative sum, then the Lloyd rounds.  Checks the restatement (and the order of the random draws)
+    against scipy on the CPU."""
+    from simkit_b200.spectral_clustering import _scipy_draws
+    n = B.shape[0]
+    first, uni = _scipy_draws(seed, n, k)
+    cen = np.empty((k, B.shape[1]))
+    cen[0] = B[first]
+    d2 = None
+    for i in range(1, k):
+        d = ((B - cen[i - 1]) ** 2).sum(axis=1)
+        d2 = d if d2 is None else np.minimum(d2, d)
+        cum = np.cumsum(d2)
+        pick = int(np.searchsorted(cum, uni[i - 1] * cum[-1]))
+        cen[i] = B[min(pick, n - 1)]
+    for _ in range(iters):
+        lab = np.argmin(((B[:, None, :] - cen[None, :, :]) ** 2).sum(axis=2), axis=1)
+        for j in range(k):
+            if np.any(lab == j):
+                cen[j] = B[lab == j].mean(axis=0)
+    return lab, cen
+
+
+@pytest.mark.parametrize("tag", ["cubature_tet", "cubature_tri"])
+def test_oracle_and_restated_kmeans_match_reference_cubature(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    X, T, W, k = g["X"], g["T"], g["W"], int(g["k"])
+    lI, mc, labels, cen = oe.spectral_cubature(X, T, W, k)
+    assert np.array_equal(lI, g["lI"]) and np.array_equal(labels, g["labels"])
+    assert rel(mc, g["mc"]) < 1e-13 and rel(cen, g["centroids"]) < 1e-13
+    l2, c2 = oe.spectral_clustering(W, k, D=g["Dw"], seed=3)
+    assert np.array_equal(l2, g["labels_w"]) and rel(c2, g["centroids_w"]) < 1e-13
+    # the restated algorithm with the host-drawn random numbers
+    lab, c = _kmeans2_pp_numpy(oe.average_onto_simplex(W, T), k, 0)
+    assert np.array_equal(lab, g["labels"]) and rel(c, g["centroids"]) < 1e-12
+    lab, c = _kmeans2_pp_numpy(W * g["Dw"], k, 3)
+    assert np.array_equal(lab, g["labels_w"]) and rel(c, g["centroids_w"]) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["cubature_tet", "cubature_tri"])
+def test_gpu_spectral_cubature(golden_dir, tag):
+    """Drop-ins against reference-frozen outputs: labels and cubature vertices exact, centroids / cluster volumes to
+    rounding (the cluster means are tree sums); then a larger mesh against the oracle (scipy's kmeans2 itself)."""
+    import simkit_b200 as sk
+    g = np.load(os.path.join(golden_dir, tag + ".npz"))
+    X, T, W, k = g["X"], g["T"], g["W"], int(g["k"])
+    assert rel(sk.average_onto_simplex(W, T), oe.average_onto_simplex(W, T)) == 0.0
+    lI, mc, labels, cen = sk.spectral_cubature(X, T, W, k, return_labels=True, return_centroids=True)
+    assert np.array_equal(lI, g["lI"]) and np.array_equal(labels, g["labels"])
+    assert rel(mc, g["mc"]) < 1e-12 and rel(cen, g["centroids"]) < 1e-12
+    assert len(sk.spectral_cubature(X, T, W, k)) == 2 and len(sk.spectral_cubature(X, T, W, k, return_labels=True)) == 3
+    l2, c2 = sk.spectral_clustering(W, k, D=g["Dw"], seed=3)
+    assert np.array_equal(l2, g["labels_w"]) and rel(c2, g["centroids_w"]) < 1e-12
+    # larger: 20^3 cells (48,000 tets) / 90 x 70 triangles, 10 modes, 40 clusters
+    cells = (20, 20, 20) if X.shape[1] == 3 else (90, 70)
+    Xb, Tb = _jittered(cells, seed=4)
+    rng = np.random.default_rng(9)
+    Wb = np.cos(Xb @ (2.0 * np.pi * rng.standard_normal((Xb.shape[1], 10))) + rng.random((1, 10)))
+    lo, mo, labo, ceno = oe.spectral_cubature(Xb, Tb, Wb, 40)
+    lg, mg, labg, ceng = sk.spectral_cubature(Xb, Tb, Wb, 40, return_labels=True, return_centroids=True)
+    assert np.array_equal(labg, labo) and np.array_equal(lg, lo)
+    assert rel(mg, mo) < 1e-12 and rel(ceng, ceno) < 1e-12
+    with pytest.raises(ValueError):
+        sk.spectral_clustering(Wb, 0)
