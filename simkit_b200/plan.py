@@ -110,6 +110,9 @@ class MeshPlan:
 
     # ------------------------------------------------------------- evaluation
     def _mats(self, mu, lam, vol):
+        # every call that passes materials overwrites the plan's device copies: an ElasticPotential's cached upload
+        # (set_materials(owner=...)) is no longer what sits there
+        self._mat_owner = None
         mu_a, mu_n = material_arg(mu, self.t, "mu")
         lam_a, lam_n = material_arg(lam, self.t, "lam")
         vol_a, vol_n = material_arg(vol, self.t, "vol")
@@ -184,9 +187,13 @@ class MeshPlan:
                                              *margs, ptr(g), ptr(vals)))
         return g, vals
 
-    def set_materials(self, mu, lam, vol):
+    def set_materials(self, mu, lam, vol, owner=None):
+        """Uploads the materials the device-resident step uses.  ``owner``: a token the caller can compare with
+        ``plan._mat_owner`` later to learn that its upload is still the one on the device (any other call that passes
+        materials resets it)."""
         keep, margs = self._mats(mu, lam, vol)
         check(self._lib.skb_set_materials(self._h, *margs))
+        self._mat_owner = owner
 
     def last_launch_count(self):
         return int(self._lib.skb_last_launch_count(self._h))
@@ -221,7 +228,10 @@ class MeshPlan:
                 "symmetric positive definite: project the Hessian (psd=True) or add inertia / penalty terms; NaN in the "
                 "state (inverted elements under neo_hookean) propagates as in the reference." % (info.last_pcg_relres,))
         n_it = info.iters + 1
-        return out, dict(iters=info.iters, alphas=[info.alphas[i] for i in range(min(n_it, 64))],
+        # The reference's ``info`` (solvers/newton.py:43-72) holds per-iteration ``g`` / ``dx`` copies (2 x 66 MB per
+        # iteration at 16 M tets); the device-resident step keeps them in HBM, so the keys exist but are empty lists.
+        # ``alphas`` holds the first 64 step lengths (NewtonInfo's fixed array); ``pcg_*`` / ``step_norm`` are extras.
+        return out, dict(iters=info.iters, alphas=[info.alphas[i] for i in range(min(n_it, 64))], g=[], dx=[],
                          pcg_iters=info.pcg_iters_total, pcg_relres=info.last_pcg_relres,
                          step_norm=info.last_step_norm)
 

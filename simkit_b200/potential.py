@@ -46,7 +46,7 @@ class ElasticPotential:
         self.f_ext = None if f_ext is None else np.asarray(f_ext, dtype=np.float64).reshape(nd, 1)
         self.pin_k = None if pin_k is None else np.asarray(pin_k, dtype=np.float64).reshape(nd, 1)
         self.pin_target = None if pin_target is None else np.asarray(pin_target, dtype=np.float64).reshape(nd, 1)
-        self._materials_set = False
+        self._mat_version = 0
         self.contact_plane = None
         if contact_plane is not None:
             c = dict(contact_plane)
@@ -129,13 +129,22 @@ class ElasticPotential:
         return H
 
     # -- device-resident steps -------------------------------------------------------------------
-    def _ensure_materials(self):
-        if not self._materials_set:
-            self.plan.set_materials(self.mu, self.lam, self.vol)
-            self._materials_set = True
+    def update_materials(self, mu=None, lam=None, vol=None):
+        """Replaces (or, with no arguments, re-reads after an in-place change) the materials of this potential.  The
+        device-resident step uploads ``mu`` / ``lam`` / ``vol`` once and reuses the device copies while nothing else
+        has written the plan's materials -- per-element arrays at 16 M tets are 390 MB per upload."""
+        if mu is not None:
+            self.mu = mu
+        if lam is not None:
+            self.lam = lam
+        if vol is not None:
+            self.vol = vol
+        self._mat_version += 1
 
     def _run(self, x0, x_tilde, mass, kin_scale, tolerance, max_iter, do_line_search, return_info, **kw):
-        self.plan.set_materials(self.mu, self.lam, self.vol)
+        tok = (id(self), self._mat_version)
+        if getattr(self.plan, "_mat_owner", None) != tok:
+            self.plan.set_materials(self.mu, self.lam, self.vol, owner=tok)
         c = self.contact_plane
         if c is not None:
             self.plan.set_contact_plane(c["k"], c["p"], c["n"], c["w"])

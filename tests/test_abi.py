@@ -121,3 +121,47 @@ def test_native_nccl_plumbing():
     assert idbuf.any()
     assert lib.skb_nccl_unique_id(_lib.ptr(idbuf), 64) != 0          # buffer too small
     assert lib.skb_nccl_set_halo(None, 0, None, None, None, None, None, None, None) != 0   # no plan / no communicator
+
+
+def test_potential_uploads_materials_once_per_change():
+    """the device-resident step re-uploaded mu / lam / vol (390 MB at 16 M tets) on every call.  The upload is
+    now tagged with an owner token on the plan; anything else that writes the plan's materials resets the token."""
+    import numpy as np
+    from simkit_b200.potential import ElasticPotential
+
+    class FakePlan:
+        ndof, n, dim, t, COARSE_MIN_ITERS = 6, 2, 3, 1, 10 ** 9
+        uploads = 0
+
+        def volume(self):
+            return np.ones(1)
+
+        def set_materials(self, mu, lam, vol, owner=None):
+            self.uploads += 1
+            self._mat_owner = owner
+
+        def set_contact_plane(self, *a):
+            pass
+
+        def set_contact_sphere(self, *a):
+            pass
+
+        def newton(self, *a, **k):
+            return np.zeros(6), dict(pcg_iters=0, iters=0)
+
+    plan = FakePlan()
+    pot = ElasticPotential("stable_neo_hookean", 1.0, 2.0, plan=plan)
+    other = ElasticPotential("arap", 3.0, 0.0, plan=plan)
+    pot.newton(np.zeros(6))
+    pot.newton(np.zeros(6))
+    assert plan.uploads == 1
+    other.newton(np.zeros(6))          # another potential on the same plan takes the device copies over
+    pot.newton(np.zeros(6))
+    assert plan.uploads == 3
+    plan._mat_owner = None             # what MeshPlan._mats does on any direct call that passes materials
+    pot.newton(np.zeros(6))
+    assert plan.uploads == 4
+    pot.update_materials(mu=5.0)
+    pot.newton(np.zeros(6))
+    pot.newton(np.zeros(6))
+    assert plan.uploads == 5 and pot.mu == 5.0
