@@ -555,6 +555,67 @@ __global__ void fst_precompute_kernel(int64_t t, int m1, int m2, int ncl, const 
   }
 }
 
+// Register-tiled form (default): a CTA owns PT rows p of one cluster and 128 columns q; the PT x D*D slice of A of
+// FST_CH elements at a time is staged in shared memory (read back as broadcasts), a thread keeps PT x D x D accumulators
+// for its column q and loads each element's D*D values of B once for all PT rows: PT*D^3 FMAs per D*D global loads
+// instead of D^3 per 2 D*D.  Same summation order per entry as fst_precompute_kernel => bit-identical values.
+// (DMMA tiles would not help: the DMMA peak of this GPU is the FMA peak)
+constexpr int FST_CH = 16;
+template <int D, int PT>
+__global__ void __launch_bounds__(128) fst_precompute_tiled_kernel(int64_t t, int m1, int m2, int ncl, const double* __restrict__ A,
+                                                                   const double* __restrict__ Bm, const int* __restrict__ order,
+                                                                   const int* __restrict__ cptr, double* __restrict__ ARBs) {
+  constexpr int B = D * D;
+  __shared__ double sa[FST_CH][PT][B];
+  const int p0 = blockIdx.x * PT, c = blockIdx.y;
+  const int q = blockIdx.z * blockDim.x + threadIdx.x;
+  double acc[PT][D][D];
+#pragma unroll
+  for (int pp = 0; pp < PT; ++pp)
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) acc[pp][i][j] = 0.0;
+  const int s_end = cptr[c + 1];
+  for (int s0 = cptr[c]; s0 < s_end; s0 += FST_CH) {
+    const int n = min(FST_CH, s_end - s0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n * PT * B; idx += blockDim.x) {
+      const int se = idx / (PT * B), rem = idx - se * (PT * B);
+      const int pp = rem / B, k = rem - pp * B;
+      const int p = p0 + pp;
+      sa[se][pp][k] = (p < m1) ? A[(int64_t)p * B * t + (int64_t)order[s0 + se] * B + k] : 0.0;
+    }
+    __syncthreads();
+    if (q < m2) {
+      for (int se = 0; se < n; ++se) {
+        const int64_t e = order[s0 + se];
+        double b[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) b[k] = Bm[(e * B + k) * m2 + q];
+#pragma unroll
+        for (int pp = 0; pp < PT; ++pp)
+#pragma unroll
+          for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+#pragma unroll
+              for (int k = 0; k < D; ++k) acc[pp][i][j] = fma(sa[se][pp][D * i + k], b[D * j + k], acc[pp][i][j]);
+      }
+    }
+  }
+  if (q < m2) {
+#pragma unroll
+    for (int pp = 0; pp < PT; ++pp) {
+      if (p0 + pp >= m1) break;
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) ARBs[((((int64_t)(p0 + pp) * m2 + q) * ncl + c) * D + i) * D + j] = acc[pp][i][j];
+    }
+  }
+}
+
 template <int D>
 static int reduced_run(skb_plan* pl, int material, int psd_mode, int64_t t, int64_t r, const double* JB_h,
                        const double* Jx0_h, const double* B_h, const double* x0_h, const double* z_h,
@@ -786,12 +847,26 @@ int skb_fst_precompute(int dim, int64_t t, int64_t m1, int64_t m2, int64_t ncl, 
   }
   dvec<double> Ad(A, A + m1 * b * t), Bd(B, B + b * t * m2), out((size_t)m1 * m2 * ncl * b);
   dvec<int> od(order.begin(), order.end()), cd(cptr.begin(), cptr.end());
-  dim3 grid((unsigned)m1, (unsigned)ncl);
-  const int threads = m2 >= 128 ? 128 : (int)((m2 + 31) / 32 * 32);
-  if (dim == 3)
-    fst_precompute_kernel<3><<<grid, threads>>>(t, (int)m1, (int)m2, (int)ncl, raw(Ad), raw(Bd), raw(od), raw(cd), raw(out));
-  else
-    fst_precompute_kernel<2><<<grid, threads>>>(t, (int)m1, (int)m2, (int)ncl, raw(Ad), raw(Bd), raw(od), raw(cd), raw(out));
+  static int fst_simple = -1;   // SKB_FST=simple: the one-row-per-CTA kernel (A/B and the bit-identity test)
+  if (fst_simple < 0) {
+    const char* ev = getenv("SKB_FST");
+    fst_simple = (ev && strcmp(ev, "simple") == 0) ? 1 : 0;
+  }
+  if (fst_simple) {
+    dim3 grid((unsigned)m1, (unsigned)ncl);
+    const int threads = m2 >= 128 ? 128 : (int)((m2 + 31) / 32 * 32);
+    if (dim == 3)
+      fst_precompute_kernel<3><<<grid, threads>>>(t, (int)m1, (int)m2, (int)ncl, raw(Ad), raw(Bd), raw(od), raw(cd), raw(out));
+    else
+      fst_precompute_kernel<2><<<grid, threads>>>(t, (int)m1, (int)m2, (int)ncl, raw(Ad), raw(Bd), raw(od), raw(cd), raw(out));
+  } else {
+    constexpr int PT = 8;
+    dim3 grid((unsigned)((m1 + PT - 1) / PT), (unsigned)ncl, (unsigned)((m2 + 127) / 128));
+    if (dim == 3)
+      fst_precompute_tiled_kernel<3, PT><<<grid, 128>>>(t, (int)m1, (int)m2, (int)ncl, raw(Ad), raw(Bd), raw(od), raw(cd), raw(out));
+    else
+      fst_precompute_tiled_kernel<2, PT><<<grid, 128>>>(t, (int)m1, (int)m2, (int)ncl, raw(Ad), raw(Bd), raw(od), raw(cd), raw(out));
+  }
   SKB_CUDA(cudaGetLastError());
   SKB_CUDA(cudaDeviceSynchronize());
   SKB_CUDA(cudaMemcpy(ARBs, raw(out), out.size() * sizeof(double), cudaMemcpyDeviceToHost));

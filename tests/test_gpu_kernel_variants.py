@@ -76,3 +76,43 @@ def test_assembly_kernels_agree(tmp_path):
         assert d <= 1e-12, "%s: pipelined vs warp-specialised kernel, %g" % (k, d)
         assert np.abs(tile[k][ok] - pipe[k][ok]).max() <= 1e-12 * scale, "%s: tile kernel vs pipelined kernel" % k
     print("largest pipelined / warp-specialised difference: %g" % worst)
+
+
+FST_CHILD = r"""
+import sys, numpy as np
+import simkit_b200 as sk
+out = sys.argv[1]
+res = {}
+rng = np.random.default_rng(17)
+for dim, t, m1, m2, ncl in ((3, 700, 37, 150, 9), (2, 900, 13, 40, 5), (3, 50, 3, 5, 40)):
+    b = dim * dim
+    A = rng.standard_normal((m1, b * t))
+    B = rng.standard_normal((b * t, m2))
+    l = rng.integers(0, ncl, size=t)
+    l[:ncl] = np.arange(ncl)
+    f = sk.fast_sandwich_transform_clustered(A, B, l, dim=dim)
+    res["ARBs_%d_%d" % (dim, t)] = f.ARBs
+    ref = np.zeros_like(f.ARBs)                      # fast_sandwich_transform_clustered.py:66-93, written as one einsum
+    A4 = A.reshape(m1, t, dim, dim)
+    B4 = B.reshape(t, dim, dim, m2)
+    for c in range(ncl):
+        ref[:, :, c] = np.einsum("peik,ejkq->pqij", A4[:, l == c], B4[l == c])
+    assert np.abs(f.ARBs - ref).max() <= 1e-12 * np.abs(ref).max()
+np.savez(out, **res)
+"""
+
+
+def test_fst_precompute_kernels_bit_identical(tmp_path):
+    """The register-tiled FST kernel (default) sums every entry over its cluster's elements in the same order as the
+    one-row-per-CTA kernel (SKB_FST=simple): identical bits; both equal the definition (einsum) to rounding.  Ragged
+    sizes: rows not a multiple of the 8-row tile, columns not a multiple of 128, clusters with a single element."""
+    outs = []
+    for mode in ("tiled", "simple"):
+        out = str(tmp_path / ("fst_%s.npz" % mode))
+        env = dict(os.environ, SKB_FST=mode)
+        r = subprocess.run([sys.executable, "-c", FST_CHILD, out], cwd=os.path.dirname(HERE), env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        outs.append(np.load(out))
+    for k in outs[0].files:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
