@@ -83,6 +83,10 @@ struct skb_plan {
   // resident subspace basis of the reduced tier (skb_plan_set_basis)
   skb::dvec<double> basis;
   int64_t basis_r = 0;
+  // work arrays of the reduced tier (F, per-element Hessians He = 81 doubles per tet, weighted stress, energies, x),
+  // kept between calls: allocating and freeing 2.7 GB per call at 4 M tets cost ~10 ms of a 120 ms call.  Released
+  // with the basis (skb_plan_set_basis(plan, 0, NULL)).
+  skb::dvec<double> rw_F, rw_He, rw_Pw, rw_psi, rw_x;
   int launches = 0;
   // optional per-kernel CUDA-event timing (skb_kernel_timing / skb_kernel_times)
   bool timing = false;

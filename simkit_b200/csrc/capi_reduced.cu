@@ -626,7 +626,17 @@ static int reduced_run(skb_plan* pl, int material, int psd_mode, int64_t t, int6
   if (material < 0 || material >= MAT_COUNT) return fail(SKB_EINVAL, "unknown material id");
   SKB_TRY
   cudaStream_t st = 0;
-  dvec<double> z(z_h, z_h + r), F((size_t)t * Bk), He((size_t)t * Bk * Bk), Pw((size_t)t * Bk), psi(t);
+  // per-element work arrays: the plan's (kept between calls) when there is a plan
+  dvec<double> F_own, He_own, Pw_own, psi_own;
+  dvec<double>& F = pl ? pl->rw_F : F_own;
+  dvec<double>& He = pl ? pl->rw_He : He_own;
+  dvec<double>& Pw = pl ? pl->rw_Pw : Pw_own;
+  dvec<double>& psi = pl ? pl->rw_psi : psi_own;
+  if (F.size() != (size_t)t * Bk) F.resize((size_t)t * Bk);
+  if (He.size() != (size_t)t * Bk * Bk) He.resize((size_t)t * Bk * Bk);
+  if (Pw.size() != (size_t)t * Bk) Pw.resize((size_t)t * Bk);
+  if (psi.size() != (size_t)t) psi.resize(t);
+  dvec<double> z(z_h, z_h + r);
   dvec<double> JB, Bm, mu, lam, vol;
   const double *mu_p, *lam_p = nullptr, *vol_p;
   const double* Bm_p = nullptr;
@@ -635,7 +645,9 @@ static int reduced_run(skb_plan* pl, int material, int psd_mode, int64_t t, int6
     // F = J (B z + x0) through the mesh plan
     const int64_t nd = pl->ndof();
     if (B_h) Bm.assign(B_h, B_h + nd * r);  // else: the plan's resident basis (skb_plan_set_basis)
-    dvec<double> x(nd), x0;
+    dvec<double>& x = pl->rw_x;
+    if (x.size() != (size_t)nd) x.resize(nd);
+    dvec<double> x0;
     if (x0_h) x0.assign(x0_h, x0_h + nd);
     Bm_p = B_h ? raw(Bm) : raw(pl->basis);
     gemv_rows_kernel<<<(unsigned)((nd * 32 + 255) / 256), 256, 0, st>>>(nd, (int)r, Bm_p, raw(z), x0_h ? raw(x0) : nullptr, raw(x));
@@ -804,6 +816,10 @@ int skb_plan_set_basis(skb_plan* pl, int64_t r, const double* B) {
     pl->basis.clear();
     pl->basis.shrink_to_fit();
     pl->basis_r = 0;
+    for (dvec<double>* w : {&pl->rw_F, &pl->rw_He, &pl->rw_Pw, &pl->rw_psi, &pl->rw_x}) {   // and the work arrays
+      w->clear();
+      w->shrink_to_fit();
+    }
     return SKB_OK;
   }
   const int64_t nd = pl->ndof();
