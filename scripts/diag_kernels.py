@@ -49,7 +49,7 @@ elif what == "reduced":
     plan.set_basis(B)
     from simkit_b200._lib import check, load, ptr
     times = np.zeros(3)
-    for s in range(3):
+    for s in range(int(sys.argv[4]) if len(sys.argv) > 4 else 3):
         t0 = time.perf_counter()
         E, g, H = plan.reduced("stable_neo_hookean", None, z, x0=X.reshape(-1))
         check(load().skb_reduced_last_times(ptr(times)))

@@ -628,10 +628,16 @@ static int reduced_run(skb_plan* pl, int material, int psd_mode, int64_t t, int6
   cudaStream_t st = 0;
   // per-element work arrays: the plan's (kept between calls) when there is a plan
   dvec<double> F_own, He_own, Pw_own, psi_own;
-  dvec<double>& F = pl ? pl->rw_F : F_own;
-  dvec<double>& He = pl ? pl->rw_He : He_own;
-  dvec<double>& Pw = pl ? pl->rw_Pw : Pw_own;
-  dvec<double>& psi = pl ? pl->rw_psi : psi_own;
+  static int keep_env = -1;   // SKB_REDUCED_KEEP=0: allocate per call (A/B)
+  if (keep_env < 0) {
+    const char* ev = getenv("SKB_REDUCED_KEEP");
+    keep_env = (ev && strcmp(ev, "0") == 0) ? 0 : 1;
+  }
+  const bool keep = pl && keep_env;
+  dvec<double>& F = keep ? pl->rw_F : F_own;
+  dvec<double>& He = keep ? pl->rw_He : He_own;
+  dvec<double>& Pw = keep ? pl->rw_Pw : Pw_own;
+  dvec<double>& psi = keep ? pl->rw_psi : psi_own;
   if (F.size() != (size_t)t * Bk) F.resize((size_t)t * Bk);
   if (He.size() != (size_t)t * Bk * Bk) He.resize((size_t)t * Bk * Bk);
   if (Pw.size() != (size_t)t * Bk) Pw.resize((size_t)t * Bk);
