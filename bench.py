@@ -428,7 +428,8 @@ def run_ours(args, rank, world, local_rank):
         v0, v1 = shard.owned_value_range()
         o0, o1 = shard.layout.own_lo * dim, shard.layout.own_hi * dim
         g_h, vals_h = pinned(o1 - o0), pinned(v1 - v0)
-        api = "Shard.gradient_hessian per rank: H2D state, fused assembly, NCCL interface exchange, D2H owned rows"
+        api = ("Shard.gradient_hessian per rank: H2D state, fused assembly (interface layer %s), D2H owned rows"
+               % ("recomputed, no communication" if shard.interface == "recompute" else "exchanged over NCCL"))
 
         def step_e2e():
             shard.gradient_hessian(MATERIAL, x_h, mu, lam, vol_h, PSD_AFTER_VOL, g_out=g_h, vals_out=vals_h)
@@ -588,7 +589,8 @@ def run_ours(args, rank, world, local_rank):
                 "vs_device_resident_step": sec_cl * 1e3 / newton["ms_per_step"],
                 "iterate_difference_vs_device_resident_step": float(np.abs(xcl.ravel() - xref.ravel()).max() / np.abs(xref).max())}
     elif args.newton:
-        # sharded implicit step: device-resident state, distributed PCG (halo exchange + 2 all-reduces per iteration)
+        # sharded implicit step: device-resident state, distributed single-reduction PCG (peer memory or NCCL; see
+        # newton.collectives_per_iter in the line)
         mass_d = shard.lumped_mass_dofs(rho)
         fext_d = torch.zeros(plan.n, dim, dtype=f64, device=dev)
         fext_d[:, 1] = -9.8

@@ -220,7 +220,8 @@ def layout_grid_slab(cells, rank, world):
 
 
 class Shard:
-    """One rank's device plan + NCCL interface exchange (needs a GPU and an initialised process group)."""
+    """One rank's device plan, its interface handling (recompute or NCCL exchange) and the distributed solve (needs a GPU
+    and an initialised process group)."""
 
     def __init__(self, layout, X_local, device=0, tile_elems=0, interface=None):
         """``interface``: how the rows this rank owns get the contributions of the lower neighbour's interface elements
